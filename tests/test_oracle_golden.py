@@ -1,0 +1,64 @@
+"""The oracle restatement against the committed reference outputs (CPU)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cae_oracle as O
+from oracle.make_golden import state_sha256
+
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+SMALL = sorted(glob.glob(os.path.join(GOLDEN, 'transforms_*.pt')))
+NAMED = sorted(glob.glob(os.path.join(GOLDEN, 'named_*.pt')))
+
+
+def _load(p):
+    return torch.load(p, map_location='cpu', weights_only=False)
+
+
+@pytest.mark.parametrize('path', SMALL, ids=[os.path.basename(p)[11:-3] for p in SMALL])
+def test_small_archs_match_reference_outputs(path):
+    torch.set_num_threads(1)
+    g = _load(path)
+    om = O.OracleModel(g['checkpoint'])
+    out = om.forward(g['x_u8'].float() / 255.0)
+    # same torch ops in the same order: bit-exact on the same build; allow 1 ulp-scale
+    # slack for a different CPU's vectorisation of conv accumulation
+    assert torch.allclose(out['y'], g['y'], rtol=0, atol=2e-6)
+    assert torch.allclose(out['x_r'][0], g['x_r'], rtol=0, atol=2e-6)
+    assert torch.equal(torch.round(out['y']), torch.round(g['y'])) or \
+        (torch.round(out['y']) != torch.round(g['y'])).float().mean() < 1e-3
+
+
+@pytest.mark.parametrize('path', NAMED, ids=[os.path.basename(p)[6:-3] for p in NAMED])
+def test_named_archs_match_reference_outputs(path):
+    torch.set_num_threads(1)
+    g = _load(path)
+    chk = O.make_checkpoint(g['arch'], seed=g['seed'])
+    assert state_sha256(chk) == g['sha256'], 'seeded weight generator drifted'
+    om = O.OracleModel(chk)
+    out = om.forward(g['x_u8'].float() / 255.0)
+    assert torch.allclose(out['y'], g['y'], rtol=0, atol=5e-6)
+    assert torch.allclose(out['x_r'][0], g['x_r'], rtol=0, atol=5e-6)
+    assert torch.allclose(out['p_y'], g['p_y'], rtol=1e-5, atol=1e-9)
+
+
+def test_plan_param_counts():
+    # parameter counts measured on the reference classes
+    for name, (enc_n, dec_n) in dict(A=(353745, 374400), B=(1256994, 1920384),
+                                     M=(2385, 4680)).items():
+        enc, dec = O.init_transform_state(O.NAMED_ARCHS[name], seed=0)
+        assert sum(v.numel() for v in enc.values()) == enc_n
+        assert sum(v.numel() for v in dec.values()) == dec_n
+
+
+def test_image_io_casts():
+    # Appendix C: true division by 255 on input, truncating cast on output
+    x = torch.tensor([[[0.0, 254.9 / 255.0, 1.2, -0.3]]]).reshape(1, 1, 4).expand(3, 1, 4)
+    u8 = O.to_uint8_hwc(x)
+    assert u8[0, :, 0].tolist() == [0, 254, 255, 0]
+    buf = np.arange(12, dtype=np.uint8).reshape(2, 2, 3)
+    f = O.to_float_chw(buf)
+    assert f.shape == (1, 3, 2, 2) and f[0, 1, 0, 1].item() == np.float32(4) / np.float32(255)
