@@ -1,0 +1,112 @@
+"""ctypes binding of ``include/cae_b200.h`` (the C ABI of the hot path).
+
+The library is built in-tree (``cnn_autoencoder_b200/lib/libcae_b200.so``) by
+``cnn_autoencoder_b200/csrc/Makefile`` for sm_100a only.  There is no CPU
+fallback: if the library is missing, :func:`lib` raises.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libcae_b200.so')
+CSRC = os.path.join(_HERE, 'csrc')
+
+FMT_NONE, FMT_U8_HWC, FMT_F32_NCHW, FMT_F16_PLANAR, FMT_F16_SPLIT = 0, 1, 2, 3, 4
+HALO_KEEP, HALO_REFLECT = 0, 1
+ACT_NONE, ACT_LEAKY_RELU, ACT_RELU = 0, 1, 2
+CONV_S1, CONV_S2, CONVT_S1, CONVT_S2 = 0, 1, 2, 3
+PAD_ZERO, PAD_REFLECT = 0, 1
+
+SYMBOLS = ['cae_abi_version', 'cae_last_error', 'cae_device_info', 'cae_launch_count',
+           'cae_packed_weight_bytes', 'cae_pack_weights', 'cae_conv_igemm', 'cae_conv_direct',
+           'cae_nchw_to_planar', 'cae_planar_to_nchw', 'cae_eb_quantize',
+           'cae_pmf_to_quantized_cdf', 'cae_rans_encode', 'cae_rans_decode']
+
+
+class Tensor(ctypes.Structure):
+    _fields_ = [('ptr', ctypes.c_void_p), ('fmt', ctypes.c_int32), ('planes', ctypes.c_int32),
+                ('halo', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [('kind', ctypes.c_int32), ('n', ctypes.c_int32), ('h_in', ctypes.c_int32),
+                ('w_in', ctypes.c_int32), ('c_in', ctypes.c_int32), ('c_out', ctypes.c_int32),
+                ('inp', Tensor), ('out', Tensor), ('skip', Tensor),
+                ('weights', ctypes.c_void_p), ('bias', ctypes.c_void_p),
+                ('pre_act', ctypes.c_int32), ('post_act', ctypes.c_int32),
+                ('pad_mode', ctypes.c_int32), ('ck', ctypes.c_int32), ('mt', ctypes.c_int32),
+                ('grid', ctypes.c_int32), ('aux_out', ctypes.c_void_p)]
+
+
+class EbTables(ctypes.Structure):
+    _fields_ = [('medians', ctypes.c_void_p), ('lut', ctypes.c_void_p),
+                ('lut_min', ctypes.c_int32), ('lut_len', ctypes.c_int32),
+                ('mlp', ctypes.c_void_p), ('n_layers', ctypes.c_int32),
+                ('mlp_stride', ctypes.c_int32), ('dims', ctypes.c_int32 * 10),
+                ('hist_min', ctypes.c_int32), ('hist_bins', ctypes.c_int32)]
+
+
+class CaeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile the shared library in-tree with nvcc (sm_100a)."""
+    out = subprocess.run(['make', '-C', CSRC, '-j8'], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise CaeError('building libcae_b200.so failed:\n' + out.stdout + out.stderr)
+    if verbose:
+        print(out.stdout + out.stderr)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CaeError(f'{LIB_PATH} is missing: run `python -c "import __graft_entry__ as g; '
+                       f'g.build()"` (there is no CPU fallback for the hot path)')
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_size_t
+    L.cae_abi_version.restype = ctypes.c_int
+    L.cae_last_error.restype = ctypes.c_char_p
+    L.cae_device_info.argtypes = [ctypes.POINTER(ctypes.c_int)] * 3
+    L.cae_launch_count.restype = ctypes.c_uint64
+    L.cae_packed_weight_bytes.restype = sz
+    L.cae_packed_weight_bytes.argtypes = [ctypes.c_int] * 4
+    L.cae_pack_weights.argtypes = [ctypes.c_int] * 4 + [vp, vp, vp, vp]
+    L.cae_conv_igemm.argtypes = [ctypes.POINTER(ConvDesc), vp]
+    L.cae_conv_direct.argtypes = [ctypes.POINTER(ConvDesc), vp]
+    L.cae_nchw_to_planar.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     Tensor, vp]
+    L.cae_planar_to_nchw.argtypes = [Tensor, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_int, vp, vp]
+    L.cae_eb_quantize.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                  ctypes.POINTER(EbTables), vp, vp, vp, vp, vp, vp, vp]
+    L.cae_pmf_to_quantized_cdf.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
+    L.cae_rans_encode.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp, vp, vp,
+                                  sz, ctypes.POINTER(sz)]
+    L.cae_rans_decode.argtypes = [vp, sz, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp, vp,
+                                  vp]
+    for name in SYMBOLS:
+        if name not in ('cae_abi_version', 'cae_last_error', 'cae_launch_count',
+                        'cae_packed_weight_bytes'):
+            getattr(L, name).restype = ctypes.c_int
+    if L.cae_abi_version() != 1:
+        raise CaeError('libcae_b200.so ABI version mismatch')
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise CaeError(f'[{rc}] ' + lib().cae_last_error().decode())
+
+
+def launch_count():
+    return int(lib().cae_launch_count())

@@ -1,0 +1,302 @@
+"""Factorized-prior entropy model with the interface the reference uses from
+CompressAI (``compressai.entropy_models.EntropyBottleneck``; imported at
+``src/models/tasks/_autoencoders.py:12``; algorithm: SURVEY.md Appendix A.1).
+
+Same constructor, state-dict keys (``_matrix{i}``, ``_bias{i}``, ``_factor{i}``,
+``quantiles``, ``target``, ``_offset``, ``_quantized_cdf``, ``_cdf_length``) and
+methods the reference calls: ``forward`` (``_taskutils.py:97``), ``compress`` /
+``decompress`` (``_autoencoders.py:549-551, 568-572, 645-647, 662-665``),
+``update(force=True)`` (``:502, :615``), ``loss()`` (``_lossutils.py:70``),
+attributes ``channels`` / ``filters`` / ``quantiles``.
+
+Eval-mode ``forward`` and the symbol extraction of ``compress`` run in one CUDA
+kernel (``cae_eb_quantize``: round, per-(channel, symbol) likelihood table,
+histogram, rate); the tables come from this module's own fp32 torch ops, so the
+table lookup equals evaluating the density.  Entropy coding is the C++ range
+coder behind the C ABI.  Training mode (additive-noise proxy, likelihood with
+gradients) stays on torch autograd ops on the device.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _cabi as C
+
+_LUT_MARGIN = 32
+
+
+class _LowerBound(torch.autograd.Function):
+    """max(x, bound); gradient passes where x >= bound or where it pushes x up."""
+
+    @staticmethod
+    def forward(ctx, x, bound):
+        ctx.save_for_backward(x, bound)
+        return torch.max(x, bound)
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, bound = ctx.saved_tensors
+        keep = (x >= bound) | (grad < 0)
+        return keep.type(grad.dtype) * grad, None
+
+
+class EntropyBottleneck(nn.Module):
+    def __init__(self, channels, *args, tail_mass=1e-9, init_scale=10, filters=(3, 3, 3, 3),
+                 likelihood_bound=1e-9, entropy_coder_precision=16, **kwargs):
+        super().__init__()
+        self.channels = int(channels)
+        self.filters = tuple(int(f) for f in filters)
+        self.init_scale = float(init_scale)
+        self.tail_mass = float(tail_mass)
+        self.entropy_coder_precision = int(entropy_coder_precision)
+        self.likelihood_bound = float(likelihood_bound)
+
+        dims = (1,) + self.filters + (1,)
+        scale = self.init_scale ** (1 / (len(self.filters) + 1))
+        for i in range(len(self.filters) + 1):
+            init = float(np.log(np.expm1(1 / scale / dims[i + 1])))
+            self.register_parameter(f'_matrix{i:d}', nn.Parameter(
+                torch.full((self.channels, dims[i + 1], dims[i]), init)))
+            self.register_parameter(f'_bias{i:d}', nn.Parameter(
+                torch.empty(self.channels, dims[i + 1], 1).uniform_(-0.5, 0.5)))
+            if i < len(self.filters):
+                self.register_parameter(f'_factor{i:d}', nn.Parameter(
+                    torch.zeros(self.channels, dims[i + 1], 1)))
+        self.quantiles = nn.Parameter(
+            torch.tensor([-self.init_scale, 0.0, self.init_scale]).repeat(self.channels, 1, 1))
+        t = float(np.log(2 / self.tail_mass - 1))
+        self.register_buffer('target', torch.tensor([-t, 0.0, t]))
+        self.register_buffer('_offset', torch.IntTensor())
+        self.register_buffer('_quantized_cdf', torch.IntTensor())
+        self.register_buffer('_cdf_length', torch.IntTensor())
+        self._tables = None
+        self._tables_key = None
+
+    # ------------------------------------------------------------- density
+    def _logits_cumulative(self, v, stop_gradient):
+        for i in range(len(self.filters) + 1):
+            m = getattr(self, f'_matrix{i:d}')
+            b = getattr(self, f'_bias{i:d}')
+            if stop_gradient:
+                m, b = m.detach(), b.detach()
+            v = torch.matmul(F.softplus(m), v) + b
+            if i < len(self.filters):
+                f = getattr(self, f'_factor{i:d}')
+                if stop_gradient:
+                    f = f.detach()
+                v = v + torch.tanh(f) * torch.tanh(v)
+        return v
+
+    def _likelihood(self, v):
+        lower = self._logits_cumulative(v - 0.5, stop_gradient=False)
+        upper = self._logits_cumulative(v + 0.5, stop_gradient=False)
+        sign = -torch.sign(lower + upper).detach()
+        return torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))
+
+    def _medians(self):
+        return self.quantiles[:, 0, 1].detach()
+
+    def _bound(self, ref):
+        return torch.tensor([self.likelihood_bound], dtype=ref.dtype, device=ref.device)
+
+    def _forward_torch(self, x, training=False):
+        """The model written with torch ops (training path; also what the tables
+        are built from).  C x 1 x M layout as in CompressAI."""
+        nd = x.dim()
+        perm = list(range(nd))
+        perm[0], perm[1] = 1, 0
+        xp = x.permute(*perm).contiguous()
+        shape = xp.size()
+        v = xp.reshape(xp.size(0), 1, -1)
+        if training:
+            v = v + torch.empty_like(v).uniform_(-0.5, 0.5)
+        else:
+            med = self.quantiles[:, :, 1:2]
+            v = torch.round(v - med) + med
+        lik = self._likelihood(v)
+        if self.likelihood_bound > 0:
+            lik = _LowerBound.apply(lik, self._bound(lik))
+        out = v.reshape(shape).permute(*perm).contiguous()
+        lik = lik.reshape(shape).permute(*perm).contiguous()
+        return out, lik
+
+    def loss(self):
+        logits = self._logits_cumulative(self.quantiles, stop_gradient=True)
+        return torch.abs(logits - self.target).sum()
+
+    # -------------------------------------------------------------- tables
+    def update(self, force=False):
+        if self._offset.numel() > 0 and not force:
+            return False
+        with torch.no_grad():
+            med = self.quantiles[:, 0, 1]
+            minima = torch.clamp(torch.ceil(med - self.quantiles[:, 0, 0]).int(), min=0)
+            maxima = torch.clamp(torch.ceil(self.quantiles[:, 0, 2] - med).int(), min=0)
+            pmf_start = med - minima
+            pmf_length = maxima + minima + 1
+            max_length = int(pmf_length.max().item())
+            samples = torch.arange(max_length, device=med.device)[None, :] + pmf_start[:, None, None]
+            lower = self._logits_cumulative(samples - 0.5, stop_gradient=True)
+            upper = self._logits_cumulative(samples + 0.5, stop_gradient=True)
+            sign = -torch.sign(lower + upper)
+            pmf = torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))[:, 0, :]
+            tail = torch.sigmoid(lower[:, 0, :1]) + torch.sigmoid(-upper[:, 0, -1:])
+            pmf_h = pmf.float().cpu().numpy()
+            tail_h = tail.float().cpu().numpy()
+            len_h = pmf_length.cpu().numpy()
+            cdf = np.zeros((self.channels, max_length + 2), dtype=np.int32)
+            L = C.lib()
+            for c in range(self.channels):
+                prob = np.ascontiguousarray(
+                    np.concatenate([pmf_h[c, :len_h[c]], tail_h[c]]), dtype=np.float32)
+                row = np.zeros(prob.shape[0] + 1, dtype=np.uint32)
+                C.check(L.cae_pmf_to_quantized_cdf(prob.ctypes.data, prob.shape[0],
+                                                   self.entropy_coder_precision, row.ctypes.data))
+                cdf[c, :row.shape[0]] = row.astype(np.int32)
+            dev = med.device
+            self._offset = (-minima).int()
+            self._quantized_cdf = torch.from_numpy(cdf).to(dev)
+            self._cdf_length = (pmf_length + 2).int()
+        self._tables = None
+        return True
+
+    def _param_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _device_tables(self):
+        """Likelihood table / MLP blob / medians on the device, rebuilt whenever a
+        parameter changed."""
+        key = self._param_key()
+        if self._tables is not None and self._tables_key == key:
+            return self._tables
+        with torch.no_grad():
+            q = self.quantiles.detach()
+            med = q[:, 0, 1]
+            lo = int(torch.floor((q[:, 0, 0] - med).min()).item()) - _LUT_MARGIN
+            hi = int(torch.ceil((q[:, 0, 2] - med).max()).item()) + _LUT_MARGIN
+            lo, hi = max(lo, -4096), min(hi, 4096)
+            syms = torch.arange(lo, hi + 1, device=q.device, dtype=torch.float32)
+            v = syms[None, None, :] + q[:, :, 1:2]
+            lik = self._likelihood(v)[:, 0, :]
+            if self.likelihood_bound > 0:
+                lik = torch.max(lik, self._bound(lik))
+            blob = []
+            K = len(self.filters)
+            for i in range(K + 1):
+                blob.append(F.softplus(getattr(self, f'_matrix{i:d}').detach()).reshape(self.channels, -1))
+                blob.append(getattr(self, f'_bias{i:d}').detach().reshape(self.channels, -1))
+                if i < K:
+                    blob.append(torch.tanh(getattr(self, f'_factor{i:d}').detach()).reshape(self.channels, -1))
+            mlp = torch.cat(blob, dim=1).contiguous().float()
+            tb = dict(medians=med.contiguous().float().clone(), lut=lik.contiguous().float(),
+                      lut_min=lo, lut_len=hi - lo + 1, mlp=mlp)
+        if max((1,) + self.filters) > 8 or K + 1 > 9:
+            tb['mlp'] = None
+        self._tables, self._tables_key = tb, key
+        return tb
+
+    def _abi_tables(self, tb):
+        t = C.EbTables()
+        t.medians = tb['medians'].data_ptr()
+        t.lut = tb['lut'].data_ptr()
+        t.lut_min, t.lut_len = tb['lut_min'], tb['lut_len']
+        dims = (1,) + self.filters + (1,)
+        if tb['mlp'] is not None:
+            t.mlp = tb['mlp'].data_ptr()
+            t.n_layers = len(self.filters) + 1
+            t.mlp_stride = tb['mlp'].shape[1]
+            for i, d in enumerate(dims):
+                t.dims[i] = d
+        t.hist_min, t.hist_bins = tb['lut_min'], tb['lut_len']
+        return t
+
+    def _quantize_cuda(self, x, want_yq=True, want_p=True, want_sym=False, want_hist=False,
+                       want_rate=False):
+        if not x.is_cuda:
+            raise C.CaeError('EntropyBottleneck: the eval path runs on the GPU only '
+                             '(no CPU fallback); move the module and the latent to cuda')
+        if self.quantiles.device != x.device:
+            raise C.CaeError('EntropyBottleneck parameters and input are on different devices')
+        x = x.contiguous().float()
+        n, c = x.shape[0], x.shape[1]
+        if c != self.channels:
+            raise ValueError(f'expected {self.channels} channels, got {c}')
+        hw = x[0, 0].numel()
+        tb = self._device_tables()
+        t = self._abi_tables(tb)
+        y_q = torch.empty_like(x) if want_yq else None
+        p_y = torch.empty_like(x) if want_p else None
+        sym = torch.empty(x.shape, dtype=torch.int32, device=x.device) if want_sym else None
+        hist = torch.zeros((c, tb['lut_len']), dtype=torch.int32, device=x.device) if want_hist else None
+        rate = torch.zeros(1, dtype=torch.float64, device=x.device) if want_rate else None
+        status = torch.zeros(1, dtype=torch.int32, device=x.device)
+        ptr = lambda a: a.data_ptr() if a is not None else None
+        stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        C.check(C.lib().cae_eb_quantize(x.data_ptr(), n, c, hw, ctypes.byref(t), ptr(y_q), ptr(p_y),
+                                        ptr(sym), ptr(hist), ptr(rate), status.data_ptr(), stream))
+        return y_q, p_y, sym, hist, rate
+
+    # -------------------------------------------------------------- forward
+    def forward(self, x, training=None):
+        if training is None:
+            training = self.training
+        if training or torch.is_grad_enabled() and x.requires_grad:
+            return self._forward_torch(x, training=training)
+        y_q, p_y, _, _, _ = self._quantize_cuda(x)
+        return y_q, p_y
+
+    def symbols_hist_rate(self, x):
+        """(int32 symbols, C x bins histogram, total bits) in one pass (K11/K14)."""
+        _, _, sym, hist, rate = self._quantize_cuda(x, want_yq=False, want_p=False, want_sym=True,
+                                                    want_hist=True, want_rate=True)
+        return sym, hist, rate
+
+    # ------------------------------------------------------ entropy coding
+    def _host_tables(self):
+        if self._offset.numel() == 0:
+            raise C.CaeError('EntropyBottleneck.update() must be called before compress/decompress')
+        cdf = np.ascontiguousarray(self._quantized_cdf.cpu().numpy(), dtype=np.int32)
+        sizes = np.ascontiguousarray(self._cdf_length.cpu().numpy().reshape(-1), dtype=np.int32)
+        offs = np.ascontiguousarray(self._offset.cpu().numpy().reshape(-1), dtype=np.int32)
+        return cdf, sizes, offs
+
+    def compress(self, x):
+        _, _, sym, _, _ = self._quantize_cuda(x, want_yq=False, want_p=False, want_sym=True)
+        sym_h = sym.reshape(sym.shape[0], sym.shape[1], -1).cpu().numpy()
+        return [encode_symbols(sym_h[i], *self._host_tables()) for i in range(sym_h.shape[0])]
+
+    def decompress(self, strings, size):
+        cdf, sizes, offs = self._host_tables()
+        hw = int(np.prod(size))
+        out = np.empty((len(strings), self.channels, hw), dtype=np.int32)
+        for i, s in enumerate(strings):
+            out[i] = decode_symbols(s, self.channels, hw, cdf, sizes, offs)
+        dev = self.quantiles.device
+        y = torch.from_numpy(out).to(dev).reshape(len(strings), self.channels, *size)
+        med = self._medians().reshape(1, -1, *([1] * len(size)))
+        return y.type_as(med) + med
+
+
+def encode_symbols(sym_chw, cdf, sizes, offs):
+    """int32 symbols (C x hw, host) -> bytes, through ``cae_rans_encode``."""
+    sym = np.ascontiguousarray(sym_chw, dtype=np.int32)
+    c, hw = sym.shape
+    cap = 4 * (2 * c * hw + 64)
+    buf = np.empty(cap, dtype=np.uint8)
+    nbytes = ctypes.c_size_t(0)
+    C.check(C.lib().cae_rans_encode(sym.ctypes.data, c, hw, cdf.ctypes.data, cdf.shape[1],
+                                    sizes.ctypes.data, offs.ctypes.data, buf.ctypes.data, cap,
+                                    ctypes.byref(nbytes)))
+    return buf[:nbytes.value].tobytes()
+
+
+def decode_symbols(data, c, hw, cdf, sizes, offs):
+    enc = np.frombuffer(bytes(data), dtype=np.uint8)
+    out = np.empty((c, hw), dtype=np.int32)
+    C.check(C.lib().cae_rans_decode(enc.ctypes.data, enc.shape[0], c, hw, cdf.ctypes.data,
+                                    cdf.shape[1], sizes.ctypes.data, offs.ctypes.data,
+                                    out.ctypes.data))
+    return out

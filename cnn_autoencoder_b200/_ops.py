@@ -1,0 +1,141 @@
+"""Thin torch-tensor front end over the C ABI: device buffers in the internal
+layouts and one Python call per ABI entry point.  PyTorch is used for device
+memory and streams only; every computation below is a kernel of
+``libcae_b200.so``.
+"""
+import ctypes
+from dataclasses import dataclass
+
+import torch
+
+from . import _cabi as C
+
+
+def _stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t, name):
+    if not t.is_cuda:
+        raise C.CaeError(f'{name} must be a CUDA tensor: the hot path has no CPU fallback')
+
+
+def planes_for(c):
+    """8-channel planes holding ``c`` channels padded to a multiple of 16 (MMA K step)."""
+    return ((c + 15) // 16) * 2
+
+
+@dataclass
+class Act:
+    """An activation tensor in one of the ABI formats."""
+    t: torch.Tensor
+    fmt: int
+    n: int
+    c: int
+    h: int
+    w: int
+    halo: int = C.HALO_KEEP
+
+    @property
+    def planes(self):
+        return self.t.shape[-4] if self.fmt in (C.FMT_F16_PLANAR, C.FMT_F16_SPLIT) else 0
+
+    def desc(self, halo=None):
+        return C.Tensor(self.t.data_ptr(), self.fmt, self.planes,
+                        self.halo if halo is None else halo, 0)
+
+
+def alloc_act(fmt, n, c, h, w, halo=C.HALO_KEEP, device='cuda', planes=None):
+    """Zero-initialised buffer (the zero halo IS the zero padding of the transposed
+    convolutions, so it is cleared once here and never written with halo KEEP)."""
+    if fmt == C.FMT_F16_PLANAR:
+        p = planes or planes_for(c)
+        t = torch.zeros((n, p, h + 2, w + 2, 8), dtype=torch.float16, device=device)
+    elif fmt == C.FMT_F16_SPLIT:
+        if h % 2 or w % 2:
+            raise C.CaeError(f'split layout needs even spatial size, got {h}x{w}')
+        p = planes or planes_for(c)
+        t = torch.zeros((n, 4, p, (h + 2) // 2, (w + 2) // 2, 8), dtype=torch.float16,
+                        device=device)
+    elif fmt == C.FMT_F32_NCHW:
+        t = torch.empty((n, c, h, w), dtype=torch.float32, device=device)
+    elif fmt == C.FMT_U8_HWC:
+        t = torch.empty((n, h, w, c), dtype=torch.uint8, device=device)
+    else:
+        raise C.CaeError(f'bad format {fmt}')
+    return Act(t, fmt, n, c, h, w, halo)
+
+
+def wrap_nchw(x):
+    _require_cuda(x, 'input')
+    x = x.contiguous()
+    if x.dtype != torch.float32:
+        x = x.float()
+    n, c, h, w = x.shape
+    return Act(x, C.FMT_F32_NCHW, n, c, h, w)
+
+
+def wrap_u8_hwc(x):
+    _require_cuda(x, 'input')
+    x = x.contiguous()
+    if x.dtype != torch.uint8 or x.dim() != 4:
+        raise C.CaeError('expected an N x H x W x C uint8 tensor')
+    n, h, w, c = x.shape
+    return Act(x, C.FMT_U8_HWC, n, c, h, w)
+
+
+KIND_OUT = {C.CONV_S1: lambda h, w: (h, w), C.CONV_S2: lambda h, w: ((h - 1) // 2 + 1, (w - 1) // 2 + 1),
+            C.CONVT_S1: lambda h, w: (h, w), C.CONVT_S2: lambda h, w: (2 * h, 2 * w)}
+
+
+def pack_weights(kind, weight, scale=None, ck=0):
+    """fp32 torch-layout weight (device) -> packed fp16 image for the igemm kernel."""
+    _require_cuda(weight, 'weight')
+    w = weight.detach().contiguous().float()
+    transposed = kind in (C.CONVT_S1, C.CONVT_S2)
+    c_in, c_out = (w.shape[0], w.shape[1]) if transposed else (w.shape[1], w.shape[0])
+    L = C.lib()
+    nbytes = L.cae_packed_weight_bytes(kind, c_in, c_out, ck)
+    packed = torch.empty(nbytes // 2, dtype=torch.float16, device=w.device)
+    sc = None
+    if scale is not None:
+        sc = scale.detach().contiguous().float()
+    C.check(L.cae_pack_weights(kind, c_in, c_out, ck, w.data_ptr(),
+                               sc.data_ptr() if sc is not None else None,
+                               packed.data_ptr(), _stream_ptr()))
+    return packed
+
+
+def conv(kind, x, weights, c_out, out, *, igemm, bias=None, skip=None, pre_act=C.ACT_NONE,
+         post_act=C.ACT_NONE, pad_mode=C.PAD_REFLECT, aux=None, ck=0, mt=0, grid=0):
+    """out = post_act(pre_act(conv(x) + bias) + skip) through the C ABI."""
+    d = C.ConvDesc()
+    d.kind = kind
+    d.n, d.h_in, d.w_in, d.c_in, d.c_out = x.n, x.h, x.w, x.c, c_out
+    d.inp = x.desc()
+    d.out = out.desc() if out is not None else C.Tensor(None, C.FMT_NONE, 0, 0, 0)
+    d.skip = skip.desc() if skip is not None else C.Tensor(None, C.FMT_NONE, 0, 0, 0)
+    d.weights = weights.data_ptr()
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.pre_act, d.post_act, d.pad_mode = pre_act, post_act, pad_mode
+    d.ck, d.mt, d.grid = ck, mt, grid
+    d.aux_out = aux.data_ptr() if aux is not None else None
+    L = C.lib()
+    fn = L.cae_conv_igemm if igemm else L.cae_conv_direct
+    C.check(fn(ctypes.byref(d), _stream_ptr()))
+    return out
+
+
+def nchw_to_planar(x, fmt=C.FMT_F16_PLANAR, halo=C.HALO_KEEP):
+    a = wrap_nchw(x)
+    out = alloc_act(fmt, a.n, a.c, a.h, a.w, halo, device=x.device)
+    C.check(C.lib().cae_nchw_to_planar(a.t.data_ptr(), a.n, a.c, a.h, a.w, out.desc(),
+                                       _stream_ptr()))
+    return out
+
+
+def planar_to_nchw(a):
+    out = torch.empty((a.n, a.c, a.h, a.w), dtype=torch.float32, device=a.t.device)
+    C.check(C.lib().cae_planar_to_nchw(a.desc(), a.n, a.c, a.h, a.w, out.data_ptr(),
+                                       _stream_ptr()))
+    return out

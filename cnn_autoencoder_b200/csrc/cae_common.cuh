@@ -1,0 +1,229 @@
+// Shared device helpers: sm_100a PTX wrappers (mbarrier, TMA, tcgen05, TMEM),
+// internal tensor addressing and the error plumbing of the C ABI.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/cae_b200.h"
+
+// ------------------------------------------------------------------ errors
+void cae_set_error(const char *fmt, ...);
+void cae_count_launch(int n = 1);
+
+#define CAE_CHECK(cond, code, ...)            \
+  do {                                        \
+    if (!(cond)) {                            \
+      cae_set_error(__VA_ARGS__);             \
+      return (code);                          \
+    }                                         \
+  } while (0)
+
+#define CAE_CUDA(expr)                                                        \
+  do {                                                                        \
+    cudaError_t _e = (expr);                                                  \
+    if (_e != cudaSuccess) {                                                  \
+      cae_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
+                    __FILE__, __LINE__);                                      \
+      return 100 + (int)_e;                                                   \
+    }                                                                         \
+  } while (0)
+
+// ------------------------------------------------------- internal layouts
+// PLANAR: [N][P][H+2][W+2][8] half.  SPLIT: [N][4][P][(H+2)/2][(W+2)/2][8] half.
+struct ActView {
+  void *ptr;
+  int fmt, planes, halo;
+  int H, W;  // logical (unpadded) spatial size
+};
+
+__host__ __device__ inline size_t cae_act_bytes(int fmt, int n, int planes, int H, int W) {
+  return (size_t)n * planes * (H + 2) * (W + 2) * 16;  // same for PLANAR and SPLIT
+}
+
+// Element offset (in 16-byte units) of padded pixel (Y,X), plane p, image n.
+__device__ __forceinline__ size_t act_unit_offset(const ActView &v, int n, int p, int Y, int X) {
+  if (v.fmt == CAE_FMT_F16_PLANAR) {
+    return (((size_t)n * v.planes + p) * (v.H + 2) + Y) * (v.W + 2) + X;
+  } else {
+    const int Hh = (v.H + 2) >> 1, Wh = (v.W + 2) >> 1;
+    const int par = ((Y & 1) << 1) | (X & 1);
+    return ((((size_t)n * 4 + par) * v.planes + p) * Hh + (Y >> 1)) * Wh + (X >> 1);
+  }
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == CAE_ACT_LEAKY_RELU) return v > 0.f ? v : v * 0.01f;
+  if (act == CAE_ACT_RELU) return v > 0.f ? v : 0.f;
+  return v;
+}
+
+// (uint8) clip(v*255, 0, 255): truncation toward zero, NaN -> 0
+__device__ __forceinline__ uint8_t to_u8_trunc(float v) {
+  float s = v * 255.0f;
+  s = fminf(fmaxf(s, 0.0f), 255.0f);
+  return (uint8_t)(int)s;
+}
+
+// ------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Bounded wait: a pipeline bug must surface as a launch failure, not as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
+  while (!mbar_try_wait(bar, parity)) {
+    if (global_timer_ns() - t0 > 4000000000ull) {
+      printf("cae_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
+             (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// TMA: 4-D tiled tensor load global -> shared, completes on an mbarrier.
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap *map, uint64_t *bar, void *dst,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3)
+      : "memory");
+}
+
+// TMA: 1-D bulk copy global -> shared (bytes multiple of 16, 16-byte aligned).
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes,
+                                             uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      :
+      : "r"(smem_u32(dst)), "l"((uint64_t)src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+// tcgen05 ---------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (fp16/bf16 in, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Arrive on an mbarrier when every tcgen05 op issued so far by this thread is done.
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+
+// 32 lanes x 16 consecutive fp32 columns: thread i of the warp gets lane (base+i).
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, no swizzle ("interleave") layout:
+// core matrix = 8 rows x 16 bytes stored as 128 contiguous bytes;
+// LBO = byte distance between the two core matrices of one K=16 step,
+// SBO = byte distance between consecutive 8-row groups.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (sm_100)
+  return d;                // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+}
+
+// Instruction descriptor for kind::f16: F16 x F16 -> F32, both operands K-major.
+__host__ __device__ inline uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4)                       // D format F32
+         | (0u << 7) | (0u << 10)        // A, B format F16
+         | ((uint32_t)(N >> 3) << 17)    // N
+         | ((uint32_t)(M >> 4) << 24);   // M
+}

@@ -1,0 +1,150 @@
+// Rounding quantizer + factorized-prior likelihood + per-channel symbol
+// histogram + rate, one pass over the latent (HBM-bound elementwise work).
+//
+// Replaces CompressAI's EntropyBottleneck.forward in eval mode and the symbol
+// extraction of EntropyBottleneck.compress, which the reference reaches from
+// src/models/tasks/_taskutils.py:97 and src/models/tasks/_autoencoders.py:549
+// (SURVEY.md Appendix A.1), plus the rate term of
+// src/models/criteria/_ratedist.py:49-54.  In eval mode y_q - median_c is an
+// integer, so the likelihood takes one value per (channel, symbol): the host
+// builds that table once with the model's own fp32 ops and the kernel looks it
+// up; symbols outside the table fall back to evaluating the density MLP here.
+#include "cae_common.cuh"
+
+namespace {
+
+constexpr int kMaxDim = 8;
+
+struct EbParams {
+  const float *y;
+  int n, c, hw;
+  cae_eb_tables t;
+  float *y_q, *p_y;
+  int32_t *symbols, *hist;
+  double *rate_bits;
+  int32_t *status;
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// logits_cumulative for one scalar input of channel c (A.1)
+__device__ float eb_logits(const cae_eb_tables &t, const float *mlp, float x) {
+  float v[kMaxDim], u[kMaxDim];
+  v[0] = x;
+  const float *q = mlp;
+  for (int i = 0; i < t.n_layers; ++i) {
+    const int din = t.dims[i], dout = t.dims[i + 1];
+    for (int o = 0; o < dout; ++o) {
+      float s = 0.f;
+      for (int k = 0; k < din; ++k) s += q[o * din + k] * v[k];
+      u[o] = s;
+    }
+    q += dout * din;
+    for (int o = 0; o < dout; ++o) u[o] += q[o];
+    q += dout;
+    if (i < t.n_layers - 1) {
+      for (int o = 0; o < dout; ++o) u[o] += q[o] * tanhf(u[o]);
+      q += dout;
+    }
+    for (int o = 0; o < dout; ++o) v[o] = u[o];
+  }
+  return v[0];
+}
+
+__device__ float eb_likelihood(const cae_eb_tables &t, int c, float v) {
+  const float *mlp = t.mlp + (size_t)c * t.mlp_stride;
+  const float lower = eb_logits(t, mlp, v - 0.5f);
+  const float upper = eb_logits(t, mlp, v + 0.5f);
+  const float s = lower + upper;
+  const float sign = s > 0.f ? -1.f : (s < 0.f ? 1.f : 0.f);
+  const float p = fabsf(sigmoidf_(sign * upper) - sigmoidf_(sign * lower));
+  return fmaxf(p, 1e-9f);
+}
+
+// grid = (N*C, blocks over hw); every block works inside one channel
+__global__ void __launch_bounds__(256) eb_quantize_kernel(const EbParams p) {
+  extern __shared__ int32_t s_hist[];
+  __shared__ float s_red[8];
+  const int nc = blockIdx.x;
+  const int c = nc % p.c;
+  const int bins = p.hist ? p.t.hist_bins : 0;
+  for (int i = threadIdx.x; i < bins; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+
+  const float med = p.t.medians[c];
+  const float *lut = p.t.lut ? p.t.lut + (size_t)c * p.t.lut_len : nullptr;
+  const size_t base = (size_t)nc * p.hw;
+  float bits = 0.f;
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < p.hw; i += gridDim.y * blockDim.x) {
+    const float y = p.y[base + i];
+    const float r = rintf(y - med);  // torch.round: half to even
+    const float yq = r + med;
+    // saturate like a float->int32 cast of an in-range value; escapes stay exact up to 2^31
+    const int sym = (int)fminf(fmaxf(r, -2147483520.f), 2147483520.f);
+    if (p.y_q) p.y_q[base + i] = yq;
+    if (p.symbols) p.symbols[base + i] = sym;
+    if (p.p_y || p.rate_bits) {
+      float lik;
+      const int li = sym - p.t.lut_min;
+      if (lut && li >= 0 && li < p.t.lut_len) {
+        lik = lut[li];
+      } else if (p.t.mlp) {
+        lik = eb_likelihood(p.t, c, yq);
+      } else {
+        lik = 1e-9f;
+        if (p.status) atomicOr(p.status, 1);
+      }
+      if (p.p_y) p.p_y[base + i] = lik;
+      bits -= log2f(lik);
+    }
+    if (bins) {
+      int b = sym - p.t.hist_min;
+      b = b < 0 ? 0 : (b >= bins ? bins - 1 : b);
+      atomicAdd(&s_hist[b], 1);
+    }
+  }
+
+  if (p.rate_bits) {
+    for (int o = 16; o > 0; o >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = bits;
+  }
+  __syncthreads();
+  if (p.rate_bits && threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += (double)s_red[w];
+    atomicAdd(p.rate_bits, tot);
+  }
+  for (int i = threadIdx.x; i < bins; i += blockDim.x) {
+    const int v = s_hist[i];
+    if (v) atomicAdd(&p.hist[(size_t)c * bins + i], v);
+  }
+}
+
+}  // namespace
+
+extern "C" int cae_eb_quantize(const float *y, int n, int c, int hw, const cae_eb_tables *t,
+                               float *y_q, float *p_y, int32_t *symbols, int32_t *hist,
+                               double *rate_bits, int32_t *status, void *stream) {
+  CAE_CHECK(y && t && t->medians, 2, "cae_eb_quantize: null argument");
+  CAE_CHECK(n > 0 && c > 0 && hw > 0, 2, "cae_eb_quantize: bad shape");
+  if (t->mlp) {
+    CAE_CHECK(t->n_layers >= 1 && t->n_layers <= 9, 2, "cae_eb_quantize: bad n_layers");
+    for (int i = 0; i <= t->n_layers; ++i)
+      CAE_CHECK(t->dims[i] >= 1 && t->dims[i] <= kMaxDim, 2, "cae_eb_quantize: filter dim %d > %d",
+                t->dims[i], kMaxDim);
+  }
+  const int bins = hist ? t->hist_bins : 0;
+  CAE_CHECK(bins >= 0 && bins <= 8192, 2, "cae_eb_quantize: hist_bins out of range");
+  EbParams p;
+  p.y = y; p.n = n; p.c = c; p.hw = hw; p.t = *t;
+  p.y_q = y_q; p.p_y = p_y; p.symbols = symbols; p.hist = hist;
+  p.rate_bits = rate_bits; p.status = status;
+  int bx = (hw + 256 * 4 - 1) / (256 * 4);
+  if (bx < 1) bx = 1;
+  if (bx > 64) bx = 64;
+  dim3 grid((unsigned)(n * c), (unsigned)bx);
+  eb_quantize_kernel<<<grid, 256, bins * sizeof(int32_t), (cudaStream_t)stream>>>(p);
+  cae_count_launch();
+  CAE_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,667 @@
+// 3x3 (transposed) convolution as an implicit GEMM on the sm_100a tensor cores.
+//
+// Replaces nn.Conv2d / nn.ConvTranspose2d forward inside the reference's
+// Analyzer.forward / Synthesizer.forward (src/models/tasks/_autoencoders.py:
+// 53-304, 359-361, 442-455).
+//
+// Design (see DESIGN.md "igemm"):
+//  * activations live in HBM as [N][C/8][H+2][W+2][8] fp16 ("planar", one-pixel
+//    halo written by the producing layer: zeros or reflected copies), or the
+//    parity-split variant of it for the stride-2 convolutions;
+//  * one CTA tile = 16 x (8*mt) output pixels.  A TMA box load brings the input
+//    patch (tile + halo, CK channels) into shared memory ONCE; in that layout
+//    every 3x3 tap is the same bytes seen through a different start address, so
+//    the nine taps are nine UMMA shared-memory descriptors (K-major, no swizzle:
+//    core matrix = 8 consecutive pixels x 8 channels = 128 contiguous bytes) and
+//    no im2col copy is ever materialised;
+//  * weights are pre-packed per (channel chunk, tap) in exactly the shared-memory
+//    image and streamed with 1-D bulk copies through a second mbarrier ring;
+//  * tcgen05.mma (M=128, N=C_out, K=16, fp16 in / fp32 accumulate) issued by one
+//    thread; accumulators in TMEM, double buffered across tiles when they fit;
+//  * four epilogue warps read TMEM (tcgen05.ld), apply bias / activation /
+//    residual add and write the next layer's input layout directly (halo copies
+//    included), or the fp32 latent, or the uint8 image.
+// Transposed stride-2 layers run as four output-phase accumulators (pixel
+// shuffle in the epilogue); the final C_out<=4 layer merges the four phases into
+// one N=16 GEMM over the 2x2 input neighbourhood.
+#include <stdlib.h>
+#include <string.h>
+
+#include "cae_common.cuh"
+
+namespace {
+
+constexpr int kMaxTaps = 9;
+constexpr int kMaxSA = 6;
+constexpr int kMaxSB = 12;
+constexpr int kThreads = 256;
+
+enum { EPI_ACT = 0, EPI_LATENT = 1, EPI_IMAGE = 2 };
+
+struct IgTap {
+  uint32_t a_off;  // byte offset of the tap's view inside an A stage
+  uint32_t acc;    // accumulator (output phase) this tap adds into
+};
+
+struct IgParams {
+  int n_img, dom_h, dom_w;
+  int tiles_x, tiles_per_img, n_tiles;
+  int mt, n_taps, n_chunks, ck;
+  int N, n_acc, n_buf, tmem_cols;
+  int PH, PW, n_par, par_stride;
+  int a_stage_bytes, a_box_bytes, b_stage_bytes, sa, sb;
+  int org_y, org_x;
+  uint32_t lbo_a, sbo_a, lbo_b, sbo_b, idesc;
+  IgTap taps[kMaxTaps];
+  const uint8_t *wpack;
+  // epilogue
+  int up;  // 1, or 2 for the pixel-shuffling transposed stride-2 layers
+  int c_out, pre_act, post_act;
+  const float *bias;
+  ActView out, skip;
+  float *aux;  // optional fp32 NCHW copy
+  int out_h, out_w;
+};
+
+struct TapDef {
+  int par, dy, dx, acc, kh, kw;
+};
+
+// Tap tables shared by the weight packer and the launcher.  kh/kw index the
+// torch weight tensor; (par, dy, dx) say where the tap reads inside the patch.
+int build_taps(int kind, bool merged, TapDef *t) {
+  int n = 0;
+  if (kind == CAE_CONV_S1) {
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) t[n++] = {0, kh, kw, 0, kh, kw};
+  } else if (kind == CAE_CONV_S2) {
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw)
+        t[n++] = {((kh & 1) << 1) | (kw & 1), kh >> 1, kw >> 1, 0, kh, kw};
+  } else if (kind == CAE_CONVT_S1) {
+    // conv_transpose(k3,s1,p1) == correlation with the flipped kernel, zero halo
+    for (int dy = 0; dy < 3; ++dy)
+      for (int dx = 0; dx < 3; ++dx) t[n++] = {0, dy, dx, 0, 2 - dy, 2 - dx};
+  } else if (merged) {
+    // one tap per 2x2 input shift; kh/kw depend on the output phase (row of B)
+    for (int dy = 0; dy < 2; ++dy)
+      for (int dx = 0; dx < 2; ++dx) t[n++] = {0, dy, dx, 0, -1, -1};
+  } else {
+    // out[2a+py, 2b+px] += W[py+1-2dy, px+1-2dx]^T in[a+dy, b+dx]
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px)
+        for (int dy = 0; dy <= py; ++dy)
+          for (int dx = 0; dx <= px; ++dx)
+            t[n++] = {0, dy, dx, py * 2 + px, py + 1 - 2 * dy, px + 1 - 2 * dx};
+  }
+  return n;
+}
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+inline bool is_merged(int kind, int c_out) { return kind == CAE_CONVT_S2 && 4 * c_out <= 16; }
+
+inline int mma_n(int kind, int c_out) {
+  return is_merged(kind, c_out) ? 16 : round_up(c_out, 16);
+}
+
+inline int auto_ck(int kind, int c_in_p) {
+  if (kind == CAE_CONV_S2) return c_in_p % 32 == 0 ? 32 : 16;
+  if (c_in_p % 64 == 0) return 64;
+  if (c_in_p % 48 == 0) return 48;
+  if (c_in_p % 32 == 0) return 32;
+  return 16;
+}
+
+// ---------------------------------------------------------------- packing
+struct PackParams {
+  int kind, merged, c_in, c_out, ck, N, n_taps, n_chunks;
+  TapDef taps[kMaxTaps];
+};
+
+// packed[chunk][tap][kplane][n][8]: the shared-memory image of operand B.
+__global__ void pack_weights_kernel(PackParams q, const float *__restrict__ w,
+                                    const float *__restrict__ scale, __half *__restrict__ out,
+                                    size_t total) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int k8 = (int)(i & 7);
+  size_t r = i >> 3;
+  const int n = (int)(r % q.N);
+  r /= q.N;
+  const int kplane = (int)(r % (q.ck / 8));
+  r /= (q.ck / 8);
+  const int t = (int)(r % q.n_taps);
+  const int chunk = (int)(r / q.n_taps);
+  const int ci = chunk * q.ck + kplane * 8 + k8;
+  int co = n, kh = q.taps[t].kh, kw = q.taps[t].kw;
+  if (q.merged) {
+    const int phase = n / q.c_out;
+    co = n % q.c_out;
+    kh = (phase >> 1) + 1 - 2 * q.taps[t].dy;
+    kw = (phase & 1) + 1 - 2 * q.taps[t].dx;
+    if (phase >= 4) co = q.c_out;  // padding rows
+  }
+  float v = 0.f;
+  if (ci < q.c_in && co < q.c_out && kh >= 0 && kh < 3 && kw >= 0 && kw < 3) {
+    const bool transposed = q.kind == CAE_CONVT_S1 || q.kind == CAE_CONVT_S2;
+    const size_t idx = transposed ? (((size_t)ci * q.c_out + co) * 3 + kh) * 3 + kw
+                                  : (((size_t)co * q.c_in + ci) * 3 + kh) * 3 + kw;
+    v = w[idx];
+    if (scale) v *= scale[co];
+  }
+  out[i] = __float2half_rn(v);
+}
+
+// --------------------------------------------------------------- epilogues
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+
+// Write one 16-byte unit (8 channels of one pixel) and its reflected halo copies.
+__device__ __forceinline__ void store_unit(const ActView &o, int n, int plane, int oy, int ox,
+                                           uint4 v) {
+  uint4 *base = reinterpret_cast<uint4 *>(o.ptr);
+  int ys[3], xs[3], ny = 1, nx = 1;
+  ys[0] = oy + 1;
+  xs[0] = ox + 1;
+  if (o.halo == CAE_HALO_REFLECT) {
+    if (oy == 1) ys[ny++] = 0;
+    if (oy == o.H - 2) ys[ny++] = o.H + 1;
+    if (ox == 1) xs[nx++] = 0;
+    if (ox == o.W - 2) xs[nx++] = o.W + 1;
+  }
+  for (int a = 0; a < ny; ++a)
+    for (int b = 0; b < nx; ++b) base[act_unit_offset(o, n, plane, ys[a], xs[b])] = v;
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_tile(const IgParams &p, uint32_t taddr, int n, int y,
+                                              int x, int phase, bool valid) {
+  const int oy = y * p.up + (phase >> 1), ox = x * p.up + (phase & 1);
+  for (int c0 = 0; c0 < p.N; c0 += 16) {
+    uint32_t r[16];
+    __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the divergent stores
+    tmem_ld16(taddr + c0, r);
+    tmem_ld_wait();
+    if (!valid) continue;
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+
+    if (EPI == EPI_IMAGE) {
+      // columns j = out_phase * c_out + c  (merged final transposed layer)
+      const int nreal = 4 * p.c_out;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (j >= nreal) break;
+        const int ph = j / p.c_out, c = j - ph * p.c_out;
+        float t = v[j] + (p.bias ? p.bias[c] : 0.f);
+        t = apply_act(apply_act(t, p.pre_act), p.post_act);
+        const int yy = y * 2 + (ph >> 1), xx = x * 2 + (ph & 1);
+        if (p.aux) p.aux[(((size_t)n * p.c_out + c) * p.out_h + yy) * p.out_w + xx] = t;
+        if (p.out.ptr)
+          reinterpret_cast<uint8_t *>(p.out.ptr)[(((size_t)n * p.out_h + yy) * p.out_w + xx) *
+                                                     p.c_out +
+                                                 c] = to_u8_trunc(t);
+      }
+      continue;
+    }
+
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = c0 + i;
+      if (p.bias && c < p.c_out) v[i] += p.bias[c];
+      v[i] = apply_act(v[i], p.pre_act);
+    }
+    if (p.skip.ptr) {
+      const uint4 *sp = reinterpret_cast<const uint4 *>(p.skip.ptr);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint4 s = sp[act_unit_offset(p.skip, n, (c0 >> 3) + h, oy + 1, ox + 1)];
+        const __half2 *sh = reinterpret_cast<const __half2 *>(&s);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(sh[k]);
+          v[h * 8 + 2 * k] += f.x;
+          v[h * 8 + 2 * k + 1] += f.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], p.post_act);
+
+    if (EPI == EPI_LATENT) {
+      float *o = reinterpret_cast<float *>(p.out.ptr);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int c = c0 + i;
+        if (c < p.c_out) o[(((size_t)n * p.c_out + c) * p.out_h + oy) * p.out_w + ox] = v[i];
+      }
+    } else {
+      if (p.aux) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int c = c0 + i;
+          if (c < p.c_out)
+            p.aux[(((size_t)n * p.c_out + c) * p.out_h + oy) * p.out_w + ox] = v[i];
+        }
+      }
+      uint4 lo, hi;
+      lo.x = pack2(v[0], v[1]);
+      lo.y = pack2(v[2], v[3]);
+      lo.z = pack2(v[4], v[5]);
+      lo.w = pack2(v[6], v[7]);
+      hi.x = pack2(v[8], v[9]);
+      hi.y = pack2(v[10], v[11]);
+      hi.z = pack2(v[12], v[13]);
+      hi.w = pack2(v[14], v[15]);
+      store_unit(p.out, n, c0 >> 3, oy, ox, lo);
+      store_unit(p.out, n, (c0 >> 3) + 1, oy, ox, hi);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ kernel
+template <int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ IgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[kMaxSA], a_empty[kMaxSA];
+  __shared__ __align__(8) uint64_t b_full[kMaxSB], b_empty[kMaxSB];
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint8_t *smem_a = smem;
+  uint8_t *smem_b = smem + (size_t)p.sa * p.a_stage_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.sa; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < p.sb; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 3) tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
+  if (warp == 0 && lane == 0) prefetch_tensormap(&tmA);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===== activation patches: TMA box loads =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int n = tile / p.tiles_per_img, rem = tile - n * p.tiles_per_img;
+        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        const int y0 = ty * 16 + p.org_y, x0 = tx * 8 * p.mt + p.org_x;
+        for (int ch = 0; ch < p.n_chunks; ++ch, ++it) {
+          const int s = it % p.sa;
+          mbar_wait(&a_empty[s], ((it / p.sa) & 1) ^ 1);
+          mbar_expect_tx(&a_full[s], (uint32_t)(p.n_par * p.a_box_bytes));
+          for (int par = 0; par < p.n_par; ++par)
+            tma_load_4d(&tmA, &a_full[s],
+                        smem_a + (size_t)s * p.a_stage_bytes + (size_t)par * p.par_stride, x0 * 8,
+                        y0, ch * (p.ck >> 3), n * p.n_par + par);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== packed weights: 1-D bulk copies =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int ch = 0; ch < p.n_chunks; ++ch) {
+          for (int t = 0; t < p.n_taps; ++t, ++it) {
+            const int s = it % p.sb;
+            mbar_wait(&b_empty[s], ((it / p.sb) & 1) ^ 1);
+            mbar_expect_tx(&b_full[s], (uint32_t)p.b_stage_bytes);
+            bulk_load_1d(smem_b + (size_t)s * p.b_stage_bytes,
+                         p.wpack + (size_t)(ch * p.n_taps + t) * p.b_stage_bytes,
+                         (uint32_t)p.b_stage_bytes, &b_full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== MMA issue (one thread) =====
+    if (lane == 0) {
+      const uint32_t sa_base = smem_base, sb_base = smem_base + (uint32_t)(p.sa * p.a_stage_bytes);
+      const int ksteps = p.ck >> 4;
+      const int acc_per_buf = p.mt * p.n_acc;
+      uint32_t ita = 0, itb = 0, j = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++j) {
+        const int buf = j % p.n_buf;
+        mbar_wait(&acc_empty[buf], ((j / p.n_buf) & 1) ^ 1);
+        tc_fence_after();
+        uint32_t started = 0;
+        for (int ch = 0; ch < p.n_chunks; ++ch, ++ita) {
+          const int sA = ita % p.sa;
+          mbar_wait(&a_full[sA], (ita / p.sa) & 1);
+          for (int t = 0; t < p.n_taps; ++t, ++itb) {
+            const int sB = itb % p.sb;
+            mbar_wait(&b_full[sB], (itb / p.sb) & 1);
+            tc_fence_after();
+            const uint32_t a_base = sa_base + (uint32_t)(sA * p.a_stage_bytes) + p.taps[t].a_off;
+            const uint32_t b_base = sb_base + (uint32_t)(sB * p.b_stage_bytes);
+            for (int m = 0; m < p.mt; ++m) {
+              const int acc = m * p.n_acc + (int)p.taps[t].acc;
+              const uint32_t d = tmem_base + (uint32_t)((buf * acc_per_buf + acc) * p.N);
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t da =
+                    make_smem_desc(a_base + m * 128 + k * 2 * p.lbo_a, p.lbo_a, p.sbo_a);
+                const uint64_t db = make_smem_desc(b_base + k * 2 * p.lbo_b, p.lbo_b, p.sbo_b);
+                umma_f16(d, da, db, p.idesc, ((started >> acc) & 1u) | (k > 0 ? 1u : 0u));
+              }
+              started |= 1u << acc;
+            }
+            umma_commit(&b_empty[sB]);
+          }
+          umma_commit(&a_empty[sA]);
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> HBM =====
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    const int ty = row >> 3, txl = row & 7;
+    const int acc_per_buf = p.mt * p.n_acc;
+    uint32_t j = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++j) {
+      const int n = tile / p.tiles_per_img, rem = tile - n * p.tiles_per_img;
+      const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
+      const int buf = j % p.n_buf;
+      mbar_wait(&acc_full[buf], (j / p.n_buf) & 1);
+      tc_fence_after();
+      const int y = tyi * 16 + ty;
+      for (int m = 0; m < p.mt; ++m) {
+        const int x = (txi * p.mt + m) * 8 + txl;
+        const bool valid = y < p.dom_h && x < p.dom_w;
+        for (int a = 0; a < p.n_acc; ++a) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) +
+                                 (uint32_t)((buf * acc_per_buf + m * p.n_acc + a) * p.N);
+          epilogue_tile<EPI>(p, taddr, n, y, x, a, valid);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------ host helpers
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+int pow2_cols(int c) {
+  int r = 32;
+  while (r < c) r <<= 1;
+  return r;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------- C ABI
+extern "C" size_t cae_packed_weight_bytes(int kind, int c_in, int c_out, int ck) {
+  const int c_in_p = round_up(c_in, 16);
+  if (ck <= 0) ck = auto_ck(kind, c_in_p);
+  TapDef taps[kMaxTaps];
+  const int n_taps = build_taps(kind, is_merged(kind, c_out), taps);
+  return (size_t)(c_in_p / ck) * n_taps * mma_n(kind, c_out) * ck * sizeof(__half);
+}
+
+extern "C" int cae_pack_weights(int kind, int c_in, int c_out, int ck, const float *w,
+                                const float *scale, void *packed, void *stream) {
+  CAE_CHECK(kind >= CAE_CONV_S1 && kind <= CAE_CONVT_S2, 2, "cae_pack_weights: bad kind %d", kind);
+  CAE_CHECK(w && packed, 2, "cae_pack_weights: null pointer");
+  const int c_in_p = round_up(c_in, 16);
+  if (ck <= 0) ck = auto_ck(kind, c_in_p);
+  CAE_CHECK(ck % 16 == 0 && ck <= 64 && c_in_p % ck == 0, 2,
+            "cae_pack_weights: ck=%d does not divide padded c_in=%d", ck, c_in_p);
+  PackParams q;
+  memset(&q, 0, sizeof(q));
+  q.kind = kind;
+  q.merged = is_merged(kind, c_out);
+  q.c_in = c_in;
+  q.c_out = c_out;
+  q.ck = ck;
+  q.N = mma_n(kind, c_out);
+  q.n_taps = build_taps(kind, q.merged, q.taps);
+  q.n_chunks = c_in_p / ck;
+  const size_t total = (size_t)q.n_chunks * q.n_taps * q.N * ck;
+  const int threads = 256;
+  pack_weights_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0,
+                        (cudaStream_t)stream>>>(q, w, scale, (__half *)packed, total);
+  cae_count_launch();
+  CAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
+  CAE_CHECK(d, 2, "cae_conv_igemm: null descriptor");
+  const int kind = d->kind;
+  CAE_CHECK(kind >= CAE_CONV_S1 && kind <= CAE_CONVT_S2, 2, "cae_conv_igemm: bad kind %d", kind);
+  CAE_CHECK(d->in.ptr && d->weights, 2, "cae_conv_igemm: null input or weights");
+  CAE_CHECK(d->n > 0 && d->h_in > 0 && d->w_in > 0, 2, "cae_conv_igemm: bad shape");
+  const int c_in_p = round_up(d->c_in, 16);
+  CAE_CHECK(d->in.planes * 8 == c_in_p, 2,
+            "cae_conv_igemm: input has %d planes, need %d (c_in padded to 16)", d->in.planes,
+            c_in_p / 8);
+  const bool merged = is_merged(kind, d->c_out);
+  const int want_fmt = kind == CAE_CONV_S2 ? CAE_FMT_F16_SPLIT : CAE_FMT_F16_PLANAR;
+  CAE_CHECK(d->in.fmt == want_fmt, 2, "cae_conv_igemm: input format %d, kind %d needs %d",
+            d->in.fmt, kind, want_fmt);
+  if (kind == CAE_CONV_S2)
+    CAE_CHECK(d->h_in % 2 == 0 && d->w_in % 2 == 0, 2,
+              "cae_conv_igemm: stride-2 conv needs even input size, got %dx%d", d->h_in, d->w_in);
+
+  IgParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_img = d->n;
+  p.N = mma_n(kind, d->c_out);
+  CAE_CHECK(p.N <= 256, 2, "cae_conv_igemm: c_out=%d too large", d->c_out);
+  p.ck = d->ck > 0 ? d->ck : auto_ck(kind, c_in_p);
+  CAE_CHECK(p.ck % 16 == 0 && p.ck <= 64 && c_in_p % p.ck == 0, 2, "cae_conv_igemm: bad ck=%d",
+            p.ck);
+  p.n_chunks = c_in_p / p.ck;
+  TapDef taps[kMaxTaps];
+  p.n_taps = build_taps(kind, merged, taps);
+  p.n_acc = (kind == CAE_CONVT_S2 && !merged) ? 4 : 1;
+  p.up = (kind == CAE_CONVT_S2) ? 2 : 1;
+
+  // M domain: output pixels, except transposed stride-2 where it is input pixels
+  if (kind == CAE_CONV_S2) {
+    p.dom_h = d->h_in / 2;
+    p.dom_w = d->w_in / 2;
+  } else {
+    p.dom_h = d->h_in;
+    p.dom_w = d->w_in;
+  }
+  p.out_h = p.dom_h * p.up;
+  p.out_w = p.dom_w * p.up;
+
+  int mt = d->mt > 0 ? d->mt : 2;
+  if (p.dom_w <= 8) mt = 1;
+  if (p.n_acc * p.N * mt > 512) mt = 1;
+  CAE_CHECK(p.n_acc * p.N * mt <= 512, 2, "cae_conv_igemm: accumulators exceed TMEM");
+  p.mt = mt;
+  p.n_buf = (512 / (p.n_acc * p.N * mt)) >= 2 ? 2 : 1;
+  p.tmem_cols = pow2_cols(p.n_buf * p.n_acc * p.N * mt);
+
+  if (kind == CAE_CONV_S1 || kind == CAE_CONVT_S1) {
+    p.PH = 18;
+    p.PW = 8 * mt + 2;
+    p.n_par = 1;
+    p.org_y = p.org_x = 0;
+  } else if (kind == CAE_CONV_S2) {
+    p.PH = 17;
+    p.PW = 8 * mt + 1;
+    p.n_par = 4;
+    p.org_y = p.org_x = 0;
+  } else {
+    p.PH = 17;
+    p.PW = 8 * mt + 1;
+    p.n_par = 1;
+    p.org_y = p.org_x = 1;
+  }
+  const int kplanes = p.ck / 8;
+  p.a_box_bytes = kplanes * p.PH * p.PW * 16;
+  p.par_stride = round_up(p.a_box_bytes, 128);
+  p.a_stage_bytes = round_up(p.par_stride * p.n_par, 1024);
+  p.b_stage_bytes = p.N * p.ck * 2;
+  p.lbo_a = (uint32_t)(p.PH * p.PW * 16);
+  p.sbo_a = (uint32_t)(p.PW * 16);
+  p.lbo_b = (uint32_t)(p.N * 16);
+  p.sbo_b = 128;
+  if (getenv("CAE_IGEMM_SWAP_LBO_SBO")) {  // bring-up knob, see DESIGN.md
+    uint32_t t = p.lbo_a; p.lbo_a = p.sbo_a; p.sbo_a = t;
+    t = p.lbo_b; p.lbo_b = p.sbo_b; p.sbo_b = t;
+  }
+  p.idesc = make_idesc_f16(128, p.N);
+  for (int t = 0; t < p.n_taps; ++t) {
+    p.taps[t].a_off = (uint32_t)(taps[t].par * p.par_stride + (taps[t].dy * p.PW + taps[t].dx) * 16);
+    p.taps[t].acc = (uint32_t)taps[t].acc;
+  }
+
+  // shared-memory rings
+  const int budget = 227 * 1024 - 2048;
+  int sa = 2, sb = 2;
+  CAE_CHECK(sa * p.a_stage_bytes + sb * p.b_stage_bytes <= budget, 2,
+            "cae_conv_igemm: tile does not fit shared memory (A %d B %d)", p.a_stage_bytes,
+            p.b_stage_bytes);
+  for (;;) {
+    bool grew = false;
+    if (sb < 4 && sa * p.a_stage_bytes + (sb + 1) * p.b_stage_bytes <= budget) { ++sb; grew = true; }
+    else if (sa < 3 && (sa + 1) * p.a_stage_bytes + sb * p.b_stage_bytes <= budget) { ++sa; grew = true; }
+    else if (sb < kMaxSB && sb < p.n_taps * 2 &&
+             sa * p.a_stage_bytes + (sb + 1) * p.b_stage_bytes <= budget) { ++sb; grew = true; }
+    else if (sa < 4 && (sa + 1) * p.a_stage_bytes + sb * p.b_stage_bytes <= budget) { ++sa; grew = true; }
+    if (!grew) break;
+  }
+  p.sa = sa;
+  p.sb = sb;
+  const int smem_bytes = sa * p.a_stage_bytes + sb * p.b_stage_bytes + 1024;
+
+  p.tiles_x = (p.dom_w + 8 * mt - 1) / (8 * mt);
+  const int tiles_y = (p.dom_h + 15) / 16;
+  p.tiles_per_img = p.tiles_x * tiles_y;
+  p.n_tiles = p.tiles_per_img * d->n;
+  p.wpack = (const uint8_t *)d->weights;
+
+  // epilogue
+  p.c_out = d->c_out;
+  p.pre_act = d->pre_act;
+  p.post_act = d->post_act;
+  p.bias = d->bias;
+  p.aux = (float *)d->aux_out;
+  int epi;
+  if (merged) {
+    epi = EPI_IMAGE;
+    CAE_CHECK(d->out.fmt == CAE_FMT_U8_HWC || d->out.fmt == CAE_FMT_NONE, 2,
+              "cae_conv_igemm: final layer writes U8_HWC (and/or aux fp32)");
+    CAE_CHECK(d->out.ptr || d->aux_out, 2, "cae_conv_igemm: no output");
+    p.out.ptr = d->out.fmt == CAE_FMT_U8_HWC ? d->out.ptr : nullptr;
+  } else if (d->out.fmt == CAE_FMT_F32_NCHW) {
+    epi = EPI_LATENT;
+    CAE_CHECK(p.up == 1 && d->out.ptr, 2, "cae_conv_igemm: fp32 NCHW output needs up==1");
+    p.out.ptr = d->out.ptr;
+  } else {
+    epi = EPI_ACT;
+    CAE_CHECK(d->out.ptr && (d->out.fmt == CAE_FMT_F16_PLANAR || d->out.fmt == CAE_FMT_F16_SPLIT),
+              2, "cae_conv_igemm: bad output format %d", d->out.fmt);
+    CAE_CHECK(d->out.planes * 8 == p.N, 2, "cae_conv_igemm: output has %d planes, need %d",
+              d->out.planes, p.N / 8);
+    if (d->out.fmt == CAE_FMT_F16_SPLIT)
+      CAE_CHECK(p.out_h % 2 == 0 && p.out_w % 2 == 0, 2, "cae_conv_igemm: split output needs even size");
+    p.out.ptr = d->out.ptr;
+  }
+  p.out.fmt = d->out.fmt;
+  p.out.planes = d->out.planes;
+  p.out.halo = d->out.halo;
+  p.out.H = p.out_h;
+  p.out.W = p.out_w;
+  if (d->skip.fmt != CAE_FMT_NONE && d->skip.ptr) {
+    CAE_CHECK(epi != EPI_IMAGE, 2, "cae_conv_igemm: skip unsupported on the final layer");
+    CAE_CHECK((d->skip.fmt == CAE_FMT_F16_PLANAR || d->skip.fmt == CAE_FMT_F16_SPLIT) &&
+                  d->skip.planes * 8 == p.N,
+              2, "cae_conv_igemm: skip must be planar fp16 with %d planes", p.N / 8);
+    p.skip.ptr = d->skip.ptr;
+    p.skip.fmt = d->skip.fmt;
+    p.skip.planes = d->skip.planes;
+    p.skip.H = p.out_h;
+    p.skip.W = p.out_w;
+  }
+
+  // tensor map over the input
+  EncodeTiledFn encode = get_encode_fn();
+  CAE_CHECK(encode, 3, "cae_conv_igemm: cuTensorMapEncodeTiled unavailable");
+  CUtensorMap tm;
+  const int Hp = d->h_in + 2, Wp = d->w_in + 2;
+  cuuint64_t gdim[4], gstr[3];
+  if (kind == CAE_CONV_S2) {
+    const int Hh = Hp / 2, Wh = Wp / 2;
+    gdim[0] = (cuuint64_t)Wh * 8; gdim[1] = Hh; gdim[2] = d->in.planes; gdim[3] = (cuuint64_t)d->n * 4;
+    gstr[0] = (cuuint64_t)Wh * 16; gstr[1] = gstr[0] * Hh; gstr[2] = gstr[1] * d->in.planes;
+  } else {
+    gdim[0] = (cuuint64_t)Wp * 8; gdim[1] = Hp; gdim[2] = d->in.planes; gdim[3] = d->n;
+    gstr[0] = (cuuint64_t)Wp * 16; gstr[1] = gstr[0] * Hp; gstr[2] = gstr[1] * d->in.planes;
+  }
+  cuuint32_t box[4] = {(cuuint32_t)(p.PW * 8), (cuuint32_t)p.PH, (cuuint32_t)kplanes, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult cr = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, d->in.ptr, gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CAE_CHECK(cr == CUDA_SUCCESS, 3, "cae_conv_igemm: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+
+  int sm_count = 0, dev = 0;
+  CAE_CUDA(cudaGetDevice(&dev));
+  CAE_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  int grid = d->grid > 0 ? d->grid : sm_count;
+  if (grid > p.n_tiles) grid = p.n_tiles;
+
+  void (*kern)(const CUtensorMap, const IgParams) =
+      epi == EPI_ACT ? igemm_conv_kernel<EPI_ACT>
+                     : (epi == EPI_LATENT ? igemm_conv_kernel<EPI_LATENT>
+                                          : igemm_conv_kernel<EPI_IMAGE>);
+  CAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  kern<<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(tm, p);
+  cae_count_launch();
+  CAE_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,165 @@
+/* cae_b200.h -- C ABI of the B200-native compress/decompress hot path.
+ *
+ * This is the drop-in boundary underneath the reference's Python surface.
+ * The reference (TheJacksonLaboratory/cnn_autoencoder) has no FFI of its own:
+ * its hot path is `torch.nn` modules plus CompressAI's C++ extension.  Each
+ * entry point below names the reference call it replaces (paths relative to
+ * the reference root, R = src/models/tasks/_autoencoders.py).  The host-side
+ * mirror in cnn_autoencoder_b200/ (same class and function names as the
+ * reference's `models` package) binds these with ctypes; INTEGRATION.md shows
+ * the stub a reference maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only (no torch types); the caller owns
+ * every buffer; device pointers unless a parameter is marked HOST; every
+ * device entry point takes the CUDA stream (a cudaStream_t passed as void*)
+ * it enqueues on and returns without synchronising; return value 0 = ok,
+ * otherwise an error code whose text cae_last_error() returns (thread-local).
+ * There is no CPU fallback: a build without sm_100a code or a missing device
+ * is an error, never a silent host path.
+ */
+#ifndef CAE_B200_H
+#define CAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAE_ABI_VERSION 1
+
+/* ---- tensor formats ------------------------------------------------------ */
+enum {
+  CAE_FMT_NONE = 0,
+  CAE_FMT_U8_HWC = 1,     /* N x H x W x C uint8. As input: value/255.0f (R:545, compress.py:55);
+                             as output: (uint8)clip(v*255,0,255), truncation (R:577-578).      */
+  CAE_FMT_F32_NCHW = 2,   /* torch-contiguous fp32                                             */
+  CAE_FMT_F16_PLANAR = 3, /* internal: [N][C/8][H+2][W+2][8] half, 1-pixel halo                 */
+  CAE_FMT_F16_SPLIT = 4   /* internal: [N][4][C/8][(H+2)/2][(W+2)/2][8] half; padded pixel
+                             (Y,X) lives in parity plane (Y&1)*2+(X&1) at (Y>>1,X>>1).
+                             Feeds the stride-2 convolutions. H and W must be even.            */
+};
+
+enum { CAE_HALO_KEEP = 0,    /* leave the halo as allocated (zeros): zero padding (ConvTranspose2d) */
+       CAE_HALO_REFLECT = 1  /* also write mirrored copies: padding_mode='reflect' (R:70,85)        */ };
+
+enum { CAE_ACT_NONE = 0, CAE_ACT_LEAKY_RELU = 1 /* slope 0.01, R:26 */, CAE_ACT_RELU = 2 /* R:28 */ };
+
+enum {
+  CAE_CONV_S1 = 0,   /* nn.Conv2d k3 s1 p1            R:63-70, 114-121, 130-137              */
+  CAE_CONV_S2 = 1,   /* nn.Conv2d k3 s2 p1            R:78-85, 148-155                        */
+  CAE_CONVT_S1 = 2,  /* nn.ConvTranspose2d k3 s1 p1   R:189-196, 241-248, 258-265             */
+  CAE_CONVT_S2 = 3   /* nn.ConvTranspose2d k3 s2 p1 output_padding 1   R:204-211, 278-285     */
+};
+
+enum { CAE_PAD_ZERO = 0, CAE_PAD_REFLECT = 1 };
+
+typedef struct {
+  void *ptr;
+  int32_t fmt;      /* CAE_FMT_*                                                         */
+  int32_t planes;   /* PLANAR/SPLIT: number of 8-channel planes (channels padded with 0) */
+  int32_t halo;     /* outputs in PLANAR/SPLIT: CAE_HALO_*                                */
+  int32_t reserved;
+} cae_tensor;
+
+/* One 3x3 (transposed) convolution with its fused epilogue:
+ *   out = post_act( pre_act(conv(in) + bias) + skip )
+ * which covers every unit of R:53-304 (bias R:41-42; activations R:19-34;
+ * residual add R:172, R:302; image casts R:545, R:577-578).                    */
+typedef struct {
+  int32_t kind;            /* CAE_CONV_* */
+  int32_t n, h_in, w_in;   /* batch and INPUT spatial size                               */
+  int32_t c_in, c_out;     /* real channel counts                                        */
+  cae_tensor in, out, skip;/* skip.fmt == CAE_FMT_NONE when absent; skip has out's size  */
+  const void *weights;     /* igemm: packed (cae_pack_weights); direct: fp32 torch layout */
+  const float *bias;       /* c_out floats or NULL                                       */
+  int32_t pre_act, post_act;
+  int32_t pad_mode;        /* direct kernel only (CAE_PAD_*); igemm reads the halo       */
+  int32_t ck;              /* igemm: channels per K chunk (16/32/48/64), 0 = auto        */
+  int32_t mt;              /* igemm: 16x8 M-tiles per CTA tile (1/2), 0 = auto           */
+  int32_t grid;            /* igemm: CTAs, 0 = one per SM                                */
+  void *aux_out;           /* optional second output (fp32 NCHW) or NULL                 */
+} cae_conv_desc;
+
+/* ---- library ------------------------------------------------------------- */
+int cae_abi_version(void);
+const char *cae_last_error(void);
+/* sm count / compute capability of the current device; fails unless cc == 10.x */
+int cae_device_info(int *sm_count, int *cc_major, int *cc_minor);
+/* number of kernels this library has launched in this process (bench "gpu_launches") */
+uint64_t cae_launch_count(void);
+
+/* ---- weights ------------------------------------------------------------- */
+/* Bytes of the packed fp16 image of one layer's weights for the implicit-GEMM
+ * kernel, and the packing itself (device -> device).  `w` is the fp32 tensor in
+ * torch layout: Conv2d (c_out, c_in, 3, 3), ConvTranspose2d (c_in, c_out, 3, 3)
+ * (SURVEY.md Appendix C).  `scale` (c_out floats or NULL) multiplies each output
+ * channel (eval-mode BatchNorm folding, R:72-73).  ck as in cae_conv_desc.    */
+size_t cae_packed_weight_bytes(int kind, int c_in, int c_out, int ck);
+int cae_pack_weights(int kind, int c_in, int c_out, int ck, const float *w,
+                     const float *scale, void *packed, void *stream);
+
+/* ---- convolutions -------------------------------------------------------- */
+/* tcgen05 / TMEM / TMA implicit-GEMM path (in: PLANAR for S1/CONVT, SPLIT for
+ * CONV_S2, c_in padded to 16).  Replaces nn.Conv2d / nn.ConvTranspose2d forward
+ * inside Analyzer.forward R:359-361 and Synthesizer.forward R:442-455.        */
+int cae_conv_igemm(const cae_conv_desc *d, void *stream);
+/* CUDA-core direct path for the thin image-side layers (c_in < 16: the 3->3
+ * stem, R:63-70 with channels_org) and tiny nets; any format combination.     */
+int cae_conv_direct(const cae_conv_desc *d, void *stream);
+
+/* ---- layout -------------------------------------------------------------- */
+/* fp32 NCHW <-> internal planar fp16 (API boundary of Analyzer/Synthesizer). */
+int cae_nchw_to_planar(const float *src, int n, int c, int h, int w, cae_tensor dst, void *stream);
+int cae_planar_to_nchw(cae_tensor src, int n, int c, int h, int w, float *dst, void *stream);
+
+/* ---- factorized-prior entropy model --------------------------------------- */
+/* EntropyBottleneck.forward in eval mode + symbols + per-channel histogram
+ * (CompressAI, reached from _taskutils.py:97 and R:549):
+ *   sym = rint(y - median_c); y_q = sym + median_c;
+ *   p   = max(lut[c][sym - lut_min], 1e-9)   (exact per-(channel,symbol) table)
+ *   hist[c][clamp(sym - hist_min, 0, hist_bins-1)] += 1
+ *   rate_bits += sum(-log2 p)
+ * y: fp32 N x C x hw.  Any output pointer may be NULL.  hist (C x hist_bins) and
+ * rate_bits are ACCUMULATED into (zero them first).  Symbols outside the table
+ * are evaluated with the density MLP; *status is set non-zero if that was needed
+ * but no MLP was given.                                                        */
+typedef struct {
+  const float *medians;     /* C */
+  const float *lut;         /* C x lut_len likelihoods (already lower-bounded) */
+  int32_t lut_min, lut_len;
+  /* density MLP for symbols outside the table (NULL = not provided: such symbols are an
+   * error reported through `status`).  Per channel `mlp_stride` floats: for layer i of
+   * n_layers: softplus(_matrix_i) [dims[i+1] x dims[i]], _bias_i [dims[i+1]], and, for
+   * i < n_layers-1, tanh(_factor_i) [dims[i+1]].  dims = (1, filters..., 1).            */
+  const float *mlp;
+  int32_t n_layers, mlp_stride;
+  int32_t dims[10];
+  int32_t hist_min, hist_bins;
+} cae_eb_tables;
+
+int cae_eb_quantize(const float *y, int n, int c, int hw, const cae_eb_tables *t,
+                    float *y_q, float *p_y, int32_t *symbols, int32_t *hist,
+                    double *rate_bits, int32_t *status, void *stream);
+
+/* ---- entropy coder (HOST, thread-safe, no globals) ------------------------ */
+/* compressai._CXX.pmf_to_quantized_cdf, reached from
+ * EntropyBottleneck.update R:502, R:615.  cdf has n+1 entries.                */
+int cae_pmf_to_quantized_cdf(const float *pmf /*HOST*/, int n, int precision,
+                             uint32_t *cdf /*HOST*/);
+/* compressai.ans.RansEncoder.encode_with_indexes / RansDecoder.decode_with_indexes
+ *  for the EntropyBottleneck index pattern: `symbols` is C-major
+ * raster (C x hw), symbol i uses table i / hw.  Reached from R:549-551, 568-572,
+ * 645-647, 662-665.  cdfs: C x cdf_stride int32.  Returns 0 and *nbytes.      */
+int cae_rans_encode(const int32_t *symbols /*HOST*/, int c, int hw, const int32_t *cdfs,
+                    int cdf_stride, const int32_t *cdf_sizes, const int32_t *offsets,
+                    uint8_t *out /*HOST*/, size_t out_cap, size_t *nbytes);
+int cae_rans_decode(const uint8_t *enc /*HOST*/, size_t nbytes, int c, int hw,
+                    const int32_t *cdfs, int cdf_stride, const int32_t *cdf_sizes,
+                    const int32_t *offsets, int32_t *symbols /*HOST*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAE_B200_H */

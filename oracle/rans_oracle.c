@@ -98,7 +98,7 @@ long oracle_rans_encode(const int32_t *symbols, const int32_t *indexes, long n,
         if (push(&l, (uint32_t)cdf[value], (uint32_t)(cdf[value + 1] - cdf[value]), 0)) goto oom;
         if (value == max_value) {
             int32_t nb = 0;
-            while ((raw >> (nb * BYPASS_BITS)) != 0) ++nb;
+            while (nb < 8 && (raw >> (nb * BYPASS_BITS)) != 0) ++nb;
             int32_t val = nb;
             while (val >= MAX_BYPASS) {
                 if (push(&l, MAX_BYPASS, MAX_BYPASS + 1, 1)) goto oom;
