@@ -1,0 +1,481 @@
+"""Host-side mirror of the reference's ``models.tasks._autoencoders`` for the
+compress/decompress hot path: same class names, constructor arguments,
+state-dict keys and call conventions, with the arithmetic executed by the
+sm_100a kernels behind ``include/cae_b200.h``.
+
+Reference (R = ``/root/reference/src/models/tasks/_autoencoders.py``):
+``DownsamplingUnit`` R:53-101, ``ResidualDownsamplingUnit`` R:104-174,
+``UpsamplingUnit`` R:177-227, ``ResidualUpsamplingUnit`` R:230-304,
+``Analyzer`` R:307-361, ``Synthesizer`` R:364-455, ``setup_modules`` R:458-479,
+``load_state_dict`` R:482-502, ``autoencoder_from_state_dict`` R:505-527,
+codecs ``'cae'`` R:530-584 and ``'cae_bn'`` R:587-673.
+
+The unit classes only *hold parameters* (``nn.Conv2d`` / ``nn.ConvTranspose2d``
+instances at the reference's Sequential indices, so checkpoints load unchanged)
+and describe their dataflow as a ``layout`` list; ``_engine`` turns a track of
+layouts into fused kernel launches.  In ``eval()`` mode ``forward`` runs only
+CUDA kernels of this repo and requires CUDA tensors (there is no CPU fallback).
+In ``train()`` mode ``forward`` is the same dataflow written with torch autograd
+ops on the device (interim: the backward kernels are scheduled).
+"""
+import base64
+import io
+import math
+import struct
+import threading
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _cabi as C
+from . import _engine as E
+from . import _ops as O
+from ._entropy import EntropyBottleneck
+
+try:                                    # zarr / numcodecs are optional at import time
+    from numcodecs.abc import Codec
+    from numcodecs.compat import ensure_contiguous_ndarray, ndarray_copy
+except ImportError:                     # same minimal surface, so the codecs still work stand-alone
+    class Codec:                        # noqa: D401
+        codec_id = None
+
+        def get_config(self):
+            cfg = {'id': self.codec_id}
+            cfg.update({k: v for k, v in self.__dict__.items() if not k.startswith('_')})
+            return cfg
+
+        @classmethod
+        def from_config(cls, config):
+            config = dict(config)
+            config.pop('id', None)
+            return cls(**config)
+
+    def ensure_contiguous_ndarray(buf):
+        return np.ascontiguousarray(buf)
+
+    def ndarray_copy(src, dst):
+        if dst is None:
+            return src
+        dst = np.asarray(dst)
+        np.copyto(dst.reshape(src.shape).view(src.dtype) if dst.dtype != src.dtype else
+                  dst.reshape(src.shape), src)
+        return dst
+
+
+_SUPPORTED_ACTS = (None, 'Identity', 'LeakyReLU', 'ReLU', 'GDN')
+
+
+def _make_act(kind, channels, track):
+    """R:19-34.  The modules are placeholders for state-dict index parity; the
+    activation itself is an epilogue flag of the preceding convolution."""
+    if kind is None or kind == 'Identity':
+        return nn.Identity()
+    if kind == 'LeakyReLU':
+        return nn.LeakyReLU(inplace=False)
+    if kind == 'ReLU':
+        return nn.ReLU(inplace=False)
+    if kind == 'GDN':
+        raise NotImplementedError('GDN / IGDN has no CUDA epilogue yet (SURVEY.md 8f-3)')
+    raise ValueError(f'Activation layer {kind} not supported')
+
+
+def initialize_weights(m):
+    """R:37-42."""
+    if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+        nn.init.xavier_uniform_(m.weight.data, gain=math.sqrt(2 / 1.01))
+        if m.bias is not None:
+            nn.init.constant_(m.bias.data, 0.01)
+
+
+class NoneColorLayer(nn.Module):
+    def forward(self, *args, **kwargs):
+        return None
+
+
+class _Unit(nn.Module):
+    """Parameter holder + dataflow description shared by the four unit classes."""
+
+    transposed = False
+    residual = False
+
+    def __init__(self, channels_in, channels_out, kernel_size=3, groups=False, batch_norm=False,
+                 dropout=0.0, bias=False, act_layer_type=None):
+        super().__init__()
+        if kernel_size != 3:
+            raise NotImplementedError('the CUDA kernels implement kernel_size=3 '
+                                      '(the only value the reference uses)')
+        if groups:
+            raise NotImplementedError('groups=True (depthwise) is scheduled: SURVEY.md 8f-3')
+        if act_layer_type not in _SUPPORTED_ACTS:
+            raise ValueError(f'Activation layer {act_layer_type} not supported')
+        track = 'synthesis' if self.transposed else 'analysis'
+        act = act_layer_type
+        pre_conv = act is not None and act != 'GDN'
+        seqs = {'model': [], 'res_model': []}
+        layout = []
+
+        def conv(seq, cin, cout, stride):
+            if self.transposed:
+                m = nn.ConvTranspose2d(cin, cout, 3, stride=stride, padding=1,
+                                       output_padding=stride - 1, bias=bias)
+            else:
+                m = nn.Conv2d(cin, cout, 3, stride=stride, padding=1, bias=bias,
+                              padding_mode='reflect')
+            layout.append(('conv', seq, len(seqs[seq])))
+            seqs[seq].append(m)
+            if batch_norm:
+                layout.append(('bn', seq, len(seqs[seq])))
+                seqs[seq].append(nn.BatchNorm2d(cout, affine=True))
+
+        def activation(seq, kind, ch):
+            layout.append(('act', seq, len(seqs[seq]), kind))
+            seqs[seq].append(_make_act(kind, ch, track))
+
+        if self.residual:
+            conv('res_model', channels_in, channels_in, 1)
+            activation('res_model', act, channels_in)
+            if pre_conv:
+                conv('res_model', channels_in, channels_in, 1)
+                if self.transposed:                      # R:270-271: decoder only
+                    activation('res_model', act, channels_in)
+            layout.append(('add',))
+            if pre_conv:
+                activation('model', act, channels_in)
+        elif pre_conv:
+            conv('model', channels_in, channels_in, 1)
+            activation('model', act, channels_in)
+        conv('model', channels_in, channels_out, 2)
+        if act is not None:
+            activation('model', act, channels_out)
+        if dropout > 0.0:
+            seqs['model'].append(nn.Dropout2d(dropout))
+        if self.residual:
+            self.res_model = nn.Sequential(*seqs['res_model'])
+        self.model = nn.Sequential(*seqs['model'])
+        self.layout = layout
+
+    def forward(self, x):
+        """torch-op dataflow (training / autograd path)."""
+        if self.residual:
+            x = self.res_model(x) + x
+        return self.model(x)
+
+
+class DownsamplingUnit(_Unit):
+    pass
+
+
+class ResidualDownsamplingUnit(_Unit):
+    residual = True
+
+
+class UpsamplingUnit(_Unit):
+    transposed = True
+
+
+class ResidualUpsamplingUnit(_Unit):
+    transposed = True
+    residual = True
+
+
+class _Track(nn.Module):
+    """Common execution plumbing of Analyzer / Synthesizer."""
+
+    def __init__(self):
+        super().__init__()
+        self._exec = None
+        self._lock = threading.Lock()
+
+    def _units(self):
+        raise NotImplementedError
+
+    def _executor(self):
+        if self._exec is None:
+            self._exec = E.TrackExecutor(E.steps_from_units(self._units()))
+        return self._exec
+
+    def _check_input(self, x):
+        if not x.is_cuda:
+            raise C.CaeError(f'{type(self).__name__}: eval-mode forward runs CUDA kernels only; '
+                             'got a CPU tensor (no CPU fallback). Move the model and data to cuda.')
+        p = next(self.parameters())
+        if p.device != x.device:
+            raise C.CaeError(f'{type(self).__name__}: parameters on {p.device}, input on {x.device}')
+
+
+class Analyzer(_Track):
+    def __init__(self, channels_org=3, channels_net=8, channels_bn=16, compression_level=3,
+                 channels_expansion=1, kernel_size=3, groups=False, batch_norm=False, dropout=0.0,
+                 bias=False, use_residual=False, act_layer_type=None, **kwargs):
+        super().__init__()
+        unit = ResidualDownsamplingUnit if use_residual else DownsamplingUnit
+        common = dict(kernel_size=kernel_size, groups=groups, batch_norm=batch_norm,
+                      dropout=dropout, bias=bias)
+        track = []
+        cin, cout = channels_org, channels_net
+        for _ in range(compression_level - 1):
+            track.append(unit(cin, cout, act_layer_type=act_layer_type, **common))
+            cin, cout = cout, cout * channels_expansion
+        if compression_level > 0:
+            track.append(unit(cin, channels_bn, act_layer_type=None, **common))
+        else:
+            track.append(nn.Identity())
+        self.analysis_track = nn.Sequential(*track)
+        self.apply(initialize_weights)
+
+    def _units(self):
+        return [u for u in self.analysis_track if isinstance(u, _Unit)]
+
+    def forward(self, x):
+        """x: fp32 N x C x H x W in [0,1] (or uint8 N x H x W x C, divided by 255 in the
+        first kernel) -> latent y, fp32 N x C_bn x H/2^L x W/2^L."""
+        if self.training:
+            if x.dtype == torch.uint8:
+                x = x.permute(0, 3, 1, 2).float() / 255.0
+            return self.analysis_track(x)
+        self._check_input(x)
+        if not self._units():
+            return x
+        with self._lock, torch.no_grad():
+            a = O.wrap_u8_hwc(x) if x.dtype == torch.uint8 else O.wrap_nchw(x)
+            if a.c > 4 and a.fmt == C.FMT_F32_NCHW:
+                first = self._executor().steps[0]
+                fmt = C.FMT_F16_SPLIT if first.kind == C.CONV_S2 else C.FMT_F16_PLANAR
+                a = O.nchw_to_planar(a.t, fmt, C.HALO_REFLECT)
+            y, _, _ = self._executor().run(a, C.FMT_F32_NCHW)
+        return y.t
+
+
+class Synthesizer(_Track):
+    def __init__(self, channels_org=3, channels_net=8, channels_bn=16, compression_level=3,
+                 channels_expansion=1, kernel_size=3, groups=False, batch_norm=False, dropout=0.0,
+                 bias=False, use_residual=False, act_layer_type=None, multiscale_analysis=False,
+                 **kwargs):
+        super().__init__()
+        unit = ResidualUpsamplingUnit if use_residual else UpsamplingUnit
+        common = dict(kernel_size=kernel_size, groups=groups, batch_norm=batch_norm,
+                      dropout=dropout, bias=bias)
+        track = []
+        cin = channels_bn
+        cout = channels_net * channels_expansion ** compression_level
+        for _ in range(compression_level - 1):
+            track.append(unit(cin, cout, act_layer_type=act_layer_type, **common))
+            cin, cout = cout, cout // channels_expansion
+        if compression_level > 0:
+            track.append(unit(cin, channels_org, act_layer_type=None, **common))
+        else:
+            track.append(nn.Identity())
+        self.synthesis_track = nn.Sequential(*track)
+        if multiscale_analysis:
+            raise NotImplementedError('multiscale_analysis colour heads are scheduled: SURVEY.md 8f-3')
+        layers = [nn.Sequential(NoneColorLayer()) for _ in range(compression_level - 1)]
+        layers.append(nn.Identity())
+        self.color_layers = nn.ModuleList(layers)
+        self.rec_level = compression_level
+        self.bridges = False       # set True to get fx_brg as fp32 tensors in eval mode
+        self.apply(initialize_weights)
+
+    def _units(self):
+        return [u for u in self.synthesis_track if isinstance(u, _Unit)]
+
+    def _unit_output_indices(self):
+        idx, k = [], 0
+        for u in self._units():
+            k += sum(1 for op in u.layout if op[0] == 'conv')
+            idx.append(k)
+        return idx
+
+    def forward(self, x, as_uint8=False):
+        """y_q fp32 N x C_bn x h x w -> (x_r, fx_brg) exactly as R:442-455: x_r[0] is the
+        full-resolution reconstruction, lower scales are None.  ``as_uint8`` (extension
+        used by the codecs) additionally returns the N x H x W x C uint8 image produced
+        by the last kernel's epilogue: ``(x_r, fx_brg, u8)``."""
+        if self.training:
+            fx, fx_brg, x_r = x, [], []
+            for up, col in zip(self.synthesis_track, self.color_layers):
+                fx = up(fx)
+                x_r.insert(0, col(fx))
+                fx_brg.append(fx)
+            return x_r, fx_brg
+        self._check_input(x)
+        n_units = len(self._units())
+        if n_units == 0:
+            return [x], [x]
+        with self._lock, torch.no_grad():
+            a = O.nchw_to_planar(x, C.FMT_F16_PLANAR, C.HALO_KEEP) if x.shape[1] > 4 \
+                else O.wrap_nchw(x)
+            outs = self._unit_output_indices()
+            keep = outs[:-1] if self.bridges else ()
+            final = C.FMT_U8_HWC if as_uint8 else C.FMT_F32_NCHW
+            last, kept, aux = self._executor().run(a, final, keep=keep, aux_last=True)
+            x_full = aux if aux is not None else last.t
+            u8 = last.t if (as_uint8 and last.fmt == C.FMT_U8_HWC) else None
+            fx_brg = [O.planar_to_nchw(kept[i]) if i in kept else None for i in outs[:-1]]
+            fx_brg.append(x_full)
+        x_r = [None] * (n_units - 1)
+        x_r.insert(0, x_full)
+        if as_uint8:
+            if u8 is None:
+                u8 = (x_full * 255.0).clip(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+            return x_r, fx_brg, u8
+        return x_r, fx_brg
+
+
+# --------------------------------------------------------------------------
+# Model dict factory (R:458-527)
+# --------------------------------------------------------------------------
+
+def setup_modules(channels_bn=192, compression_level=4, K=4, r=3, enabled_modules=None, **kwargs):
+    if enabled_modules is None:
+        enabled_modules = ['encoder', 'decoder', 'fact_ent']
+    model = {}
+    if 'encoder' in enabled_modules:
+        model['encoder'] = Analyzer(channels_bn=channels_bn, compression_level=compression_level,
+                                    **kwargs)
+    if 'decoder' in enabled_modules:
+        model['decoder'] = Synthesizer(channels_bn=channels_bn,
+                                       compression_level=compression_level, **kwargs)
+    if 'fact_ent' in enabled_modules:
+        model['fact_ent'] = EntropyBottleneck(channels=channels_bn, filters=[r] * K)
+    return model
+
+
+def load_state_dict(model, encoder=None, decoder=None, fact_ent=None, **kwargs):
+    if 'encoder' in model and encoder is not None:
+        model['encoder'].load_state_dict(encoder, strict=False)
+    if 'decoder' in model and decoder is not None:
+        model['decoder'].load_state_dict(decoder, strict=False)
+    if 'fact_ent' in model and fact_ent is not None:
+        for k in ('_quantized_cdf', '_offset', '_cdf_length'):
+            if k in fact_ent:
+                setattr(model['fact_ent'], k, fact_ent[k])
+        model['fact_ent'].load_state_dict(fact_ent)
+        model['fact_ent'].update(force=True)
+
+
+class ModuleHandle(nn.Module):
+    """The ``nn.DataParallel`` slot of the reference's model dict (R:514-520):
+    callable, ``.module`` reach-through, ``train/eval/cuda/state_dict``.  One
+    process drives one GPU here (tiles are sharded across processes by chunk
+    range), so the handle simply forwards to the module."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+
+def autoencoder_from_state_dict(checkpoint, gpu=False, train=False):
+    """R:505-527.  ``gpu=False`` builds the modules on the CPU exactly like the
+    reference; their eval-mode ``forward`` then refuses to run (no CPU fallback)."""
+    if isinstance(checkpoint, str):
+        state = torch.load(checkpoint, map_location='cpu', weights_only=False)
+    else:
+        state = checkpoint
+    model = setup_modules(**state)
+    load_state_dict(model, **state)
+    for k in model:
+        model[k] = ModuleHandle(model[k])
+        if gpu and torch.cuda.is_available():
+            model[k].cuda()
+        model[k].train() if train else model[k].eval()
+    return model
+
+
+# --------------------------------------------------------------------------
+# numcodecs codecs (R:530-673)
+# --------------------------------------------------------------------------
+
+def _device_of(handle):
+    return next(handle.parameters()).device
+
+
+class ConvolutionalAutoencoder(Codec):
+    """zarr chunk codec ``'cae'``: uint8 HWC tile <-> 16-byte '>QQ' (h, w) header + rANS
+    stream (R:530-584).  ``gpu`` is kept in the config for compatibility; the codec
+    always executes on the current CUDA device."""
+    codec_id = 'cae'
+
+    def __init__(self, checkpoint, gpu=False):
+        self.checkpoint = checkpoint
+        self.gpu = gpu
+        self._model = autoencoder_from_state_dict(checkpoint, gpu=True, train=False)
+        if not torch.cuda.is_available():
+            raise C.CaeError("codec 'cae' needs a CUDA device (no CPU fallback)")
+
+    def encode(self, buf):
+        buf = np.ascontiguousarray(buf)
+        h, w, c = buf.shape
+        dev = _device_of(self._model['encoder'])
+        x = torch.from_numpy(buf).to(dev, non_blocking=True).reshape(1, h, w, c)
+        y = self._model['encoder'](x)
+        strings = self._model['fact_ent'].module.compress(y)
+        return struct.pack('>QQ', h, w) + strings[0]
+
+    def decode(self, buf, out=None):
+        if out is not None:
+            out = ensure_contiguous_ndarray(out)
+        buf = bytes(buf)
+        level = len(self._model['decoder'].module.synthesis_track)
+        h, w = struct.unpack('>QQ', buf[:16])
+        y_q = self._model['fact_ent'].module.decompress([buf[16:]],
+                                                        size=(h // 2 ** level, w // 2 ** level))
+        _, _, u8 = self._model['decoder'](y_q, as_uint8=True)
+        img = np.ascontiguousarray(u8[0].cpu().numpy())
+        return ndarray_copy(img, out)
+
+
+class ConvolutionalAutoencoderBottleneck(Codec):
+    """zarr chunk codec ``'cae_bn'``: fp32 latent HWC <-> header + rANS stream (R:587-673)."""
+    codec_id = 'cae_bn'
+
+    def __init__(self, channels_bn, fact_ent=None, filters=None, fact_ent_checkpoint=None,
+                 gpu=False):
+        if fact_ent is not None:
+            filters = list(fact_ent.filters)
+            fact_ent_checkpoint = {n: self._tensor2bytes(p)
+                                   for n, p in fact_ent.named_parameters()}
+        self.filters = filters
+        self.channels_bn = channels_bn
+        self.fact_ent_checkpoint = fact_ent_checkpoint
+        self.gpu = gpu
+        self._setup_encoder()
+
+    def _setup_encoder(self):
+        if not torch.cuda.is_available():
+            raise C.CaeError("codec 'cae_bn' needs a CUDA device (no CPU fallback)")
+        self._fact_ent = EntropyBottleneck(channels=self.channels_bn, filters=self.filters)
+        state = {n: self._bytes2tensor(b) for n, b in self.fact_ent_checkpoint.items()}
+        self._fact_ent.load_state_dict(state, strict=False)
+        self._fact_ent.cuda().eval()
+        self._fact_ent.update(force=True)
+
+    @staticmethod
+    def _tensor2bytes(tensor):
+        buf = io.BytesIO()
+        torch.save(tensor.cpu().detach(), buf)
+        return base64.b64encode(buf.getvalue()).decode('ascii')
+
+    @staticmethod
+    def _bytes2tensor(buf):
+        return torch.load(io.BytesIO(base64.b64decode(buf)), weights_only=False)
+
+    def encode(self, buf):
+        buf = np.ascontiguousarray(buf, dtype=np.float32)
+        h, w, c = buf.shape
+        y = torch.from_numpy(buf).cuda().permute(2, 0, 1).reshape(1, c, h, w).contiguous()
+        strings = self._fact_ent.compress(y)
+        return struct.pack('>QQ', h, w) + strings[0]
+
+    def decode(self, buf, out=None):
+        if out is not None:
+            out = ensure_contiguous_ndarray(out)
+        buf = bytes(buf)
+        h, w = struct.unpack('>QQ', buf[:16])
+        y_q = self._fact_ent.decompress([buf[16:]], size=(h, w))
+        arr = np.ascontiguousarray(y_q[0].permute(1, 2, 0).float().cpu().numpy())
+        return ndarray_copy(arr, out)

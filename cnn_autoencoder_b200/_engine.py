@@ -1,0 +1,232 @@
+"""Layer-plan executor: turns a track of units (the parameter-holding modules
+of ``_autoencoders.py``) into a list of fused convolution steps and runs them
+through the C ABI.
+
+One step = one ABI call ``out = post_act(pre_act(conv(in) + bias) + skip)``;
+the unit structure of the reference (``src/models/tasks/_autoencoders.py``
+53-304) maps onto steps as:
+
+  plain unit     [conv s1 -> act] -> conv s2 -> [act]
+                 = step(conv s1, pre=act) ; step(conv s2, pre=act)
+  residual unit  res = conv_a -> act_a -> [conv_b (-> act_b in the decoder)];
+                 fx = res + x ; [act_m] -> conv_c -> [act_c]
+                 = step(conv_a, pre=act_a) ;
+                   step(conv_b, pre=act_b, skip=x, post=act_m) ; step(conv_c, pre=act_c)
+                 (without conv_b: step(conv_a, pre=act_a, skip=x, post=act_m))
+
+Eval-mode BatchNorm (R:72-73) is folded into the weights/bias when they are
+packed.  Every tensor between steps lives in the internal fp16 layout its
+consumer wants (planar for stride-1 / transposed, parity-split for stride-2;
+reflect halo for Conv2d consumers, zero halo for ConvTranspose2d consumers).
+"""
+import torch
+import torch.nn as nn
+
+from . import _cabi as C
+from . import _ops as O
+
+_ACT_CODE = {None: C.ACT_NONE, 'Identity': C.ACT_NONE, 'LeakyReLU': C.ACT_LEAKY_RELU,
+             'ReLU': C.ACT_RELU}
+
+
+def act_code(kind):
+    if kind not in _ACT_CODE:
+        raise NotImplementedError(
+            f'activation {kind!r} has no CUDA epilogue yet (GDN is scheduled: SURVEY.md 8f-3)')
+    return _ACT_CODE[kind]
+
+
+class Step:
+    """One fused convolution."""
+
+    def __init__(self, conv, bn=None, pre_act=None, skip=None, post_act=None):
+        self.conv = conv            # nn.Conv2d / nn.ConvTranspose2d used as the parameter holder
+        self.bn = bn
+        self.pre_act = pre_act
+        self.skip = skip            # index of the tensor added before post_act (0 = track input)
+        self.post_act = post_act
+        self.transposed = isinstance(conv, nn.ConvTranspose2d)
+        stride = conv.stride[0]
+        if conv.kernel_size != (3, 3) or conv.groups != 1 or conv.dilation != (1, 1):
+            raise NotImplementedError('only dense 3x3 convolutions have CUDA kernels '
+                                      '(groups=True is scheduled: SURVEY.md 8f-3)')
+        self.kind = ({1: C.CONVT_S1, 2: C.CONVT_S2} if self.transposed
+                     else {1: C.CONV_S1, 2: C.CONV_S2})[stride]
+        self.c_in = conv.in_channels
+        self.c_out = conv.out_channels
+        self.pad_mode = C.PAD_ZERO if self.transposed else (
+            C.PAD_REFLECT if conv.padding_mode == 'reflect' else C.PAD_ZERO)
+        self._cache_key = None
+        self._cache = None
+
+    # weights in the form the chosen kernel wants, rebuilt when a parameter changes
+    def materialise(self, igemm):
+        params = [self.conv.weight, self.conv.bias]
+        if self.bn is not None:
+            params += [self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var]
+        key = (igemm,) + tuple((p.data_ptr(), p._version) if p is not None else None
+                               for p in params)
+        if key == self._cache_key:
+            return self._cache
+        with torch.no_grad():
+            w = self.conv.weight.detach().float()
+            b = self.conv.bias.detach().float() if self.conv.bias is not None else None
+            scale = None
+            if self.bn is not None:
+                inv = torch.rsqrt(self.bn.running_var.float() + self.bn.eps)
+                gamma = self.bn.weight.float() if self.bn.weight is not None else torch.ones_like(inv)
+                beta = self.bn.bias.float() if self.bn.bias is not None else torch.zeros_like(inv)
+                scale = gamma * inv
+                b0 = b if b is not None else torch.zeros_like(inv)
+                b = (b0 - self.bn.running_mean.float()) * scale + beta
+            if igemm:
+                wdev = O.pack_weights(self.kind, w, scale=scale)
+            else:
+                if scale is not None:
+                    w = w * (scale.view(1, -1, 1, 1) if self.transposed else scale.view(-1, 1, 1, 1))
+                wdev = w.contiguous()
+            self._cache = (wdev, b.contiguous() if b is not None else None)
+        self._cache_key = key
+        return self._cache
+
+
+def steps_from_units(units):
+    """units: iterable of unit modules exposing ``layout`` (list of op tuples built
+    by ``_autoencoders._unit_layout``), ``model`` and (residual) ``res_model``."""
+    steps = []
+    tensor_idx = 0            # index of the tensor currently flowing (0 = input)
+    for unit in units:
+        unit_in = tensor_idx
+        pending = None        # last Step, still accepting a trailing bn / activation
+        skip_armed = False
+        for op in unit.layout:
+            tag = op[0]
+            if tag == 'conv':
+                seq = getattr(unit, op[1])
+                pending = Step(seq[op[2]])
+                steps.append(pending)
+                tensor_idx = len(steps)
+            elif tag == 'bn':
+                seq = getattr(unit, op[1])
+                if pending is None or pending.pre_act is not None or pending.skip is not None:
+                    raise NotImplementedError('BatchNorm2d not directly after a convolution')
+                pending.bn = seq[op[2]]
+            elif tag == 'act':
+                kind = op[3]
+                if kind in (None, 'Identity'):
+                    continue
+                act_code(kind)
+                if pending is None:
+                    raise NotImplementedError('activation on the raw track input')
+                if pending.skip is not None or skip_armed:
+                    if pending.post_act is not None:
+                        raise NotImplementedError('two activations after a residual add')
+                    pending.post_act = kind
+                else:
+                    if pending.pre_act is not None:
+                        raise NotImplementedError('two activations after one convolution')
+                    pending.pre_act = kind
+            elif tag == 'add':
+                if pending is None:
+                    raise NotImplementedError('residual add without a convolution')
+                pending.skip = unit_in
+                skip_armed = True
+            else:
+                raise ValueError(tag)
+            if tag == 'conv':
+                skip_armed = False
+    return steps
+
+
+class TrackExecutor:
+    """Runs a list of Steps on one input through the C ABI."""
+
+    def __init__(self, steps):
+        self.steps = steps
+        self._buffers = {}
+        self.last_calls = {}      # step index -> (args, kwargs) of its last _ops.conv call
+
+    @staticmethod
+    def _use_igemm(step, x):
+        if x.fmt in (C.FMT_F32_NCHW, C.FMT_U8_HWC):
+            return False                      # raw image / latent from the caller: direct kernel
+        return not (step.c_in <= 4 and step.c_out <= 4)
+
+    def _consumer_layout(self, k, final_fmt):
+        """(fmt, halo) of the tensor produced by step k-1 (k = consumer index)."""
+        if k >= len(self.steps):
+            return final_fmt, C.HALO_KEEP
+        nxt = self.steps[k]
+        fmt = C.FMT_F16_SPLIT if nxt.kind == C.CONV_S2 else C.FMT_F16_PLANAR
+        halo = C.HALO_REFLECT if (not nxt.transposed and nxt.pad_mode == C.PAD_REFLECT) else C.HALO_KEEP
+        return fmt, halo
+
+    def _buffer(self, key, fmt, n, c, h, w, halo, device):
+        full = (key, fmt, n, c, h, w, halo, str(device))
+        buf = self._buffers.get(key)
+        if buf is None or buf[0] != full:
+            if len(self._buffers) > 64:
+                self._buffers.clear()
+            buf = (full, O.alloc_act(fmt, n, c, h, w, halo, device=device))
+            self._buffers[key] = buf
+        return buf[1]
+
+    def run(self, x, final_fmt, keep=(), aux_last=False):
+        """x: Act.  final_fmt: format of the last step's output (F32_NCHW, U8_HWC or
+        planar).  keep: indices of intermediate tensors to return as well.
+        aux_last: also return the last output as fp32 NCHW (alongside U8_HWC).
+        Returns (last Act or None, {index: Act}, aux tensor or None)."""
+        tensors = {0: x}
+        cur = x
+        aux = None
+        n_steps = len(self.steps)
+        for k, st in enumerate(self.steps):
+            igemm = self._use_igemm(st, cur)
+            if igemm and cur.fmt not in (C.FMT_F16_PLANAR, C.FMT_F16_SPLIT):
+                raise C.CaeError('internal: igemm step fed a non-planar tensor')
+            wdev, bias = st.materialise(igemm)
+            ho, wo = O.KIND_OUT[st.kind](cur.h, cur.w)
+            last = k == n_steps - 1
+            fmt, halo = self._consumer_layout(k + 1, final_fmt)
+            merged = st.kind == C.CONVT_S2 and 4 * st.c_out <= 16
+            out = None
+            aux_t = None
+            convert_after = None
+            if last and igemm and merged:
+                # the final image layer writes uint8 HWC and / or fp32 NCHW
+                if fmt == C.FMT_U8_HWC:
+                    out = O.alloc_act(C.FMT_U8_HWC, cur.n, st.c_out, ho, wo, device=cur.t.device)
+                if aux_last or fmt != C.FMT_U8_HWC:
+                    aux_t = torch.empty((cur.n, st.c_out, ho, wo), dtype=torch.float32,
+                                        device=cur.t.device)
+            else:
+                if igemm and merged:
+                    raise NotImplementedError('a <=4-channel transposed layer in the middle of a track')
+                if igemm and st.kind == C.CONVT_S2 and fmt in (C.FMT_F32_NCHW, C.FMT_U8_HWC):
+                    # wide (>4 channel) image layer: pixel-shuffle epilogue writes planar fp16
+                    convert_after = fmt
+                    fmt = C.FMT_F16_PLANAR
+                if fmt in (C.FMT_F32_NCHW, C.FMT_U8_HWC):
+                    out = O.alloc_act(fmt, cur.n, st.c_out, ho, wo, device=cur.t.device)
+                    if last and aux_last and fmt == C.FMT_U8_HWC:
+                        aux_t = torch.empty((cur.n, st.c_out, ho, wo), dtype=torch.float32,
+                                            device=cur.t.device)
+                else:
+                    out = self._buffer(k, fmt, cur.n, st.c_out, ho, wo, halo, cur.t.device)
+            skip = tensors[st.skip] if st.skip is not None else None
+            call = ((st.kind, cur, wdev, st.c_out, out),
+                    dict(igemm=igemm, bias=bias, skip=skip, pre_act=act_code(st.pre_act),
+                         post_act=act_code(st.post_act), pad_mode=st.pad_mode, aux=aux_t))
+            O.conv(*call[0], **call[1])
+            self.last_calls[k] = call
+            if out is None:
+                out = O.Act(aux_t, C.FMT_F32_NCHW, cur.n, st.c_out, ho, wo)
+            if convert_after is not None:
+                aux_t = O.planar_to_nchw(out)
+                out = O.Act(aux_t, C.FMT_F32_NCHW, cur.n, st.c_out, ho, wo)
+            tensors[k + 1] = out
+            cur = out
+            if last:
+                aux = aux_t
+        kept = {i: tensors[i] for i in keep if i in tensors}
+        return cur, kept, aux

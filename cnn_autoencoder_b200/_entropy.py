@@ -248,6 +248,13 @@ class EntropyBottleneck(nn.Module):
         y_q, p_y, _, _, _ = self._quantize_cuda(x)
         return y_q, p_y
 
+    def quantize_rate(self, x):
+        """(y_q, C x bins histogram, total bits) in one pass: what the encode+rate+decode
+        pipeline needs between the two transforms."""
+        y_q, _, _, hist, rate = self._quantize_cuda(x, want_yq=True, want_p=False,
+                                                    want_hist=True, want_rate=True)
+        return y_q, hist, rate
+
     def symbols_hist_rate(self, x):
         """(int32 symbols, C x bins histogram, total bits) in one pass (K11/K14)."""
         _, _, sym, hist, rate = self._quantize_cuda(x, want_yq=False, want_p=False, want_sym=True,

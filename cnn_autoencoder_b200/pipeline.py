@@ -1,0 +1,27 @@
+"""The measured hot path as one call: uint8 tiles -> analysis transform ->
+quantize + likelihood/rate + histogram -> synthesis transform -> uint8 tiles.
+
+This is the body of the reference's per-tile work (``ConvolutionalAutoencoder.
+encode/decode``, ``/root/reference/src/models/tasks/_autoencoders.py:539-584``,
+and ``forward_func``, ``_taskutils.py:95-108``) for a BATCH of tiles, with the
+entropy coder left out (it is host code; see ``compress.py``).
+"""
+import torch
+
+
+class CodecPipeline:
+    def __init__(self, model):
+        self.model = model
+        self.level = len(model['decoder'].module.synthesis_track)
+
+    @torch.no_grad()
+    def __call__(self, x_u8):
+        """x_u8: N x H x W x C uint8 on the device.  Returns dict(x_r_u8, y, y_q, hist,
+        bits, bpp): bpp is the estimated rate ``-sum(log2 p_y) / (N*H*W)``
+        (``_ratedist.py:49-54``)."""
+        n, h, w, _ = x_u8.shape
+        y = self.model['encoder'](x_u8)
+        y_q, hist, bits = self.model['fact_ent'].module.quantize_rate(y)
+        _, _, x_r_u8 = self.model['decoder'](y_q, as_uint8=True)
+        return dict(x_r_u8=x_r_u8, y=y, y_q=y_q, hist=hist, bits=bits,
+                    bpp=bits / float(n * h * w))

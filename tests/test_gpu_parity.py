@@ -1,0 +1,248 @@
+"""Parity of the CUDA path (through the public API and the C ABI) against the CPU
+oracle and the committed reference outputs.  Runs on the B200 box.
+
+Bars (BASELINE.json north_star): quantized latents agree on >= 99.9 % of symbols
+with flips only at rounding boundaries; decoded PSNR within 0.05 dB; estimated
+bpp within 0.5 %; integer histograms and entropy-coded streams bit-exact given
+identical symbols.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+SMALL = [p for p in sorted(glob.glob(os.path.join(GOLDEN, 'transforms_*.pt'))) if 'gdn' not in p]
+NAMED = sorted(glob.glob(os.path.join(GOLDEN, 'named_*.pt')))
+
+
+def _load(p):
+    return torch.load(p, map_location='cpu', weights_only=False)
+
+
+def _model(chk):
+    import cnn_autoencoder_b200 as M
+    return M.autoencoder_from_state_dict(chk, gpu=True, train=False)
+
+
+def _symbol_report(y_gpu, y_ref, medians):
+    """fraction of agreeing symbols, and the largest distance of a flipped value from its
+    rounding boundary (flips may only happen where y - median is within eps of k + 0.5)."""
+    med = medians.reshape(1, -1, 1, 1)
+    s_gpu = torch.round(y_gpu - med)
+    s_ref = torch.round(y_ref - med)
+    flips = s_gpu != s_ref
+    agree = 1.0 - flips.float().mean().item()
+    frac = (y_ref - med) - torch.floor(y_ref - med)
+    dist = (frac - 0.5).abs()[flips]
+    return agree, (dist.max().item() if flips.any() else 0.0), int(flips.sum().item())
+
+
+def _psnr(a, b):
+    from oracle import cae_oracle as O
+    return O.psnr_u8(a, b)
+
+
+def _to_u8(x_r):
+    return (x_r * 255.0).clip(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().cpu().numpy()
+
+
+@pytest.mark.parametrize('path', SMALL, ids=[os.path.basename(p)[11:-3] for p in SMALL])
+def test_small_archs_against_reference_outputs(path):
+    g = _load(path)
+    model = _model(g['checkpoint'])
+    x = g['x_u8'].float() / 255.0
+    y = model['encoder'](x.cuda()).cpu()
+    assert y.shape == g['y'].shape
+    med = g['checkpoint']['fact_ent']['quantiles'][:, 0, 1]
+    agree, boundary, nflip = _symbol_report(y, g['y'], med)
+    # tiny tensors (<= 1.5 k symbols): allow 2 boundary flips
+    assert nflip <= max(2, 1e-3 * y.numel()), (agree, nflip)
+    assert boundary < 0.02
+    assert torch.allclose(y, g['y'], atol=2e-2, rtol=2e-2)
+    x_r, fx_brg = model['decoder'](g['y_q'].cuda())
+    assert len(x_r) == len(fx_brg) == g['arch']['compression_level']
+    assert all(v is None for v in x_r[1:])
+    img = g['x_u8'].permute(0, 2, 3, 1).numpy()
+    d = abs(_psnr(img, _to_u8(x_r[0])) - _psnr(img, _to_u8(g['x_r'])))
+    assert d <= 0.05, d
+    assert torch.allclose(x_r[0].cpu(), g['x_r'], atol=3e-3, rtol=1e-2)
+    # the uint8 epilogue is the truncating cast of the fp32 output
+    _, _, u8 = model['decoder'](g['y_q'].cuda(), as_uint8=True)
+    assert np.array_equal(u8.cpu().numpy(), _to_u8(x_r[0]))
+    # uint8 HWC input path == fp32 NCHW input path
+    y2 = model['encoder'](g['x_u8'].permute(0, 2, 3, 1).contiguous().cuda()).cpu()
+    assert torch.equal(y2, y)
+
+
+@pytest.mark.parametrize('path', NAMED, ids=[os.path.basename(p)[6:-3] for p in NAMED])
+def test_named_archs_against_reference_outputs(path):
+    from oracle import cae_oracle as O
+    g = _load(path)
+    chk = O.make_checkpoint(g['arch'], seed=g['seed'])
+    model = _model(chk)
+    y = model['encoder']((g['x_u8'].float() / 255.0).cuda()).cpu()
+    med = chk['fact_ent']['quantiles'][:, 0, 1]
+    agree, boundary, nflip = _symbol_report(y, g['y'], med)
+    assert nflip <= max(2, 1e-3 * y.numel()), (agree, nflip)
+    assert boundary < 0.02
+    y_q, p_y = model['fact_ent'](g['y'].cuda())
+    assert torch.equal(y_q.cpu(), g['y_q'])
+    assert torch.allclose(p_y.cpu(), g['p_y'], rtol=2e-4, atol=1e-12)
+    x_r, _ = model['decoder'](g['y_q'].cuda())
+    img = g['x_u8'].permute(0, 2, 3, 1).numpy()
+    d = abs(_psnr(img, _to_u8(x_r[0])) - _psnr(img, _to_u8(g['x_r'])))
+    assert d <= 0.05, d
+
+
+@pytest.mark.parametrize('name,n,size', [('A', 4, 256), ('A_res', 2, 256), ('B', 2, 256),
+                                         ('A', 1, 512)])
+def test_full_size_pipeline_against_oracle(name, n, size):
+    """configs[1]/[2] shapes: whole pipeline vs the oracle on the same seeded inputs."""
+    from oracle import cae_oracle as O
+    from cnn_autoencoder_b200.pipeline import CodecPipeline
+    torch.set_num_threads(os.cpu_count() or 8)
+    chk = O.make_checkpoint(O.NAMED_ARCHS[name], seed=1234)
+    model = _model(chk)
+    oracle = O.OracleModel(chk)
+    x_u8 = O.synth_natural(n, 3, size, size, seed=1)
+    out = CodecPipeline(model)(x_u8.permute(0, 2, 3, 1).contiguous().cuda())
+    ref = oracle.forward(x_u8.float() / 255.0)
+    med = chk['fact_ent']['quantiles'][:, 0, 1]
+    agree, boundary, nflip = _symbol_report(out['y'].cpu(), ref['y'], med)
+    assert agree >= 0.999, (agree, nflip)
+    assert boundary < 0.02, boundary
+    img = x_u8.permute(0, 2, 3, 1).numpy()
+    ref_u8 = _to_u8(ref['x_r'][0])
+    d_psnr = abs(_psnr(img, out['x_r_u8'].cpu().numpy()) - _psnr(img, ref_u8))
+    assert d_psnr <= 0.05, d_psnr
+    bpp_ref = O.rate_loss(x_u8.float(), ref['p_y']).item()
+    assert abs(out['bpp'].item() - bpp_ref) <= 0.005 * bpp_ref
+    # histogram == bincount of the symbols the kernel itself produced (integer work: exact)
+    sym, hist, bits = model['fact_ent'].module.symbols_hist_rate(out['y'])
+    tb = model['fact_ent'].module._device_tables()
+    s = sym.cpu().numpy()
+    for c in (0, s.shape[1] // 2, s.shape[1] - 1):
+        idx = np.clip(s[:, c].reshape(-1) - tb['lut_min'], 0, tb['lut_len'] - 1)
+        assert np.array_equal(np.bincount(idx, minlength=tb['lut_len']), hist[c].cpu().numpy())
+    assert hist.sum().item() == s.size
+
+
+def test_entropy_coder_streams_bit_exact_given_identical_symbols():
+    from oracle import cae_oracle as O
+    chk = O.make_checkpoint(O.NAMED_ARCHS['A'], seed=1234)
+    model = _model(chk)
+    oracle = O.OracleModel(chk)
+    g = torch.Generator().manual_seed(3)
+    y = torch.randn(2, 48, 16, 24, generator=g) * 9
+    y[0, 0, 0, 0] = 4000.2
+    y[1, 47, 15, 23] = -77777.0
+    mine = model['fact_ent'].module.compress(y.cuda())
+    ref = oracle.fact_ent.compress(y)
+    assert mine == ref
+    back = model['fact_ent'].module.decompress(mine, size=(16, 24))
+    assert torch.equal(back.cpu(), oracle.fact_ent.decompress(ref, (16, 24)))
+    assert torch.equal(back.cpu(), torch.round(y))
+
+
+def test_cae_codec_roundtrip_against_oracle_codec():
+    from oracle import cae_oracle as O
+    import cnn_autoencoder_b200 as M
+    arch = dict(channels_org=3, channels_net=32, channels_bn=16, compression_level=3,
+                act_layer_type='LeakyReLU')
+    chk = O.make_checkpoint(arch, seed=77)
+    codec = M.ConvolutionalAutoencoder(checkpoint=chk, gpu=True)
+    oracle = O.OracleModel(chk)
+    tile = O.synth_tissue_tile(1, 2, ps=128, seed=2)
+    enc = codec.encode(tile)
+    enc_ref = oracle.codec_encode(tile)
+    assert enc[:16] == enc_ref[:16]
+    # the oracle decodes the product's stream into the product's symbols (format parity)
+    sym = oracle.fact_ent.decompress([enc[16:]], (16, 16))
+    sym_ref = oracle.fact_ent.decompress([enc_ref[16:]], (16, 16))
+    assert (sym == sym_ref).float().mean().item() >= 0.999
+    assert abs(len(enc) - len(enc_ref)) <= 0.005 * len(enc_ref) + 8
+    rec = codec.decode(enc)
+    rec_ref = oracle.codec_decode(enc_ref)
+    assert rec.shape == tile.shape and rec.dtype == np.uint8
+    assert abs(O.psnr_u8(tile, rec) - O.psnr_u8(tile, rec_ref)) <= 0.05
+    out = np.empty_like(tile)
+    assert codec.decode(enc, out=out) is not None and np.array_equal(out, rec)
+
+
+def test_cae_bn_codec_roundtrip():
+    from oracle import cae_oracle as O
+    import cnn_autoencoder_b200 as M
+    chk = O.make_checkpoint(O.NAMED_ARCHS['M'], seed=9)
+    model = _model(chk)
+    codec = M.ConvolutionalAutoencoderBottleneck(channels_bn=16, fact_ent=model['fact_ent'].module,
+                                                 gpu=True)
+    cfg = codec.get_config()
+    assert cfg['id'] == 'cae_bn' and cfg['channels_bn'] == 16
+    lat = (np.random.default_rng(0).normal(0, 5, size=(8, 12, 16))).astype(np.float32)
+    enc = codec.encode(lat)
+    dec = codec.decode(enc)
+    assert dec.shape == lat.shape and dec.dtype == np.float32
+    assert np.array_equal(dec, np.round(lat))
+    oracle = O.OracleModel(chk)
+    y = torch.from_numpy(lat).permute(2, 0, 1).unsqueeze(0)
+    assert enc[16:] == oracle.fact_ent.compress(y)[0]
+
+
+def test_step_closure_and_criterion_match_oracle():
+    from oracle import cae_oracle as O
+    import cnn_autoencoder_b200 as M
+    arch = O.NAMED_ARCHS['A']
+    chk = O.make_checkpoint(arch, seed=1234)
+    model = _model(chk)
+    oracle = O.OracleModel(chk)
+    x_u8 = O.synth_natural(2, 3, 128, 128, seed=8)
+    x = x_u8.float() / 255.0
+    fwd = M.decorate_trainable_modules(trainable_modules=[],
+                                       enabled_modules=['encoder', 'decoder', 'fact_ent'])
+    out = fwd(x.cuda(), model)
+    assert set(out) == {'x_r', 'fx_brg', 'y', 'y_q', 'p_y', 't_pred', 't_aux_pred', 's_pred',
+                        's_aux_pred'}
+    crit = M.setup_loss('RateMSE', distortion_lambda=0.01)
+    loss = crit(inputs=x.cuda(), outputs=out, net=model)
+    ref = oracle.forward(x)
+    want = O.general_loss(x, ref, oracle.fact_ent, distortion_lambda=0.01)
+    assert abs(loss['rate_loss'].item() - want['rate_loss'].item()) <= 0.005 * want['rate_loss'].item()
+    assert abs(loss['dist'][0].item() - want['dist'][0].item()) <= 0.02 * want['dist'][0].item()
+    assert torch.allclose(loss['entropy_loss'].cpu(), want['entropy_loss'], rtol=1e-4)
+
+
+def test_no_cpu_fallback():
+    from oracle import cae_oracle as O
+    import cnn_autoencoder_b200 as M
+    from cnn_autoencoder_b200 import _cabi
+    chk = O.make_checkpoint(O.NAMED_ARCHS['M'], seed=1)
+    model = M.autoencoder_from_state_dict(chk, gpu=False, train=False)
+    with pytest.raises(_cabi.CaeError):
+        model['encoder'](torch.zeros(1, 1, 32, 32))
+    with pytest.raises(_cabi.CaeError):
+        model['fact_ent'](torch.zeros(1, 16, 4, 4))
+
+
+def test_ragged_and_edge_sizes():
+    """Edge chunks of a slide (336 px) and non-multiples of the CTA tile."""
+    from oracle import cae_oracle as O
+    arch = dict(channels_org=3, channels_net=32, channels_bn=16, compression_level=3,
+                act_layer_type='LeakyReLU')
+    chk = O.make_checkpoint(arch, seed=21)
+    model = _model(chk)
+    oracle = O.OracleModel(chk)
+    for (h, w) in ((336, 336), (8, 8), (40, 264), (16, 8)):
+        x_u8 = O.synth_natural(1, 3, h, w, seed=h + w)
+        x = x_u8.float() / 255.0
+        y = model['encoder'](x.cuda()).cpu()
+        ref = oracle.forward(x)
+        med = chk['fact_ent']['quantiles'][:, 0, 1]
+        agree, boundary, nflip = _symbol_report(y, ref['y'], med)
+        assert nflip <= max(2, 1e-3 * y.numel()) and boundary < 0.02, (h, w, agree)
+        x_r, _ = model['decoder'](ref['y_q'].cuda())
+        assert torch.allclose(x_r[0].cpu(), ref['x_r'][0], atol=4e-3, rtol=1e-2), (h, w)

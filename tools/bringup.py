@@ -56,6 +56,9 @@ def fp16_vals(shape, gen, scale=1.0):
 
 def check(name, got, want, tol):
     torch, *_ = _mods()
+    if got.numel() == 0:
+        print(f'  {name}: empty ok')
+        return True
     err = (got - want).abs().max().item()
     ref = want.abs().max().item()
     ok = err <= tol * max(1.0, ref)
