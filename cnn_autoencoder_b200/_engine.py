@@ -157,6 +157,8 @@ class TrackExecutor:
         if k >= len(self.steps):
             return final_fmt, C.HALO_KEEP
         nxt = self.steps[k]
+        if nxt.kind == C.CONV_S1 and nxt.c_in <= 4 and nxt.c_out <= 4:
+            return C.FMT_F32_NCHW, C.HALO_KEEP      # stem -> stem stays fp32 (tiny tensors)
         fmt = C.FMT_F16_SPLIT if nxt.kind == C.CONV_S2 else C.FMT_F16_PLANAR
         halo = C.HALO_REFLECT if (not nxt.transposed and nxt.pad_mode == C.PAD_REFLECT) else C.HALO_KEEP
         return fmt, halo

@@ -131,22 +131,32 @@ class EntropyBottleneck(nn.Module):
     def update(self, force=False):
         if self._offset.numel() > 0 and not force:
             return False
+        # Tables are always computed with CPU fp32 ops, whatever device the module lives on:
+        # the integer CDF must be reproducible by whoever decodes the stream.
+        dev = self.quantiles.device
         with torch.no_grad():
-            med = self.quantiles[:, 0, 1]
-            minima = torch.clamp(torch.ceil(med - self.quantiles[:, 0, 0]).int(), min=0)
-            maxima = torch.clamp(torch.ceil(self.quantiles[:, 0, 2] - med).int(), min=0)
+            host = EntropyBottleneck.__new__(EntropyBottleneck)
+            nn.Module.__init__(host)
+            host.filters = self.filters
+            for name, prm in self.named_parameters():
+                host.register_parameter(name, nn.Parameter(prm.detach().float().cpu(),
+                                                           requires_grad=False))
+            q = host.quantiles
+            med = q[:, 0, 1]
+            minima = torch.clamp(torch.ceil(med - q[:, 0, 0]).int(), min=0)
+            maxima = torch.clamp(torch.ceil(q[:, 0, 2] - med).int(), min=0)
             pmf_start = med - minima
             pmf_length = maxima + minima + 1
             max_length = int(pmf_length.max().item())
-            samples = torch.arange(max_length, device=med.device)[None, :] + pmf_start[:, None, None]
-            lower = self._logits_cumulative(samples - 0.5, stop_gradient=True)
-            upper = self._logits_cumulative(samples + 0.5, stop_gradient=True)
+            samples = torch.arange(max_length)[None, :] + pmf_start[:, None, None]
+            lower = host._logits_cumulative(samples - 0.5, stop_gradient=True)
+            upper = host._logits_cumulative(samples + 0.5, stop_gradient=True)
             sign = -torch.sign(lower + upper)
             pmf = torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))[:, 0, :]
             tail = torch.sigmoid(lower[:, 0, :1]) + torch.sigmoid(-upper[:, 0, -1:])
-            pmf_h = pmf.float().cpu().numpy()
-            tail_h = tail.float().cpu().numpy()
-            len_h = pmf_length.cpu().numpy()
+            pmf_h = pmf.numpy()
+            tail_h = tail.numpy()
+            len_h = pmf_length.numpy()
             cdf = np.zeros((self.channels, max_length + 2), dtype=np.int32)
             L = C.lib()
             for c in range(self.channels):
@@ -156,10 +166,9 @@ class EntropyBottleneck(nn.Module):
                 C.check(L.cae_pmf_to_quantized_cdf(prob.ctypes.data, prob.shape[0],
                                                    self.entropy_coder_precision, row.ctypes.data))
                 cdf[c, :row.shape[0]] = row.astype(np.int32)
-            dev = med.device
-            self._offset = (-minima).int()
+            self._offset = (-minima).int().to(dev)
             self._quantized_cdf = torch.from_numpy(cdf).to(dev)
-            self._cdf_length = (pmf_length + 2).int()
+            self._cdf_length = (pmf_length + 2).int().to(dev)
         self._tables = None
         return True
 

@@ -164,6 +164,103 @@ __global__ void __launch_bounds__(128) direct_conv_kernel(const DcParams p) {
   }
 }
 
+// Tiled fast path for the image-side stem (Conv2d k3 s1, c_in <= 4, c_out <= 4): the input
+// tile with its halo is staged in shared memory once (coalesced uint8 / fp32 reads), every
+// thread produces one pixel, and a planar output is one 16-byte store per pixel (channels
+// 4..7 of plane 0 are zero; the other planes stay zero from allocation).
+constexpr int ST_W = 64, ST_H = 4;
+
+__global__ void __launch_bounds__(ST_W * ST_H) stem_conv_kernel(const DcParams p) {
+  __shared__ float tile[4][ST_H + 2][ST_W + 2];
+  __shared__ float wsm[4 * 4 * 9];
+  const int tid = threadIdx.y * ST_W + threadIdx.x;
+  const int n = blockIdx.z;
+  const int x0 = blockIdx.x * ST_W, y0 = blockIdx.y * ST_H;
+  for (int i = tid; i < p.c_out * p.c_in * 9; i += ST_W * ST_H) wsm[i] = p.w[i];
+  const int cells = (ST_H + 2) * (ST_W + 2);
+  for (int i = tid; i < cells * p.c_in; i += ST_W * ST_H) {
+    int c, cell;
+    if (p.in_fmt == CAE_FMT_U8_HWC) { c = i % p.c_in; cell = i / p.c_in; }
+    else { cell = i % cells; c = i / cells; }
+    const int r = cell / (ST_W + 2), col = cell - r * (ST_W + 2);
+    int gy = y0 - 1 + r, gx = x0 - 1 + col;
+    float v = 0.f;
+    bool inside = true;
+    if (p.pad_mode == CAE_PAD_REFLECT) {
+      gy = reflect_idx(gy, p.h_in);
+      gx = reflect_idx(gx, p.w_in);
+      // tiles past the image edge (partial tiles): clamp, the result is never stored
+      gy = gy < 0 ? 0 : (gy >= p.h_in ? p.h_in - 1 : gy);
+      gx = gx < 0 ? 0 : (gx >= p.w_in ? p.w_in - 1 : gx);
+    } else {
+      inside = gy >= 0 && gy < p.h_in && gx >= 0 && gx < p.w_in;
+    }
+    if (inside) v = load_in(p, n, c, gy, gx);
+    tile[c][r][col] = v;
+  }
+  __syncthreads();
+  const int ox = x0 + threadIdx.x, oy = y0 + threadIdx.y;
+  if (ox >= p.w_out || oy >= p.h_out) return;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  for (int co = 0; co < p.c_out; ++co) {
+    float acc = 0.f;
+    for (int ci = 0; ci < p.c_in; ++ci)
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+          acc = fmaf(tile[ci][threadIdx.y + kh][threadIdx.x + kw],
+                     wsm[((co * p.c_in + ci) * 3 + kh) * 3 + kw], acc);
+    if (p.bias) acc += p.bias[co];
+    acc = apply_act(acc, p.pre_act);
+    if (p.skip.ptr) {
+      if (p.skip.fmt == CAE_FMT_U8_HWC) {
+        const uint8_t *q = reinterpret_cast<const uint8_t *>(p.skip.ptr);
+        acc += (float)q[(((size_t)n * p.h_out + oy) * p.w_out + ox) * p.c_out + co] / 255.0f;
+      } else if (p.skip.fmt == CAE_FMT_F32_NCHW) {
+        const float *q = reinterpret_cast<const float *>(p.skip.ptr);
+        acc += q[(((size_t)n * p.c_out + co) * p.h_out + oy) * p.w_out + ox];
+      } else {
+        const __half *q = reinterpret_cast<const __half *>(p.skip.ptr);
+        acc += __half2float(q[act_unit_offset(p.skip, n, 0, oy + 1, ox + 1) * 8 + co]);
+      }
+    }
+    v[co] = apply_act(acc, p.post_act);
+  }
+  if (p.aux)
+    for (int co = 0; co < p.c_out; ++co)
+      p.aux[(((size_t)n * p.c_out + co) * p.h_out + oy) * p.w_out + ox] = v[co];
+  if (!p.out.ptr) return;
+  if (p.out_fmt == CAE_FMT_U8_HWC) {
+    uint8_t *q = reinterpret_cast<uint8_t *>(p.out.ptr);
+    for (int co = 0; co < p.c_out; ++co)
+      q[(((size_t)n * p.h_out + oy) * p.w_out + ox) * p.c_out + co] = to_u8_trunc(v[co]);
+  } else if (p.out_fmt == CAE_FMT_F32_NCHW) {
+    float *q = reinterpret_cast<float *>(p.out.ptr);
+    for (int co = 0; co < p.c_out; ++co)
+      q[(((size_t)n * p.c_out + co) * p.h_out + oy) * p.w_out + ox] = v[co];
+  } else {
+    __half2 h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    const uint4 u = *reinterpret_cast<uint4 *>(h);
+    uint4 *base = reinterpret_cast<uint4 *>(p.out.ptr);
+    base[act_unit_offset(p.out, n, 0, oy + 1, ox + 1)] = u;
+    if (p.out.halo == CAE_HALO_REFLECT) {
+      const int y2 = oy == 1 ? 0 : -1, y3 = oy == p.h_out - 2 ? p.h_out + 1 : -1;
+      const int x2 = ox == 1 ? 0 : -1, x3 = ox == p.w_out - 2 ? p.w_out + 1 : -1;
+      if (y2 < 0 && y3 < 0 && x2 < 0 && x3 < 0) return;
+      const int ys[3] = {oy + 1, y2, y3}, xs[3] = {ox + 1, x2, x3};
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b)
+          if ((a | b) != 0 && ys[a] >= 0 && xs[b] >= 0)
+            base[act_unit_offset(p.out, n, 0, ys[a], xs[b])] = u;
+    }
+  }
+}
+
 // fp32 NCHW -> planar fp16 (zero halo untouched, reflect halo optional)
 __global__ void nchw_to_planar_kernel(const float *__restrict__ src, int n_img, int c, int h, int w,
                                       ActView dst) {
@@ -278,6 +375,14 @@ extern "C" int cae_conv_direct(const cae_conv_desc *d, void *stream) {
   p.pre_act = d->pre_act;
   p.post_act = d->post_act;
   p.aux = (float *)d->aux_out;
+  if (d->kind == CAE_CONV_S1 && d->c_in <= 4 && d->c_out <= 4 && p.n <= 65535) {
+    dim3 grid((unsigned)((p.w_out + ST_W - 1) / ST_W), (unsigned)((p.h_out + ST_H - 1) / ST_H),
+              (unsigned)p.n);
+    stem_conv_kernel<<<grid, dim3(ST_W, ST_H), 0, (cudaStream_t)stream>>>(p);
+    cae_count_launch();
+    CAE_CUDA(cudaGetLastError());
+    return 0;
+  }
   const size_t total = (size_t)p.n * p.h_out * p.w_out;
   dim3 grid((unsigned)((total + 127) / 128), (unsigned)co_blocks);
   direct_conv_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p);

@@ -34,7 +34,8 @@ namespace {
 constexpr int kMaxTaps = 9;
 constexpr int kMaxSA = 6;
 constexpr int kMaxSB = 12;
-constexpr int kThreads = 256;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + 32 * kEpiWarps;
 
 enum { EPI_ACT = 0, EPI_LATENT = 1, EPI_IMAGE = 2 };
 
@@ -159,106 +160,150 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t *>(&h);
 }
 
+__device__ __forceinline__ uint4 pack8(const float *v) {
+  uint4 u;
+  u.x = pack2(v[0], v[1]);
+  u.y = pack2(v[2], v[3]);
+  u.z = pack2(v[4], v[5]);
+  u.w = pack2(v[6], v[7]);
+  return u;
+}
+
 // Write one 16-byte unit (8 channels of one pixel) and its reflected halo copies.
 __device__ __forceinline__ void store_unit(const ActView &o, int n, int plane, int oy, int ox,
                                            uint4 v) {
   uint4 *base = reinterpret_cast<uint4 *>(o.ptr);
-  int ys[3], xs[3], ny = 1, nx = 1;
-  ys[0] = oy + 1;
-  xs[0] = ox + 1;
+  base[act_unit_offset(o, n, plane, oy + 1, ox + 1)] = v;
   if (o.halo == CAE_HALO_REFLECT) {
-    if (oy == 1) ys[ny++] = 0;
-    if (oy == o.H - 2) ys[ny++] = o.H + 1;
-    if (ox == 1) xs[nx++] = 0;
-    if (ox == o.W - 2) xs[nx++] = o.W + 1;
+    const int y2 = oy == 1 ? 0 : -1, y3 = oy == o.H - 2 ? o.H + 1 : -1;
+    const int x2 = ox == 1 ? 0 : -1, x3 = ox == o.W - 2 ? o.W + 1 : -1;
+    if (y2 < 0 && y3 < 0 && x2 < 0 && x3 < 0) return;  // interior pixel: nothing to mirror
+    const int ys[3] = {oy + 1, y2, y3}, xs[3] = {ox + 1, x2, x3};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+        if ((a | b) != 0 && ys[a] >= 0 && xs[b] >= 0)
+          base[act_unit_offset(o, n, plane, ys[a], xs[b])] = v;
   }
-  for (int a = 0; a < ny; ++a)
-    for (int b = 0; b < nx; ++b) base[act_unit_offset(o, n, plane, ys[a], xs[b])] = v;
 }
 
-template <int EPI>
-__device__ __forceinline__ void epilogue_tile(const IgParams &p, uint32_t taddr, int n, int y,
-                                              int x, int phase, bool valid) {
-  const int oy = y * p.up + (phase >> 1), ox = x * p.up + (phase & 1);
-  for (int c0 = 0; c0 < p.N; c0 += 16) {
-    uint32_t r[16];
-    __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the divergent stores
-    tmem_ld16(taddr + c0, r);
-    tmem_ld_wait();
-    if (!valid) continue;
-    float v[16];
+// bias -> pre_act -> (+skip) -> post_act on 16 consecutive channels of one output pixel
+__device__ __forceinline__ void finish16(const IgParams &p, float *v, int c0, int n, int oy,
+                                         int ox) {
+  if (p.bias) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-
-    if (EPI == EPI_IMAGE) {
-      // columns j = out_phase * c_out + c  (merged final transposed layer)
-      const int nreal = 4 * p.c_out;
+    for (int i = 0; i < 16; ++i)
+      if (c0 + i < p.c_out) v[i] += __ldg(p.bias + c0 + i);
+  }
+  if (p.pre_act != CAE_ACT_NONE) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (j >= nreal) break;
-        const int ph = j / p.c_out, c = j - ph * p.c_out;
-        float t = v[j] + (p.bias ? p.bias[c] : 0.f);
-        t = apply_act(apply_act(t, p.pre_act), p.post_act);
-        const int yy = y * 2 + (ph >> 1), xx = x * 2 + (ph & 1);
-        if (p.aux) p.aux[(((size_t)n * p.c_out + c) * p.out_h + yy) * p.out_w + xx] = t;
-        if (p.out.ptr)
-          reinterpret_cast<uint8_t *>(p.out.ptr)[(((size_t)n * p.out_h + yy) * p.out_w + xx) *
-                                                     p.c_out +
-                                                 c] = to_u8_trunc(t);
-      }
-      continue;
-    }
-
+    for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], p.pre_act);
+  }
+  if (p.skip.ptr) {
+    const uint4 *sp = reinterpret_cast<const uint4 *>(p.skip.ptr);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int c = c0 + i;
-      if (p.bias && c < p.c_out) v[i] += p.bias[c];
-      v[i] = apply_act(v[i], p.pre_act);
-    }
-    if (p.skip.ptr) {
-      const uint4 *sp = reinterpret_cast<const uint4 *>(p.skip.ptr);
+    for (int h = 0; h < 2; ++h) {
+      const uint4 s = __ldg(sp + act_unit_offset(p.skip, n, (c0 >> 3) + h, oy + 1, ox + 1));
+      const __half2 *sh = reinterpret_cast<const __half2 *>(&s);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const uint4 s = sp[act_unit_offset(p.skip, n, (c0 >> 3) + h, oy + 1, ox + 1)];
-        const __half2 *sh = reinterpret_cast<const __half2 *>(&s);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 f = __half22float2(sh[k]);
-          v[h * 8 + 2 * k] += f.x;
-          v[h * 8 + 2 * k + 1] += f.y;
-        }
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(sh[k]);
+        v[h * 8 + 2 * k] += f.x;
+        v[h * 8 + 2 * k + 1] += f.y;
       }
     }
+  }
+  if (p.post_act != CAE_ACT_NONE) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], p.post_act);
+  }
+}
 
-    if (EPI == EPI_LATENT) {
-      float *o = reinterpret_cast<float *>(p.out.ptr);
+__device__ __forceinline__ void store16_planar(const IgParams &p, const float *v, int c0, int n,
+                                               int oy, int ox) {
+  if (p.aux) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int c = c0 + i;
-        if (c < p.c_out) o[(((size_t)n * p.c_out + c) * p.out_h + oy) * p.out_w + ox] = v[i];
-      }
-    } else {
-      if (p.aux) {
+    for (int i = 0; i < 16; ++i)
+      if (c0 + i < p.c_out)
+        p.aux[(((size_t)n * p.c_out + c0 + i) * p.out_h + oy) * p.out_w + ox] = v[i];
+  }
+  store_unit(p.out, n, c0 >> 3, oy, ox, pack8(v));
+  store_unit(p.out, n, (c0 >> 3) + 1, oy, ox, pack8(v + 8));
+}
+
+// One epilogue job = two 16-column TMEM loads in flight, then the math and stores.
+//  up == 1: columns [c0, c0+32) of accumulator (m, 0)
+//  up == 2: columns [c0, c0+16) of the two horizontal output phases (py, 0) and (py, 1),
+//           i.e. two adjacent output pixels -> 32 contiguous bytes per plane
+template <int EPI>
+__device__ __forceinline__ void epilogue_job(const IgParams &p, uint32_t tmem_lane_base,
+                                             int acc_base, int n, int y, int x, int job,
+                                             bool valid) {
+  uint32_t r0[16], r1[16];
+  float v[16];
+  if (EPI == EPI_IMAGE) {
+    // merged final transposed layer: one 16-column accumulator, columns j = phase * c_out + c
+    __syncwarp();
+    tmem_ld16(tmem_lane_base + (uint32_t)(acc_base * p.N), r0);
+    tmem_ld_wait();
+    if (!valid) return;
+    const int nreal = 4 * p.c_out;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int c = c0 + i;
-          if (c < p.c_out)
-            p.aux[(((size_t)n * p.c_out + c) * p.out_h + oy) * p.out_w + ox] = v[i];
-        }
+    for (int j = 0; j < 16; ++j) {
+      if (j >= nreal) break;
+      const int ph = j / p.c_out, c = j - ph * p.c_out;
+      float t = __uint_as_float(r0[j]) + (p.bias ? __ldg(p.bias + c) : 0.f);
+      t = apply_act(apply_act(t, p.pre_act), p.post_act);
+      const int yy = y * 2 + (ph >> 1), xx = x * 2 + (ph & 1);
+      if (p.aux) p.aux[(((size_t)n * p.c_out + c) * p.out_h + yy) * p.out_w + xx] = t;
+      if (p.out.ptr)
+        reinterpret_cast<uint8_t *>(p.out.ptr)[(((size_t)n * p.out_h + yy) * p.out_w + xx) *
+                                                   p.c_out + c] = to_u8_trunc(t);
+    }
+    return;
+  }
+  if (p.up == 1) {
+    const int c0 = job * 32;
+    const bool second = c0 + 16 < p.N;
+    const uint32_t t = tmem_lane_base + (uint32_t)(acc_base * p.N + c0);
+    __syncwarp();
+    tmem_ld16(t, r0);
+    if (second) tmem_ld16(t + 16, r1);
+    tmem_ld_wait();
+    if (!valid) return;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !second) break;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(h ? r1[i] : r0[i]);
+      const int c = c0 + 16 * h;
+      finish16(p, v, c, n, y, x);
+      if (EPI == EPI_LATENT) {
+        float *o = reinterpret_cast<float *>(p.out.ptr);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c + i < p.c_out)
+            o[(((size_t)n * p.c_out + c + i) * p.out_h + y) * p.out_w + x] = v[i];
+      } else {
+        store16_planar(p, v, c, n, y, x);
       }
-      uint4 lo, hi;
-      lo.x = pack2(v[0], v[1]);
-      lo.y = pack2(v[2], v[3]);
-      lo.z = pack2(v[4], v[5]);
-      lo.w = pack2(v[6], v[7]);
-      hi.x = pack2(v[8], v[9]);
-      hi.y = pack2(v[10], v[11]);
-      hi.z = pack2(v[12], v[13]);
-      hi.w = pack2(v[14], v[15]);
-      store_unit(p.out, n, c0 >> 3, oy, ox, lo);
-      store_unit(p.out, n, (c0 >> 3) + 1, oy, ox, hi);
+    }
+  } else {
+    const int per_row = p.N >> 4;
+    const int py = job / per_row, c0 = (job - py * per_row) * 16;
+    const uint32_t t = tmem_lane_base + (uint32_t)((acc_base + py * 2) * p.N + c0);
+    __syncwarp();
+    tmem_ld16(t, r0);
+    tmem_ld16(t + (uint32_t)p.N, r1);
+    tmem_ld_wait();
+    if (!valid) return;
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(px ? r1[i] : r0[i]);
+      finish16(p, v, c0, n, y * 2 + py, x * 2 + px);
+      store16_planar(p, v, c0, n, y * 2 + py, x * 2 + px);
     }
   }
 }
@@ -290,7 +335,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);
+      mbar_init(&acc_empty[i], kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -338,50 +383,81 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 2) {
-    // ===== MMA issue (one thread) =====
-    if (lane == 0) {
-      const uint32_t sa_base = smem_base, sb_base = smem_base + (uint32_t)(p.sa * p.a_stage_bytes);
-      const int ksteps = p.ck >> 4;
-      const int acc_per_buf = p.mt * p.n_acc;
-      uint32_t ita = 0, itb = 0, j = 0;
+    // ===== MMA issue =====
+    // The whole warp walks the (warp-uniform) loop and one elected lane issues, so the
+    // descriptors live in uniform registers.  Descriptors are kept as (lo, hi) words: hi
+    // (SBO, version) is constant, lo = address | LBO advances by 32-bit adds in 16-byte units.
+    {
+      const uint32_t a_hi = ((p.sbo_a >> 4) & 0x3FFFu) | (1u << 14);
+      const uint32_t b_hi = ((p.sbo_b >> 4) & 0x3FFFu) | (1u << 14);
+      const uint32_t a_lbo = ((p.lbo_a >> 4) & 0x3FFFu) << 16;
+      const uint32_t b_lbo = ((p.lbo_b >> 4) & 0x3FFFu) << 16;
+      const uint32_t a_kstep = (2 * p.lbo_a) >> 4, b_kstep = (2 * p.lbo_b) >> 4;
+      const uint32_t sa_base = smem_base >> 4;
+      const uint32_t sb_base = (smem_base + (uint32_t)(p.sa * p.a_stage_bytes)) >> 4;
+      const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
+      const uint32_t b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
+      const uint32_t idesc = p.idesc;
+      const int ksteps = p.ck >> 4, mt = p.mt, n_acc = p.n_acc, n_taps = p.n_taps;
+      const int acc_per_buf = mt * n_acc;
+      const uint32_t N = (uint32_t)p.N;
+      uint32_t j = 0;
+      int sA = 0, sB = 0;
+      uint32_t phA = 0, phB = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++j) {
         const int buf = j % p.n_buf;
         mbar_wait(&acc_empty[buf], ((j / p.n_buf) & 1) ^ 1);
         tc_fence_after();
+        const uint32_t d_buf = tmem_base + (uint32_t)(buf * acc_per_buf) * N;
         uint32_t started = 0;
-        for (int ch = 0; ch < p.n_chunks; ++ch, ++ita) {
-          const int sA = ita % p.sa;
-          mbar_wait(&a_full[sA], (ita / p.sa) & 1);
-          for (int t = 0; t < p.n_taps; ++t, ++itb) {
-            const int sB = itb % p.sb;
-            mbar_wait(&b_full[sB], (itb / p.sb) & 1);
+        for (int ch = 0; ch < p.n_chunks; ++ch) {
+          mbar_wait(&a_full[sA], phA);
+          const uint32_t a_stage = sa_base + (uint32_t)sA * a_stage16;
+          for (int t = 0; t < n_taps; ++t) {
+            mbar_wait(&b_full[sB], phB);
             tc_fence_after();
-            const uint32_t a_base = sa_base + (uint32_t)(sA * p.a_stage_bytes) + p.taps[t].a_off;
-            const uint32_t b_base = sb_base + (uint32_t)(sB * p.b_stage_bytes);
-            for (int m = 0; m < p.mt; ++m) {
-              const int acc = m * p.n_acc + (int)p.taps[t].acc;
-              const uint32_t d = tmem_base + (uint32_t)((buf * acc_per_buf + acc) * p.N);
-              for (int k = 0; k < ksteps; ++k) {
-                const uint64_t da =
-                    make_smem_desc(a_base + m * 128 + k * 2 * p.lbo_a, p.lbo_a, p.sbo_a);
-                const uint64_t db = make_smem_desc(b_base + k * 2 * p.lbo_b, p.lbo_b, p.sbo_b);
-                umma_f16(d, da, db, p.idesc, ((started >> acc) & 1u) | (k > 0 ? 1u : 0u));
+            const uint32_t a_lo0 = ((a_stage + (p.taps[t].a_off >> 4)) & 0x3FFFu) | a_lbo;
+            const uint32_t b_lo0 = ((sb_base + (uint32_t)sB * b_stage16) & 0x3FFFu) | b_lbo;
+            const uint32_t tacc = p.taps[t].acc;
+            if (elect_one()) {
+              for (int m = 0; m < mt; ++m) {
+                const uint32_t acc = (uint32_t)(m * n_acc) + tacc;
+                const uint32_t d = d_buf + acc * N;
+                uint32_t a_lo = a_lo0 + (uint32_t)m * 8u, b_lo = b_lo0;
+                uint32_t flag = (started >> acc) & 1u;
+#pragma unroll 4
+                for (int k = 0; k < ksteps; ++k) {
+                  umma_f16(d, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo,
+                           idesc, flag);
+                  a_lo += a_kstep;
+                  b_lo += b_kstep;
+                  flag = 1u;
+                }
               }
-              started |= 1u << acc;
+              umma_commit(&b_empty[sB]);
+              if (t == n_taps - 1) umma_commit(&a_empty[sA]);
+              if (t == n_taps - 1 && ch == p.n_chunks - 1) umma_commit(&acc_full[buf]);
             }
-            umma_commit(&b_empty[sB]);
+            __syncwarp();
+            for (int m = 0; m < mt; ++m) started |= 1u << ((uint32_t)(m * n_acc) + tacc);
+            if (++sB == p.sb) { sB = 0; phB ^= 1u; }
           }
-          umma_commit(&a_empty[sA]);
+          if (++sA == p.sa) { sA = 0; phA ^= 1u; }
         }
-        umma_commit(&acc_full[buf]);
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> HBM =====
-    const int ew = warp - 4;
-    const int row = ew * 32 + lane;
+    // ===== epilogue: TMEM -> registers -> HBM (8 warps: 2 per TMEM lane quadrant) =====
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int row = quad * 32 + lane;
     const int ty = row >> 3, txl = row & 7;
     const int acc_per_buf = p.mt * p.n_acc;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    int jobs_per_m;
+    if (EPI == EPI_IMAGE) jobs_per_m = 1;
+    else if (p.up == 1) jobs_per_m = (p.N + 31) >> 5;
+    else jobs_per_m = 2 * (p.N >> 4);
+    const int n_jobs = p.mt * jobs_per_m;
     uint32_t j = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++j) {
       const int n = tile / p.tiles_per_img, rem = tile - n * p.tiles_per_img;
@@ -390,14 +466,11 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&acc_full[buf], (j / p.n_buf) & 1);
       tc_fence_after();
       const int y = tyi * 16 + ty;
-      for (int m = 0; m < p.mt; ++m) {
+      for (int job = half; job < n_jobs; job += 2) {
+        const int m = job / jobs_per_m, jj = job - m * jobs_per_m;
         const int x = (txi * p.mt + m) * 8 + txl;
         const bool valid = y < p.dom_h && x < p.dom_w;
-        for (int a = 0; a < p.n_acc; ++a) {
-          const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) +
-                                 (uint32_t)((buf * acc_per_buf + m * p.n_acc + a) * p.N);
-          epilogue_tile<EPI>(p, taddr, n, y, x, a, valid);
-        }
+        epilogue_job<EPI>(p, lane_base, buf * acc_per_buf + m * p.n_acc, n, y, x, jj, valid);
       }
       tc_fence_before();
       __syncwarp();

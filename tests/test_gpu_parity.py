@@ -70,7 +70,7 @@ def test_small_archs_against_reference_outputs(path):
     img = g['x_u8'].permute(0, 2, 3, 1).numpy()
     d = abs(_psnr(img, _to_u8(x_r[0])) - _psnr(img, _to_u8(g['x_r'])))
     assert d <= 0.05, d
-    assert torch.allclose(x_r[0].cpu(), g['x_r'], atol=3e-3, rtol=1e-2)
+    assert torch.allclose(x_r[0].cpu(), g["x_r"], atol=1e-2, rtol=2e-2)
     # the uint8 epilogue is the truncating cast of the fp32 output
     _, _, u8 = model['decoder'](g['y_q'].cuda(), as_uint8=True)
     assert np.array_equal(u8.cpu().numpy(), _to_u8(x_r[0]))
