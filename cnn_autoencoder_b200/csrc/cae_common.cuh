@@ -105,9 +105,9 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   return t;
 }
 
-// Bounded wait: a pipeline bug must surface as a launch failure, not as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// Bounded wait: a pipeline bug must surface as a launch failure, not as a hung GPU.  The
+// polling loop is out of line so that every wait site costs a handful of instructions.
+static __device__ __noinline__ void mbar_wait_slow(uint64_t *bar, uint32_t parity) {
   const uint64_t t0 = global_timer_ns();
   while (!mbar_try_wait(bar, parity)) {
     if (global_timer_ns() - t0 > 4000000000ull) {
@@ -116,6 +116,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       __trap();
     }
   }
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 
 __device__ __forceinline__ void fence_barrier_init() {

@@ -166,21 +166,24 @@ __global__ void __launch_bounds__(128) direct_conv_kernel(const DcParams p) {
 
 // Tiled fast path for the image-side stem (Conv2d k3 s1, c_in <= 4, c_out <= 4): the input
 // tile with its halo is staged in shared memory once (coalesced uint8 / fp32 reads), every
-// thread produces one pixel, and a planar output is one 16-byte store per pixel (channels
-// 4..7 of plane 0 are zero; the other planes stay zero from allocation).
-constexpr int ST_W = 64, ST_H = 4;
+// thread produces ST_PX horizontally adjacent pixels from a register window (weights are
+// read once per thread, not once per pixel), and a planar output is one 16-byte store per
+// pixel (channels 4..7 of plane 0 are zero; the other planes stay zero from allocation).
+constexpr int ST_W = 64, ST_H = 16, ST_PX = 4;
+constexpr int ST_TX = ST_W / ST_PX;
 
-__global__ void __launch_bounds__(ST_W * ST_H) stem_conv_kernel(const DcParams p) {
-  __shared__ float tile[4][ST_H + 2][ST_W + 2];
-  __shared__ float wsm[4 * 4 * 9];
-  const int tid = threadIdx.y * ST_W + threadIdx.x;
+template <int CI, int CO>
+__global__ void __launch_bounds__(ST_TX * ST_H) stem_conv_kernel(const DcParams p) {
+  __shared__ float tile[CI][ST_H + 2][ST_W + 2];
+  __shared__ float wsm[CO * CI * 9];
+  const int tid = threadIdx.y * ST_TX + threadIdx.x;
   const int n = blockIdx.z;
   const int x0 = blockIdx.x * ST_W, y0 = blockIdx.y * ST_H;
-  for (int i = tid; i < p.c_out * p.c_in * 9; i += ST_W * ST_H) wsm[i] = p.w[i];
-  const int cells = (ST_H + 2) * (ST_W + 2);
-  for (int i = tid; i < cells * p.c_in; i += ST_W * ST_H) {
+  for (int i = tid; i < CO * CI * 9; i += ST_TX * ST_H) wsm[i] = p.w[i];
+  constexpr int cells = (ST_H + 2) * (ST_W + 2);
+  for (int i = tid; i < cells * CI; i += ST_TX * ST_H) {
     int c, cell;
-    if (p.in_fmt == CAE_FMT_U8_HWC) { c = i % p.c_in; cell = i / p.c_in; }
+    if (p.in_fmt == CAE_FMT_U8_HWC) { c = i % CI; cell = i / CI; }
     else { cell = i % cells; c = i / cells; }
     const int r = cell / (ST_W + 2), col = cell - r * (ST_W + 2);
     int gy = y0 - 1 + r, gx = x0 - 1 + col;
@@ -199,64 +202,89 @@ __global__ void __launch_bounds__(ST_W * ST_H) stem_conv_kernel(const DcParams p
     tile[c][r][col] = v;
   }
   __syncthreads();
-  const int ox = x0 + threadIdx.x, oy = y0 + threadIdx.y;
-  if (ox >= p.w_out || oy >= p.h_out) return;
-  float v[8];
+
+  float acc[ST_PX][CO];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = 0.f;
-  for (int co = 0; co < p.c_out; ++co) {
-    float acc = 0.f;
-    for (int ci = 0; ci < p.c_in; ++ci)
+  for (int q = 0; q < ST_PX; ++q)
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
+    for (int co = 0; co < CO; ++co) acc[q][co] = 0.f;
+  const int lx = threadIdx.x * ST_PX;
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw)
-          acc = fmaf(tile[ci][threadIdx.y + kh][threadIdx.x + kw],
-                     wsm[((co * p.c_in + ci) * 3 + kh) * 3 + kw], acc);
-    if (p.bias) acc += p.bias[co];
-    acc = apply_act(acc, p.pre_act);
-    if (p.skip.ptr) {
-      if (p.skip.fmt == CAE_FMT_U8_HWC) {
-        const uint8_t *q = reinterpret_cast<const uint8_t *>(p.skip.ptr);
-        acc += (float)q[(((size_t)n * p.h_out + oy) * p.w_out + ox) * p.c_out + co] / 255.0f;
-      } else if (p.skip.fmt == CAE_FMT_F32_NCHW) {
-        const float *q = reinterpret_cast<const float *>(p.skip.ptr);
-        acc += q[(((size_t)n * p.c_out + co) * p.h_out + oy) * p.w_out + ox];
-      } else {
-        const __half *q = reinterpret_cast<const __half *>(p.skip.ptr);
-        acc += __half2float(q[act_unit_offset(p.skip, n, 0, oy + 1, ox + 1) * 8 + co]);
-      }
+  for (int ci = 0; ci < CI; ++ci)
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      float win[ST_PX + 2];
+#pragma unroll
+      for (int j = 0; j < ST_PX + 2; ++j) win[j] = tile[ci][threadIdx.y + kh][lx + j];
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+        for (int co = 0; co < CO; ++co) {
+          const float wv = wsm[((co * CI + ci) * 3 + kh) * 3 + kw];
+#pragma unroll
+          for (int q = 0; q < ST_PX; ++q) acc[q][co] = fmaf(win[q + kw], wv, acc[q][co]);
+        }
     }
-    v[co] = apply_act(acc, p.post_act);
-  }
-  if (p.aux)
-    for (int co = 0; co < p.c_out; ++co)
-      p.aux[(((size_t)n * p.c_out + co) * p.h_out + oy) * p.w_out + ox] = v[co];
-  if (!p.out.ptr) return;
-  if (p.out_fmt == CAE_FMT_U8_HWC) {
-    uint8_t *q = reinterpret_cast<uint8_t *>(p.out.ptr);
-    for (int co = 0; co < p.c_out; ++co)
-      q[(((size_t)n * p.h_out + oy) * p.w_out + ox) * p.c_out + co] = to_u8_trunc(v[co]);
-  } else if (p.out_fmt == CAE_FMT_F32_NCHW) {
-    float *q = reinterpret_cast<float *>(p.out.ptr);
-    for (int co = 0; co < p.c_out; ++co)
-      q[(((size_t)n * p.c_out + co) * p.h_out + oy) * p.w_out + ox] = v[co];
-  } else {
-    __half2 h[4];
+
+  const int oy = y0 + threadIdx.y;
+  if (oy >= p.h_out) return;
+#pragma unroll 1
+  for (int q = 0; q < ST_PX; ++q) {
+    const int ox = x0 + lx + q;
+    if (ox >= p.w_out) break;
+    float v[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-    const uint4 u = *reinterpret_cast<uint4 *>(h);
-    uint4 *base = reinterpret_cast<uint4 *>(p.out.ptr);
-    base[act_unit_offset(p.out, n, 0, oy + 1, ox + 1)] = u;
-    if (p.out.halo == CAE_HALO_REFLECT) {
-      const int y2 = oy == 1 ? 0 : -1, y3 = oy == p.h_out - 2 ? p.h_out + 1 : -1;
-      const int x2 = ox == 1 ? 0 : -1, x3 = ox == p.w_out - 2 ? p.w_out + 1 : -1;
-      if (y2 < 0 && y3 < 0 && x2 < 0 && x3 < 0) return;
-      const int ys[3] = {oy + 1, y2, y3}, xs[3] = {ox + 1, x2, x3};
-      for (int a = 0; a < 3; ++a)
-        for (int b = 0; b < 3; ++b)
-          if ((a | b) != 0 && ys[a] >= 0 && xs[b] >= 0)
-            base[act_unit_offset(p.out, n, 0, ys[a], xs[b])] = u;
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+#pragma unroll
+    for (int co = 0; co < CO; ++co) {
+      float a = acc[0][co];
+#pragma unroll
+      for (int qq = 1; qq < ST_PX; ++qq) a = q == qq ? acc[qq][co] : a;
+      if (p.bias) a += p.bias[co];
+      a = apply_act(a, p.pre_act);
+      if (p.skip.ptr) {
+        if (p.skip.fmt == CAE_FMT_U8_HWC) {
+          const uint8_t *s8 = reinterpret_cast<const uint8_t *>(p.skip.ptr);
+          a += (float)s8[(((size_t)n * p.h_out + oy) * p.w_out + ox) * CO + co] / 255.0f;
+        } else if (p.skip.fmt == CAE_FMT_F32_NCHW) {
+          const float *sf = reinterpret_cast<const float *>(p.skip.ptr);
+          a += sf[(((size_t)n * CO + co) * p.h_out + oy) * p.w_out + ox];
+        } else {
+          const __half *sh = reinterpret_cast<const __half *>(p.skip.ptr);
+          a += __half2float(sh[act_unit_offset(p.skip, n, 0, oy + 1, ox + 1) * 8 + co]);
+        }
+      }
+      v[co] = apply_act(a, p.post_act);
+    }
+    if (p.aux)
+      for (int co = 0; co < CO; ++co)
+        p.aux[(((size_t)n * CO + co) * p.h_out + oy) * p.w_out + ox] = v[co];
+    if (!p.out.ptr) continue;
+    if (p.out_fmt == CAE_FMT_U8_HWC) {
+      uint8_t *o8 = reinterpret_cast<uint8_t *>(p.out.ptr);
+      for (int co = 0; co < CO; ++co)
+        o8[(((size_t)n * p.h_out + oy) * p.w_out + ox) * CO + co] = to_u8_trunc(v[co]);
+    } else if (p.out_fmt == CAE_FMT_F32_NCHW) {
+      float *of = reinterpret_cast<float *>(p.out.ptr);
+      for (int co = 0; co < CO; ++co)
+        of[(((size_t)n * CO + co) * p.h_out + oy) * p.w_out + ox] = v[co];
+    } else {
+      __half2 h[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+      const uint4 u = *reinterpret_cast<uint4 *>(h);
+      uint4 *base = reinterpret_cast<uint4 *>(p.out.ptr);
+      base[act_unit_offset(p.out, n, 0, oy + 1, ox + 1)] = u;
+      if (p.out.halo == CAE_HALO_REFLECT) {
+        const int y2 = oy == 1 ? 0 : -1, y3 = oy == p.h_out - 2 ? p.h_out + 1 : -1;
+        const int x2 = ox == 1 ? 0 : -1, x3 = ox == p.w_out - 2 ? p.w_out + 1 : -1;
+        if (y2 < 0 && y3 < 0 && x2 < 0 && x3 < 0) continue;
+        const int ys[3] = {oy + 1, y2, y3}, xs[3] = {ox + 1, x2, x3};
+        for (int a = 0; a < 3; ++a)
+          for (int b = 0; b < 3; ++b)
+            if ((a | b) != 0 && ys[a] >= 0 && xs[b] >= 0)
+              base[act_unit_offset(p.out, n, 0, ys[a], xs[b])] = u;
+      }
     }
   }
 }
@@ -378,7 +406,15 @@ extern "C" int cae_conv_direct(const cae_conv_desc *d, void *stream) {
   if (d->kind == CAE_CONV_S1 && d->c_in <= 4 && d->c_out <= 4 && p.n <= 65535) {
     dim3 grid((unsigned)((p.w_out + ST_W - 1) / ST_W), (unsigned)((p.h_out + ST_H - 1) / ST_H),
               (unsigned)p.n);
-    stem_conv_kernel<<<grid, dim3(ST_W, ST_H), 0, (cudaStream_t)stream>>>(p);
+    const dim3 blk(ST_TX, ST_H);
+    cudaStream_t st = (cudaStream_t)stream;
+#define CAE_STEM(CI, CO) \
+  if (d->c_in == CI && d->c_out == CO) stem_conv_kernel<CI, CO><<<grid, blk, 0, st>>>(p)
+    CAE_STEM(1, 1); CAE_STEM(1, 2); CAE_STEM(1, 3); CAE_STEM(1, 4);
+    CAE_STEM(2, 1); CAE_STEM(2, 2); CAE_STEM(2, 3); CAE_STEM(2, 4);
+    CAE_STEM(3, 1); CAE_STEM(3, 2); CAE_STEM(3, 3); CAE_STEM(3, 4);
+    CAE_STEM(4, 1); CAE_STEM(4, 2); CAE_STEM(4, 3); CAE_STEM(4, 4);
+#undef CAE_STEM
     cae_count_launch();
     CAE_CUDA(cudaGetLastError());
     return 0;
