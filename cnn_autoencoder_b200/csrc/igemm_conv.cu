@@ -34,8 +34,8 @@ namespace {
 constexpr int kMaxTaps = 9;
 constexpr int kMaxSA = 6;
 constexpr int kMaxSB = 12;
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 128 + 32 * kEpiWarps;
+constexpr int kMaxEpiWarps = 12;  // 3 per TMEM lane quadrant
+constexpr int kThreads = 128 + 32 * kMaxEpiWarps;
 
 enum { EPI_ACT = 0, EPI_LATENT = 1, EPI_IMAGE = 2 };
 
@@ -51,6 +51,7 @@ struct IgParams {
   int N, n_acc, n_buf, tmem_cols;
   int PH, PW, n_par, par_stride;
   int a_stage_bytes, a_box_bytes, b_stage_bytes, sa, sb;
+  int epi_warps;  // 4, 8 or 12
   int org_y, org_x;
   uint32_t lbo_a, sbo_a, lbo_b, sbo_b, idesc;
   IgTap taps[kMaxTaps];
@@ -60,8 +61,10 @@ struct IgParams {
   int c_out, pre_act, post_act;
   const float *bias;
   ActView out, skip;
-  float *aux;  // optional fp32 NCHW copy
+  float *aux;  // optional fp32 NCHW copy (final image layer only)
   int out_h, out_w;
+  // 16-byte-unit strides of out / skip (32-bit: buffers are < 2^31 units)
+  uint32_t out_pitch, out_ps, out_is, skip_pitch, skip_ps, skip_is;
 };
 
 struct TapDef {
@@ -177,41 +180,30 @@ __device__ __forceinline__ float act_slope(int act) {
   return act == CAE_ACT_LEAKY_RELU ? 0.01f : (act == CAE_ACT_RELU ? 0.f : 1.f);
 }
 
-// 16-byte-unit offset of plane 0 of padded pixel (Y,X) and the distance between planes
-__device__ __forceinline__ void pixel_offset(const ActView &v, int n, int Y, int X, size_t &off0,
-                                             size_t &pstride) {
-  if (v.fmt == CAE_FMT_F16_PLANAR) {
-    pstride = (size_t)(v.H + 2) * (v.W + 2);
-    off0 = (size_t)n * v.planes * pstride + (size_t)Y * (v.W + 2) + X;
-  } else {
-    const int Hh = (v.H + 2) >> 1, Wh = (v.W + 2) >> 1;
-    pstride = (size_t)Hh * Wh;
-    off0 = ((size_t)n * 4 + (((Y & 1) << 1) | (X & 1))) * v.planes * pstride +
-           (size_t)(Y >> 1) * Wh + (X >> 1);
-  }
+// 16-byte-unit offset of plane 0 of padded pixel (Y,X); pitch / ps / is are the row, plane and
+// image strides precomputed on the host (is = planes * ps, times 4 parities for SPLIT).
+__device__ __forceinline__ uint32_t pixel_unit(int fmt, uint32_t pitch, uint32_t ps, uint32_t is,
+                                               int planes, int n, int Y, int X) {
+  if (fmt == CAE_FMT_F16_PLANAR) return (uint32_t)n * is + (uint32_t)Y * pitch + (uint32_t)X;
+  const uint32_t par = (uint32_t)(((Y & 1) << 1) | (X & 1));
+  return (uint32_t)n * is + par * (uint32_t)planes * ps + (uint32_t)(Y >> 1) * pitch +
+         (uint32_t)(X >> 1);
 }
 
 // Mirrored halo copies of two consecutive planes of a border pixel (padding_mode='reflect').
-__device__ __noinline__ void store_halo2(const ActView &o, int n, int plane, int oy, int ox,
+__device__ __noinline__ void store_halo2(const IgParams &p, int n, int plane, int oy, int ox,
                                          uint4 v0, uint4 v1) {
-  uint4 *base = reinterpret_cast<uint4 *>(o.ptr);
-  const int ys[3] = {oy + 1, oy == 1 ? 0 : -1, oy == o.H - 2 ? o.H + 1 : -1};
-  const int xs[3] = {ox + 1, ox == 1 ? 0 : -1, ox == o.W - 2 ? o.W + 1 : -1};
+  uint4 *base = reinterpret_cast<uint4 *>(p.out.ptr);
+  const int ys[3] = {oy + 1, oy == 1 ? 0 : -1, oy == p.out.H - 2 ? p.out.H + 1 : -1};
+  const int xs[3] = {ox + 1, ox == 1 ? 0 : -1, ox == p.out.W - 2 ? p.out.W + 1 : -1};
   for (int a = 0; a < 3; ++a)
     for (int b = 0; b < 3; ++b)
       if ((a | b) != 0 && ys[a] >= 0 && xs[b] >= 0) {
-        size_t off, ps;
-        pixel_offset(o, n, ys[a], xs[b], off, ps);
-        base[off + plane * ps] = v0;
-        base[off + (plane + 1) * ps] = v1;
+        const uint32_t off = pixel_unit(p.out.fmt, p.out_pitch, p.out_ps, p.out_is, p.out.planes,
+                                        n, ys[a], xs[b]) + (uint32_t)plane * p.out_ps;
+        base[off] = v0;
+        base[off + p.out_ps] = v1;
       }
-}
-
-__device__ __noinline__ void store_aux16(const IgParams &p, const float *v, int c0, int n, int oy,
-                                         int ox) {
-  for (int i = 0; i < 16; ++i)
-    if (c0 + i < p.c_out)
-      p.aux[(((size_t)n * p.c_out + c0 + i) * p.out_h + oy) * p.out_w + ox] = v[i];
 }
 
 // One epilogue job = two 16-column TMEM loads in flight, then the math and stores.
@@ -283,21 +275,34 @@ __device__ __forceinline__ void epilogue_job(const IgParams &p, uint32_t tmem_la
     const int c0 = part ? c_second : c_first;
     const int ox = ox0 + (p.up == 2 ? part : 0);
     if (p.bias) {
+      if (c0 + 16 <= p.c_out) {
+        const float4 *bp = reinterpret_cast<const float4 *>(p.bias + c0);
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (c0 + i < p.c_out) v[i] += __ldg(p.bias + c0 + i);
+        for (int q = 0; q < 4; ++q) {
+          const float4 bv = __ldg(bp + q);
+          v[4 * q] += bv.x;
+          v[4 * q + 1] += bv.y;
+          v[4 * q + 2] += bv.z;
+          v[4 * q + 3] += bv.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c0 + i < p.c_out) v[i] += __ldg(p.bias + c0 + i);
+      }
     }
     if (pre_s != 1.f) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * pre_s);
     }
     if (p.skip.ptr) {
-      size_t off, ps;
-      pixel_offset(p.skip, n, oy + 1, ox + 1, off, ps);
-      const uint4 *sp = reinterpret_cast<const uint4 *>(p.skip.ptr) + off + (c0 >> 3) * ps;
+      const uint32_t off = pixel_unit(p.skip.fmt, p.skip_pitch, p.skip_ps, p.skip_is,
+                                      p.skip.planes, n, oy + 1, ox + 1) +
+                           (uint32_t)(c0 >> 3) * p.skip_ps;
+      const uint4 *sp = reinterpret_cast<const uint4 *>(p.skip.ptr) + off;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const uint4 sv = __ldg(sp + h * ps);
+        const uint4 sv = __ldg(sp + h * p.skip_ps);
         const __half2 *sh = reinterpret_cast<const __half2 *>(&sv);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -319,16 +324,15 @@ __device__ __forceinline__ void epilogue_job(const IgParams &p, uint32_t tmem_la
       for (int i = 0; i < 16; ++i)
         if (c0 + i < p.c_out) o[i * cs] = v[i];
     } else {
-      if (p.aux) store_aux16(p, v, c0, n, oy, ox);
       const uint4 lo = pack8(v), hi = pack8(v + 8);
-      size_t off, ps;
-      pixel_offset(p.out, n, oy + 1, ox + 1, off, ps);
-      uint4 *dst = reinterpret_cast<uint4 *>(p.out.ptr) + off + (c0 >> 3) * ps;
+      const uint32_t off = pixel_unit(p.out.fmt, p.out_pitch, p.out_ps, p.out_is, p.out.planes,
+                                      n, oy + 1, ox + 1) + (uint32_t)(c0 >> 3) * p.out_ps;
+      uint4 *dst = reinterpret_cast<uint4 *>(p.out.ptr) + off;
       dst[0] = lo;
-      dst[ps] = hi;
+      dst[p.out_ps] = hi;
       if (p.out.halo == CAE_HALO_REFLECT &&
           (oy == 1 || oy == p.out.H - 2 || ox == 1 || ox == p.out.W - 2))
-        store_halo2(p.out, n, c0 >> 3, oy, ox, lo, hi);
+        store_halo2(p, n, c0 >> 3, oy, ox, lo, hi);
     }
   }
 }
@@ -360,7 +364,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], kEpiWarps);
+      mbar_init(&acc_empty[i], (uint32_t)p.epi_warps);
     }
     fence_barrier_init();
   }
@@ -471,9 +475,9 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
-  } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> HBM (8 warps: 2 per TMEM lane quadrant) =====
-    const int quad = warp & 3, half = (warp - 4) >> 2;
+  } else if (warp >= 4 && warp < 4 + p.epi_warps) {
+    // ===== epilogue: TMEM -> registers -> HBM (epi_warps / 4 warps per TMEM lane quadrant) =====
+    const int quad = warp & 3, half = (warp - 4) >> 2, n_halves = p.epi_warps >> 2;
     const int row = quad * 32 + lane;
     const int ty = row >> 3, txl = row & 7;
     const int acc_per_buf = p.mt * p.n_acc;
@@ -492,7 +496,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&acc_full[buf], (j / p.n_buf) & 1);
       tc_fence_after();
       const int y = tyi * 16 + ty;
-      for (int job = half; job < n_jobs; job += 2) {
+      for (int job = half; job < n_jobs; job += n_halves) {
         const int m = job / jobs_per_m, jj = job - m * jobs_per_m;
         const int x = (txi * p.mt + m) * 8 + txl;
         const bool valid = y < p.dom_h && x < p.dom_w;
@@ -617,6 +621,8 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   p.out_w = p.dom_w * p.up;
 
   int mt = d->mt > 0 ? d->mt : 2;
+  if (d->mt <= 0)
+    if (const char *e = getenv("CAE_IGEMM_MT")) mt = atoi(e) == 1 ? 1 : 2;
   if (p.dom_w <= 8) mt = 1;
   if (p.n_acc * p.N * mt > 512) mt = 1;
   CAE_CHECK(p.n_acc * p.N * mt <= 512, 2, "cae_conv_igemm: accumulators exceed TMEM");
@@ -716,6 +722,24 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   p.out.halo = d->out.halo;
   p.out.H = p.out_h;
   p.out.W = p.out_w;
+  auto strides = [](int fmt, int planes, int H, int W, uint32_t &pitch, uint32_t &ps,
+                    uint32_t &is) {
+    if (fmt == CAE_FMT_F16_SPLIT) {
+      pitch = (uint32_t)((W + 2) / 2);
+      ps = pitch * (uint32_t)((H + 2) / 2);
+      is = 4u * (uint32_t)planes * ps;
+    } else {
+      pitch = (uint32_t)(W + 2);
+      ps = pitch * (uint32_t)(H + 2);
+      is = (uint32_t)planes * ps;
+    }
+  };
+  if (epi == EPI_ACT) {
+    CAE_CHECK(!d->aux_out, 2, "cae_conv_igemm: aux_out is only available on the final image layer");
+    CAE_CHECK((double)d->n * d->out.planes * (p.out_h + 2) * (p.out_w + 2) < 2147483648.0, 2,
+              "cae_conv_igemm: output tensor too large for 32-bit unit offsets; split the batch");
+    strides(p.out.fmt, p.out.planes, p.out_h, p.out_w, p.out_pitch, p.out_ps, p.out_is);
+  }
   if (d->skip.fmt != CAE_FMT_NONE && d->skip.ptr) {
     CAE_CHECK(epi != EPI_IMAGE, 2, "cae_conv_igemm: skip unsupported on the final layer");
     CAE_CHECK((d->skip.fmt == CAE_FMT_F16_PLANAR || d->skip.fmt == CAE_FMT_F16_SPLIT) &&
@@ -726,6 +750,7 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
     p.skip.planes = d->skip.planes;
     p.skip.H = p.out_h;
     p.skip.W = p.out_w;
+    strides(p.skip.fmt, p.skip.planes, p.out_h, p.out_w, p.skip_pitch, p.skip_ps, p.skip_is);
   }
 
   // tensor map over the input
@@ -755,12 +780,18 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   int grid = d->grid > 0 ? d->grid : sm_count;
   if (grid > p.n_tiles) grid = p.n_tiles;
 
+  p.epi_warps = 8;
+  if (const char *e = getenv("CAE_IGEMM_EPI_WARPS")) {
+    const int v = atoi(e);
+    if (v == 4 || v == 8 || v == 12) p.epi_warps = v;
+  }
+  const int threads = 128 + 32 * p.epi_warps;
   void (*kern)(const CUtensorMap, const IgParams) =
       epi == EPI_ACT ? igemm_conv_kernel<EPI_ACT>
                      : (epi == EPI_LATENT ? igemm_conv_kernel<EPI_LATENT>
                                           : igemm_conv_kernel<EPI_IMAGE>);
   CAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  kern<<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(tm, p);
+  kern<<<grid, threads, smem_bytes, (cudaStream_t)stream>>>(tm, p);
   cae_count_launch();
   CAE_CUDA(cudaGetLastError());
   return 0;
