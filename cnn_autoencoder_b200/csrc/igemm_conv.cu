@@ -356,14 +356,14 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.sa; ++i) {
       mbar_init(&a_full[i], 1);
-      mbar_init(&a_empty[i], 1);
+      mbar_init(&a_empty[i], 2);
     }
     for (int i = 0; i < p.sb; ++i) {
       mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
+      mbar_init(&b_empty[i], 2);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_full[i], 2);
       mbar_init(&acc_empty[i], (uint32_t)p.epi_warps);
     }
     fence_barrier_init();
@@ -411,68 +411,73 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
-  } else if (warp == 2) {
-    // ===== MMA issue =====
-    // The whole warp walks the (warp-uniform) loop and one elected lane issues, so the
-    // descriptors live in uniform registers.  Descriptors are kept as (lo, hi) words: hi
-    // (SBO, version) is constant, lo = address | LBO advances by 32-bit adds in 16-byte units.
-    {
-      const uint32_t a_hi = ((p.sbo_a >> 4) & 0x3FFFu) | (1u << 14);
-      const uint32_t b_hi = ((p.sbo_b >> 4) & 0x3FFFu) | (1u << 14);
-      const uint32_t a_lbo = ((p.lbo_a >> 4) & 0x3FFFu) << 16;
-      const uint32_t b_lbo = ((p.lbo_b >> 4) & 0x3FFFu) << 16;
-      const uint32_t a_kstep = (2 * p.lbo_a) >> 4, b_kstep = (2 * p.lbo_b) >> 4;
-      const uint32_t sa_base = smem_base >> 4;
-      const uint32_t sb_base = (smem_base + (uint32_t)(p.sa * p.a_stage_bytes)) >> 4;
-      const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
-      const uint32_t b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
-      const uint32_t idesc = p.idesc;
-      const int ksteps = p.ck >> 4, mt = p.mt, n_acc = p.n_acc, n_taps = p.n_taps;
-      const int acc_per_buf = mt * n_acc;
-      const uint32_t N = (uint32_t)p.N;
-      uint32_t j = 0;
-      int sA = 0, sB = 0;
-      uint32_t phA = 0, phB = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++j) {
-        const int buf = j % p.n_buf;
-        mbar_wait(&acc_empty[buf], ((j / p.n_buf) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_buf = tmem_base + (uint32_t)(buf * acc_per_buf) * N;
-        uint32_t started = 0;
-        for (int ch = 0; ch < p.n_chunks; ++ch) {
-          mbar_wait(&a_full[sA], phA);
-          const uint32_t a_stage = sa_base + (uint32_t)sA * a_stage16;
-          for (int t = 0; t < n_taps; ++t) {
-            mbar_wait(&b_full[sB], phB);
-            tc_fence_after();
-            const uint32_t a_lo0 = ((a_stage + (p.taps[t].a_off >> 4)) & 0x3FFFu) | a_lbo;
-            const uint32_t b_lo0 = ((sb_base + (uint32_t)sB * b_stage16) & 0x3FFFu) | b_lbo;
-            const uint32_t tacc = p.taps[t].acc;
-            if (elect_one()) {
-              for (int m = 0; m < mt; ++m) {
-                const uint32_t acc = (uint32_t)(m * n_acc) + tacc;
-                const uint32_t d = d_buf + acc * N;
-                uint32_t a_lo = a_lo0 + (uint32_t)m * 8u, b_lo = b_lo0;
-                uint32_t flag = (started >> acc) & 1u;
+  }
+  if (warp == 2 || warp == 3) {
+    // ===== MMA issue: two issuing warps =====
+    // tcgen05.mma is issued by one thread, and with M=128,N<=128 tiles an instruction only
+    // covers 64 tensor-pipe cycles, so a single issuing thread cannot keep the pipe busy.
+    // Warps 2 and 3 each issue the MMAs of the accumulators with (index & 1) == issuer and
+    // each commit to the empty / full barriers (which expect two arrivals).  Each warp walks
+    // the warp-uniform loop and one elected lane issues, so the descriptors stay in uniform
+    // registers: hi word (SBO, version) constant, lo word = address | LBO advanced by 32-bit
+    // adds in 16-byte units.
+    const uint32_t issuer = (uint32_t)(warp - 2);
+    const uint32_t a_hi = ((p.sbo_a >> 4) & 0x3FFFu) | (1u << 14);
+    const uint32_t b_hi = ((p.sbo_b >> 4) & 0x3FFFu) | (1u << 14);
+    const uint32_t a_lbo = ((p.lbo_a >> 4) & 0x3FFFu) << 16;
+    const uint32_t b_lbo = ((p.lbo_b >> 4) & 0x3FFFu) << 16;
+    const uint32_t a_kstep = (2 * p.lbo_a) >> 4, b_kstep = (2 * p.lbo_b) >> 4;
+    const uint32_t sa_base = smem_base >> 4;
+    const uint32_t sb_base = (smem_base + (uint32_t)(p.sa * p.a_stage_bytes)) >> 4;
+    const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
+    const uint32_t b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
+    const uint32_t idesc = p.idesc;
+    const int ksteps = p.ck >> 4, mt = p.mt, n_acc = p.n_acc, n_taps = p.n_taps;
+    const int acc_per_buf = mt * n_acc;
+    const uint32_t N = (uint32_t)p.N;
+    uint32_t j = 0;
+    int sA = 0, sB = 0;
+    uint32_t phA = 0, phB = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++j) {
+      const int buf = j % p.n_buf;
+      mbar_wait(&acc_empty[buf], ((j / p.n_buf) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_buf = tmem_base + (uint32_t)(buf * acc_per_buf) * N;
+      uint32_t started = 0;
+      for (int ch = 0; ch < p.n_chunks; ++ch) {
+        mbar_wait(&a_full[sA], phA);
+        const uint32_t a_stage = sa_base + (uint32_t)sA * a_stage16;
+        for (int t = 0; t < n_taps; ++t) {
+          mbar_wait(&b_full[sB], phB);
+          tc_fence_after();
+          const uint32_t a_lo0 = ((a_stage + (p.taps[t].a_off >> 4)) & 0x3FFFu) | a_lbo;
+          const uint32_t b_lo0 = ((sb_base + (uint32_t)sB * b_stage16) & 0x3FFFu) | b_lbo;
+          const uint32_t tacc = p.taps[t].acc;
+          if (elect_one()) {
+            for (int m = 0; m < mt; ++m) {
+              const uint32_t acc = (uint32_t)(m * n_acc) + tacc;
+              if ((acc & 1u) != issuer) continue;
+              const uint32_t d = d_buf + acc * N;
+              uint32_t a_lo = a_lo0 + (uint32_t)m * 8u, b_lo = b_lo0;
+              uint32_t flag = (started >> acc) & 1u;
 #pragma unroll 4
-                for (int k = 0; k < ksteps; ++k) {
-                  umma_f16(d, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo,
-                           idesc, flag);
-                  a_lo += a_kstep;
-                  b_lo += b_kstep;
-                  flag = 1u;
-                }
+              for (int k = 0; k < ksteps; ++k) {
+                umma_f16(d, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc,
+                         flag);
+                a_lo += a_kstep;
+                b_lo += b_kstep;
+                flag = 1u;
               }
-              umma_commit(&b_empty[sB]);
-              if (t == n_taps - 1) umma_commit(&a_empty[sA]);
-              if (t == n_taps - 1 && ch == p.n_chunks - 1) umma_commit(&acc_full[buf]);
             }
-            __syncwarp();
-            for (int m = 0; m < mt; ++m) started |= 1u << ((uint32_t)(m * n_acc) + tacc);
-            if (++sB == p.sb) { sB = 0; phB ^= 1u; }
+            umma_commit(&b_empty[sB]);
+            if (t == n_taps - 1) umma_commit(&a_empty[sA]);
+            if (t == n_taps - 1 && ch == p.n_chunks - 1) umma_commit(&acc_full[buf]);
           }
-          if (++sA == p.sa) { sA = 0; phA ^= 1u; }
+          __syncwarp();
+          for (int m = 0; m < mt; ++m) started |= 1u << ((uint32_t)(m * n_acc) + tacc);
+          if (++sB == p.sb) { sB = 0; phB ^= 1u; }
         }
+        if (++sA == p.sa) { sA = 0; phA ^= 1u; }
       }
     }
   } else if (warp >= 4 && warp < 4 + p.epi_warps) {
