@@ -51,7 +51,7 @@ struct IgParams {
   int N, n_acc, n_buf, tmem_cols;
   int PH, PW, n_par, par_stride;
   int a_stage_bytes, a_box_bytes, b_stage_bytes, sa, sb;
-  int epi_warps;  // 4, 8 or 12
+  int epi_warps;  // 4, 8, 12 (or 16 on the fast-epilogue kernel)
   int org_y, org_x;
   uint32_t lbo_a, sbo_a, lbo_b, sbo_b, idesc;
   IgTap taps[kMaxTaps];
@@ -206,11 +206,57 @@ __device__ __noinline__ void store_halo2(const IgParams &p, int n, int plane, in
       }
 }
 
+// Fast path of the planar epilogue (no residual input): bias in fp32, then convert to
+// half2 and run the activations as packed fp16 max(v, v*slope) -- half the instructions of
+// the fp32 form; the result only differs by fp16 rounding of already-rounded negatives.
+__device__ __forceinline__ void emit16_fast(const IgParams &p, const uint32_t (&r)[16], int c0,
+                                            int n, int oy, int ox, __half2 pre2, __half2 post2) {
+  __half2 h[8];
+  if (p.bias) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + 2 * i;
+      const float b0 = c < p.c_out ? __ldg(p.bias + c) : 0.f;
+      const float b1 = c + 1 < p.c_out ? __ldg(p.bias + c + 1) : 0.f;
+      h[i] = __floats2half2_rn(__uint_as_float(r[2 * i]) + b0, __uint_as_float(r[2 * i + 1]) + b1);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      h[i] = __floats2half2_rn(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+  }
+  if (p.pre_act != CAE_ACT_NONE) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = __hmax2(h[i], __hmul2(h[i], pre2));
+  }
+  if (p.post_act != CAE_ACT_NONE) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = __hmax2(h[i], __hmul2(h[i], post2));
+  }
+  uint4 lo, hi;
+  lo.x = *reinterpret_cast<uint32_t *>(&h[0]);
+  lo.y = *reinterpret_cast<uint32_t *>(&h[1]);
+  lo.z = *reinterpret_cast<uint32_t *>(&h[2]);
+  lo.w = *reinterpret_cast<uint32_t *>(&h[3]);
+  hi.x = *reinterpret_cast<uint32_t *>(&h[4]);
+  hi.y = *reinterpret_cast<uint32_t *>(&h[5]);
+  hi.z = *reinterpret_cast<uint32_t *>(&h[6]);
+  hi.w = *reinterpret_cast<uint32_t *>(&h[7]);
+  const uint32_t off = pixel_unit(p.out.fmt, p.out_pitch, p.out_ps, p.out_is, p.out.planes, n,
+                                  oy + 1, ox + 1) + (uint32_t)(c0 >> 3) * p.out_ps;
+  uint4 *dst = reinterpret_cast<uint4 *>(p.out.ptr) + off;
+  dst[0] = lo;
+  dst[p.out_ps] = hi;
+  if (p.out.halo == CAE_HALO_REFLECT &&
+      (oy == 1 || oy == p.out.H - 2 || ox == 1 || ox == p.out.W - 2))
+    store_halo2(p, n, c0 >> 3, oy, ox, lo, hi);
+}
+
 // One epilogue job = two 16-column TMEM loads in flight, then the math and stores.
 //  up == 1: columns [c0, c0+32) of accumulator m
 //  up == 2: columns [c0, c0+16) of the two horizontal output phases (py,0) and (py,1), i.e.
 //           two adjacent output pixels -> 32 contiguous bytes per plane
-template <int EPI>
+template <int EPI, bool FAST>
 __device__ __forceinline__ void epilogue_job(const IgParams &p, uint32_t tmem_lane_base,
                                              int acc_base, int n, int y, int x, int job,
                                              bool valid, float pre_s, float post_s) {
@@ -265,6 +311,13 @@ __device__ __forceinline__ void epilogue_job(const IgParams &p, uint32_t tmem_la
   }
   tmem_ld_wait();
   if (!valid) return;
+
+  if (FAST) {
+    const __half2 pre2 = __float2half2_rn(pre_s), post2 = __float2half2_rn(post_s);
+    emit16_fast(p, r0, c_first, n, oy, ox0, pre2, post2);
+    if (second) emit16_fast(p, r1, c_second, n, oy, ox0 + (p.up == 2 ? 1 : 0), pre2, post2);
+    return;
+  }
 
 #pragma unroll 1
   for (int part = 0; part < 2; ++part) {
@@ -338,8 +391,8 @@ __device__ __forceinline__ void epilogue_job(const IgParams &p, uint32_t tmem_la
 }
 
 // ------------------------------------------------------------------ kernel
-template <int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int EPI, bool FAST>
+__global__ void __launch_bounds__(FAST ? 128 + 32 * 16 : kThreads, 1)
 igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ IgParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[kMaxSA], a_empty[kMaxSA];
@@ -505,7 +558,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int m = job / jobs_per_m, jj = job - m * jobs_per_m;
         const int x = (txi * p.mt + m) * 8 + txl;
         const bool valid = y < p.dom_h && x < p.dom_w;
-        epilogue_job<EPI>(p, lane_base, buf * acc_per_buf + m * p.n_acc, n, y, x, jj, valid, pre_s,
+        epilogue_job<EPI, FAST>(p, lane_base, buf * acc_per_buf + m * p.n_acc, n, y, x, jj, valid, pre_s,
                           post_s);
       }
       tc_fence_before();
@@ -788,13 +841,15 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   p.epi_warps = 8;
   if (const char *e = getenv("CAE_IGEMM_EPI_WARPS")) {
     const int v = atoi(e);
-    if (v == 4 || v == 8 || v == 12) p.epi_warps = v;
+    if (v == 4 || v == 8 || v == 12 || v == 16) p.epi_warps = v;
   }
+  const bool fast = epi == EPI_ACT && !p.skip.ptr && !getenv("CAE_IGEMM_NO_FAST_EPILOGUE");
+  if (!fast && p.epi_warps > kMaxEpiWarps) p.epi_warps = kMaxEpiWarps;
   const int threads = 128 + 32 * p.epi_warps;
   void (*kern)(const CUtensorMap, const IgParams) =
-      epi == EPI_ACT ? igemm_conv_kernel<EPI_ACT>
-                     : (epi == EPI_LATENT ? igemm_conv_kernel<EPI_LATENT>
-                                          : igemm_conv_kernel<EPI_IMAGE>);
+      epi == EPI_ACT ? (fast ? igemm_conv_kernel<EPI_ACT, true> : igemm_conv_kernel<EPI_ACT, false>)
+                     : (epi == EPI_LATENT ? igemm_conv_kernel<EPI_LATENT, false>
+                                          : igemm_conv_kernel<EPI_IMAGE, false>);
   CAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   kern<<<grid, threads, smem_bytes, (cudaStream_t)stream>>>(tm, p);
   cae_count_launch();

@@ -52,10 +52,10 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
     settings = [dict()]
     if args.sweep:
-        settings = [dict(), dict(CAE_IGEMM_EPI_WARPS='12'), dict(CAE_IGEMM_EPI_WARPS='4'),
-                    dict(CAE_IGEMM_MT='1'), dict(CAE_IGEMM_MT='1', CAE_IGEMM_EPI_WARPS='12')]
+        settings = [dict(), dict(CAE_IGEMM_EPI_WARPS='12'), dict(CAE_IGEMM_EPI_WARPS='16'),
+                    dict(CAE_IGEMM_NO_FAST_EPILOGUE='1')]
     for env in settings:
-        for k in ('CAE_IGEMM_EPI_WARPS', 'CAE_IGEMM_MT'):
+        for k in ('CAE_IGEMM_EPI_WARPS', 'CAE_IGEMM_MT', 'CAE_IGEMM_NO_FAST_EPILOGUE'):
             os.environ.pop(k, None)
         os.environ.update(env)
         print('== settings', env or 'default')
