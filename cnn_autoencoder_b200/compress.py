@@ -1,0 +1,228 @@
+"""Whole-slide compression tile loop, mirroring ``src/compress.py`` of the
+reference (``compress_image`` :29-168, ``compress`` :171-209) for the CAE codecs.
+
+The reference hands every ``patch_size`` chunk to the codec one at a time from
+dask's threaded scheduler (``z.rechunk(...)`` :101, ``to_zarr(compressor=codec)``
+:121-128).  Here the same chunks are processed B200-first: tiles are gathered
+into pinned batches, the analysis transform + quantizer run once per batch on the
+GPU, the integer symbols come back in one copy and are entropy coded by a pool of
+host threads (the C++ coder releases the GIL) while the next batch is on the GPU.
+Tiles are independent (no halo between chunks), so ``world_size`` processes -- one
+per GPU -- each take a contiguous range of the chunk grid and write their own chunk
+files; there is no collective.  The output is a zarr-v2 directory array whose
+compressor entry is the codec config, chunk for chunk what the reference writes.
+"""
+import argparse
+import math
+import os
+import struct
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import torch
+
+from . import _autoencoders as AE
+from ._entropy import encode_symbols
+from ._store import DirArray, padded_tile
+
+
+def shard_range(n_items, rank, world_size):
+    """Contiguous chunk range [k*n/G, (k+1)*n/G) of rank k."""
+    return range(rank * n_items // world_size, (rank + 1) * n_items // world_size)
+
+
+def _dist_info(rank, world_size):
+    if rank is None:
+        rank = int(os.environ.get('RANK', 0))
+    if world_size is None:
+        world_size = int(os.environ.get('WORLD_SIZE', 1))
+    return rank, world_size
+
+
+def open_source(input_filename, data_group='0/0'):
+    """H x W x C uint8 array-like from: an ndarray, a ``.npy`` path (memory mapped), a
+    directory array written by ``_store.DirArray`` (``<path>/<data_group>``), or -- when
+    the optional ``zarr`` package is installed -- any zarr v2 array."""
+    if isinstance(input_filename, np.ndarray):
+        return input_filename
+    if input_filename.endswith('.npy'):
+        return np.load(input_filename, mmap_mode='r')
+    path = os.path.join(input_filename, data_group) if data_group else input_filename
+    try:
+        import zarr                                    # optional
+        return zarr.open(input_filename, mode='r')[data_group]
+    except ImportError:
+        pass
+    arr = DirArray(path, mode='r')
+    if arr.compressor_config is not None:
+        raise ValueError('source array is compressed; only raw directory arrays can be read '
+                         'without the zarr package')
+
+    class _View:
+        shape, dtype = arr.shape, arr.dtype
+
+        def __getitem__(self, key):
+            ys, xs = key[0], key[1]
+            out = np.empty((ys.stop - ys.start, xs.stop - xs.start, arr.shape[2]), arr.dtype)
+            cy, cx = arr.chunks[0], arr.chunks[1]
+            for iy in range(ys.start // cy, -(-ys.stop // cy)):
+                for ix in range(xs.start // cx, -(-xs.stop // cx)):
+                    blk = arr.read_chunk((iy, ix, 0))
+                    y0, x0 = iy * cy, ix * cx
+                    a, b = max(ys.start, y0), min(ys.stop, y0 + blk.shape[0])
+                    c, d = max(xs.start, x0), min(xs.stop, x0 + blk.shape[1])
+                    out[a - ys.start:b - ys.start, c - xs.start:d - xs.start] = \
+                        blk[a - y0:b - y0, c - x0:d - x0]
+            return out
+
+    return _View()
+
+
+def compress_image(codec, checkpoint, input_filename, output_filename, patch_size=512,
+                   source_format='zarr', data_group='0/0', data_axes='TCZYX',
+                   progress_bar=False, save_as_bottleneck=False, gpu=False, *,
+                   rank=None, world_size=None, batch_tiles=16, workers=None):
+    """Same positional signature as the reference (``compress.py:29-36``); the keyword-only
+    arguments select this process's shard and the GPU batch size.  Returns a dict of
+    counters (tiles, pixels, bytes, seconds) for the caller's throughput report."""
+    if 'CAE' not in codec:
+        raise ValueError('Codec %s not supported' % codec)
+    if not torch.cuda.is_available():
+        raise RuntimeError('compress_image needs a CUDA device (no CPU fallback)')
+    rank, world_size = _dist_info(rank, world_size)
+    workers = workers or min(32, os.cpu_count() or 4)
+    src = open_source(input_filename, data_group)
+    H, W, C = src.shape
+    ps = patch_size
+
+    model = AE.autoencoder_from_state_dict(checkpoint=checkpoint, gpu=True, train=False)
+    fact_ent = model['fact_ent'].module
+    channels_bn = fact_ent.channels
+    level = len(model['encoder'].module.analysis_track)
+    cdf, sizes, offs = fact_ent._host_tables()
+
+    gy, gx = -(-H // ps), -(-W // ps)
+    out_path = os.path.join(output_filename, data_group) if data_group else output_filename
+    if save_as_bottleneck:
+        # '-sbn': the stored array is the latent; chunks ceil(cs / 2^L) (compress.py:103-109)
+        comp = AE.ConvolutionalAutoencoderBottleneck(channels_bn=channels_bn, fact_ent=fact_ent,
+                                                     gpu=True)
+        lat = lambda v: int(math.ceil(v / 2 ** level))
+        shape = (sum(lat(min(ps, H - i * ps)) for i in range(gy)),
+                 sum(lat(min(ps, W - j * ps)) for j in range(gx)), channels_bn)
+        meta = dict(shape=shape, chunks=(lat(ps), lat(ps), channels_bn), dtype=np.float32)
+    else:
+        comp = _CodecConfig('cae', checkpoint=checkpoint if isinstance(checkpoint, str) else '<dict>',
+                            gpu=gpu)
+        meta = dict(shape=(H, W, C), chunks=(ps, ps, C), dtype=np.uint8)
+    if rank == 0:
+        dst = DirArray(out_path, compressor=comp, mode='w', **meta)
+    else:
+        while not os.path.exists(os.path.join(out_path, '.zarray')):
+            time.sleep(0.05)
+        dst = DirArray(out_path, mode='r')
+
+    tiles = [(i, j) for i in range(gy) for j in range(gx)]
+    mine = [tiles[k] for k in shard_range(len(tiles), rank, world_size)]
+    stats = dict(tiles=len(mine), pixels=0, bytes=0, seconds=0.0)
+    t_start = time.perf_counter()
+    pool = ThreadPoolExecutor(max_workers=workers)
+    pending = []
+
+    def flush(pending):
+        for fut, idx in pending:
+            data = fut.result()
+            dst.write_encoded(idx, data)
+            stats['bytes'] += len(data)
+
+    def code_tile(sym_chw, h, w):
+        return struct.pack('>QQ', h, w) + encode_symbols(sym_chw, cdf, sizes, offs)
+
+    def run_batch(batch):
+        """batch: list of ((i, j), tile ndarray) with identical tile shapes."""
+        th, tw = batch[0][1].shape[:2]
+        pin = torch.empty((len(batch), th, tw, C), dtype=torch.uint8).pin_memory()
+        for k, (_, t) in enumerate(batch):
+            pin[k] = torch.from_numpy(t)
+        x = pin.cuda(non_blocking=True)
+        y = model['encoder'](x)
+        _, _, sym, _, _ = fact_ent._quantize_cuda(y, want_yq=False, want_p=False, want_sym=True)
+        sym_h = sym.reshape(sym.shape[0], sym.shape[1], -1).cpu().numpy()
+        lh, lw = y.shape[2], y.shape[3]
+        out = []
+        for k, (idx, t) in enumerate(batch):
+            hh, ww = (lh, lw) if save_as_bottleneck else (th, tw)
+            out.append((pool.submit(code_tile, sym_h[k], hh, ww), (idx[0], idx[1], 0)))
+        stats['pixels'] += len(batch) * th * tw
+        return out
+
+    groups = {}
+    for (i, j) in mine:
+        if save_as_bottleneck:
+            tile = np.ascontiguousarray(src[i * ps:min((i + 1) * ps, H), j * ps:min((j + 1) * ps, W)])
+        else:
+            tile = padded_tile(src, i * ps, j * ps, ps)
+        g = groups.setdefault(tile.shape, [])
+        g.append(((i, j), tile))
+        if len(g) == batch_tiles:
+            new = run_batch(g)
+            flush(pending)              # previous batch was coded while this one ran on the GPU
+            pending = new
+            groups[tile.shape] = []
+    for g in groups.values():
+        if g:
+            new = run_batch(g)
+            flush(pending)
+            pending = new
+    flush(pending)
+    pool.shutdown()
+    torch.cuda.synchronize()
+    stats['seconds'] = time.perf_counter() - t_start
+    return stats
+
+
+class _CodecConfig:
+    """Carries the 'cae' codec config into ``.zarray`` without loading a second model."""
+
+    def __init__(self, codec_id, **cfg):
+        self.codec_id = codec_id
+        self._cfg = cfg
+
+    def get_config(self):
+        return dict(id=self.codec_id, **self._cfg)
+
+
+def compress(args):
+    """CLI driver (``compress.py:171-209``): every input file -> ``<name>.zarr``."""
+    inputs = args.data_dir if isinstance(args.data_dir, (list, tuple)) else [args.data_dir]
+    for fn in inputs:
+        if '.zarr' in args.output_dir.lower():
+            out = args.output_dir
+        else:
+            base = os.path.basename(fn.rstrip('/')).split('.')[0]
+            out = os.path.join(args.output_dir, base + '.zarr')
+        st = compress_image(codec=args.codec, checkpoint=args.checkpoint, input_filename=fn,
+                            output_filename=out, patch_size=args.patch_size,
+                            data_group=args.data_group, save_as_bottleneck=args.save_as_bottleneck,
+                            gpu=True, batch_tiles=args.batch_tiles)
+        print('Compressed image %s into %s: %d tiles, %.1f MP/s' % (
+            fn, out, st['tiles'], st['pixels'] / 1e6 / max(st['seconds'], 1e-9)))
+
+
+def _parser():
+    ap = argparse.ArgumentParser(description='B200 CAE whole-slide compression')
+    ap.add_argument('-chk', '--checkpoint', required=True)
+    ap.add_argument('-dd', '--data-dir', nargs='+', required=True)
+    ap.add_argument('-o', '--output-dir', required=True)
+    ap.add_argument('-ps', '--patch-size', type=int, default=512)
+    ap.add_argument('-cod', '--codec', default='CAE')
+    ap.add_argument('-dg', '--data-group', default='0/0')
+    ap.add_argument('-sbn', '--save-as-bottleneck', action='store_true')
+    ap.add_argument('-g', '--gpu', action='store_true')
+    ap.add_argument('--batch-tiles', type=int, default=16)
+    return ap
+
+
+if __name__ == '__main__':
+    compress(_parser().parse_args())

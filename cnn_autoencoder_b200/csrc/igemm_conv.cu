@@ -51,7 +51,9 @@ struct IgParams {
   int N, n_acc, n_buf, tmem_cols;
   int PH, PW, n_par, par_stride;
   int a_stage_bytes, a_box_bytes, b_stage_bytes, sa, sb;
+  int tpb, b_tap_bytes;  // taps per weight stage, bytes of one tap's weights
   int epi_warps;  // 4, 8, 12 (or 16 on the fast-epilogue kernel)
+  int debug;      // bring-up bit mask (CAE_IGEMM_DEBUG): 1 no A loads, 2 no B loads, 4 no MMA, 8 no stores
   int org_y, org_x;
   uint32_t lbo_a, sbo_a, lbo_b, sbo_b, idesc;
   IgTap taps[kMaxTaps];
@@ -310,7 +312,7 @@ __device__ __forceinline__ void epilogue_job(const IgParams &p, uint32_t tmem_la
     tmem_ld16(t + (uint32_t)p.N, r1);
   }
   tmem_ld_wait();
-  if (!valid) return;
+  if (!valid || (p.debug & 8)) return;
 
   if (FAST) {
     const __half2 pre2 = __float2half2_rn(pre_s), post2 = __float2half2_rn(post_s);
@@ -439,6 +441,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int ch = 0; ch < p.n_chunks; ++ch, ++it) {
           const int s = it % p.sa;
           mbar_wait(&a_empty[s], ((it / p.sa) & 1) ^ 1);
+          if (p.debug & 1) { mbar_arrive(&a_full[s]); continue; }
           mbar_expect_tx(&a_full[s], (uint32_t)(p.n_par * p.a_box_bytes));
           for (int par = 0; par < p.n_par; ++par)
             tma_load_4d(&tmA, &a_full[s],
@@ -453,12 +456,13 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int ch = 0; ch < p.n_chunks; ++ch) {
-          for (int t = 0; t < p.n_taps; ++t, ++it) {
+          for (int t = 0; t < p.n_taps; t += p.tpb, ++it) {
             const int s = it % p.sb;
             mbar_wait(&b_empty[s], ((it / p.sb) & 1) ^ 1);
+            if (p.debug & 2) { mbar_arrive(&b_full[s]); continue; }
             mbar_expect_tx(&b_full[s], (uint32_t)p.b_stage_bytes);
             bulk_load_1d(smem_b + (size_t)s * p.b_stage_bytes,
-                         p.wpack + (size_t)(ch * p.n_taps + t) * p.b_stage_bytes,
+                         p.wpack + (size_t)(ch * p.n_taps + t) * p.b_tap_bytes,
                          (uint32_t)p.b_stage_bytes, &b_full[s]);
           }
         }
@@ -485,9 +489,10 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
     const uint32_t b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
     const uint32_t idesc = p.idesc;
-    const int ksteps = p.ck >> 4, mt = p.mt, n_acc = p.n_acc, n_taps = p.n_taps;
+    const int ksteps = p.ck >> 4, mt = p.mt, n_acc = p.n_acc, n_taps = p.n_taps, tpb = p.tpb;
     const int acc_per_buf = mt * n_acc;
     const uint32_t N = (uint32_t)p.N;
+    const uint32_t b_tap16 = (uint32_t)p.b_tap_bytes >> 4;
     uint32_t j = 0;
     int sA = 0, sB = 0;
     uint32_t phA = 0, phB = 0;
@@ -500,34 +505,42 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int ch = 0; ch < p.n_chunks; ++ch) {
         mbar_wait(&a_full[sA], phA);
         const uint32_t a_stage = sa_base + (uint32_t)sA * a_stage16;
-        for (int t = 0; t < n_taps; ++t) {
+        for (int t0 = 0; t0 < n_taps; t0 += tpb) {
           mbar_wait(&b_full[sB], phB);
           tc_fence_after();
-          const uint32_t a_lo0 = ((a_stage + (p.taps[t].a_off >> 4)) & 0x3FFFu) | a_lbo;
-          const uint32_t b_lo0 = ((sb_base + (uint32_t)sB * b_stage16) & 0x3FFFu) | b_lbo;
-          const uint32_t tacc = p.taps[t].acc;
+          const uint32_t b_stage = ((sb_base + (uint32_t)sB * b_stage16) & 0x3FFFu) | b_lbo;
+          const bool last_stage = t0 + tpb >= n_taps;
           if (elect_one()) {
-            for (int m = 0; m < mt; ++m) {
-              const uint32_t acc = (uint32_t)(m * n_acc) + tacc;
-              if ((acc & 1u) != issuer) continue;
-              const uint32_t d = d_buf + acc * N;
-              uint32_t a_lo = a_lo0 + (uint32_t)m * 8u, b_lo = b_lo0;
-              uint32_t flag = (started >> acc) & 1u;
+            for (int tt = 0; tt < tpb; ++tt) {
+              const int t = t0 + tt;
+              const uint32_t a_lo0 = ((a_stage + (p.taps[t].a_off >> 4)) & 0x3FFFu) | a_lbo;
+              const uint32_t b_lo0 = b_stage + (uint32_t)tt * b_tap16;
+              const uint32_t tacc = p.taps[t].acc;
+              for (int m = 0; m < mt; ++m) {
+                const uint32_t acc = (uint32_t)(m * n_acc) + tacc;
+                if ((acc & 1u) != issuer || (p.debug & 4)) continue;
+                const uint32_t d = d_buf + acc * N;
+                uint32_t a_lo = a_lo0 + (uint32_t)m * 8u, b_lo = b_lo0;
+                uint32_t flag = (started >> acc) & 1u;
 #pragma unroll 4
-              for (int k = 0; k < ksteps; ++k) {
-                umma_f16(d, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc,
-                         flag);
-                a_lo += a_kstep;
-                b_lo += b_kstep;
-                flag = 1u;
+                for (int k = 0; k < ksteps; ++k) {
+                  umma_f16(d, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc,
+                           flag);
+                  a_lo += a_kstep;
+                  b_lo += b_kstep;
+                  flag = 1u;
+                }
+                started |= 1u << acc;
               }
             }
             umma_commit(&b_empty[sB]);
-            if (t == n_taps - 1) umma_commit(&a_empty[sA]);
-            if (t == n_taps - 1 && ch == p.n_chunks - 1) umma_commit(&acc_full[buf]);
+            if (last_stage) umma_commit(&a_empty[sA]);
+            if (last_stage && ch == p.n_chunks - 1) umma_commit(&acc_full[buf]);
           }
           __syncwarp();
-          for (int m = 0; m < mt; ++m) started |= 1u << ((uint32_t)(m * n_acc) + tacc);
+          for (int tt = 0; tt < tpb; ++tt)
+            for (int m = 0; m < mt; ++m)
+              started |= 1u << ((uint32_t)(m * n_acc) + p.taps[t0 + tt].acc);
           if (++sB == p.sb) { sB = 0; phB ^= 1u; }
         }
         if (++sA == p.sa) { sA = 0; phA ^= 1u; }
@@ -707,8 +720,7 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   const int kplanes = p.ck / 8;
   p.a_box_bytes = kplanes * p.PH * p.PW * 16;
   p.par_stride = round_up(p.a_box_bytes, 128);
-  p.a_stage_bytes = round_up(p.par_stride * p.n_par, 1024);
-  p.b_stage_bytes = p.N * p.ck * 2;
+  p.a_stage_bytes = round_up(p.par_stride * p.n_par, 128);
   p.lbo_a = (uint32_t)(p.PH * p.PW * 16);
   p.sbo_a = (uint32_t)(p.PW * 16);
   p.lbo_b = (uint32_t)(p.N * 16);
@@ -723,19 +735,37 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
     p.taps[t].acc = (uint32_t)taps[t].acc;
   }
 
-  // shared-memory rings
+  // shared-memory rings.  A weight stage holds `tpb` taps: every stage costs the issuing
+  // warps one barrier round trip (~700 cycles), so a stage must carry well over that much
+  // tensor work; tpb is the largest divisor of the tap count that leaves room for two stages
+  // of each ring.
   const int budget = 227 * 1024 - 2048;
+  p.b_tap_bytes = p.N * p.ck * 2;
+  int tpb = 1;
+  for (int cand = p.n_taps; cand >= 1; --cand) {
+    if (p.n_taps % cand) continue;
+    if (2 * p.a_stage_bytes + 2 * cand * p.b_tap_bytes <= budget && cand * p.b_tap_bytes <= 73728) {
+      tpb = cand;
+      break;
+    }
+  }
+  if (const char *e = getenv("CAE_IGEMM_TPB")) {
+    const int v = atoi(e);
+    if (v >= 1 && p.n_taps % v == 0 && 2 * p.a_stage_bytes + 2 * v * p.b_tap_bytes <= budget) tpb = v;
+  }
+  p.tpb = tpb;
+  p.b_stage_bytes = tpb * p.b_tap_bytes;
   int sa = 2, sb = 2;
   CAE_CHECK(sa * p.a_stage_bytes + sb * p.b_stage_bytes <= budget, 2,
             "cae_conv_igemm: tile does not fit shared memory (A %d B %d)", p.a_stage_bytes,
             p.b_stage_bytes);
   for (;;) {
     bool grew = false;
-    if (sb < 4 && sa * p.a_stage_bytes + (sb + 1) * p.b_stage_bytes <= budget) { ++sb; grew = true; }
+    if (sb < 3 && sa * p.a_stage_bytes + (sb + 1) * p.b_stage_bytes <= budget) { ++sb; grew = true; }
     else if (sa < 3 && (sa + 1) * p.a_stage_bytes + sb * p.b_stage_bytes <= budget) { ++sa; grew = true; }
-    else if (sb < kMaxSB && sb < p.n_taps * 2 &&
-             sa * p.a_stage_bytes + (sb + 1) * p.b_stage_bytes <= budget) { ++sb; grew = true; }
+    else if (sb < 4 && sa * p.a_stage_bytes + (sb + 1) * p.b_stage_bytes <= budget) { ++sb; grew = true; }
     else if (sa < 4 && (sa + 1) * p.a_stage_bytes + sb * p.b_stage_bytes <= budget) { ++sa; grew = true; }
+    else if (sb < kMaxSB && sa * p.a_stage_bytes + (sb + 1) * p.b_stage_bytes <= budget) { ++sb; grew = true; }
     if (!grew) break;
   }
   p.sa = sa;
@@ -838,6 +868,8 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   int grid = d->grid > 0 ? d->grid : sm_count;
   if (grid > p.n_tiles) grid = p.n_tiles;
 
+  p.debug = 0;
+  if (const char *e = getenv("CAE_IGEMM_DEBUG")) p.debug = atoi(e);
   p.epi_warps = 8;
   if (const char *e = getenv("CAE_IGEMM_EPI_WARPS")) {
     const int v = atoi(e);

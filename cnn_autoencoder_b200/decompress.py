@@ -1,0 +1,161 @@
+"""Whole-slide decompression tile loop, mirroring ``src/decompress.py`` of the
+reference (``decompress_fn_impl`` :24-37, ``decompress_image`` :40-140,
+``decompress`` :143-180).
+
+Chunks are entropy decoded by a pool of host threads (C++ coder, GIL released),
+stacked into batches, and the synthesis transform with its fused
+``*255 -> clip -> uint8 -> HWC`` epilogue runs once per batch on the GPU.  As in
+``compress.py`` the chunk grid is sharded across processes by contiguous range;
+no collective.  The reconstruction goes to ``<output>/<decomp_group>/<group>/0``
+like the reference (:81-96); chunks are stored raw (the reference's Blosc-zlib
+compressor comes from ``numcodecs``, which is optional here).
+"""
+import argparse
+import os
+import struct
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import torch
+
+from . import _autoencoders as AE
+from ._entropy import decode_symbols
+from ._store import DirArray
+from .compress import _dist_info, shard_range
+
+
+def decompress_image(input_filename, output_filename, destination_format='zarr',
+                     data_group='0/0', decomp_group='decompressed', checkpoint=None,
+                     progress_bar=False, gpu=False, *, rank=None, world_size=None,
+                     batch_tiles=16, workers=None):
+    """Same positional signature as the reference (``decompress.py:40-47``).  Returns a
+    dict of counters (tiles, pixels, seconds)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError('decompress_image needs a CUDA device (no CPU fallback)')
+    if checkpoint is None or (isinstance(checkpoint, str) and not len(checkpoint)):
+        raise ValueError('a checkpoint is required to run the synthesis transform')
+    rank, world_size = _dist_info(rank, world_size)
+    workers = workers or min(32, os.cpu_count() or 4)
+    src = DirArray(os.path.join(input_filename, data_group) if data_group else input_filename,
+                   mode='r')
+    cfg = src.compressor_config or {}
+    codec_id = cfg.get('id')
+    if codec_id not in ('cae', 'cae_bn'):
+        raise ValueError('array compressor %r is not a CAE codec' % codec_id)
+
+    model = AE.autoencoder_from_state_dict(checkpoint=checkpoint, gpu=True, train=False)
+    fact_ent = model['fact_ent'].module
+    decoder = model['decoder']
+    level = decoder.module.rec_level
+    cdf, sizes, offs = fact_ent._host_tables()
+    med = fact_ent._medians().reshape(1, -1, 1, 1)
+    C_bn = fact_ent.channels
+    c_img = decoder.module.synthesis_track[-1].model[-1].out_channels \
+        if hasattr(decoder.module.synthesis_track[-1], 'model') else 3
+
+    gy, gx = src.grid[0], src.grid[1]
+    if codec_id == 'cae':
+        H, W = src.shape[0], src.shape[1]
+        ps = src.chunks[0]
+    else:
+        ps = src.chunks[0] * 2 ** level
+        H, W = src.shape[0] * 2 ** level, src.shape[1] * 2 ** level
+
+    component = '%s/%s' % (decomp_group, data_group) if len(decomp_group) else data_group
+    comp_r = '/'.join(component.split('/')[:-1]) + '/0'
+    out_path = os.path.join(output_filename, comp_r)
+    want_png = 'zarr' not in destination_format
+    if want_png:
+        canvas = np.zeros((H, W, c_img), dtype=np.uint8)
+    elif rank == 0:
+        dst = DirArray(out_path, shape=(H, W, c_img), chunks=(ps, ps, c_img), dtype=np.uint8,
+                       compressor=None, mode='w')
+    else:
+        while not os.path.exists(os.path.join(out_path, '.zarray')):
+            time.sleep(0.05)
+        dst = DirArray(out_path, mode='r')
+
+    tiles = [(i, j) for i in range(gy) for j in range(gx)]
+    mine = [tiles[k] for k in shard_range(len(tiles), rank, world_size)]
+    stats = dict(tiles=len(mine), pixels=0, seconds=0.0)
+    t_start = time.perf_counter()
+    pool = ThreadPoolExecutor(max_workers=workers)
+
+    def decode_tile(idx):
+        buf = src.read_encoded((idx[0], idx[1], 0))
+        h, w = struct.unpack('>QQ', buf[:16])
+        lh, lw = (h // 2 ** level, w // 2 ** level) if codec_id == 'cae' else (h, w)
+        sym = decode_symbols(buf[16:], C_bn, lh * lw, cdf, sizes, offs)
+        return idx, sym.reshape(C_bn, lh, lw)
+
+    def run_batch(batch):
+        sym = np.stack([s for _, s in batch])
+        y_q = torch.from_numpy(sym).pin_memory().cuda(non_blocking=True).float() + med
+        _, _, u8 = decoder(y_q, as_uint8=True)
+        img = u8.cpu().numpy()
+        for k, (idx, _) in enumerate(batch):
+            y0, x0 = idx[0] * ps, idx[1] * ps
+            tile = img[k][:min(ps, H - y0), :min(ps, W - x0)]
+            if want_png:
+                canvas[y0:y0 + tile.shape[0], x0:x0 + tile.shape[1]] = tile
+            else:
+                dst.write_chunk((idx[0], idx[1], 0), tile)
+            stats['pixels'] += tile.shape[0] * tile.shape[1]
+
+    groups = {}
+    futures = [pool.submit(decode_tile, idx) for idx in mine]
+    for fut in futures:
+        idx, sym = fut.result()
+        g = groups.setdefault(sym.shape, [])
+        g.append((idx, sym))
+        if len(g) == batch_tiles:
+            run_batch(g)
+            groups[sym.shape] = []
+    for g in groups.values():
+        if g:
+            run_batch(g)
+    pool.shutdown()
+    torch.cuda.synchronize()
+    if want_png:
+        from PIL import Image
+        fn_out = output_filename.split(destination_format)[0] + destination_format
+        Image.fromarray(canvas if c_img != 1 else canvas[..., 0]).save(fn_out)
+    stats['seconds'] = time.perf_counter() - t_start
+    return stats
+
+
+def decompress(args):
+    """CLI driver (``decompress.py:143-180``)."""
+    inputs = args.data_dir if isinstance(args.data_dir, (list, tuple)) else [args.data_dir]
+    fmt = args.destination_format if args.destination_format.startswith('.') \
+        else '.' + args.destination_format
+    for fn in inputs:
+        if fmt.lower() in args.output_dir.lower():
+            out = args.output_dir
+        else:
+            base = os.path.basename(fn.rstrip('/')).split('.zarr')[0]
+            out = os.path.join(args.output_dir, base + fmt)
+        st = decompress_image(input_filename=fn, output_filename=out, destination_format=fmt,
+                              data_group=args.data_group,
+                              decomp_group=args.task_label_identifier or 'decompressed',
+                              checkpoint=args.checkpoint, gpu=True, batch_tiles=args.batch_tiles)
+        print('Decompressed %s into %s: %d tiles, %.1f MP/s' % (
+            fn, out, st['tiles'], st['pixels'] / 1e6 / max(st['seconds'], 1e-9)))
+
+
+def _parser():
+    ap = argparse.ArgumentParser(description='B200 CAE whole-slide decompression')
+    ap.add_argument('-chk', '--checkpoint', required=True)
+    ap.add_argument('-dd', '--data-dir', nargs='+', required=True)
+    ap.add_argument('-o', '--output-dir', required=True)
+    ap.add_argument('-df', '--destination-format', default='zarr')
+    ap.add_argument('-dg', '--data-group', default='0/0')
+    ap.add_argument('-tli', '--task-label-identifier', default='decompressed')
+    ap.add_argument('-g', '--gpu', action='store_true')
+    ap.add_argument('--batch-tiles', type=int, default=16)
+    return ap
+
+
+if __name__ == '__main__':
+    decompress(_parser().parse_args())

@@ -1,0 +1,122 @@
+"""Host-side logic of the tile loops: chunk-range sharding (also across two gloo ranks),
+the zarr-v2 directory array, edge-tile padding, and the reference-facing signatures."""
+import inspect
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cnn_autoencoder_b200 import _store, compress, decompress
+
+
+def test_shard_ranges_partition_the_chunk_grid():
+    for n in (1, 7, 64, 9604):
+        for g in (1, 2, 4, 8):
+            parts = [list(compress.shard_range(n, k, g)) for k in range(g)]
+            flat = [i for p in parts for i in p]
+            assert flat == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_wsi_chunk_grid_matches_survey():
+    # 50 000 x 50 000 slide, 512 px chunks -> 98 x 98 = 9 604 chunks, edge chunks 336 px
+    H = W = 50000
+    gy, gx = -(-H // 512), -(-W // 512)
+    assert (gy, gx, gy * gx) == (98, 98, 9604)
+    assert H - (gy - 1) * 512 == 336
+
+
+def test_dir_array_roundtrip_and_metadata(tmp_path):
+    class Cfg:
+        codec_id = 'cae'
+
+        def get_config(self):
+            return dict(id='cae', checkpoint='x.pth', gpu=True)
+
+    a = _store.DirArray(str(tmp_path / 'a'), shape=(5, 7, 3), chunks=(4, 4, 3), dtype=np.uint8,
+                        compressor=None, mode='w')
+    assert a.grid == (2, 2, 1)
+    src = np.arange(5 * 7 * 3, dtype=np.uint8).reshape(5, 7, 3)
+    for i in range(2):
+        for j in range(2):
+            sl = a.chunk_slices((i, j, 0))
+            a.write_chunk((i, j, 0), src[sl])
+    b = _store.DirArray(str(tmp_path / 'a'), mode='r')
+    out = np.zeros_like(src)
+    for i in range(2):
+        for j in range(2):
+            out[b.chunk_slices((i, j, 0))] = b.read_chunk((i, j, 0))
+    assert np.array_equal(out, src)
+    c = _store.DirArray(str(tmp_path / 'c'), shape=(8, 8, 3), chunks=(4, 4, 3), dtype=np.uint8,
+                        compressor=Cfg(), mode='w')
+    c.write_encoded((1, 0, 0), b'abc')
+    meta = json.load(open(tmp_path / 'c' / '.zarray'))
+    assert meta['zarr_format'] == 2 and meta['compressor']['id'] == 'cae'
+    assert meta['chunks'] == [4, 4, 3] and meta['dtype'] == '|u1'
+    assert c.read_encoded((1, 0, 0)) == b'abc' and c.nbytes_stored() == 3
+    view = compress.open_source(str(tmp_path / 'a'), data_group='')
+    assert np.array_equal(view[slice(1, 5), slice(2, 7)], src[1:5, 2:7])
+
+
+def test_edge_tiles_are_padded_like_zarr_chunks():
+    img = np.full((10, 6, 3), 9, dtype=np.uint8)
+    t = _store.padded_tile(img, 8, 4, 4)
+    assert t.shape == (4, 4, 3)
+    assert (t[:2, :2] == 9).all() and (t[2:] == 0).all() and (t[:, 2:] == 0).all()
+    assert _store.padded_tile(img, 0, 0, 4).flags['C_CONTIGUOUS']
+
+
+def test_reference_signatures_are_kept():
+    # compress.py:29-36 and decompress.py:40-47 of the reference
+    ci = list(inspect.signature(compress.compress_image).parameters)
+    assert ci[:11] == ['codec', 'checkpoint', 'input_filename', 'output_filename', 'patch_size',
+                       'source_format', 'data_group', 'data_axes', 'progress_bar',
+                       'save_as_bottleneck', 'gpu']
+    di = list(inspect.signature(decompress.decompress_image).parameters)
+    assert di[:8] == ['input_filename', 'output_filename', 'destination_format', 'data_group',
+                      'decomp_group', 'checkpoint', 'progress_bar', 'gpu']
+    with pytest.raises(ValueError):
+        compress.compress_image('Blosc', None, np.zeros((4, 4, 3), np.uint8), '/tmp/x')
+
+
+def _gloo_worker(rank, world, port, n_chunks, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    mine = torch.zeros(n_chunks, dtype=torch.int32)
+    for i in compress.shard_range(n_chunks, rank, world):
+        mine[i] = rank + 1
+    dist.all_reduce(mine)            # test-only check; the data path itself has no collective
+    if rank == 0:
+        torch.save(mine, out)
+    dist.destroy_process_group()
+
+
+def test_two_ranks_cover_every_chunk_exactly_once(tmp_path):
+    out = str(tmp_path / 'cover.pt')
+    mp.spawn(_gloo_worker, args=(2, 29517, 97, out), nprocs=2, join=True)
+    cover = torch.load(out)
+    assert (cover > 0).all()
+    assert (cover[:48] == 1).all() and (cover[48:] == 2).all()
+
+
+def test_model_mirror_builds_on_cpu_and_refuses_to_run():
+    import cnn_autoencoder_b200 as M
+    from cnn_autoencoder_b200 import _cabi
+    m = M.setup_modules(channels_org=3, channels_net=16, channels_bn=8, compression_level=2,
+                        act_layer_type='LeakyReLU', use_residual=True)
+    assert set(m) == {'encoder', 'decoder', 'fact_ent'}
+    keys = set(m['encoder'].state_dict())
+    assert 'analysis_track.0.res_model.0.weight' in keys and 'analysis_track.1.model.0.weight' in keys
+    m['encoder'].eval()
+    with pytest.raises(_cabi.CaeError):
+        m['encoder'](torch.zeros(1, 3, 16, 16))
+    with pytest.raises(NotImplementedError):
+        M.setup_modules(channels_org=3, channels_net=16, channels_bn=8, compression_level=2,
+                        act_layer_type='GDN')
+    with pytest.raises(ValueError):
+        M.Analyzer(act_layer_type='LeakyRelU')      # the reference's own typo default is rejected

@@ -42,6 +42,7 @@ def main():
     ap.add_argument('--batch', type=int, default=128)
     ap.add_argument('--size', type=int, default=256)
     ap.add_argument('--sweep', action='store_true')
+    ap.add_argument('--debug-sweep', action='store_true')
     args = ap.parse_args()
     chk = O.make_checkpoint(O.NAMED_ARCHS[args.arch], seed=1234)
     model = M.autoencoder_from_state_dict(chk, gpu=True, train=False)
@@ -52,10 +53,14 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
     settings = [dict()]
     if args.sweep:
-        settings = [dict(), dict(CAE_IGEMM_EPI_WARPS='12'), dict(CAE_IGEMM_EPI_WARPS='16'),
-                    dict(CAE_IGEMM_NO_FAST_EPILOGUE='1')]
+        settings = [dict(), dict(CAE_IGEMM_TPB='1'), dict(CAE_IGEMM_TPB='3'),
+                    dict(CAE_IGEMM_EPI_WARPS='16')]
+    if args.debug_sweep:
+        settings = [dict(), dict(CAE_IGEMM_DEBUG='8'), dict(CAE_IGEMM_DEBUG='1'),
+                    dict(CAE_IGEMM_DEBUG='2'), dict(CAE_IGEMM_DEBUG='3'), dict(CAE_IGEMM_DEBUG='4'),
+                    dict(CAE_IGEMM_DEBUG='11'), dict(CAE_IGEMM_DEBUG='15')]
     for env in settings:
-        for k in ('CAE_IGEMM_EPI_WARPS', 'CAE_IGEMM_MT', 'CAE_IGEMM_NO_FAST_EPILOGUE'):
+        for k in ('CAE_IGEMM_EPI_WARPS', 'CAE_IGEMM_MT', 'CAE_IGEMM_NO_FAST_EPILOGUE', 'CAE_IGEMM_DEBUG', 'CAE_IGEMM_TPB'):
             os.environ.pop(k, None)
         os.environ.update(env)
         print('== settings', env or 'default')
