@@ -291,7 +291,8 @@ class Synthesizer(_Track):
         """y_q fp32 N x C_bn x h x w -> (x_r, fx_brg) exactly as R:442-455: x_r[0] is the
         full-resolution reconstruction, lower scales are None.  ``as_uint8`` (extension
         used by the codecs) additionally returns the N x H x W x C uint8 image produced
-        by the last kernel's epilogue: ``(x_r, fx_brg, u8)``."""
+        by the last kernel's epilogue: ``(x_r, fx_brg, u8)``; ``as_uint8='only'`` skips the
+        fp32 copy (``x_r`` / ``fx_brg`` entries are then None)."""
         if self.training:
             fx, fx_brg, x_r = x, [], []
             for up, col in zip(self.synthesis_track, self.color_layers):
@@ -309,7 +310,10 @@ class Synthesizer(_Track):
             outs = self._unit_output_indices()
             keep = outs[:-1] if self.bridges else ()
             final = C.FMT_U8_HWC if as_uint8 else C.FMT_F32_NCHW
-            last, kept, aux = self._executor().run(a, final, keep=keep, aux_last=True)
+            only_u8 = as_uint8 == 'only'
+            last, kept, aux = self._executor().run(a, final, keep=keep, aux_last=not only_u8)
+            if only_u8 and last.fmt == C.FMT_U8_HWC:
+                return [None] * n_units, [None] * n_units, last.t
             x_full = aux if aux is not None else last.t
             u8 = last.t if (as_uint8 and last.fmt == C.FMT_U8_HWC) else None
             fx_brg = [O.planar_to_nchw(kept[i]) if i in kept else None for i in outs[:-1]]
@@ -424,7 +428,7 @@ class ConvolutionalAutoencoder(Codec):
         h, w = struct.unpack('>QQ', buf[:16])
         y_q = self._model['fact_ent'].module.decompress([buf[16:]],
                                                         size=(h // 2 ** level, w // 2 ** level))
-        _, _, u8 = self._model['decoder'](y_q, as_uint8=True)
+        _, _, u8 = self._model['decoder'](y_q, as_uint8='only')
         img = np.ascontiguousarray(u8[0].cpu().numpy())
         return ndarray_copy(img, out)
 

@@ -201,6 +201,22 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       : "memory");
 }
 
+// Same, with each descriptor passed as (lo, hi) 32-bit words and assembled inside the asm
+// block: the issuing loop then only advances the lo words (no 64-bit arithmetic per MMA).
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi,
+                                              uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Arrive on an mbarrier when every tcgen05 op issued so far by this thread is done.
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(

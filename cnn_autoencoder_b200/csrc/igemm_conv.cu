@@ -44,6 +44,16 @@ struct IgTap {
   uint32_t acc;    // accumulator (output phase) this tap adds into
 };
 
+constexpr int kMaxItems = 18;
+constexpr int kMaxStages = 9;
+
+// One MMA group of the per-chunk work list of an issuing warp: tap view offset into the A
+// stage (16-byte units, M-tile offset included), weight offset inside the B stage, TMEM
+// column offset of the accumulator, and whether this is the first group writing it.
+struct IgItem {
+  uint32_t a_off16, b_off16, d_off, first;
+};
+
 struct IgParams {
   int n_img, dom_h, dom_w;
   int tiles_x, tiles_per_img, n_tiles;
@@ -52,6 +62,9 @@ struct IgParams {
   int PH, PW, n_par, par_stride;
   int a_stage_bytes, a_box_bytes, b_stage_bytes, sa, sb;
   int tpb, b_tap_bytes;  // taps per weight stage, bytes of one tap's weights
+  int n_stages;           // weight stages per channel chunk
+  IgItem items[2][kMaxItems];
+  int item_start[2][kMaxStages + 1];
   int epi_warps;  // 4, 8, 12 (or 16 on the fast-epilogue kernel)
   int debug;      // bring-up bit mask (CAE_IGEMM_DEBUG): 1 no A loads, 2 no B loads, 4 no MMA, 8 no stores
   int org_y, org_x;
@@ -254,6 +267,40 @@ __device__ __forceinline__ void emit16_fast(const IgParams &p, const uint32_t (&
     store_halo2(p, n, c0 >> 3, oy, ox, lo, hi);
 }
 
+// Final image layer (merged transposed conv): accumulator columns j = phase * CO + c with
+// phase = py * 2 + px.  Thread = input pixel (y, x); per output row 2y+py it owns the two
+// adjacent pixels 2x, 2x+1 = 2*CO contiguous uint8 in HWC (always 2-byte aligned: out_w even).
+template <int CO>
+__device__ __forceinline__ void image_store(const IgParams &p, const uint32_t (&r)[16], int n, int y,
+                                            int x, float pre_s, float post_s) {
+  float t[4 * CO];
+#pragma unroll
+  for (int j = 0; j < 4 * CO; ++j) {
+    float u = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + (j % CO)) : 0.f);
+    u = fmaxf(u, u * pre_s);
+    t[j] = fmaxf(u, u * post_s);
+  }
+  if (p.aux) {
+#pragma unroll
+    for (int j = 0; j < 4 * CO; ++j) {
+      const int ph = j / CO, c = j % CO;
+      p.aux[(((size_t)n * CO + c) * p.out_h + (y * 2 + (ph >> 1))) * p.out_w + x * 2 + (ph & 1)] = t[j];
+    }
+  }
+  if (p.out.ptr) {
+    uint8_t *o = reinterpret_cast<uint8_t *>(p.out.ptr);
+#pragma unroll
+    for (int py = 0; py < 2; ++py) {
+      uint16_t *row = reinterpret_cast<uint16_t *>(
+          o + (((size_t)n * p.out_h + (y * 2 + py)) * p.out_w + x * 2) * CO);
+#pragma unroll
+      for (int q = 0; q < CO; ++q)
+        row[q] = (uint16_t)(to_u8_trunc(t[py * 2 * CO + 2 * q]) |
+                            ((uint16_t)to_u8_trunc(t[py * 2 * CO + 2 * q + 1]) << 8));
+    }
+  }
+}
+
 // One epilogue job = two 16-column TMEM loads in flight, then the math and stores.
 //  up == 1: columns [c0, c0+32) of accumulator m
 //  up == 2: columns [c0, c0+16) of the two horizontal output phases (py,0) and (py,1), i.e.
@@ -269,21 +316,11 @@ __device__ __forceinline__ void epilogue_job(const IgParams &p, uint32_t tmem_la
     tmem_ld16(tmem_lane_base + (uint32_t)(acc_base * p.N), r0);
     tmem_ld_wait();
     if (!valid) return;
-    const int nreal = 4 * p.c_out;
-    int ph = 0, c = 0;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      if (j < nreal) {
-        float t = __uint_as_float(r0[j]) + (p.bias ? __ldg(p.bias + c) : 0.f);
-        t = fmaxf(t, t * pre_s);
-        t = fmaxf(t, t * post_s);
-        const int yy = y * 2 + (ph >> 1), xx = x * 2 + (ph & 1);
-        if (p.aux) p.aux[(((size_t)n * p.c_out + c) * p.out_h + yy) * p.out_w + xx] = t;
-        if (p.out.ptr)
-          reinterpret_cast<uint8_t *>(p.out.ptr)[(((size_t)n * p.out_h + yy) * p.out_w + xx) *
-                                                     p.c_out + c] = to_u8_trunc(t);
-        if (++c == p.c_out) { c = 0; ++ph; }
-      }
+    switch (p.c_out) {
+      case 1: image_store<1>(p, r0, n, y, x, pre_s, post_s); break;
+      case 2: image_store<2>(p, r0, n, y, x, pre_s, post_s); break;
+      case 3: image_store<3>(p, r0, n, y, x, pre_s, post_s); break;
+      default: image_store<4>(p, r0, n, y, x, pre_s, post_s); break;
     }
     return;
   }
@@ -472,13 +509,16 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 2 || warp == 3) {
     // ===== MMA issue: two issuing warps =====
     // tcgen05.mma is issued by one thread, and with M=128,N<=128 tiles an instruction only
-    // covers 64 tensor-pipe cycles, so a single issuing thread cannot keep the pipe busy.
-    // Warps 2 and 3 each issue the MMAs of the accumulators with (index & 1) == issuer and
-    // each commit to the empty / full barriers (which expect two arrivals).  Each warp walks
-    // the warp-uniform loop and one elected lane issues, so the descriptors stay in uniform
-    // registers: hi word (SBO, version) constant, lo word = address | LBO advanced by 32-bit
+    // covers 64 tensor-pipe cycles, so issue cost bounds the pipe.  Hence: (1) warps 2 and 3
+    // each issue the MMAs of the accumulators with (index & 1) == issuer and each commit to
+    // the empty / full barriers (which expect two arrivals); (2) the per-chunk work of an
+    // issuer is a precomputed list in the kernel parameters (constant bank), walked with
+    // warp-uniform control flow so every descriptor lives in uniform registers, and only the
+    // MMA / commit instructions themselves are predicated on the elected lane; (3) descriptors
+    // are (lo, hi) words: hi (SBO, version) constant, lo = address | LBO advanced by 32-bit
     // adds in 16-byte units.
-    const uint32_t issuer = (uint32_t)(warp - 2);
+    const int issuer = warp - 2;
+    const bool leader = elect_one();
     const uint32_t a_hi = ((p.sbo_a >> 4) & 0x3FFFu) | (1u << 14);
     const uint32_t b_hi = ((p.sbo_b >> 4) & 0x3FFFu) | (1u << 14);
     const uint32_t a_lbo = ((p.lbo_a >> 4) & 0x3FFFu) << 16;
@@ -489,10 +529,9 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
     const uint32_t b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
     const uint32_t idesc = p.idesc;
-    const int ksteps = p.ck >> 4, mt = p.mt, n_acc = p.n_acc, n_taps = p.n_taps, tpb = p.tpb;
-    const int acc_per_buf = mt * n_acc;
-    const uint32_t N = (uint32_t)p.N;
-    const uint32_t b_tap16 = (uint32_t)p.b_tap_bytes >> 4;
+    const int ksteps = p.ck >> 4, n_stages = p.n_stages;
+    const uint32_t buf_cols = (uint32_t)(p.mt * p.n_acc * p.N);
+    const bool no_mma = (p.debug & 4) != 0;
     uint32_t j = 0;
     int sA = 0, sB = 0;
     uint32_t phA = 0, phB = 0;
@@ -500,47 +539,36 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int buf = j % p.n_buf;
       mbar_wait(&acc_empty[buf], ((j / p.n_buf) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t d_buf = tmem_base + (uint32_t)(buf * acc_per_buf) * N;
-      uint32_t started = 0;
+      const uint32_t d_buf = tmem_base + (uint32_t)buf * buf_cols;
       for (int ch = 0; ch < p.n_chunks; ++ch) {
         mbar_wait(&a_full[sA], phA);
-        const uint32_t a_stage = sa_base + (uint32_t)sA * a_stage16;
-        for (int t0 = 0; t0 < n_taps; t0 += tpb) {
+        const uint32_t a_stage = ((sa_base + (uint32_t)sA * a_stage16) & 0x3FFFu) | a_lbo;
+        const uint32_t later = ch > 0 ? 1u : 0u;
+        for (int st = 0; st < n_stages; ++st) {
           mbar_wait(&b_full[sB], phB);
           tc_fence_after();
           const uint32_t b_stage = ((sb_base + (uint32_t)sB * b_stage16) & 0x3FFFu) | b_lbo;
-          const bool last_stage = t0 + tpb >= n_taps;
-          if (elect_one()) {
-            for (int tt = 0; tt < tpb; ++tt) {
-              const int t = t0 + tt;
-              const uint32_t a_lo0 = ((a_stage + (p.taps[t].a_off >> 4)) & 0x3FFFu) | a_lbo;
-              const uint32_t b_lo0 = b_stage + (uint32_t)tt * b_tap16;
-              const uint32_t tacc = p.taps[t].acc;
-              for (int m = 0; m < mt; ++m) {
-                const uint32_t acc = (uint32_t)(m * n_acc) + tacc;
-                if ((acc & 1u) != issuer || (p.debug & 4)) continue;
-                const uint32_t d = d_buf + acc * N;
-                uint32_t a_lo = a_lo0 + (uint32_t)m * 8u, b_lo = b_lo0;
-                uint32_t flag = (started >> acc) & 1u;
+          const int i1 = p.item_start[issuer][st + 1];
+          for (int i = p.item_start[issuer][st]; i < i1; ++i) {
+            const IgItem it = p.items[issuer][i];
+            const uint32_t d = d_buf + it.d_off;
+            uint32_t a_lo = a_stage + it.a_off16, b_lo = b_stage + it.b_off16;
+            uint32_t flag = later | (it.first ^ 1u);
+            if (leader && !no_mma) {
 #pragma unroll 4
-                for (int k = 0; k < ksteps; ++k) {
-                  umma_f16(d, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc,
-                           flag);
-                  a_lo += a_kstep;
-                  b_lo += b_kstep;
-                  flag = 1u;
-                }
-                started |= 1u << acc;
+              for (int k = 0; k < ksteps; ++k) {
+                umma_f16_lohi(d, a_lo, a_hi, b_lo, b_hi, idesc, flag);
+                a_lo += a_kstep;
+                b_lo += b_kstep;
+                flag = 1u;
               }
             }
-            umma_commit(&b_empty[sB]);
-            if (last_stage) umma_commit(&a_empty[sA]);
-            if (last_stage && ch == p.n_chunks - 1) umma_commit(&acc_full[buf]);
           }
-          __syncwarp();
-          for (int tt = 0; tt < tpb; ++tt)
-            for (int m = 0; m < mt; ++m)
-              started |= 1u << ((uint32_t)(m * n_acc) + p.taps[t0 + tt].acc);
+          if (leader) {
+            umma_commit(&b_empty[sB]);
+            if (st == n_stages - 1) umma_commit(&a_empty[sA]);
+            if (st == n_stages - 1 && ch == p.n_chunks - 1) umma_commit(&acc_full[buf]);
+          }
           if (++sB == p.sb) { sB = 0; phB ^= 1u; }
         }
         if (++sA == p.sa) { sA = 0; phA ^= 1u; }
@@ -755,6 +783,32 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   }
   p.tpb = tpb;
   p.b_stage_bytes = tpb * p.b_tap_bytes;
+  p.n_stages = p.n_taps / tpb;
+  {
+    int cnt[2] = {0, 0};
+    uint32_t seen = 0;
+    for (int st = 0; st < p.n_stages; ++st) {
+      p.item_start[0][st] = cnt[0];
+      p.item_start[1][st] = cnt[1];
+      for (int tt = 0; tt < tpb; ++tt) {
+        const int t = st * tpb + tt;
+        for (int m = 0; m < p.mt; ++m) {
+          const int acc = m * p.n_acc + taps[t].acc;
+          const int who = acc & 1;
+          CAE_CHECK(cnt[who] < kMaxItems, 2, "cae_conv_igemm: work list overflow");
+          IgItem &it = p.items[who][cnt[who]++];
+          it.a_off16 = (uint32_t)((taps[t].par * p.par_stride + (taps[t].dy * p.PW + taps[t].dx) * 16 +
+                                   m * 128) >> 4);
+          it.b_off16 = (uint32_t)((tt * p.b_tap_bytes) >> 4);
+          it.d_off = (uint32_t)(acc * p.N);
+          it.first = (seen >> acc) & 1u ? 0u : 1u;
+          seen |= 1u << acc;
+        }
+      }
+    }
+    p.item_start[0][p.n_stages] = cnt[0];
+    p.item_start[1][p.n_stages] = cnt[1];
+  }
   int sa = 2, sb = 2;
   CAE_CHECK(sa * p.a_stage_bytes + sb * p.b_stage_bytes <= budget, 2,
             "cae_conv_igemm: tile does not fit shared memory (A %d B %d)", p.a_stage_bytes,
@@ -876,6 +930,7 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
     if (v == 4 || v == 8 || v == 12 || v == 16) p.epi_warps = v;
   }
   const bool fast = epi == EPI_ACT && !p.skip.ptr && !getenv("CAE_IGEMM_NO_FAST_EPILOGUE");
+  if (fast && !getenv("CAE_IGEMM_EPI_WARPS")) p.epi_warps = 16;
   if (!fast && p.epi_warps > kMaxEpiWarps) p.epi_warps = kMaxEpiWarps;
   const int threads = 128 + 32 * p.epi_warps;
   void (*kern)(const CUtensorMap, const IgParams) =

@@ -92,7 +92,7 @@ def decompress_image(input_filename, output_filename, destination_format='zarr',
     def run_batch(batch):
         sym = np.stack([s for _, s in batch])
         y_q = torch.from_numpy(sym).pin_memory().cuda(non_blocking=True).float() + med
-        _, _, u8 = decoder(y_q, as_uint8=True)
+        _, _, u8 = decoder(y_q, as_uint8='only')
         img = u8.cpu().numpy()
         for k, (idx, _) in enumerate(batch):
             y0, x0 = idx[0] * ps, idx[1] * ps

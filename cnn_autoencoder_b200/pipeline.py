@@ -22,6 +22,6 @@ class CodecPipeline:
         n, h, w, _ = x_u8.shape
         y = self.model['encoder'](x_u8)
         y_q, hist, bits = self.model['fact_ent'].module.quantize_rate(y)
-        _, _, x_r_u8 = self.model['decoder'](y_q, as_uint8=True)
+        _, _, x_r_u8 = self.model['decoder'](y_q, as_uint8='only')
         return dict(x_r_u8=x_r_u8, y=y, y_q=y_q, hist=hist, bits=bits,
                     bpp=bits / float(n * h * w))
