@@ -181,25 +181,57 @@ __global__ void __launch_bounds__(ST_TX * ST_H) stem_conv_kernel(const DcParams 
   const int x0 = blockIdx.x * ST_W, y0 = blockIdx.y * ST_H;
   for (int i = tid; i < CO * CI * 9; i += ST_TX * ST_H) wsm[i] = p.w[i];
   constexpr int cells = (ST_H + 2) * (ST_W + 2);
-  for (int i = tid; i < cells * CI; i += ST_TX * ST_H) {
-    int c, cell;
-    if (p.in_fmt == CAE_FMT_U8_HWC) { c = i % CI; cell = i / CI; }
-    else { cell = i % cells; c = i / cells; }
-    const int r = cell / (ST_W + 2), col = cell - r * (ST_W + 2);
-    int gy = y0 - 1 + r, gx = x0 - 1 + col;
-    float v = 0.f;
-    bool inside = true;
-    if (p.pad_mode == CAE_PAD_REFLECT) {
-      gy = reflect_idx(gy, p.h_in);
-      gx = reflect_idx(gx, p.w_in);
-      // tiles past the image edge (partial tiles): clamp, the result is never stored
-      gy = gy < 0 ? 0 : (gy >= p.h_in ? p.h_in - 1 : gy);
-      gx = gx < 0 ? 0 : (gx >= p.w_in ? p.w_in - 1 : gx);
-    } else {
-      inside = gy >= 0 && gy < p.h_in && gx >= 0 && gx < p.w_in;
+  if (p.in_fmt == CAE_FMT_U8_HWC) {
+    // uint8 HWC rows are contiguous bytes: one row of the tile (+halo) = (ST_W+2)*CI bytes,
+    // loaded by consecutive threads; (float)b / 255.0f is precomputed per byte value (exact).
+    __shared__ float lut[256];
+    lut[tid & 255] = (float)(tid & 255) / 255.0f;
+    __syncthreads();
+    const uint8_t *src = reinterpret_cast<const uint8_t *>(p.in.ptr) +
+                         (size_t)n * p.h_in * p.w_in * CI;
+    constexpr int row_bytes = (ST_W + 2) * CI;
+    for (int r = 0; r < ST_H + 2; ++r) {
+      int gy = y0 - 1 + r;
+      bool row_ok = true;
+      if (p.pad_mode == CAE_PAD_REFLECT) {
+        gy = reflect_idx(gy, p.h_in);
+        gy = gy < 0 ? 0 : (gy >= p.h_in ? p.h_in - 1 : gy);
+      } else {
+        row_ok = gy >= 0 && gy < p.h_in;
+      }
+      const uint8_t *row = src + (size_t)gy * p.w_in * CI;
+      for (int t = tid; t < row_bytes; t += ST_TX * ST_H) {
+        const int col = t / CI, c = t - col * CI;
+        int gx = x0 - 1 + col;
+        bool ok = row_ok;
+        if (p.pad_mode == CAE_PAD_REFLECT) {
+          gx = reflect_idx(gx, p.w_in);
+          gx = gx < 0 ? 0 : (gx >= p.w_in ? p.w_in - 1 : gx);
+        } else {
+          ok = ok && gx >= 0 && gx < p.w_in;
+        }
+        tile[c][r][col] = ok ? lut[row[gx * CI + c]] : 0.f;
+      }
     }
-    if (inside) v = load_in(p, n, c, gy, gx);
-    tile[c][r][col] = v;
+  } else {
+    for (int i = tid; i < cells * CI; i += ST_TX * ST_H) {
+      const int cell = i % cells, c = i / cells;
+      const int r = cell / (ST_W + 2), col = cell - r * (ST_W + 2);
+      int gy = y0 - 1 + r, gx = x0 - 1 + col;
+      float v = 0.f;
+      bool inside = true;
+      if (p.pad_mode == CAE_PAD_REFLECT) {
+        gy = reflect_idx(gy, p.h_in);
+        gx = reflect_idx(gx, p.w_in);
+        // tiles past the image edge (partial tiles): clamp, the result is never stored
+        gy = gy < 0 ? 0 : (gy >= p.h_in ? p.h_in - 1 : gy);
+        gx = gx < 0 ? 0 : (gx >= p.w_in ? p.w_in - 1 : gx);
+      } else {
+        inside = gy >= 0 && gy < p.h_in && gx >= 0 && gx < p.w_in;
+      }
+      if (inside) v = load_in(p, n, c, gy, gx);
+      tile[c][r][col] = v;
+    }
   }
   __syncthreads();
 
@@ -228,6 +260,9 @@ __global__ void __launch_bounds__(ST_TX * ST_H) stem_conv_kernel(const DcParams 
 
   const int oy = y0 + threadIdx.y;
   if (oy >= p.h_out) return;
+  // max(v, v*slope): slope 1 identity, 0.01 LeakyReLU, 0 ReLU
+  const float pre_s = p.pre_act == CAE_ACT_LEAKY_RELU ? 0.01f : (p.pre_act == CAE_ACT_RELU ? 0.f : 1.f);
+  const float post_s = p.post_act == CAE_ACT_LEAKY_RELU ? 0.01f : (p.post_act == CAE_ACT_RELU ? 0.f : 1.f);
 #pragma unroll 1
   for (int q = 0; q < ST_PX; ++q) {
     const int ox = x0 + lx + q;
@@ -241,7 +276,7 @@ __global__ void __launch_bounds__(ST_TX * ST_H) stem_conv_kernel(const DcParams 
 #pragma unroll
       for (int qq = 1; qq < ST_PX; ++qq) a = q == qq ? acc[qq][co] : a;
       if (p.bias) a += p.bias[co];
-      a = apply_act(a, p.pre_act);
+      a = fmaxf(a, a * pre_s);
       if (p.skip.ptr) {
         if (p.skip.fmt == CAE_FMT_U8_HWC) {
           const uint8_t *s8 = reinterpret_cast<const uint8_t *>(p.skip.ptr);
@@ -254,7 +289,7 @@ __global__ void __launch_bounds__(ST_TX * ST_H) stem_conv_kernel(const DcParams 
           a += __half2float(sh[act_unit_offset(p.skip, n, 0, oy + 1, ox + 1) * 8 + co]);
         }
       }
-      v[co] = apply_act(a, p.post_act);
+      v[co] = fmaxf(a, a * post_s);
     }
     if (p.aux)
       for (int co = 0; co < CO; ++co)
