@@ -190,28 +190,35 @@ __global__ void __launch_bounds__(ST_TX * ST_H) stem_conv_kernel(const DcParams 
     const uint8_t *src = reinterpret_cast<const uint8_t *>(p.in.ptr) +
                          (size_t)n * p.h_in * p.w_in * CI;
     constexpr int row_bytes = (ST_W + 2) * CI;
-    for (int r = 0; r < ST_H + 2; ++r) {
-      int gy = y0 - 1 + r;
-      bool row_ok = true;
+    static_assert(row_bytes <= ST_TX * ST_H, "one thread per byte of a tile row");
+    if (tid < row_bytes) {
+      const int col = tid / CI, c = tid - col * CI;
+      int gx = x0 - 1 + col;
+      bool col_ok = true;
       if (p.pad_mode == CAE_PAD_REFLECT) {
-        gy = reflect_idx(gy, p.h_in);
-        gy = gy < 0 ? 0 : (gy >= p.h_in ? p.h_in - 1 : gy);
+        gx = reflect_idx(gx, p.w_in);
+        gx = gx < 0 ? 0 : (gx >= p.w_in ? p.w_in - 1 : gx);
       } else {
-        row_ok = gy >= 0 && gy < p.h_in;
+        col_ok = gx >= 0 && gx < p.w_in;
       }
-      const uint8_t *row = src + (size_t)gy * p.w_in * CI;
-      for (int t = tid; t < row_bytes; t += ST_TX * ST_H) {
-        const int col = t / CI, c = t - col * CI;
-        int gx = x0 - 1 + col;
-        bool ok = row_ok;
+      // all row loads are issued before any is consumed (18 independent global loads in flight)
+      uint8_t b[ST_H + 2];
+      bool ok[ST_H + 2];
+#pragma unroll
+      for (int r = 0; r < ST_H + 2; ++r) {
+        int gy = y0 - 1 + r;
+        ok[r] = col_ok;
         if (p.pad_mode == CAE_PAD_REFLECT) {
-          gx = reflect_idx(gx, p.w_in);
-          gx = gx < 0 ? 0 : (gx >= p.w_in ? p.w_in - 1 : gx);
+          gy = reflect_idx(gy, p.h_in);
+          gy = gy < 0 ? 0 : (gy >= p.h_in ? p.h_in - 1 : gy);
         } else {
-          ok = ok && gx >= 0 && gx < p.w_in;
+          ok[r] = ok[r] && gy >= 0 && gy < p.h_in;
+          gy = gy < 0 ? 0 : (gy >= p.h_in ? p.h_in - 1 : gy);
         }
-        tile[c][r][col] = ok ? lut[row[gx * CI + c]] : 0.f;
+        b[r] = ok[r] ? __ldg(src + ((size_t)gy * p.w_in + gx) * CI + c) : (uint8_t)0;
       }
+#pragma unroll
+      for (int r = 0; r < ST_H + 2; ++r) tile[c][r][col] = ok[r] ? lut[b[r]] : 0.f;
     }
   } else {
     for (int i = tid; i < cells * CI; i += ST_TX * ST_H) {
