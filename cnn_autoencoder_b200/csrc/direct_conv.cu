@@ -190,9 +190,12 @@ __global__ void __launch_bounds__(ST_TX * ST_H) stem_conv_kernel(const DcParams 
     const uint8_t *src = reinterpret_cast<const uint8_t *>(p.in.ptr) +
                          (size_t)n * p.h_in * p.w_in * CI;
     constexpr int row_bytes = (ST_W + 2) * CI;
-    static_assert(row_bytes <= ST_TX * ST_H, "one thread per byte of a tile row");
-    if (tid < row_bytes) {
-      const int col = tid / CI, c = tid - col * CI;
+    constexpr int passes = (row_bytes + ST_TX * ST_H - 1) / (ST_TX * ST_H);
+#pragma unroll
+    for (int pass = 0; pass < passes; ++pass) {
+      const int t = tid + pass * ST_TX * ST_H;
+      if (t >= row_bytes) break;
+      const int col = t / CI, c = t - col * CI;
       int gx = x0 - 1 + col;
       bool col_ok = true;
       if (p.pad_mode == CAE_PAD_REFLECT) {
