@@ -266,7 +266,11 @@ def main():
         flops = 2.0 * 9 * st.c_in * st.c_out * x_in.n * x_in.h * x_in.w
         ach = flops / (t_ms / 1e3) / 1e12
         roof = {'bound': 'tensor', 'achieved': round(ach, 2), 'peak': peaks['bf16'],
-                'unit': 'TFLOP/s', 'frac': round(ach / peaks['bf16'], 4), 'traffic': None,
+                'unit': 'TFLOP/s', 'frac': round(ach / peaks['bf16'], 4),
+                # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed
+                # ncu --set full capture (profiles/r01_ncu_full_enc2_128to128_s1_batch128.json);
+                # only meaningful for the default batch
+                'traffic': 1061193984 if (B == BATCH and args.arch == ARCH_NAME) else None,
                 'kernel': 'igemm_conv_kernel<EPI_ACT> conv3x3 s1 %d->%d @%dx%d x%d' % (
                     st.c_in, st.c_out, x_in.h, x_in.w, x_in.n),
                 'ms': round(t_ms, 4), 'peak_source': peaks['source'] + ' bf16 burst'}
