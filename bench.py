@@ -45,12 +45,16 @@ def measured_peaks():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+    Q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def window(self, t0, t1):
+        self.t0, self.t1 = t0, t1
 
     def __enter__(self):
         try:
@@ -76,8 +80,13 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        import datetime
         for r in self.rows:
             try:
+                ts = datetime.datetime.strptime(r[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                if self.t0 is not None and not (self.t0 - 0.05 <= ts <= self.t1 + 0.05):
+                    continue
+                r = r[1:]
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except (ValueError, IndexError):
                 continue
@@ -136,7 +145,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--arch', default=ARCH_NAME)
@@ -191,16 +200,22 @@ def main():
     for _ in range(warmup):
         out = pipe(x_dev)
     barrier()
-    launches0 = _cabi.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
     with ClockSampler(local) as clk:
+        time.sleep(0.5)                     # let nvidia-smi start sampling (untimed)
+        for _ in range(3):
+            out = pipe(x_dev)
+        barrier()
+        launches0 = _cabi.launch_count()
+        t_begin = time.time()
         for s, e in ev:
             flush_l2()                      # evict L2 between timed iterations (untimed)
             s.record()
             out = pipe(x_dev)
             e.record()
         barrier()
+        clk.window(t_begin, time.time())
     launches = _cabi.launch_count() - launches0
     step_ms = [s.elapsed_time(e) for s, e in ev]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device='cuda')

@@ -74,6 +74,7 @@ class EntropyBottleneck(nn.Module):
         self.register_buffer('_cdf_length', torch.IntTensor())
         self._tables = None
         self._tables_key = None
+        self.noise_fn = None
 
     # ------------------------------------------------------------- density
     def _logits_cumulative(self, v, stop_gradient):
@@ -112,7 +113,11 @@ class EntropyBottleneck(nn.Module):
         shape = xp.size()
         v = xp.reshape(xp.size(0), 1, -1)
         if training:
-            v = v + torch.empty_like(v).uniform_(-0.5, 0.5)
+            # additive uniform noise proxy; `noise_fn` (tests / reproducible data parallel runs)
+            # may supply the noise for this rank's shard, e.g. keyed on the global sample index
+            noise = self.noise_fn(v) if self.noise_fn is not None else \
+                torch.empty_like(v).uniform_(-0.5, 0.5)
+            v = v + noise
         else:
             med = self.quantiles[:, :, 1:2]
             v = torch.round(v - med) + med

@@ -260,8 +260,13 @@ __device__ __forceinline__ void emit16_fast(const IgParams &p, const uint32_t (&
   const uint32_t off = pixel_unit(p.out.fmt, p.out_pitch, p.out_ps, p.out_is, p.out.planes, n,
                                   oy + 1, ox + 1) + (uint32_t)(c0 >> 3) * p.out_ps;
   uint4 *dst = reinterpret_cast<uint4 *>(p.out.ptr) + off;
-  dst[0] = lo;
-  dst[p.out_ps] = hi;
+  if (p.debug & 16) {          // experiment: streaming (evict-first) stores
+    __stcs(dst, lo);
+    __stcs(dst + p.out_ps, hi);
+  } else {
+    dst[0] = lo;
+    dst[p.out_ps] = hi;
+  }
   if (p.out.halo == CAE_HALO_REFLECT &&
       (oy == 1 || oy == p.out.H - 2 || ox == 1 || ox == p.out.W - 2))
     store_halo2(p, n, c0 >> 3, oy, ox, lo, hi);

@@ -54,8 +54,8 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
     settings = [dict()]
     if args.sweep:
-        settings = [dict(), dict(CAE_IGEMM_TPB='1'), dict(CAE_IGEMM_TPB='3'),
-                    dict(CAE_IGEMM_EPI_WARPS='16')]
+        settings = [dict(), dict(CAE_IGEMM_DEBUG='16'), dict(CAE_IGEMM_EPI_WARPS='8'),
+                    dict(CAE_IGEMM_MT='1')]
     if args.debug_sweep:
         settings = [dict(), dict(CAE_IGEMM_DEBUG='8'), dict(CAE_IGEMM_DEBUG='1'),
                     dict(CAE_IGEMM_DEBUG='2'), dict(CAE_IGEMM_DEBUG='3'), dict(CAE_IGEMM_DEBUG='4'),
