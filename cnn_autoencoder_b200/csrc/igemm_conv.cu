@@ -62,9 +62,14 @@ struct IgParams {
   int PH, PW, n_par, par_stride;
   int a_stage_bytes, a_box_bytes, b_stage_bytes, sa, sb;
   int tpb, b_tap_bytes;  // taps per weight stage, bytes of one tap's weights
-  int n_stages;           // weight stages per channel chunk
-  IgItem items[2][kMaxItems];
-  int item_start[2][kMaxStages + 1];
+  // Passes: a transposed stride-2 layer is run as two passes per tile (output rows 2y and
+  // 2y+1), each with two phase accumulators, so the accumulators stay double buffered and the
+  // epilogue of one pass overlaps the MMAs of the next.  Every other kind has one pass.
+  int n_pass;
+  int pass_tap0[2];        // first tap of the pass (taps are ordered by output row phase)
+  int n_stages[2];         // weight stages per channel chunk, per pass
+  IgItem items[2][2][kMaxItems];              // [pass][issuer][item]
+  int item_start[2][2][kMaxStages + 1];
   int epi_warps;  // 4, 8, 12 (or 16 on the fast-epilogue kernel)
   int debug;      // bring-up bit mask (CAE_IGEMM_DEBUG): 1 no A loads, 2 no B loads, 4 no MMA, 8 no stores
   int org_y, org_x;
@@ -313,7 +318,7 @@ __device__ __forceinline__ void image_store(const IgParams &p, const uint32_t (&
 template <int EPI, bool FAST>
 __device__ __forceinline__ void epilogue_job(const IgParams &p, uint32_t tmem_lane_base,
                                              int acc_base, int n, int y, int x, int job,
-                                             bool valid, float pre_s, float post_s) {
+                                             bool valid, float pre_s, float post_s, int pass) {
   uint32_t r0[16], r1[16];
   if (EPI == EPI_IMAGE) {
     // merged final transposed layer: one 16-column accumulator, columns j = phase * c_out + c
@@ -343,12 +348,14 @@ __device__ __forceinline__ void epilogue_job(const IgParams &p, uint32_t tmem_la
     tmem_ld16(t, r0);
     if (second) tmem_ld16(t + 16, r1);
   } else {
+    // two-pass layers hold one output row phase (two accumulators) per pass
     const int per_row = p.N >> 4;
-    const int py = job / per_row;
-    c_first = c_second = (job - py * per_row) * 16;
+    const int prow = p.n_pass == 2 ? 0 : job / per_row;
+    const int py = p.n_pass == 2 ? pass : prow;
+    c_first = c_second = (job - prow * per_row) * 16;
     oy = y * 2 + py;
     ox0 = x * 2;
-    const uint32_t t = tmem_lane_base + (uint32_t)((acc_base + py * 2) * p.N + c_first);
+    const uint32_t t = tmem_lane_base + (uint32_t)((acc_base + prow * 2) * p.N + c_first);
     __syncwarp();
     tmem_ld16(t, r0);
     tmem_ld16(t + (uint32_t)p.N, r1);
@@ -476,7 +483,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===== activation patches: TMA box loads =====
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int vt = blockIdx.x; vt < p.n_tiles * p.n_pass; vt += gridDim.x) {
+        const int tile = vt / p.n_pass;
         const int n = tile / p.tiles_per_img, rem = tile - n * p.tiles_per_img;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         const int y0 = ty * 16 + p.org_y, x0 = tx * 8 * p.mt + p.org_x;
@@ -496,15 +504,17 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===== packed weights: 1-D bulk copies =====
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int vt = blockIdx.x; vt < p.n_tiles * p.n_pass; vt += gridDim.x) {
+        const int pass = vt % p.n_pass;
         for (int ch = 0; ch < p.n_chunks; ++ch) {
-          for (int t = 0; t < p.n_taps; t += p.tpb, ++it) {
+          for (int st = 0; st < p.n_stages[pass]; ++st, ++it) {
             const int s = it % p.sb;
             mbar_wait(&b_empty[s], ((it / p.sb) & 1) ^ 1);
             if (p.debug & 2) { mbar_arrive(&b_full[s]); continue; }
             mbar_expect_tx(&b_full[s], (uint32_t)p.b_stage_bytes);
             bulk_load_1d(smem_b + (size_t)s * p.b_stage_bytes,
-                         p.wpack + (size_t)(ch * p.n_taps + t) * p.b_tap_bytes,
+                         p.wpack + (size_t)(ch * p.n_taps + p.pass_tap0[pass] + st * p.tpb) *
+                                       p.b_tap_bytes,
                          (uint32_t)p.b_stage_bytes, &b_full[s]);
           }
         }
@@ -534,13 +544,15 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
     const uint32_t b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
     const uint32_t idesc = p.idesc;
-    const int ksteps = p.ck >> 4, n_stages = p.n_stages;
+    const int ksteps = p.ck >> 4;
     const uint32_t buf_cols = (uint32_t)(p.mt * p.n_acc * p.N);
     const bool no_mma = (p.debug & 4) != 0;
     uint32_t j = 0;
     int sA = 0, sB = 0;
     uint32_t phA = 0, phB = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++j) {
+    for (int vt = blockIdx.x; vt < p.n_tiles * p.n_pass; vt += gridDim.x, ++j) {
+      const int pass = vt % p.n_pass;
+      const int n_stages = p.n_stages[pass];
       const int buf = j % p.n_buf;
       mbar_wait(&acc_empty[buf], ((j / p.n_buf) & 1) ^ 1);
       tc_fence_after();
@@ -553,9 +565,9 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&b_full[sB], phB);
           tc_fence_after();
           const uint32_t b_stage = ((sb_base + (uint32_t)sB * b_stage16) & 0x3FFFu) | b_lbo;
-          const int i1 = p.item_start[issuer][st + 1];
-          for (int i = p.item_start[issuer][st]; i < i1; ++i) {
-            const IgItem it = p.items[issuer][i];
+          const int i1 = p.item_start[pass][issuer][st + 1];
+          for (int i = p.item_start[pass][issuer][st]; i < i1; ++i) {
+            const IgItem it = p.items[pass][issuer][i];
             const uint32_t d = d_buf + it.d_off;
             uint32_t a_lo = a_stage + it.a_off16, b_lo = b_stage + it.b_off16;
             uint32_t flag = later | (it.first ^ 1u);
@@ -589,11 +601,12 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int jobs_per_m;
     if (EPI == EPI_IMAGE) jobs_per_m = 1;
     else if (p.up == 1) jobs_per_m = (p.N + 31) >> 5;
-    else jobs_per_m = 2 * (p.N >> 4);
+    else jobs_per_m = (p.n_pass == 2 ? 1 : 2) * (p.N >> 4);
     const int n_jobs = p.mt * jobs_per_m;
     const float pre_s = act_slope(p.pre_act), post_s = act_slope(p.post_act);
     uint32_t j = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++j) {
+    for (int vt = blockIdx.x; vt < p.n_tiles * p.n_pass; vt += gridDim.x, ++j) {
+      const int tile = vt / p.n_pass, pass = vt - tile * p.n_pass;
       const int n = tile / p.tiles_per_img, rem = tile - n * p.tiles_per_img;
       const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
       const int buf = j % p.n_buf;
@@ -604,8 +617,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int m = job / jobs_per_m, jj = job - m * jobs_per_m;
         const int x = (txi * p.mt + m) * 8 + txl;
         const bool valid = y < p.dom_h && x < p.dom_w;
-        epilogue_job<EPI, FAST>(p, lane_base, buf * acc_per_buf + m * p.n_acc, n, y, x, jj, valid, pre_s,
-                          post_s);
+        epilogue_job<EPI, FAST>(p, lane_base, buf * acc_per_buf + m * p.n_acc, n, y, x, jj, valid,
+                                pre_s, post_s, pass);
       }
       tc_fence_before();
       __syncwarp();
@@ -710,7 +723,9 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   p.n_chunks = c_in_p / p.ck;
   TapDef taps[kMaxTaps];
   p.n_taps = build_taps(kind, merged, taps);
-  p.n_acc = (kind == CAE_CONVT_S2 && !merged) ? 4 : 1;
+  // transposed stride-2 (not merged): two passes (output rows 2y, 2y+1) x two phase accumulators
+  p.n_pass = (kind == CAE_CONVT_S2 && !merged && !getenv("CAE_IGEMM_ONE_PASS")) ? 2 : 1;
+  p.n_acc = (kind == CAE_CONVT_S2 && !merged) ? (p.n_pass == 2 ? 2 : 4) : 1;
   p.up = (kind == CAE_CONVT_S2) ? 2 : 1;
 
   // M domain: output pixels, except transposed stride-2 where it is input pixels
@@ -729,6 +744,7 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
     if (const char *e = getenv("CAE_IGEMM_MT")) mt = atoi(e) == 1 ? 1 : 2;
   if (p.dom_w <= 8) mt = 1;
   if (p.n_acc * p.N * mt > 512) mt = 1;
+  if (p.n_pass == 2 && p.n_acc * p.N * mt > 256) mt = 1;   // keep the accumulators double buffered
   CAE_CHECK(p.n_acc * p.N * mt <= 512, 2, "cae_conv_igemm: accumulators exceed TMEM");
   p.mt = mt;
   p.n_buf = (512 / (p.n_acc * p.N * mt)) >= 2 ? 2 : 1;
@@ -774,9 +790,19 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   // of each ring.
   const int budget = 227 * 1024 - 2048;
   p.b_tap_bytes = p.N * p.ck * 2;
+  int pass_ntaps[2] = {p.n_taps, 0};
+  p.pass_tap0[0] = p.pass_tap0[1] = 0;
+  if (p.n_pass == 2) {
+    pass_ntaps[0] = 0;
+    for (int t = 0; t < p.n_taps; ++t) pass_ntaps[taps[t].acc >> 1]++;   // taps are sorted by row phase
+    p.pass_tap0[1] = pass_ntaps[0];
+  }
+  auto divides = [&](int v) {
+    return pass_ntaps[0] % v == 0 && (p.n_pass == 1 || pass_ntaps[1] % v == 0);
+  };
   int tpb = 1;
   for (int cand = p.n_taps; cand >= 1; --cand) {
-    if (p.n_taps % cand) continue;
+    if (!divides(cand)) continue;
     if (2 * p.a_stage_bytes + 2 * cand * p.b_tap_bytes <= budget && cand * p.b_tap_bytes <= 73728) {
       tpb = cand;
       break;
@@ -784,24 +810,25 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   }
   if (const char *e = getenv("CAE_IGEMM_TPB")) {
     const int v = atoi(e);
-    if (v >= 1 && p.n_taps % v == 0 && 2 * p.a_stage_bytes + 2 * v * p.b_tap_bytes <= budget) tpb = v;
+    if (v >= 1 && divides(v) && 2 * p.a_stage_bytes + 2 * v * p.b_tap_bytes <= budget) tpb = v;
   }
   p.tpb = tpb;
   p.b_stage_bytes = tpb * p.b_tap_bytes;
-  p.n_stages = p.n_taps / tpb;
-  {
+  for (int ps = 0; ps < p.n_pass; ++ps) {
+    p.n_stages[ps] = pass_ntaps[ps] / tpb;
+    CAE_CHECK(p.n_stages[ps] <= kMaxStages, 2, "cae_conv_igemm: too many weight stages");
     int cnt[2] = {0, 0};
     uint32_t seen = 0;
-    for (int st = 0; st < p.n_stages; ++st) {
-      p.item_start[0][st] = cnt[0];
-      p.item_start[1][st] = cnt[1];
+    for (int st = 0; st < p.n_stages[ps]; ++st) {
+      p.item_start[ps][0][st] = cnt[0];
+      p.item_start[ps][1][st] = cnt[1];
       for (int tt = 0; tt < tpb; ++tt) {
-        const int t = st * tpb + tt;
+        const int t = p.pass_tap0[ps] + st * tpb + tt;
         for (int m = 0; m < p.mt; ++m) {
-          const int acc = m * p.n_acc + taps[t].acc;
+          const int acc = m * p.n_acc + (p.n_pass == 2 ? (taps[t].acc & 1) : taps[t].acc);
           const int who = acc & 1;
           CAE_CHECK(cnt[who] < kMaxItems, 2, "cae_conv_igemm: work list overflow");
-          IgItem &it = p.items[who][cnt[who]++];
+          IgItem &it = p.items[ps][who][cnt[who]++];
           it.a_off16 = (uint32_t)((taps[t].par * p.par_stride + (taps[t].dy * p.PW + taps[t].dx) * 16 +
                                    m * 128) >> 4);
           it.b_off16 = (uint32_t)((tt * p.b_tap_bytes) >> 4);
@@ -811,8 +838,8 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
         }
       }
     }
-    p.item_start[0][p.n_stages] = cnt[0];
-    p.item_start[1][p.n_stages] = cnt[1];
+    p.item_start[ps][0][p.n_stages[ps]] = cnt[0];
+    p.item_start[ps][1][p.n_stages[ps]] = cnt[1];
   }
   int sa = 2, sb = 2;
   CAE_CHECK(sa * p.a_stage_bytes + sb * p.b_stage_bytes <= budget, 2,
@@ -925,7 +952,7 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   CAE_CUDA(cudaGetDevice(&dev));
   CAE_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   int grid = d->grid > 0 ? d->grid : sm_count;
-  if (grid > p.n_tiles) grid = p.n_tiles;
+  if (grid > p.n_tiles * p.n_pass) grid = p.n_tiles * p.n_pass;
 
   p.debug = 0;
   if (const char *e = getenv("CAE_IGEMM_DEBUG")) p.debug = atoi(e);
