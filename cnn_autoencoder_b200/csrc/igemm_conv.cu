@@ -724,7 +724,9 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   TapDef taps[kMaxTaps];
   p.n_taps = build_taps(kind, merged, taps);
   // transposed stride-2 (not merged): two passes (output rows 2y, 2y+1) x two phase accumulators
-  p.n_pass = (kind == CAE_CONVT_S2 && !merged && !getenv("CAE_IGEMM_ONE_PASS")) ? 2 : 1;
+  // (measured: not faster than one pass with four accumulators -- these layers are bound by
+  //  their DRAM writes, not by the epilogue/MMA serialisation -- so it is opt-in)
+  p.n_pass = (kind == CAE_CONVT_S2 && !merged && getenv("CAE_IGEMM_TWO_PASS")) ? 2 : 1;
   p.n_acc = (kind == CAE_CONVT_S2 && !merged) ? (p.n_pass == 2 ? 2 : 4) : 1;
   p.up = (kind == CAE_CONVT_S2) ? 2 : 1;
 
