@@ -77,8 +77,59 @@ def _make_act(kind, channels, track):
     if kind == 'ReLU':
         return nn.ReLU(inplace=False)
     if kind == 'GDN':
-        raise NotImplementedError('GDN / IGDN has no CUDA epilogue yet (SURVEY.md 8f-3)')
+        return GDN(in_channels=channels, inverse=track == 'synthesis')
     raise ValueError(f'Activation layer {kind} not supported')
+
+
+class _LowerBoundBuffer(nn.Module):
+    def __init__(self, bound):
+        super().__init__()
+        self.register_buffer('bound', torch.tensor([float(bound)]))
+
+
+class _NonNegativeParam(nn.Module):
+    """State-dict shell of CompressAI's NonNegativeParametrizer (buffers ``pedestal`` and
+    ``lower_bound.bound``) so GDN checkpoints load key for key."""
+
+    def __init__(self, minimum=0.0, reparam_offset=2 ** -18):
+        super().__init__()
+        pedestal = float(reparam_offset) ** 2
+        self.register_buffer('pedestal', torch.tensor([pedestal]))
+        self.lower_bound = _LowerBoundBuffer((float(minimum) + pedestal) ** 0.5)
+
+    def init(self, x):
+        return torch.sqrt(torch.max(x + self.pedestal, self.pedestal))
+
+    def forward(self, x):
+        return torch.max(x, self.lower_bound.bound) ** 2 - self.pedestal
+
+
+class GDN(nn.Module):
+    """Generalised divisive normalisation with CompressAI's parameters (``beta``, ``gamma`` and
+    the re-parametrisation buffers), the ``act_layer_type='GDN'`` choice of
+    R:29-30.  Eval-mode tracks run it as the ``cae_gdn`` kernel; this ``forward`` is the torch
+    autograd form used in ``train()`` mode."""
+
+    def __init__(self, in_channels, inverse=False, beta_min=1e-6, gamma_init=0.1):
+        super().__init__()
+        self.inverse = bool(inverse)
+        self.beta_reparam = _NonNegativeParam(minimum=float(beta_min))
+        self.gamma_reparam = _NonNegativeParam()
+        self.beta = nn.Parameter(self.beta_reparam.init(torch.ones(int(in_channels))))
+        self.gamma = nn.Parameter(self.gamma_reparam.init(float(gamma_init) * torch.eye(int(in_channels))))
+
+    def effective(self):
+        """(beta, gamma) after re-parametrisation, fp32, as the kernel consumes them."""
+        return (self.beta_reparam(self.beta).detach().float().contiguous(),
+                self.gamma_reparam(self.gamma).detach().float().contiguous())
+
+    def forward(self, x):
+        C = x.size(1)
+        beta = self.beta_reparam(self.beta)
+        gamma = self.gamma_reparam(self.gamma).reshape(C, C, 1, 1)
+        norm = F.conv2d(x ** 2, gamma, beta)
+        norm = torch.sqrt(norm) if self.inverse else torch.rsqrt(norm)
+        return x * norm
 
 
 def initialize_weights(m):

@@ -20,7 +20,7 @@ PAD_ZERO, PAD_REFLECT = 0, 1
 
 SYMBOLS = ['cae_abi_version', 'cae_last_error', 'cae_device_info', 'cae_launch_count',
            'cae_packed_weight_bytes', 'cae_pack_weights', 'cae_conv_igemm', 'cae_conv_direct',
-           'cae_nchw_to_planar', 'cae_planar_to_nchw', 'cae_eb_quantize',
+           'cae_nchw_to_planar', 'cae_planar_to_nchw', 'cae_eb_quantize', 'cae_gdn',
            'cae_pmf_to_quantized_cdf', 'cae_rans_encode', 'cae_rans_decode']
 
 
@@ -86,6 +86,8 @@ def lib():
                                      Tensor, vp]
     L.cae_planar_to_nchw.argtypes = [Tensor, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_int, vp, vp]
+    L.cae_gdn.argtypes = [Tensor, Tensor, Tensor, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                          ctypes.c_int, vp, vp, ctypes.c_int, vp]
     L.cae_eb_quantize.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                   ctypes.POINTER(EbTables), vp, vp, vp, vp, vp, vp, vp]
     L.cae_pmf_to_quantized_cdf.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]

@@ -31,8 +31,7 @@ _ACT_CODE = {None: C.ACT_NONE, 'Identity': C.ACT_NONE, 'LeakyReLU': C.ACT_LEAKY_
 
 def act_code(kind):
     if kind not in _ACT_CODE:
-        raise NotImplementedError(
-            f'activation {kind!r} has no CUDA epilogue yet (GDN is scheduled: SURVEY.md 8f-3)')
+        raise NotImplementedError(f'activation {kind!r} has no CUDA epilogue')
     return _ACT_CODE[kind]
 
 
@@ -45,6 +44,7 @@ class Step:
         self.pre_act = pre_act
         self.skip = skip            # index of the tensor added before post_act (0 = track input)
         self.post_act = post_act
+        self.gdn = None             # GDN module applied to the conv output before the skip add
         self.transposed = isinstance(conv, nn.ConvTranspose2d)
         stride = conv.stride[0]
         if conv.kernel_size != (3, 3) or conv.groups != 1 or conv.dilation != (1, 1):
@@ -115,9 +115,14 @@ def steps_from_units(units):
                 kind = op[3]
                 if kind in (None, 'Identity'):
                     continue
-                act_code(kind)
                 if pending is None:
                     raise NotImplementedError('activation on the raw track input')
+                if kind == 'GDN':
+                    if pending.gdn is not None or pending.pre_act is not None or skip_armed:
+                        raise NotImplementedError('GDN must directly follow a convolution')
+                    pending.gdn = getattr(unit, op[1])[op[2]]
+                    continue
+                act_code(kind)
                 if pending.skip is not None or skip_armed:
                     if pending.post_act is not None:
                         raise NotImplementedError('two activations after a residual add')
@@ -216,10 +221,25 @@ class TrackExecutor:
                 else:
                     out = self._buffer(k, fmt, cur.n, st.c_out, ho, wo, halo, cur.t.device)
             skip = tensors[st.skip] if st.skip is not None else None
-            call = ((st.kind, cur, wdev, st.c_out, out),
-                    dict(igemm=igemm, bias=bias, skip=skip, pre_act=act_code(st.pre_act),
-                         post_act=act_code(st.post_act), pad_mode=st.pad_mode, aux=aux_t))
-            O.conv(*call[0], **call[1])
+            if st.gdn is not None:
+                # conv -> (fp16 planar scratch) -> GDN (+ skip) -> the consumer's layout
+                if out is None or out.fmt not in (C.FMT_F16_PLANAR, C.FMT_F16_SPLIT):
+                    raise NotImplementedError('GDN on the last layer of a track')
+                tmp = self._buffer((k, 'gdn'), C.FMT_F16_PLANAR, cur.n, st.c_out, ho, wo,
+                                   C.HALO_KEEP, cur.t.device)
+                call = ((st.kind, cur, wdev, st.c_out, tmp),
+                        dict(igemm=igemm, bias=bias, skip=None, pre_act=C.ACT_NONE,
+                             post_act=C.ACT_NONE, pad_mode=st.pad_mode, aux=None))
+                O.conv(*call[0], **call[1])
+                beta, gamma = st.gdn.effective()
+                O.gdn(tmp, out, beta, gamma, st.gdn.inverse, skip=skip)
+                if st.post_act is not None:
+                    raise NotImplementedError('activation after a GDN residual add')
+            else:
+                call = ((st.kind, cur, wdev, st.c_out, out),
+                        dict(igemm=igemm, bias=bias, skip=skip, pre_act=act_code(st.pre_act),
+                             post_act=act_code(st.post_act), pad_mode=st.pad_mode, aux=aux_t))
+                O.conv(*call[0], **call[1])
             self.last_calls[k] = call
             if out is None:
                 out = O.Act(aux_t, C.FMT_F32_NCHW, cur.n, st.c_out, ho, wo)

@@ -139,3 +139,12 @@ def planar_to_nchw(a):
     C.check(C.lib().cae_planar_to_nchw(a.desc(), a.n, a.c, a.h, a.w, out.data_ptr(),
                                        _stream_ptr()))
     return out
+
+
+def gdn(x, out, beta, gamma, inverse, skip=None):
+    """out = GDN(x) (+ skip) through ``cae_gdn``; x / out / skip are planar fp16 Acts."""
+    none = C.Tensor(None, C.FMT_NONE, 0, 0, 0)
+    C.check(C.lib().cae_gdn(x.desc(), out.desc(), skip.desc() if skip is not None else none,
+                            x.n, x.h, x.w, x.c, beta.data_ptr(), gamma.data_ptr(),
+                            1 if inverse else 0, _stream_ptr()))
+    return out

@@ -109,6 +109,14 @@ int cae_conv_igemm(const cae_conv_desc *d, void *stream);
  * stem, R:63-70 with channels_org) and tiny nets; any format combination.     */
 int cae_conv_direct(const cae_conv_desc *d, void *stream);
 
+/* ---- GDN / IGDN ---------------------------------------------------------- */
+/* compressai.layers.GDN forward as used by _define_act_layer (R:29-30):
+ * out = x * rsqrt(beta + gamma . x^2)  (inverse: x * sqrt(...)), then "+ skip" when given
+ * (the residual add of R:172 / R:302).  in/out/skip: PLANAR or SPLIT fp16, same H x W x C.
+ * beta (c) and gamma (c x c, row i = output channel) are the re-parametrised fp32 values.  */
+int cae_gdn(cae_tensor in, cae_tensor out, cae_tensor skip, int n, int h, int w, int c,
+            const float *beta, const float *gamma, int inverse, void *stream);
+
 /* ---- layout -------------------------------------------------------------- */
 /* fp32 NCHW <-> internal planar fp16 (API boundary of Analyzer/Synthesizer). */
 int cae_nchw_to_planar(const float *src, int n, int c, int h, int w, cae_tensor dst, void *stream);

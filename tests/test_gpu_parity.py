@@ -16,7 +16,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
-SMALL = [p for p in sorted(glob.glob(os.path.join(GOLDEN, 'transforms_*.pt'))) if 'gdn' not in p]
+SMALL = sorted(glob.glob(os.path.join(GOLDEN, 'transforms_*.pt')))
 NAMED = sorted(glob.glob(os.path.join(GOLDEN, 'named_*.pt')))
 
 
@@ -298,3 +298,32 @@ def test_tile_loop_roundtrip_and_sharding(tmp_path):
     bpp_ref = O.bpp(sum(len(oracle.codec_encode(_store.padded_tile(slide, i * ps, j * ps, ps)))
                         for i in range(2) for j in range(3)), *slide.shape[:2])
     assert abs(bpp - bpp_ref) <= 0.005 * bpp_ref
+
+
+@pytest.mark.parametrize('residual', [False, True])
+def test_gdn_archs_against_oracle(residual):
+    """act_layer_type='GDN' (R:29-30): GDN in the analysis track, IGDN in the synthesis track."""
+    from oracle import cae_oracle as O
+    arch = dict(channels_org=3, channels_net=32, channels_bn=16, compression_level=3,
+                act_layer_type='GDN', use_residual=residual)
+    chk = O.make_checkpoint(arch, seed=44)
+    g = torch.Generator().manual_seed(2)
+    for part in ('encoder', 'decoder'):          # make beta / gamma non-trivial
+        for k, v in chk[part].items():
+            if k.endswith('.gamma'):
+                v.add_(torch.rand(v.shape, generator=g) * 0.05)
+            elif k.endswith('.beta'):
+                v.add_(torch.rand(v.shape, generator=g) * 0.3)
+    model = _model(chk)
+    oracle = O.OracleModel(chk)
+    x_u8 = O.synth_natural(2, 3, 64, 96, seed=6)
+    x = x_u8.float() / 255.0
+    ref = oracle.forward(x)
+    y = model['encoder'](x.cuda()).cpu()
+    med = chk['fact_ent']['quantiles'][:, 0, 1]
+    agree, boundary, nflip = _symbol_report(y, ref['y'], med)
+    assert nflip <= max(2, 2e-3 * y.numel()) and boundary < 0.03, (agree, nflip, boundary)
+    x_r, _ = model['decoder'](ref['y_q'].cuda())
+    img = x_u8.permute(0, 2, 3, 1).numpy()
+    assert abs(_psnr(img, _to_u8(x_r[0])) - _psnr(img, _to_u8(ref['x_r'][0]))) <= 0.05
+    assert torch.allclose(x_r[0].cpu(), ref['x_r'][0], atol=2e-2, rtol=3e-2)

@@ -115,8 +115,14 @@ def test_model_mirror_builds_on_cpu_and_refuses_to_run():
     m['encoder'].eval()
     with pytest.raises(_cabi.CaeError):
         m['encoder'](torch.zeros(1, 3, 16, 16))
+    g = M.setup_modules(channels_org=3, channels_net=16, channels_bn=8, compression_level=2,
+                        act_layer_type='GDN')
+    gk = set(g['encoder'].state_dict())
+    assert {'analysis_track.0.model.1.beta', 'analysis_track.0.model.1.gamma',
+            'analysis_track.0.model.1.beta_reparam.pedestal',
+            'analysis_track.0.model.1.gamma_reparam.lower_bound.bound'} <= gk
     with pytest.raises(NotImplementedError):
         M.setup_modules(channels_org=3, channels_net=16, channels_bn=8, compression_level=2,
-                        act_layer_type='GDN')
+                        act_layer_type='LeakyReLU', groups=True)
     with pytest.raises(ValueError):
         M.Analyzer(act_layer_type='LeakyRelU')      # the reference's own typo default is rejected
