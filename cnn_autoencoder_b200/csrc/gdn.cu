@@ -78,7 +78,18 @@ __global__ void __launch_bounds__(256) gdn_kernel(const GdnParams p) {
       }
       o[k] = val;
     }
-    if (p.skip.ptr) {
+    if (p.skip.ptr && p.skip.fmt == CAE_FMT_U8_HWC) {      // unit input is the raw image
+      const uint8_t *q = reinterpret_cast<const uint8_t *>(p.skip.ptr);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (plane * 8 + k < C)
+          o[k] += (float)q[(((size_t)n * p.h + y) * p.w + x) * C + plane * 8 + k] / 255.0f;
+    } else if (p.skip.ptr && p.skip.fmt == CAE_FMT_F32_NCHW) {
+      const float *q = reinterpret_cast<const float *>(p.skip.ptr);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (plane * 8 + k < C) o[k] += q[(((size_t)n * C + plane * 8 + k) * p.h + y) * p.w + x];
+    } else if (p.skip.ptr) {
       const uint4 raw = reinterpret_cast<const uint4 *>(p.skip.ptr)[unit_off(p.skip, n, plane, y + 1, x + 1)];
       const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
 #pragma unroll
@@ -122,7 +133,9 @@ extern "C" int cae_gdn(cae_tensor in, cae_tensor out, cae_tensor skip, int n, in
   p.out.ptr = out.ptr; p.out.fmt = out.fmt; p.out.planes = out.planes; p.out.halo = out.halo;
   p.out.H = h; p.out.W = w;
   if (skip.fmt != CAE_FMT_NONE && skip.ptr) {
-    CAE_CHECK(planar_like(skip.fmt) && skip.planes * 8 >= Cp, 2, "cae_gdn: bad skip tensor");
+    CAE_CHECK((planar_like(skip.fmt) && skip.planes * 8 >= Cp) || skip.fmt == CAE_FMT_F32_NCHW ||
+                  skip.fmt == CAE_FMT_U8_HWC,
+              2, "cae_gdn: bad skip tensor");
     p.skip.ptr = skip.ptr; p.skip.fmt = skip.fmt; p.skip.planes = skip.planes;
     p.skip.H = h; p.skip.W = w;
   }
