@@ -21,7 +21,8 @@ PAD_ZERO, PAD_REFLECT = 0, 1
 SYMBOLS = ['cae_abi_version', 'cae_last_error', 'cae_device_info', 'cae_launch_count',
            'cae_packed_weight_bytes', 'cae_pack_weights', 'cae_conv_igemm', 'cae_conv_direct',
            'cae_nchw_to_planar', 'cae_planar_to_nchw', 'cae_eb_quantize', 'cae_gdn',
-           'cae_pmf_to_quantized_cdf', 'cae_rans_encode', 'cae_rans_decode']
+           'cae_pmf_to_quantized_cdf', 'cae_rans_encode', 'cae_rans_decode',
+           'cae_rans_encode_batch', 'cae_rans_compact', 'cae_rans_decode_batch']
 
 
 class Tensor(ctypes.Structure):
@@ -95,6 +96,11 @@ def lib():
                                   sz, ctypes.POINTER(sz)]
     L.cae_rans_decode.argtypes = [vp, sz, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp, vp,
                                   vp]
+    L.cae_rans_encode_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp,
+                                        ctypes.c_int, vp, vp, vp, ctypes.c_int, vp, vp, vp]
+    L.cae_rans_compact.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
+    L.cae_rans_decode_batch.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp,
+                                        ctypes.c_int, vp, vp, vp, vp, vp]
     for name in SYMBOLS:
         if name not in ('cae_abi_version', 'cae_last_error', 'cae_launch_count',
                         'cae_packed_weight_bytes'):

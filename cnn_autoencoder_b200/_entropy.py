@@ -284,14 +284,84 @@ class EntropyBottleneck(nn.Module):
         offs = np.ascontiguousarray(self._offset.cpu().numpy().reshape(-1), dtype=np.int32)
         return cdf, sizes, offs
 
+    # streams per call from which the batched device coder is used instead of the host coder
+    GPU_CODER_MIN_STREAMS = 48
+
     def compress(self, x):
         _, _, sym, _, _ = self._quantize_cuda(x, want_yq=False, want_p=False, want_sym=True)
+        if sym.shape[0] >= self.GPU_CODER_MIN_STREAMS:
+            return self.encode_symbols_gpu(sym)
         sym_h = sym.reshape(sym.shape[0], sym.shape[1], -1).cpu().numpy()
         return [encode_symbols(sym_h[i], *self._host_tables()) for i in range(sym_h.shape[0])]
 
+    def _dev_tables(self, device):
+        return (self._quantized_cdf.to(device=device, dtype=torch.int32).contiguous(),
+                self._cdf_length.to(device=device, dtype=torch.int32).reshape(-1).contiguous(),
+                self._offset.to(device=device, dtype=torch.int32).reshape(-1).contiguous())
+
+    def encode_symbols_gpu(self, sym):
+        """int32 symbols N x C x ... (device) -> list of N byte strings, all streams coded
+        concurrently on the device (one thread per stream, ``cae_rans_encode_batch``)."""
+        if self._offset.numel() == 0:
+            raise C.CaeError('EntropyBottleneck.update() must be called before compress/decompress')
+        sym = sym.contiguous()
+        n, c = sym.shape[0], sym.shape[1]
+        hw = sym[0, 0].numel()
+        dev = sym.device
+        cdf, sizes, offs = self._dev_tables(dev)
+        cap = c * hw + 64
+        words = torch.empty((n, cap), dtype=torch.int32, device=dev)
+        nwords = torch.empty(n, dtype=torch.int32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        L = C.lib()
+        C.check(L.cae_rans_encode_batch(sym.data_ptr(), n, c, hw, cdf.data_ptr(), cdf.shape[1],
+                                        sizes.data_ptr(), offs.data_ptr(), words.data_ptr(), cap,
+                                        nwords.data_ptr(), status.data_ptr(), stream))
+        ends = torch.cumsum(nwords.long(), 0)
+        starts = (ends - nwords.long()).contiguous()
+        total = int(ends[-1].item())                       # sync: stream lengths are data dependent
+        if int(status.item()) & 1:
+            raise C.CaeError('device entropy coder: a stream overflowed its staging buffer')
+        packed = torch.empty(total, dtype=torch.int32, device=dev)
+        C.check(L.cae_rans_compact(words.data_ptr(), n, cap, nwords.data_ptr(), starts.data_ptr(),
+                                   packed.data_ptr(), stream))
+        host = packed.cpu().numpy().view(np.uint8)
+        e = ends.cpu().numpy()
+        return [host[4 * (int(e[i - 1]) if i else 0):4 * int(e[i])].tobytes() for i in range(n)]
+
+    def decode_streams_gpu(self, strings, hw):
+        """list of N byte strings -> int32 symbols N x C x hw on the device."""
+        if self._offset.numel() == 0:
+            raise C.CaeError('EntropyBottleneck.update() must be called before compress/decompress')
+        dev = self.quantiles.device
+        n, c = len(strings), self.channels
+        lens = np.array([len(s) for s in strings], dtype=np.int64)
+        if (lens % 4).any() or (lens < 8).any():
+            raise C.CaeError('entropy-coded stream is not a whole number of words >= 2')
+        off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(lens // 4, out=off[1:])
+        blob = torch.from_numpy(np.frombuffer(b''.join(bytes(s) for s in strings), dtype=np.int32).copy())
+        words = blob.to(dev, non_blocking=True)
+        off_d = torch.from_numpy(off).to(dev)
+        cdf, sizes, offs = self._dev_tables(dev)
+        sym = torch.empty((n, c, hw), dtype=torch.int32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        C.check(C.lib().cae_rans_decode_batch(words.data_ptr(), off_d.data_ptr(), n, c, hw,
+                                              cdf.data_ptr(), cdf.shape[1], sizes.data_ptr(),
+                                              offs.data_ptr(), sym.data_ptr(), status.data_ptr(), stream))
+        if int(status.item()) & 2:
+            raise C.CaeError('device entropy decoder: a stream is truncated')
+        return sym
+
     def decompress(self, strings, size):
-        cdf, sizes, offs = self._host_tables()
         hw = int(np.prod(size))
+        if len(strings) >= self.GPU_CODER_MIN_STREAMS and self.quantiles.is_cuda:
+            sym = self.decode_streams_gpu(strings, hw)
+            med = self._medians().reshape(1, -1, *([1] * len(size)))
+            return sym.reshape(len(strings), self.channels, *size).type_as(med) + med
+        cdf, sizes, offs = self._host_tables()
         out = np.empty((len(strings), self.channels, hw), dtype=np.int32)
         for i, s in enumerate(strings):
             out[i] = decode_symbols(s, self.channels, hw, cdf, sizes, offs)

@@ -148,13 +148,18 @@ def compress_image(codec, checkpoint, input_filename, output_filename, patch_siz
         x = pin.cuda(non_blocking=True)
         y = model['encoder'](x)
         _, _, sym, _, _ = fact_ent._quantize_cuda(y, want_yq=False, want_p=False, want_sym=True)
-        sym_h = sym.reshape(sym.shape[0], sym.shape[1], -1).cpu().numpy()
         lh, lw = y.shape[2], y.shape[3]
+        hh, ww = (lh, lw) if save_as_bottleneck else (th, tw)
+        stats['pixels'] += len(batch) * th * tw
+        if len(batch) >= fact_ent.GPU_CODER_MIN_STREAMS:
+            # enough independent streams to fill the device coder: symbols never leave the GPU
+            header = struct.pack('>QQ', hh, ww)
+            streams = fact_ent.encode_symbols_gpu(sym)
+            return [(_Done(header + s), (idx[0], idx[1], 0)) for (idx, _), s in zip(batch, streams)]
+        sym_h = sym.reshape(sym.shape[0], sym.shape[1], -1).cpu().numpy()
         out = []
         for k, (idx, t) in enumerate(batch):
-            hh, ww = (lh, lw) if save_as_bottleneck else (th, tw)
             out.append((pool.submit(code_tile, sym_h[k], hh, ww), (idx[0], idx[1], 0)))
-        stats['pixels'] += len(batch) * th * tw
         return out
 
     groups = {}
@@ -180,6 +185,16 @@ def compress_image(codec, checkpoint, input_filename, output_filename, patch_siz
     torch.cuda.synchronize()
     stats['seconds'] = time.perf_counter() - t_start
     return stats
+
+
+class _Done:
+    """A finished result with the Future interface the flush loop expects."""
+
+    def __init__(self, value):
+        self._value = value
+
+    def result(self):
+        return self._value
 
 
 class _CodecConfig:

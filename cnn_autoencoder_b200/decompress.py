@@ -82,19 +82,28 @@ def decompress_image(input_filename, output_filename, destination_format='zarr',
     t_start = time.perf_counter()
     pool = ThreadPoolExecutor(max_workers=workers)
 
-    def decode_tile(idx):
+    def read_tile(idx):
         buf = src.read_encoded((idx[0], idx[1], 0))
         h, w = struct.unpack('>QQ', buf[:16])
         lh, lw = (h // 2 ** level, w // 2 ** level) if codec_id == 'cae' else (h, w)
-        sym = decode_symbols(buf[16:], C_bn, lh * lw, cdf, sizes, offs)
-        return idx, sym.reshape(C_bn, lh, lw)
+        return idx, (lh, lw), buf[16:]
+
+    def decode_tile(item):
+        idx, (lh, lw), stream = item
+        return decode_symbols(stream, C_bn, lh * lw, cdf, sizes, offs).reshape(C_bn, lh, lw)
 
     def run_batch(batch):
-        sym = np.stack([s for _, s in batch])
-        y_q = torch.from_numpy(sym).pin_memory().cuda(non_blocking=True).float() + med
+        """batch: list of (idx, (lh, lw), stream bytes) with one latent shape."""
+        lh, lw = batch[0][1]
+        if len(batch) >= fact_ent.GPU_CODER_MIN_STREAMS:
+            sym = fact_ent.decode_streams_gpu([b[2] for b in batch], lh * lw)
+            y_q = sym.reshape(len(batch), C_bn, lh, lw).float() + med
+        else:
+            sym = np.stack(list(pool.map(decode_tile, batch)))
+            y_q = torch.from_numpy(sym).pin_memory().cuda(non_blocking=True).float() + med
         _, _, u8 = decoder(y_q, as_uint8='only')
         img = u8.cpu().numpy()
-        for k, (idx, _) in enumerate(batch):
+        for k, (idx, _, _) in enumerate(batch):
             y0, x0 = idx[0] * ps, idx[1] * ps
             tile = img[k][:min(ps, H - y0), :min(ps, W - x0)]
             if want_png:
@@ -104,14 +113,12 @@ def decompress_image(input_filename, output_filename, destination_format='zarr',
             stats['pixels'] += tile.shape[0] * tile.shape[1]
 
     groups = {}
-    futures = [pool.submit(decode_tile, idx) for idx in mine]
-    for fut in futures:
-        idx, sym = fut.result()
-        g = groups.setdefault(sym.shape, [])
-        g.append((idx, sym))
+    for item in pool.map(read_tile, mine):
+        g = groups.setdefault(item[1], [])
+        g.append(item)
         if len(g) == batch_tiles:
             run_batch(g)
-            groups[sym.shape] = []
+            groups[item[1]] = []
     for g in groups.values():
         if g:
             run_batch(g)

@@ -167,6 +167,25 @@ int cae_rans_decode(const uint8_t *enc /*HOST*/, size_t nbytes, int c, int hw,
                     const int32_t *cdfs, int cdf_stride, const int32_t *cdf_sizes,
                     const int32_t *offsets, int32_t *symbols /*HOST*/);
 
+/* ---- entropy coder (DEVICE, batched: one thread per tile stream) ------------ */
+/* Same stream format as cae_rans_encode / cae_rans_decode, for n independent streams at once
+ * (the tiles of a slide).  symbols: n x C x hw int32.  Encoding writes stream k
+ * into the TAIL of words[k*cap_words .. (k+1)*cap_words) and its length into nwords[k]
+ * (cap_words >= C*hw + 64 is always enough short of pathological escape counts; overflow sets
+ * bit 0 of *status).  cae_rans_compact packs the tails back to back at out_offsets[k] (an
+ * exclusive prefix sum of nwords, in words).  Decoding reads stream k from
+ * words[word_offsets[k] .. word_offsets[k+1]) (bit 1 of *status: a stream was truncated).
+ * All pointers are device pointers; tables as in the host entry points.                   */
+int cae_rans_encode_batch(const int32_t *symbols, int n, int c, int hw, const int32_t *cdfs,
+                          int cdf_stride, const int32_t *cdf_sizes, const int32_t *offsets,
+                          uint32_t *words, int cap_words, int32_t *nwords, int32_t *status,
+                          void *stream);
+int cae_rans_compact(const uint32_t *words, int n, int cap_words, const int32_t *nwords,
+                     const int64_t *out_offsets, uint32_t *out, void *stream);
+int cae_rans_decode_batch(const uint32_t *words, const int64_t *word_offsets, int n, int c, int hw,
+                          const int32_t *cdfs, int cdf_stride, const int32_t *cdf_sizes,
+                          const int32_t *offsets, int32_t *symbols, int32_t *status, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -329,3 +329,31 @@ def test_gdn_archs_against_oracle(residual):
     # random-init IGDN chains amplify (|x_r| reaches the hundreds): compare in relative L2
     rel = (x_r[0].cpu() - ref['x_r'][0]).norm() / ref['x_r'][0].norm()
     assert rel < 2e-2, rel
+
+
+def test_device_entropy_coder_is_byte_identical_to_host_coder():
+    """cae_rans_encode_batch / cae_rans_decode_batch vs. the host coder (itself byte-identical
+    to the oracle, tests/test_host_coder.py): same bytes per stream, escapes included."""
+    from oracle import cae_oracle as O
+    from cnn_autoencoder_b200 import _entropy as E
+    chk = O.make_checkpoint(O.NAMED_ARCHS['A'], seed=1234)
+    fe = _model(chk)['fact_ent'].module
+    n, c, hw = 70, 48, 24 * 20
+    g = torch.Generator().manual_seed(8)
+    sym = torch.round(torch.randn(n, c, hw, generator=g) * 7).int()
+    idx = torch.randint(0, sym.numel(), (400,), generator=g)
+    sym.view(-1)[idx] = torch.randint(-90000, 90000, (400,), generator=g, dtype=torch.int32)
+    sym[3, 0, 0] = 2 ** 27
+    sym[3, 47, hw - 1] = -(2 ** 27)
+    streams = fe.encode_symbols_gpu(sym.cuda())
+    cdf, sizes, offs = fe._host_tables()
+    for k in (0, 3, 33, 69):
+        assert streams[k] == E.encode_symbols(sym[k].numpy(), cdf, sizes, offs)
+    back = fe.decode_streams_gpu(streams, hw).cpu()
+    assert torch.equal(back, sym)
+    # through the module API (>= GPU_CODER_MIN_STREAMS tiles): compress / decompress
+    y = torch.randn(64, 48, 8, 8, generator=g) * 6
+    s2 = fe.compress(y.cuda())
+    assert len(s2) == 64
+    assert s2[5] == O.OracleModel(chk).fact_ent.compress(y[5:6])[0]
+    assert torch.equal(fe.decompress(s2, (8, 8)).cpu(), torch.round(y))
