@@ -353,6 +353,7 @@ def test_device_entropy_coder_is_byte_identical_to_host_coder():
     assert torch.equal(back, sym)
     # through the module API (>= GPU_CODER_MIN_STREAMS tiles): compress / decompress
     y = torch.randn(64, 48, 8, 8, generator=g) * 6
+    fe.GPU_CODER_MIN_STREAMS = 32           # instance override: force the device coder
     s2 = fe.compress(y.cuda())
     assert len(s2) == 64
     assert s2[5] == O.OracleModel(chk).fact_ent.compress(y[5:6])[0]
