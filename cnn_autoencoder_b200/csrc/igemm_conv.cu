@@ -226,28 +226,55 @@ __device__ __noinline__ void store_halo2(const IgParams &p, int n, int plane, in
       }
 }
 
-// Fast path of the planar epilogue (no residual input): bias in fp32, then convert to
-// half2 and run the activations as packed fp16 max(v, v*slope) -- half the instructions of
-// the fp32 form; the result only differs by fp16 rounding of already-rounded negatives.
+// Fast path of the planar epilogue: bias in fp32, then convert to half2 and run the
+// activations as packed fp16 max(v, v*slope) -- half the instructions of the fp32 form; the
+// result only differs by fp16 rounding of already-rounded negatives.
+template <bool SKIP>
 __device__ __forceinline__ void emit16_fast(const IgParams &p, const uint32_t (&r)[16], int c0,
-                                            int n, int oy, int ox, __half2 pre2, __half2 post2) {
+                                            int n, int oy, int ox, float pre_s, __half2 pre2,
+                                            __half2 post2, const uint4 *skip2) {
   __half2 h[8];
-  if (p.bias) {
+  if (SKIP) {
+    // residual layers: bias, pre-activation and the skip add stay in fp32 (the residual path is
+    // the precision-critical one), only the post-activation is packed
+    float v[16];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = c0 + 2 * i;
-      const float b0 = c < p.c_out ? __ldg(p.bias + c) : 0.f;
-      const float b1 = c + 1 < p.c_out ? __ldg(p.bias + c + 1) : 0.f;
-      h[i] = __floats2half2_rn(__uint_as_float(r[2 * i]) + b0, __uint_as_float(r[2 * i + 1]) + b1);
+    for (int i = 0; i < 16; ++i) {
+      v[i] = __uint_as_float(r[i]);
+      if (p.bias && c0 + i < p.c_out) v[i] += __ldg(p.bias + c0 + i);
+    }
+    if (p.pre_act != CAE_ACT_NONE) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * pre_s);
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const uint4 sv = skip2[hh];
+      const __half2 *sh = reinterpret_cast<const __half2 *>(&sv);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(sh[k]);
+        h[hh * 4 + k] = __floats2half2_rn(v[hh * 8 + 2 * k] + f.x, v[hh * 8 + 2 * k + 1] + f.y);
+      }
     }
   } else {
+    if (p.bias) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      h[i] = __floats2half2_rn(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-  }
-  if (p.pre_act != CAE_ACT_NONE) {
+      for (int i = 0; i < 8; ++i) {
+        const int c = c0 + 2 * i;
+        const float b0 = c < p.c_out ? __ldg(p.bias + c) : 0.f;
+        const float b1 = c + 1 < p.c_out ? __ldg(p.bias + c + 1) : 0.f;
+        h[i] = __floats2half2_rn(__uint_as_float(r[2 * i]) + b0, __uint_as_float(r[2 * i + 1]) + b1);
+      }
+    } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) h[i] = __hmax2(h[i], __hmul2(h[i], pre2));
+      for (int i = 0; i < 8; ++i)
+        h[i] = __floats2half2_rn(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+    }
+    if (p.pre_act != CAE_ACT_NONE) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h[i] = __hmax2(h[i], __hmul2(h[i], pre2));
+    }
   }
   if (p.post_act != CAE_ACT_NONE) {
 #pragma unroll
@@ -315,7 +342,7 @@ __device__ __forceinline__ void image_store(const IgParams &p, const uint32_t (&
 //  up == 1: columns [c0, c0+32) of accumulator m
 //  up == 2: columns [c0, c0+16) of the two horizontal output phases (py,0) and (py,1), i.e.
 //           two adjacent output pixels -> 32 contiguous bytes per plane
-template <int EPI, bool FAST>
+template <int EPI, int FAST>
 __device__ __forceinline__ void epilogue_job(const IgParams &p, uint32_t tmem_lane_base,
                                              int acc_base, int n, int y, int x, int job,
                                              bool valid, float pre_s, float post_s, int pass) {
@@ -360,13 +387,32 @@ __device__ __forceinline__ void epilogue_job(const IgParams &p, uint32_t tmem_la
     tmem_ld16(t, r0);
     tmem_ld16(t + (uint32_t)p.N, r1);
   }
+  uint4 sk[4] = {};
+  if (FAST == 2 && valid && !(p.debug & 32)) {
+    // residual input of this job: in flight together with the TMEM loads
+    const int ox1 = ox0 + (p.up == 2 ? 1 : 0);
+    const uint4 *s0 = reinterpret_cast<const uint4 *>(p.skip.ptr) +
+                      pixel_unit(p.skip.fmt, p.skip_pitch, p.skip_ps, p.skip_is, p.skip.planes, n,
+                                 oy + 1, ox0 + 1) + (uint32_t)(c_first >> 3) * p.skip_ps;
+    const uint4 *s1 = reinterpret_cast<const uint4 *>(p.skip.ptr) +
+                      pixel_unit(p.skip.fmt, p.skip_pitch, p.skip_ps, p.skip_is, p.skip.planes, n,
+                                 oy + 1, ox1 + 1) + (uint32_t)(c_second >> 3) * p.skip_ps;
+    sk[0] = __ldg(s0);
+    sk[1] = __ldg(s0 + p.skip_ps);
+    if (second) {
+      sk[2] = __ldg(s1);
+      sk[3] = __ldg(s1 + p.skip_ps);
+    }
+  }
   tmem_ld_wait();
   if (!valid || (p.debug & 8)) return;
 
   if (FAST) {
     const __half2 pre2 = __float2half2_rn(pre_s), post2 = __float2half2_rn(post_s);
-    emit16_fast(p, r0, c_first, n, oy, ox0, pre2, post2);
-    if (second) emit16_fast(p, r1, c_second, n, oy, ox0 + (p.up == 2 ? 1 : 0), pre2, post2);
+    emit16_fast<FAST == 2>(p, r0, c_first, n, oy, ox0, pre_s, pre2, post2, sk);
+    if (second)
+      emit16_fast<FAST == 2>(p, r1, c_second, n, oy, ox0 + (p.up == 2 ? 1 : 0), pre_s, pre2, post2,
+                             sk + 2);
     return;
   }
 
@@ -442,8 +488,8 @@ __device__ __forceinline__ void epilogue_job(const IgParams &p, uint32_t tmem_la
 }
 
 // ------------------------------------------------------------------ kernel
-template <int EPI, bool FAST>
-__global__ void __launch_bounds__(FAST ? 128 + 32 * 16 : kThreads, 1)
+template <int EPI, int FAST>
+__global__ void __launch_bounds__(FAST == 1 ? 128 + 32 * 16 : kThreads, 1)
 igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ IgParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[kMaxSA], a_empty[kMaxSA];
@@ -610,9 +656,25 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int n = tile / p.tiles_per_img, rem = tile - n * p.tiles_per_img;
       const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
       const int buf = j % p.n_buf;
+      const int y = tyi * 16 + ty;
+      if (FAST == 2 && p.up == 1 && (txl == 0 || txl == 7) && y < p.dom_h && !(p.debug & 64)) {
+        // pull this warp's share of the residual tile into L2 while the MMAs still run: 8
+        // pixels x 16 B per plane row, so the first and last lane of a row cover its lines
+        for (int job = half; job < n_jobs; job += n_halves) {
+          const int m = job / jobs_per_m, jj = job - m * jobs_per_m;
+          const int x = (txi * p.mt + m) * 8 + txl;
+          if (x >= p.dom_w) continue;
+          const uint4 *sp = reinterpret_cast<const uint4 *>(p.skip.ptr) +
+                            pixel_unit(p.skip.fmt, p.skip_pitch, p.skip_ps, p.skip_is,
+                                       p.skip.planes, n, y + 1, x + 1) +
+                            (uint32_t)(jj * 4) * p.skip_ps;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + q * p.skip_ps));
+        }
+      }
       mbar_wait(&acc_full[buf], (j / p.n_buf) & 1);
       tc_fence_after();
-      const int y = tyi * 16 + ty;
       for (int job = half; job < n_jobs; job += n_halves) {
         const int m = job / jobs_per_m, jj = job - m * jobs_per_m;
         const int x = (txi * p.mt + m) * 8 + txl;
@@ -963,14 +1025,19 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
     const int v = atoi(e);
     if (v == 4 || v == 8 || v == 12 || v == 16) p.epi_warps = v;
   }
-  const bool fast = epi == EPI_ACT && !p.skip.ptr && !getenv("CAE_IGEMM_NO_FAST_EPILOGUE");
-  if (fast && !getenv("CAE_IGEMM_EPI_WARPS")) p.epi_warps = 16;
-  if (!fast && p.epi_warps > kMaxEpiWarps) p.epi_warps = kMaxEpiWarps;
+  // epilogue variant: 1 = packed half2 (16 epilogue warps), 2 = the same after an fp32 residual
+  // add (12 warps: more registers), 0 = plain fp32 (bring-up / latent / image layers)
+  int fast = 0;
+  if (epi == EPI_ACT && !getenv("CAE_IGEMM_NO_FAST_EPILOGUE")) fast = p.skip.ptr ? 2 : 1;
+  if (!getenv("CAE_IGEMM_EPI_WARPS")) p.epi_warps = fast == 1 ? 16 : (fast == 2 ? 12 : 8);
+  if (fast != 1 && p.epi_warps > kMaxEpiWarps) p.epi_warps = kMaxEpiWarps;
   const int threads = 128 + 32 * p.epi_warps;
   void (*kern)(const CUtensorMap, const IgParams) =
-      epi == EPI_ACT ? (fast ? igemm_conv_kernel<EPI_ACT, true> : igemm_conv_kernel<EPI_ACT, false>)
-                     : (epi == EPI_LATENT ? igemm_conv_kernel<EPI_LATENT, false>
-                                          : igemm_conv_kernel<EPI_IMAGE, false>);
+      epi == EPI_ACT ? (fast == 1 ? igemm_conv_kernel<EPI_ACT, 1>
+                                  : (fast == 2 ? igemm_conv_kernel<EPI_ACT, 2>
+                                               : igemm_conv_kernel<EPI_ACT, 0>))
+                     : (epi == EPI_LATENT ? igemm_conv_kernel<EPI_LATENT, 0>
+                                          : igemm_conv_kernel<EPI_IMAGE, 0>);
   CAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   kern<<<grid, threads, smem_bytes, (cudaStream_t)stream>>>(tm, p);
   cae_count_launch();

@@ -44,6 +44,7 @@ def main():
     ap.add_argument('--size', type=int, default=256)
     ap.add_argument('--sweep', action='store_true')
     ap.add_argument('--debug-sweep', action='store_true')
+    ap.add_argument('--skip-sweep', action='store_true')
     args = ap.parse_args()
     chk = O.make_checkpoint(O.NAMED_ARCHS[args.arch], seed=1234)
     model = M.autoencoder_from_state_dict(chk, gpu=True, train=False)
@@ -60,6 +61,10 @@ def main():
         settings = [dict(), dict(CAE_IGEMM_DEBUG='8'), dict(CAE_IGEMM_DEBUG='1'),
                     dict(CAE_IGEMM_DEBUG='2'), dict(CAE_IGEMM_DEBUG='3'), dict(CAE_IGEMM_DEBUG='4'),
                     dict(CAE_IGEMM_DEBUG='11'), dict(CAE_IGEMM_DEBUG='15')]
+    if args.skip_sweep:
+        settings = [dict(), dict(CAE_IGEMM_DEBUG='32'), dict(CAE_IGEMM_DEBUG='64'),
+                    dict(CAE_IGEMM_DEBUG='96'), dict(CAE_IGEMM_EPI_WARPS='8'),
+                    dict(CAE_IGEMM_NO_FAST_EPILOGUE='1')]
     for env in settings:
         for k in ('CAE_IGEMM_EPI_WARPS', 'CAE_IGEMM_MT', 'CAE_IGEMM_NO_FAST_EPILOGUE', 'CAE_IGEMM_DEBUG', 'CAE_IGEMM_TPB'):
             os.environ.pop(k, None)
@@ -78,7 +83,7 @@ def main():
                     flops /= 4
                 print(f'  {name[:3]}{k} {KIND[st.kind]:9s} {st.c_in:4d}->{st.c_out:4d} @{xin.h}x{xin.w} '
                       f'{"igemm" if call[1]["igemm"] else "direct":6s} {ms * 1e3:9.1f} us '
-                      f'{flops / ms / 1e9:8.1f} TFLOP/s')
+                      f'{flops / ms / 1e9:8.1f} TFLOP/s{" +skip" if call[1].get("skip") is not None else ""}')
         print(f'  sum of conv layers {total * 1e3:.1f} us')
 
 
