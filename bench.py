@@ -292,7 +292,7 @@ def main():
     if dom is not None and ex.last_calls:
         call = ex.last_calls[dom]
         for _ in range(3):
-            _ops.conv(*call[0], **call[1])
+            _ops.replay(call)
         torch.cuda.synchronize()
         reps = 10
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -300,7 +300,7 @@ def main():
         for s, e in evs:
             flush_l2()
             s.record()
-            _ops.conv(*call[0], **call[1])
+            _ops.replay(call)
             e.record()
         torch.cuda.synchronize()
         t_ms = statistics.mean(s.elapsed_time(e) for s, e in evs)

@@ -20,6 +20,7 @@ PAD_ZERO, PAD_REFLECT = 0, 1
 
 SYMBOLS = ['cae_abi_version', 'cae_last_error', 'cae_device_info', 'cae_launch_count',
            'cae_packed_weight_bytes', 'cae_pack_weights', 'cae_conv_igemm', 'cae_conv_direct',
+           'cae_conv_head',
            'cae_nchw_to_planar', 'cae_planar_to_nchw', 'cae_eb_quantize', 'cae_gdn',
            'cae_pmf_to_quantized_cdf', 'cae_rans_encode', 'cae_rans_decode',
            'cae_rans_encode_batch', 'cae_rans_compact', 'cae_rans_decode_batch']
@@ -38,6 +39,16 @@ class ConvDesc(ctypes.Structure):
                 ('pre_act', ctypes.c_int32), ('post_act', ctypes.c_int32),
                 ('pad_mode', ctypes.c_int32), ('ck', ctypes.c_int32), ('mt', ctypes.c_int32),
                 ('grid', ctypes.c_int32), ('aux_out', ctypes.c_void_p)]
+
+
+class HeadDesc(ctypes.Structure):
+    _fields_ = [('n', ctypes.c_int32), ('h_in', ctypes.c_int32), ('w_in', ctypes.c_int32),
+                ('c_in', ctypes.c_int32), ('c_out', ctypes.c_int32),
+                ('inp', Tensor), ('out', Tensor),
+                ('w_stem', ctypes.c_void_p), ('b_stem', ctypes.c_void_p),
+                ('w_down', ctypes.c_void_p), ('b_down', ctypes.c_void_p),
+                ('act_stem', ctypes.c_int32), ('act_down', ctypes.c_int32),
+                ('pad_mode', ctypes.c_int32), ('reserved', ctypes.c_int32)]
 
 
 class EbTables(ctypes.Structure):
@@ -83,6 +94,7 @@ def lib():
     L.cae_pack_weights.argtypes = [ctypes.c_int] * 4 + [vp, vp, vp, vp]
     L.cae_conv_igemm.argtypes = [ctypes.POINTER(ConvDesc), vp]
     L.cae_conv_direct.argtypes = [ctypes.POINTER(ConvDesc), vp]
+    L.cae_conv_head.argtypes = [ctypes.POINTER(HeadDesc), vp]
     L.cae_nchw_to_planar.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      Tensor, vp]
     L.cae_planar_to_nchw.argtypes = [Tensor, ctypes.c_int, ctypes.c_int, ctypes.c_int,

@@ -19,6 +19,8 @@ packed.  Every tensor between steps lives in the internal fp16 layout its
 consumer wants (planar for stride-1 / transposed, parity-split for stride-2;
 reflect halo for Conv2d consumers, zero halo for ConvTranspose2d consumers).
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -149,7 +151,10 @@ class TrackExecutor:
     def __init__(self, steps):
         self.steps = steps
         self._buffers = {}
-        self.last_calls = {}      # step index -> (args, kwargs) of its last _ops.conv call
+        # step index -> (args, kwargs) of its last _ops.conv call, or ('head', args, kwargs)
+        # for a fused stem + stride-2 pair (recorded under the stem's index); _ops.replay
+        self.last_calls = {}
+        self.fuse_head = not os.environ.get('CAE_NO_HEAD_FUSION')
 
     @staticmethod
     def _use_igemm(step, x):
@@ -167,6 +172,23 @@ class TrackExecutor:
         fmt = C.FMT_F16_SPLIT if nxt.kind == C.CONV_S2 else C.FMT_F16_PLANAR
         halo = C.HALO_REFLECT if (not nxt.transposed and nxt.pad_mode == C.PAD_REFLECT) else C.HALO_KEEP
         return fmt, halo
+
+    def _head_pair(self, k, cur, keep, final_fmt):
+        """True when steps k, k+1 are the stem + stride-2 pair of the first downsampling unit
+        reading the raw image, and the fused kernel covers them."""
+        if not self.fuse_head or k + 2 > len(self.steps) - 1 or (k + 1) in keep:
+            return False
+        a, b = self.steps[k], self.steps[k + 1]
+        if cur.fmt not in (C.FMT_U8_HWC, C.FMT_F32_NCHW):
+            return False
+        plain = lambda s: (s.skip is None and s.gdn is None and s.post_act is None
+                           and not s.transposed)
+        if not (plain(a) and plain(b) and a.kind == C.CONV_S1 and b.kind == C.CONV_S2):
+            return False
+        if not (a.c_in <= 4 and a.c_out == a.c_in and b.c_in == a.c_in and b.c_out <= 128):
+            return False
+        fmt, _ = self._consumer_layout(k + 2, final_fmt)
+        return a.pad_mode == b.pad_mode and fmt == C.FMT_F16_PLANAR
 
     def _buffer(self, key, fmt, n, c, h, w, halo, device):
         full = (key, fmt, n, c, h, w, halo, str(device))
@@ -187,7 +209,28 @@ class TrackExecutor:
         cur = x
         aux = None
         n_steps = len(self.steps)
+        self.last_calls = {}
+        fused = False
         for k, st in enumerate(self.steps):
+            if fused:                     # consumed by the fused head launched at k - 1
+                fused = False
+                continue
+            if self._head_pair(k, cur, keep, final_fmt):
+                nxt = self.steps[k + 1]
+                w1, b1 = st.materialise(False)
+                w2, b2 = nxt.materialise(False)
+                ho, wo = O.KIND_OUT[nxt.kind](cur.h, cur.w)
+                fmt, halo = self._consumer_layout(k + 2, final_fmt)
+                out = self._buffer(k + 1, fmt, cur.n, nxt.c_out, ho, wo, halo, cur.t.device)
+                call = ('head', (cur, w1, b1, w2, b2, nxt.c_out, out),
+                        dict(act_stem=act_code(st.pre_act), act_down=act_code(nxt.pre_act),
+                             pad_mode=st.pad_mode))
+                O.conv_head(*call[1], **call[2])
+                self.last_calls[k] = call
+                tensors[k + 2] = out
+                cur = out
+                fused = True
+                continue
             igemm = self._use_igemm(st, cur)
             if igemm and cur.fmt not in (C.FMT_F16_PLANAR, C.FMT_F16_SPLIT):
                 raise C.CaeError('internal: igemm step fed a non-planar tensor')

@@ -126,6 +126,28 @@ def conv(kind, x, weights, c_out, out, *, igemm, bias=None, skip=None, pre_act=C
     return out
 
 
+def conv_head(x, w_stem, b_stem, w_down, b_down, c_out, out, *, act_stem=C.ACT_NONE,
+              act_down=C.ACT_NONE, pad_mode=C.PAD_REFLECT):
+    """out = act_down(conv_s2(act_stem(conv_s1(x) + b_stem)) + b_down): the fused first
+    downsampling unit (``cae_conv_head``).  x: U8_HWC / F32_NCHW Act, out: planar Act."""
+    d = C.HeadDesc()
+    d.n, d.h_in, d.w_in, d.c_in, d.c_out = x.n, x.h, x.w, x.c, c_out
+    d.inp = x.desc()
+    d.out = out.desc()
+    d.w_stem, d.b_stem = w_stem.data_ptr(), (b_stem.data_ptr() if b_stem is not None else None)
+    d.w_down, d.b_down = w_down.data_ptr(), (b_down.data_ptr() if b_down is not None else None)
+    d.act_stem, d.act_down, d.pad_mode = act_stem, act_down, pad_mode
+    C.check(C.lib().cae_conv_head(ctypes.byref(d), _stream_ptr()))
+    return out
+
+
+def replay(call):
+    """Re-issue a call recorded by ``TrackExecutor.last_calls`` (benchmarks / profiling)."""
+    if call[0] == 'head':
+        return conv_head(*call[1], **call[2])
+    return conv(*call[0], **call[1])
+
+
 def nchw_to_planar(x, fmt=C.FMT_F16_PLANAR, halo=C.HALO_KEEP):
     a = wrap_nchw(x)
     out = alloc_act(fmt, a.n, a.c, a.h, a.w, halo, device=x.device)

@@ -122,6 +122,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 
+// Wait that yields its issue slots while it polls: for warps that wait a long time next to
+// warps doing CUDA-core work on the same SM (the fused head kernel).
+static __device__ __noinline__ void mbar_wait_backoff_slow(uint64_t *bar, uint32_t parity) {
+  const uint64_t t0 = global_timer_ns();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(100);
+    if (global_timer_ns() - t0 > 4000000000ull) {
+      printf("cae_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
+             (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_backoff_slow(bar, parity);
+}
+
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }

@@ -109,6 +109,29 @@ int cae_conv_igemm(const cae_conv_desc *d, void *stream);
  * stem, R:63-70 with channels_org) and tiny nets; any format combination.     */
 int cae_conv_direct(const cae_conv_desc *d, void *stream);
 
+/* Fused head of an analysis track: the first DownsamplingUnit of the reference
+ * (R:53-77: Conv2d(c_in, c_in, k3 s1) -> act -> Conv2d(c_in, c_out, k3 s2) [-> act],
+ * called from Analyzer.forward R:359-361) in one launch,
+ *   out = act_down( conv_s2( act_stem( conv_s1(in) + b_stem ) ) + b_down ).
+ * The stem result stays in shared memory and feeds the tensor cores as an im2col
+ * operand with K = 9 * c_in.  Weights are fp32 in torch Conv2d layout
+ * (c_out, c_in, 3, 3) with any BatchNorm already folded; both convolutions use
+ * `pad_mode`.  c_in 1..4, c_out <= 128.                                         */
+typedef struct cae_head_desc {
+  int32_t n, h_in, w_in;   /* input images                                        */
+  int32_t c_in, c_out;
+  cae_tensor in;           /* CAE_FMT_U8_HWC (x/255 applied) or CAE_FMT_F32_NCHW     */
+  cae_tensor out;          /* CAE_FMT_F16_PLANAR, ceil(h/2) x ceil(w/2), halo KEEP/REFLECT */
+  const float *w_stem;     /* [c_in][c_in][3][3]                                    */
+  const float *b_stem;     /* [c_in] or NULL                                        */
+  const float *w_down;     /* [c_out][c_in][3][3]                                   */
+  const float *b_down;     /* [c_out] or NULL                                       */
+  int32_t act_stem, act_down; /* CAE_ACT_*                                         */
+  int32_t pad_mode;        /* CAE_PAD_*                                             */
+  int32_t reserved;
+} cae_head_desc;
+int cae_conv_head(const cae_head_desc *d, void *stream);
+
 /* ---- GDN / IGDN ---------------------------------------------------------- */
 /* compressai.layers.GDN forward as used by _define_act_layer (R:29-30):
  * out = x * rsqrt(beta + gamma . x^2)  (inverse: x * sqrt(...)), then "+ skip" when given

@@ -180,6 +180,38 @@ def _igemm_case(kind_name, n, ci, co, h, w, *, out_fmt=None, halo_out=None, mt=0
     return ok
 
 
+def case_head(n, ci, co, h, w, *, u8=True, pad_name='reflect', halo_out=None, act1=1, act2=1,
+              tol=3e-3):
+    """cae_conv_head against conv_s2(fp16(act(conv_s1(x)))) in torch fp32."""
+    torch, F, C, O = _mods()
+    g = torch.Generator(device='cuda').manual_seed(11)
+    pad = C.PAD_REFLECT if pad_name == 'reflect' else C.PAD_ZERO
+    if u8:
+        img = torch.randint(0, 256, (n, h, w, ci), generator=g, device='cuda', dtype=torch.uint8)
+        x = img.permute(0, 3, 1, 2).float() / 255.0
+        xin = O.wrap_u8_hwc(img)
+    else:
+        x = torch.rand((n, ci, h, w), generator=g, device='cuda')
+        xin = O.wrap_nchw(x)
+    w1 = torch.randn((ci, ci, 3, 3), generator=g, device='cuda') * 0.4
+    b1 = torch.randn((ci,), generator=g, device='cuda') * 0.1
+    w2 = fp16_vals((co, ci, 3, 3), g, scale=0.3)
+    b2 = torch.randn((co,), generator=g, device='cuda') * 0.1
+    act = {0: lambda t: t, 1: lambda t: F.leaky_relu(t, 0.01), 2: torch.relu}
+    s = act[act1](ref_conv(C.CONV_S1, x, w1, pad) + b1.view(1, -1, 1, 1)).half().float()
+    want = act[act2](ref_conv(C.CONV_S2, s, w2, pad) + b2.view(1, -1, 1, 1))
+    ho, wo = O.KIND_OUT[C.CONV_S2](h, w)
+    halo = halo_out if halo_out is not None else C.HALO_REFLECT
+    out = O.alloc_act(C.FMT_F16_PLANAR, n, co, ho, wo, halo=halo)
+    O.conv_head(xin, w1, b1, w2, b2, co, out, act_stem=act1, act_down=act2, pad_mode=pad)
+    pv = padded_view(out)
+    ok = check('interior', pv[:, :co, 1:-1, 1:-1], want, tol)
+    mode = 'reflect' if halo == C.HALO_REFLECT else 'constant'
+    ok &= check('halo', pv, F.pad(pv[:, :, 1:-1, 1:-1], (1, 1, 1, 1), mode=mode), 0)
+    ok &= check('pad-ch', pv[:, co:], torch.zeros_like(pv[:, co:]), 0)
+    return ok
+
+
 def case_eb():
     torch, F, C, O = _mods()
     import ctypes
@@ -229,6 +261,11 @@ CASES = {
     'igemm_t2_128': lambda: _igemm_case('CONVT_S2', 1, 128, 128, 32, 32),
     'igemm_t2_merged': lambda: _igemm_case('CONVT_S2', 2, 128, 3, 24, 40, bias=True),
     'igemm_t2_merged_c1': lambda: _igemm_case('CONVT_S2', 1, 16, 1, 16, 16),
+    'head_u8_3_128': lambda: case_head(2, 3, 128, 64, 96),
+    'head_u8_multi_tile': lambda: case_head(3, 3, 128, 256, 256),
+    'head_odd_c1': lambda: case_head(2, 1, 24, 37, 51, u8=False, act2=0),
+    'head_c4_zero_pad': lambda: case_head(1, 4, 64, 40, 72, pad_name='zero', halo_out=0, act1=2),
+    'head_small': lambda: case_head(1, 3, 48, 6, 10, u8=False),
     'eb': case_eb,
 }
 

@@ -23,14 +23,14 @@ KIND = {0: 'conv_s1', 1: 'conv_s2', 2: 'convT_s1', 3: 'convT_s2'}
 
 def time_call(call, flush, reps=5):
     for _ in range(2):
-        _ops.conv(*call[0], **call[1])
+        _ops.replay(call)
     ts = []
     for _ in range(reps):
         flush.fill_(1)
         flush.view(torch.int64).sum()   # leave the L2 clean (see bench.py)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        _ops.conv(*call[0], **call[1])
+        _ops.replay(call)
         e.record()
         torch.cuda.synchronize()
         ts.append(s.elapsed_time(e))
@@ -45,6 +45,7 @@ def main():
     ap.add_argument('--sweep', action='store_true')
     ap.add_argument('--debug-sweep', action='store_true')
     ap.add_argument('--skip-sweep', action='store_true')
+    ap.add_argument('--head-sweep', action='store_true')
     args = ap.parse_args()
     chk = O.make_checkpoint(O.NAMED_ARCHS[args.arch], seed=1234)
     model = M.autoencoder_from_state_dict(chk, gpu=True, train=False)
@@ -65,8 +66,10 @@ def main():
         settings = [dict(), dict(CAE_IGEMM_DEBUG='32'), dict(CAE_IGEMM_DEBUG='64'),
                     dict(CAE_IGEMM_DEBUG='96'), dict(CAE_IGEMM_EPI_WARPS='8'),
                     dict(CAE_IGEMM_NO_FAST_EPILOGUE='1')]
+    if args.head_sweep:
+        settings = [dict(), dict(CAE_HEAD_DEBUG='4'), dict(CAE_HEAD_DEBUG='6'), dict(CAE_HEAD_DEBUG='2')]
     for env in settings:
-        for k in ('CAE_IGEMM_EPI_WARPS', 'CAE_IGEMM_MT', 'CAE_IGEMM_NO_FAST_EPILOGUE', 'CAE_IGEMM_DEBUG', 'CAE_IGEMM_TPB'):
+        for k in ('CAE_IGEMM_EPI_WARPS', 'CAE_IGEMM_MT', 'CAE_IGEMM_NO_FAST_EPILOGUE', 'CAE_IGEMM_DEBUG', 'CAE_IGEMM_TPB', 'CAE_HEAD_DEBUG'):
             os.environ.pop(k, None)
         os.environ.update(env)
         print('== settings', env or 'default')
@@ -74,10 +77,17 @@ def main():
         for name in ('encoder', 'decoder'):
             ex = model[name].module._executor()
             for k, st in enumerate(ex.steps):
-                call = ex.last_calls[k]
-                xin = call[0][1]
+                call = ex.last_calls.get(k)
+                if call is None:          # second half of a fused head pair
+                    continue
                 ms = time_call(call, flush)
                 total += ms
+                if call[0] == 'head':
+                    xin = call[1][0]
+                    print(f'  {name[:3]}{k}+{k + 1} fused head {st.c_in}->{st.c_in}->{call[1][5]} '
+                          f'@{xin.h}x{xin.w} {ms * 1e3:9.1f} us')
+                    continue
+                xin = call[0][1]
                 flops = 2.0 * 9 * st.c_in * st.c_out * xin.n * xin.h * xin.w
                 if st.kind == C.CONV_S2:
                     flops /= 4
