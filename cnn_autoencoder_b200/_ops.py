@@ -20,6 +20,9 @@ def _require_cuda(t, name):
         raise C.CaeError(f'{name} must be a CUDA tensor: the hot path has no CPU fallback')
 
 
+COL_PAD = 3     # CAE_COL_PAD of include/cae_b200.h: unused units left / right of the halo
+
+
 def planes_for(c):
     """8-channel planes holding ``c`` channels padded to a multiple of 16 (MMA K step)."""
     return ((c + 15) // 16) * 2
@@ -50,12 +53,12 @@ def alloc_act(fmt, n, c, h, w, halo=C.HALO_KEEP, device='cuda', planes=None):
     convolutions, so it is cleared once here and never written with halo KEEP)."""
     if fmt == C.FMT_F16_PLANAR:
         p = planes or planes_for(c)
-        t = torch.zeros((n, p, h + 2, w + 2, 8), dtype=torch.float16, device=device)
+        t = torch.zeros((n, p, h + 2, w + 2 + 2 * COL_PAD, 8), dtype=torch.float16, device=device)
     elif fmt == C.FMT_F16_SPLIT:
         if h % 2 or w % 2:
             raise C.CaeError(f'split layout needs even spatial size, got {h}x{w}')
         p = planes or planes_for(c)
-        t = torch.zeros((n, 4, p, (h + 2) // 2, (w + 2) // 2, 8), dtype=torch.float16,
+        t = torch.zeros((n, 4, p, (h + 2) // 2, (w + 2 + 2 * COL_PAD) // 2, 8), dtype=torch.float16,
                         device=device)
     elif fmt == C.FMT_F32_NCHW:
         t = torch.empty((n, c, h, w), dtype=torch.float32, device=device)

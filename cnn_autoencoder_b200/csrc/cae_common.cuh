@@ -33,7 +33,11 @@ void cae_count_launch(int n = 1);
   } while (0)
 
 // ------------------------------------------------------- internal layouts
-// PLANAR: [N][P][H+2][W+2][8] half.  SPLIT: [N][4][P][(H+2)/2][(W+2)/2][8] half.
+// PLANAR: [N][P][H+2][W+8][8] half.  SPLIT: [N][4][P][(H+2)/2][(W+8)/2][8] half.
+// Rows carry CAE_COL_PAD unused units on each side of the 1-pixel halo: pixel x = 0 starts on a
+// 32-byte sector, so a warp's run of consecutive pixels is written as whole sectors (a 16-byte
+// shift costs ~35 % of the store bandwidth, tools/micro/storebench.cu).
+__host__ __device__ inline int cae_row_units(int W) { return W + 2 + 2 * CAE_COL_PAD; }
 struct ActView {
   void *ptr;
   int fmt, planes, halo;
@@ -41,17 +45,17 @@ struct ActView {
 };
 
 __host__ __device__ inline size_t cae_act_bytes(int fmt, int n, int planes, int H, int W) {
-  return (size_t)n * planes * (H + 2) * (W + 2) * 16;  // same for PLANAR and SPLIT
+  return (size_t)n * planes * (H + 2) * cae_row_units(W) * 16;  // same for PLANAR and SPLIT
 }
 
 // Element offset (in 16-byte units) of padded pixel (Y,X), plane p, image n.
 __device__ __forceinline__ size_t act_unit_offset(const ActView &v, int n, int p, int Y, int X) {
   if (v.fmt == CAE_FMT_F16_PLANAR) {
-    return (((size_t)n * v.planes + p) * (v.H + 2) + Y) * (v.W + 2) + X;
+    return (((size_t)n * v.planes + p) * (v.H + 2) + Y) * cae_row_units(v.W) + X + CAE_COL_PAD;
   } else {
-    const int Hh = (v.H + 2) >> 1, Wh = (v.W + 2) >> 1;
-    const int par = ((Y & 1) << 1) | (X & 1);
-    return ((((size_t)n * 4 + par) * v.planes + p) * Hh + (Y >> 1)) * Wh + (X >> 1);
+    const int Hh = (v.H + 2) >> 1, Wh = cae_row_units(v.W) >> 1, Xc = X + CAE_COL_PAD;
+    const int par = ((Y & 1) << 1) | (Xc & 1);
+    return ((((size_t)n * 4 + par) * v.planes + p) * Hh + (Y >> 1)) * Wh + (Xc >> 1);
   }
 }
 

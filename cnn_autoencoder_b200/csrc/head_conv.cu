@@ -27,10 +27,10 @@ constexpr int WPITCH = 72, SPITCH = SC + 1;       // window rows: 16-byte aligne
 constexpr int kLut = 260;                        // x/255 for a byte; entry 256 = 0 (zero padding)
 constexpr int PXT = 4;                           // stem pixels per thread
 constexpr int SG = (SC + PXT - 1) / PXT;         // pixel groups per patch row
-constexpr int kStemWarps = 11, kStemThreads = 32 * kStemWarps, kEpiWarps = 4;
-constexpr int kHeadThreads = kStemThreads + 32 + 32 * kEpiWarps;   // 11 + 1 (MMA) + 4 = 512
+constexpr int kStemWarps = 11, kStemThreads = 32 * kStemWarps, kEpiWarps = 8;
+constexpr int kHeadThreads = kStemThreads + 32 + 32 * kEpiWarps;   // 11 + 1 (MMA) + 8 = 640
 static_assert(SR * SG <= kStemThreads && 2 * 128 <= kStemThreads, "stem group too small");
-static_assert(kHeadThreads == 512 && (kStemWarps + 1) % 4 == 0, "epilogue warps must start at a TMEM quadrant 0");
+static_assert((kStemWarps + 1) % 4 == 0, "epilogue warps must start at a TMEM quadrant 0");
 
 struct HeadParams {
   int n, h_in, w_in, h_out, w_out, c_out, N;
@@ -344,11 +344,13 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
   } else {
     // ============================================================ epilogue
     const int q = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int m_first = kEpiWarps == 8 ? (warp - kStemWarps - 1) >> 2 : 0;   // 8 warps: one M tile each
+    const int m_step = kEpiWarps == 8 ? 2 : 1;
     const int tx = lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const __half2 post2 = __float2half2_rn(p.s2);
     uint4 *obase = reinterpret_cast<uint4 *>(p.out.ptr);
-    const int PW = p.out.W + 2, PH = p.out.H + 2;
+    const int PW = cae_row_units(p.out.W), PH = p.out.H + 2;
     const size_t plane_stride = (size_t)PH * PW;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
@@ -359,7 +361,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
       mbar_wait_backoff(&acc_full[buf], (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int m = 0; m < 2; ++m) {
+      for (int m = m_first; m < 2; m += m_step) {
         const int oy = tyi * TH + m * 4 + q;
         const bool valid = oy < p.h_out && ox < p.w_out;
         // reflect halo of the consumer: a border pixel is stored again in the halo row, the
@@ -376,7 +378,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
         const int Yh = y2 >= 0 ? y2 : y3, Xh = x2 >= 0 ? x2 : x3;
         const uint32_t t0 = lane_base + (uint32_t)((buf * 2 + m) * p.N);
         uint4 *px = obase + (size_t)n * p.out.planes * plane_stride + (size_t)(oy + 1) * PW + ox + 1 +
-                    ((p.debug >> 2) & 1);
+                    CAE_COL_PAD;
         const ptrdiff_t d_x = Xh - (ox + 1), d_y = (ptrdiff_t)(Yh - (oy + 1)) * PW;
         for (int c0 = 0; c0 < p.N; c0 += 32, px += 4 * plane_stride) {
           uint32_t r0[16], r1[16];

@@ -101,7 +101,10 @@ int build_taps(int kind, bool merged, TapDef *t) {
   } else if (kind == CAE_CONV_S2) {
     for (int kh = 0; kh < 3; ++kh)
       for (int kw = 0; kw < 3; ++kw)
-        t[n++] = {((kh & 1) << 1) | (kw & 1), kh >> 1, kw >> 1, 0, kh, kw};
+        // padded column X = 2 ox + kw is physical column X + CAE_COL_PAD (odd shift): parity
+        // (kw + 1) & 1 at half index ox + ((kw + 3) >> 1); the box origin is ox + 1 (org_x)
+        t[n++] = {((kh & 1) << 1) | ((kw + CAE_COL_PAD) & 1), kh >> 1,
+                  ((kw + CAE_COL_PAD) >> 1) - 1, 0, kh, kw};
   } else if (kind == CAE_CONVT_S1) {
     // conv_transpose(k3,s1,p1) == correlation with the flipped kernel, zero halo
     for (int dy = 0; dy < 3; ++dy)
@@ -204,10 +207,10 @@ __device__ __forceinline__ float act_slope(int act) {
 // image strides precomputed on the host (is = planes * ps, times 4 parities for SPLIT).
 __device__ __forceinline__ uint32_t pixel_unit(int fmt, uint32_t pitch, uint32_t ps, uint32_t is,
                                                int planes, int n, int Y, int X) {
-  if (fmt == CAE_FMT_F16_PLANAR) return (uint32_t)n * is + (uint32_t)Y * pitch + (uint32_t)X;
-  const uint32_t par = (uint32_t)(((Y & 1) << 1) | (X & 1));
-  return (uint32_t)n * is + par * (uint32_t)planes * ps + (uint32_t)(Y >> 1) * pitch +
-         (uint32_t)(X >> 1);
+  const uint32_t Xc = (uint32_t)(X + CAE_COL_PAD);
+  if (fmt == CAE_FMT_F16_PLANAR) return (uint32_t)n * is + (uint32_t)Y * pitch + Xc;
+  const uint32_t par = (uint32_t)(((Y & 1) << 1) | (Xc & 1));
+  return (uint32_t)n * is + par * (uint32_t)planes * ps + (uint32_t)(Y >> 1) * pitch + (Xc >> 1);
 }
 
 // Mirrored halo copies of two consecutive planes of a border pixel (padding_mode='reflect').
@@ -818,17 +821,20 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
     p.PH = 18;
     p.PW = 8 * mt + 2;
     p.n_par = 1;
-    p.org_y = p.org_x = 0;
+    p.org_y = 0;
+    p.org_x = CAE_COL_PAD;
   } else if (kind == CAE_CONV_S2) {
     p.PH = 17;
     p.PW = 8 * mt + 1;
     p.n_par = 4;
-    p.org_y = p.org_x = 0;
+    p.org_y = 0;
+    p.org_x = 1;             // half index of physical column 2 ox + CAE_COL_PAD, rounded down
   } else {
     p.PH = 17;
     p.PW = 8 * mt + 1;
     p.n_par = 1;
-    p.org_y = p.org_x = 1;
+    p.org_y = 1;
+    p.org_x = 1 + CAE_COL_PAD;
   }
   const int kplanes = p.ck / 8;
   p.a_box_bytes = kplanes * p.PH * p.PW * 16;
@@ -963,18 +969,18 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   auto strides = [](int fmt, int planes, int H, int W, uint32_t &pitch, uint32_t &ps,
                     uint32_t &is) {
     if (fmt == CAE_FMT_F16_SPLIT) {
-      pitch = (uint32_t)((W + 2) / 2);
+      pitch = (uint32_t)(cae_row_units(W) / 2);
       ps = pitch * (uint32_t)((H + 2) / 2);
       is = 4u * (uint32_t)planes * ps;
     } else {
-      pitch = (uint32_t)(W + 2);
+      pitch = (uint32_t)cae_row_units(W);
       ps = pitch * (uint32_t)(H + 2);
       is = (uint32_t)planes * ps;
     }
   };
   if (epi == EPI_ACT) {
     CAE_CHECK(!d->aux_out, 2, "cae_conv_igemm: aux_out is only available on the final image layer");
-    CAE_CHECK((double)d->n * d->out.planes * (p.out_h + 2) * (p.out_w + 2) < 2147483648.0, 2,
+    CAE_CHECK((double)d->n * d->out.planes * (p.out_h + 2) * cae_row_units(p.out_w) < 2147483648.0, 2,
               "cae_conv_igemm: output tensor too large for 32-bit unit offsets; split the batch");
     strides(p.out.fmt, p.out.planes, p.out_h, p.out_w, p.out_pitch, p.out_ps, p.out_is);
   }
@@ -995,7 +1001,7 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   EncodeTiledFn encode = get_encode_fn();
   CAE_CHECK(encode, 3, "cae_conv_igemm: cuTensorMapEncodeTiled unavailable");
   CUtensorMap tm;
-  const int Hp = d->h_in + 2, Wp = d->w_in + 2;
+  const int Hp = d->h_in + 2, Wp = cae_row_units(d->w_in);
   cuuint64_t gdim[4], gstr[3];
   if (kind == CAE_CONV_S2) {
     const int Hh = Hp / 2, Wh = Wp / 2;

@@ -35,11 +35,16 @@ enum {
   CAE_FMT_U8_HWC = 1,     /* N x H x W x C uint8. As input: value/255.0f (R:545, compress.py:55);
                              as output: (uint8)clip(v*255,0,255), truncation (R:577-578).      */
   CAE_FMT_F32_NCHW = 2,   /* torch-contiguous fp32                                             */
-  CAE_FMT_F16_PLANAR = 3, /* internal: [N][C/8][H+2][W+2][8] half, 1-pixel halo                 */
-  CAE_FMT_F16_SPLIT = 4   /* internal: [N][4][C/8][(H+2)/2][(W+2)/2][8] half; padded pixel
-                             (Y,X) lives in parity plane (Y&1)*2+(X&1) at (Y>>1,X>>1).
+  CAE_FMT_F16_PLANAR = 3, /* internal: [N][C/8][H+2][W+8][8] half, 1-pixel halo.  Padded pixel
+                             (Y,X) = (y+1,x+1) is row Y, column X+3 (CAE_COL_PAD): pixel x=0
+                             sits at column 4, so 8-channel units of a pixel run start on a
+                             32-byte DRAM sector and every row is a whole number of sectors. */
+  CAE_FMT_F16_SPLIT = 4   /* internal: [N][4][C/8][(H+2)/2][(W+8)/2][8] half; padded pixel
+                             (Y,X) lives in parity plane (Y&1)*2+((X+3)&1) at (Y>>1,(X+3)>>1).
                              Feeds the stride-2 convolutions. H and W must be even.            */
 };
+
+#define CAE_COL_PAD 3     /* unused 16-byte units before the left halo column of a row */
 
 enum { CAE_HALO_KEEP = 0,    /* leave the halo as allocated (zeros): zero padding (ConvTranspose2d) */
        CAE_HALO_REFLECT = 1  /* also write mirrored copies: padding_mode='reflect' (R:70,85)        */ };

@@ -40,13 +40,13 @@ def padded_view(act):
     t = act.t.float()
     if act.fmt == C.FMT_F16_PLANAR:
         n, p, hp, wp, _ = t.shape
-        return t.permute(0, 1, 4, 2, 3).reshape(n, p * 8, hp, wp)
+        return t.permute(0, 1, 4, 2, 3).reshape(n, p * 8, hp, wp)[..., O.COL_PAD:wp - O.COL_PAD]
     n, _, p, hh, wh, _ = t.shape
     full = torch.zeros(n, p * 8, hh * 2, wh * 2, device=t.device)
     for par in range(4):
         py, px = par >> 1, par & 1
         full[:, :, py::2, px::2] = t[:, par].permute(0, 1, 4, 2, 3).reshape(n, p * 8, hh, wh)
-    return full
+    return full[..., O.COL_PAD:wh * 2 - O.COL_PAD]
 
 
 def fp16_vals(shape, gen, scale=1.0):
