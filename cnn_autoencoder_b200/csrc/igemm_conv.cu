@@ -85,6 +85,7 @@ struct IgParams {
   int out_h, out_w;
   // 16-byte-unit strides of out / skip (32-bit: buffers are < 2^31 units)
   uint32_t out_pitch, out_ps, out_is, skip_pitch, skip_ps, skip_is;
+  int pair_store;   // up == 2, planar output without reflect halo: 32-byte stores of pixel pairs
 };
 
 struct TapDef {
@@ -233,10 +234,9 @@ __device__ __noinline__ void store_halo2(const IgParams &p, int n, int plane, in
 // activations as packed fp16 max(v, v*slope) -- half the instructions of the fp32 form; the
 // result only differs by fp16 rounding of already-rounded negatives.
 template <bool SKIP>
-__device__ __forceinline__ void emit16_fast(const IgParams &p, const uint32_t (&r)[16], int c0,
-                                            int n, int oy, int ox, float pre_s, __half2 pre2,
-                                            __half2 post2, const uint4 *skip2) {
-  __half2 h[8];
+__device__ __forceinline__ void fast_half16(const IgParams &p, const uint32_t (&r)[16], int c0,
+                                            float pre_s, __half2 pre2, __half2 post2,
+                                            const uint4 *skip2, __half2 (&h)[8]) {
   if (SKIP) {
     // residual layers: bias, pre-activation and the skip add stay in fp32 (the residual path is
     // the precision-critical one), only the post-activation is packed
@@ -283,6 +283,32 @@ __device__ __forceinline__ void emit16_fast(const IgParams &p, const uint32_t (&
 #pragma unroll
     for (int i = 0; i < 8; ++i) h[i] = __hmax2(h[i], __hmul2(h[i], post2));
   }
+}
+
+__device__ __forceinline__ uint32_t h2u(const __half2 &h) {
+  return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+// Transposed stride-2 layers: one thread owns the two horizontally adjacent output pixels
+// 2x, 2x+1 of a plane = 32 contiguous, sector-aligned bytes -> one 256-bit store per plane
+// (two 16-byte stores from separate instructions would each write half a sector).
+__device__ __forceinline__ void store16_pair(const IgParams &p, const __half2 (&a)[8],
+                                             const __half2 (&b)[8], int c0, int n, int oy, int ox0) {
+  const uint32_t off = pixel_unit(p.out.fmt, p.out_pitch, p.out_ps, p.out_is, p.out.planes, n,
+                                  oy + 1, ox0 + 1) + (uint32_t)(c0 >> 3) * p.out_ps;
+  uint4 *dst = reinterpret_cast<uint4 *>(p.out.ptr) + off;
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(h2u(a[0])),
+               "r"(h2u(a[1])), "r"(h2u(a[2])), "r"(h2u(a[3])), "r"(h2u(b[0])), "r"(h2u(b[1])),
+               "r"(h2u(b[2])), "r"(h2u(b[3]))
+               : "memory");
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + p.out_ps),
+               "r"(h2u(a[4])), "r"(h2u(a[5])), "r"(h2u(a[6])), "r"(h2u(a[7])), "r"(h2u(b[4])),
+               "r"(h2u(b[5])), "r"(h2u(b[6])), "r"(h2u(b[7]))
+               : "memory");
+}
+
+__device__ __forceinline__ void store16(const IgParams &p, __half2 (&h)[8], int c0, int n, int oy,
+                                        int ox) {
   uint4 lo, hi;
   lo.x = *reinterpret_cast<uint32_t *>(&h[0]);
   lo.y = *reinterpret_cast<uint32_t *>(&h[1]);
@@ -305,6 +331,15 @@ __device__ __forceinline__ void emit16_fast(const IgParams &p, const uint32_t (&
   if (p.out.halo == CAE_HALO_REFLECT &&
       (oy == 1 || oy == p.out.H - 2 || ox == 1 || ox == p.out.W - 2))
     store_halo2(p, n, c0 >> 3, oy, ox, lo, hi);
+}
+
+template <bool SKIP>
+__device__ __forceinline__ void emit16_fast(const IgParams &p, const uint32_t (&r)[16], int c0,
+                                            int n, int oy, int ox, float pre_s, __half2 pre2,
+                                            __half2 post2, const uint4 *skip2) {
+  __half2 h[8];
+  fast_half16<SKIP>(p, r, c0, pre_s, pre2, post2, skip2, h);
+  store16(p, h, c0, n, oy, ox);
 }
 
 // Final image layer (merged transposed conv): accumulator columns j = phase * CO + c with
@@ -412,6 +447,13 @@ __device__ __forceinline__ void epilogue_job(const IgParams &p, uint32_t tmem_la
 
   if (FAST) {
     const __half2 pre2 = __float2half2_rn(pre_s), post2 = __float2half2_rn(post_s);
+    if (FAST == 1 && p.pair_store) {
+      __half2 ha[8], hb[8];
+      fast_half16<false>(p, r0, c_first, pre_s, pre2, post2, sk, ha);
+      fast_half16<false>(p, r1, c_second, pre_s, pre2, post2, sk, hb);
+      store16_pair(p, ha, hb, c_first, n, oy, ox0);
+      return;
+    }
     emit16_fast<FAST == 2>(p, r0, c_first, n, oy, ox0, pre_s, pre2, post2, sk);
     if (second)
       emit16_fast<FAST == 2>(p, r1, c_second, n, oy, ox0 + (p.up == 2 ? 1 : 0), pre_s, pre2, post2,
@@ -1026,6 +1068,8 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
 
   p.debug = 0;
   if (const char *e = getenv("CAE_IGEMM_DEBUG")) p.debug = atoi(e);
+  p.pair_store = epi == EPI_ACT && p.up == 2 && p.out.fmt == CAE_FMT_F16_PLANAR &&
+                 p.out.halo != CAE_HALO_REFLECT && !(p.debug & 16) && !getenv("CAE_IGEMM_NO_PAIR_STORE");
   p.epi_warps = 8;
   if (const char *e = getenv("CAE_IGEMM_EPI_WARPS")) {
     const int v = atoi(e);
