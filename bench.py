@@ -151,6 +151,8 @@ def main():
     ap.add_argument('--arch', default=ARCH_NAME)
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true',
+                    help='issue every kernel from Python instead of replaying a CUDA graph')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -197,26 +199,37 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput ----------------
+    # One step = one replay of the pipeline captured in a CUDA graph (the same kernels, in the
+    # same order, as the eager call; --no-graph issues them one by one from Python).
+    if args.no_graph:
+        run_dev = lambda: pipe(x_dev)
+        launches_per_step = None
+    else:
+        g_dev = pipe.graphed(x_dev, warmup=warmup)
+        run_dev = g_dev.replay
+        launches_per_step = g_dev.launches
     for _ in range(warmup):
-        out = pipe(x_dev)
+        out = run_dev()
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
     with ClockSampler(local) as clk:
         time.sleep(0.5)                     # let nvidia-smi start sampling (untimed)
         for _ in range(3):
-            out = pipe(x_dev)
+            out = run_dev()
         barrier()
         launches0 = _cabi.launch_count()
         t_begin = time.time()
         for s, e in ev:
             flush_l2()                      # evict L2 between timed iterations (untimed)
             s.record()
-            out = pipe(x_dev)
+            out = run_dev()
             e.record()
         barrier()
         clk.window(t_begin, time.time())
     launches = _cabi.launch_count() - launches0
+    if launches_per_step is not None:
+        launches = launches_per_step * args.steps     # graph replays bypass the ABI's counter
     step_ms = [s.elapsed_time(e) for s, e in ev]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -239,6 +252,8 @@ def main():
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]
     ev_done = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
+    g_e2e = None if args.no_graph else [pipe.graphed(x_stage[k]) for k in range(2)]
 
     def e2e_run(n_steps):
         for i in range(n_steps):
@@ -249,15 +264,22 @@ def main():
                 x_stage[k].copy_(x_pin, non_blocking=True)
                 ev_in[k].record(s_in)
             main.wait_event(ev_in[k])
-            o = pipe(x_stage[k])
+            if g_e2e is None:
+                o = pipe(x_stage[k])
+            else:
+                if i >= 2:
+                    main.wait_event(ev_out[k])           # step i-2's results have left the device
+                o = g_e2e[k].replay()
             ev_free[k].record(main)
             ev_done[k].record(main)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_done[k])
-                o['x_r_u8'].record_stream(s_out)
-                o['bpp'].record_stream(s_out)
+                if g_e2e is None:
+                    o['x_r_u8'].record_stream(s_out)
+                    o['bpp'].record_stream(s_out)
                 out_stage[k].copy_(o['x_r_u8'], non_blocking=True)
                 bpp_stage[k].copy_(o['bpp'], non_blocking=True)
+                ev_out[k].record(s_out)
         s_out.synchronize()
         s_in.synchronize()
 
@@ -354,7 +376,9 @@ def main():
                                f'{B}x3x{SIZE}x{SIZE} uint8 patches per GPU, '
                                'encode+quantize+rate+decode',
                    'l2': 'flushed between timed iterations (256 MiB write, then read back)',
-                   'accumulate': 'f32', 'est_bpp': round(bpp, 4)},
+                   'accumulate': 'f32', 'est_bpp': round(bpp, 4),
+                   'launch': 'eager, one ABI call per kernel' if args.no_graph
+                   else 'one CUDA graph replay per step'},
         'clocks': clk.summary(),
         'e2e': {'value': round(e2e_value, 2), 'unit': 'MP/s',
                 'h2d_bytes_per_step': int(x_pin.numel()),

@@ -134,7 +134,13 @@ inline int mma_n(int kind, int c_out) {
 }
 
 inline int auto_ck(int kind, int c_in_p) {
-  if (kind == CAE_CONV_S2) return c_in_p % 32 == 0 ? 32 : 16;
+  if (kind == CAE_CONV_S2) {
+    if (const char *e = getenv("CAE_IGEMM_CK_S2")) {      // experiment knob (pack and launch agree)
+      const int v = atoi(e);
+      if ((v == 16 || v == 32) && c_in_p % v == 0) return v;
+    }
+    return c_in_p % 32 == 0 ? 32 : 16;
+  }
   if (c_in_p % 64 == 0) return 64;
   if (c_in_p % 48 == 0) return 48;
   if (c_in_p % 32 == 0) return 32;
@@ -830,10 +836,14 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   p.n_chunks = c_in_p / p.ck;
   TapDef taps[kMaxTaps];
   p.n_taps = build_taps(kind, merged, taps);
-  // transposed stride-2 (not merged): two passes (output rows 2y, 2y+1) x two phase accumulators
-  // (measured: not faster than one pass with four accumulators -- these layers are bound by
-  //  their DRAM writes, not by the epilogue/MMA serialisation -- so it is opt-in)
-  p.n_pass = (kind == CAE_CONVT_S2 && !merged && getenv("CAE_IGEMM_TWO_PASS")) ? 2 : 1;
+  // transposed stride-2 (not merged): four phase accumulators of N columns.  When they do not
+  // fit TMEM twice, the tile is done in two passes (output rows 2y, then 2y+1) of two
+  // accumulators each, so that the epilogue of one pass overlaps the MMAs of the next
+  // (measured with the 256-bit pair stores: 128->128 @64x64 209 -> 199 us, 48->128 43 -> 37 us)
+  const bool convt2 = kind == CAE_CONVT_S2 && !merged;
+  p.n_pass = 1;
+  if (convt2 && (getenv("CAE_IGEMM_TWO_PASS") || (4 * p.N > 256 && !getenv("CAE_IGEMM_ONE_PASS"))))
+    p.n_pass = 2;
   p.n_acc = (kind == CAE_CONVT_S2 && !merged) ? (p.n_pass == 2 ? 2 : 4) : 1;
   p.up = (kind == CAE_CONVT_S2) ? 2 : 1;
 

@@ -8,6 +8,35 @@ entropy coder left out (it is host code; see ``compress.py``).
 """
 import torch
 
+from . import _cabi
+
+
+class GraphedPipeline:
+    """``CodecPipeline.__call__`` on one fixed input buffer, captured once into a CUDA graph
+    and replayed: a step is one graph launch instead of ~11 kernel launches issued from
+    Python, which is what keeps a host-fed tile loop GPU-bound.  ``x`` (the static input)
+    must be refilled in stream order before each ``replay()``; the returned dict holds the
+    static outputs of the capture (valid until the next replay)."""
+
+    def __init__(self, pipe, x_static, warmup=3):
+        self.x = x_static
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):           # executor buffers / packed weights: normal pool
+            for _ in range(warmup):
+                pipe(x_static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _cabi.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.out = pipe(x_static)
+        self.launches = _cabi.launch_count() - n0   # kernels of this library per replay
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
+
 
 class CodecPipeline:
     def __init__(self, model):
@@ -25,3 +54,7 @@ class CodecPipeline:
         _, _, x_r_u8 = self.model['decoder'](y_q, as_uint8='only')
         return dict(x_r_u8=x_r_u8, y=y, y_q=y_q, hist=hist, bits=bits,
                     bpp=bits / float(n * h * w))
+
+    def graphed(self, x_static, warmup=3):
+        """Capture this pipeline on the device buffer ``x_static`` (see GraphedPipeline)."""
+        return GraphedPipeline(self, x_static, warmup)

@@ -358,3 +358,27 @@ def test_device_entropy_coder_is_byte_identical_to_host_coder():
     assert len(s2) == 64
     assert s2[5] == O.OracleModel(chk).fact_ent.compress(y[5:6])[0]
     assert torch.equal(fe.decompress(s2, (8, 8)).cpu(), torch.round(y))
+
+
+def test_graphed_pipeline_matches_eager():
+    """The CUDA-graph replay of the pipeline (what bench.py times) returns exactly what the
+    eager call returns, also after the static input buffer is refilled."""
+    from oracle import cae_oracle as O
+    from cnn_autoencoder_b200.pipeline import CodecPipeline
+    chk = O.make_checkpoint(O.NAMED_ARCHS['A'], seed=7)
+    model = _model(chk)
+    pipe = CodecPipeline(model)
+    x0 = O.synth_natural(4, 3, 64, 96, seed=3).permute(0, 2, 3, 1).contiguous().cuda()
+    x1 = O.synth_natural(4, 3, 64, 96, seed=4).permute(0, 2, 3, 1).contiguous().cuda()
+    static = x0.clone()
+    g = pipe.graphed(static)
+    assert g.launches >= 8
+    for x in (x0, x1, x0):
+        static.copy_(x)
+        got = g.replay()
+        want = pipe(x)
+        torch.cuda.synchronize()
+        assert torch.equal(got['x_r_u8'], want['x_r_u8'])
+        assert torch.equal(got['y_q'], want['y_q'])
+        assert torch.equal(got['hist'], want['hist'])
+        assert got['bits'].item() == want['bits'].item()

@@ -46,6 +46,8 @@ def main():
     ap.add_argument('--debug-sweep', action='store_true')
     ap.add_argument('--skip-sweep', action='store_true')
     ap.add_argument('--head-sweep', action='store_true')
+    ap.add_argument('--env', action='append', default=[],
+                    help='KEY=VAL[,KEY=VAL] : one extra settings row per option')
     args = ap.parse_args()
     chk = O.make_checkpoint(O.NAMED_ARCHS[args.arch], seed=1234)
     model = M.autoencoder_from_state_dict(chk, gpu=True, train=False)
@@ -68,8 +70,12 @@ def main():
                     dict(CAE_IGEMM_NO_FAST_EPILOGUE='1')]
     if args.head_sweep:
         settings = [dict(), dict(CAE_HEAD_DEBUG='4'), dict(CAE_HEAD_DEBUG='6'), dict(CAE_HEAD_DEBUG='2')]
+    for spec in args.env:
+        settings.append(dict(kv.split('=', 1) for kv in spec.split(',')))
+    known = set(k for e in settings for k in e)
     for env in settings:
-        for k in ('CAE_IGEMM_EPI_WARPS', 'CAE_IGEMM_MT', 'CAE_IGEMM_NO_FAST_EPILOGUE', 'CAE_IGEMM_DEBUG', 'CAE_IGEMM_TPB', 'CAE_HEAD_DEBUG'):
+        for k in set(('CAE_IGEMM_EPI_WARPS', 'CAE_IGEMM_MT', 'CAE_IGEMM_NO_FAST_EPILOGUE', 'CAE_IGEMM_DEBUG',
+                      'CAE_IGEMM_TPB', 'CAE_HEAD_DEBUG')) | known:
             os.environ.pop(k, None)
         os.environ.update(env)
         print('== settings', env or 'default')
