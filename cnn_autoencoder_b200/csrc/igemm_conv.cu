@@ -133,7 +133,10 @@ inline int mma_n(int kind, int c_out) {
   return is_merged(kind, c_out) ? 16 : round_up(c_out, 16);
 }
 
-inline int auto_ck(int kind, int c_in_p) {
+inline int auto_ck(int kind, int c_in_p, bool merged = false) {
+  // final image layer (N = 16): the MMAs are tiny and the layer is bound by the barrier round
+  // trips per stage, so take the whole K = 128 in one stage
+  if (merged && c_in_p % 128 == 0 && !getenv("CAE_IGEMM_MERGED_CK64")) return 128;
   if (kind == CAE_CONV_S2) {
     if (const char *e = getenv("CAE_IGEMM_CK_S2")) {      // experiment knob (pack and launch agree)
       const int v = atoi(e);
@@ -774,7 +777,7 @@ int pow2_cols(int c) {
 // ------------------------------------------------------------------- C ABI
 extern "C" size_t cae_packed_weight_bytes(int kind, int c_in, int c_out, int ck) {
   const int c_in_p = round_up(c_in, 16);
-  if (ck <= 0) ck = auto_ck(kind, c_in_p);
+  if (ck <= 0) ck = auto_ck(kind, c_in_p, is_merged(kind, c_out));
   TapDef taps[kMaxTaps];
   const int n_taps = build_taps(kind, is_merged(kind, c_out), taps);
   return (size_t)(c_in_p / ck) * n_taps * mma_n(kind, c_out) * ck * sizeof(__half);
@@ -785,8 +788,8 @@ extern "C" int cae_pack_weights(int kind, int c_in, int c_out, int ck, const flo
   CAE_CHECK(kind >= CAE_CONV_S1 && kind <= CAE_CONVT_S2, 2, "cae_pack_weights: bad kind %d", kind);
   CAE_CHECK(w && packed, 2, "cae_pack_weights: null pointer");
   const int c_in_p = round_up(c_in, 16);
-  if (ck <= 0) ck = auto_ck(kind, c_in_p);
-  CAE_CHECK(ck % 16 == 0 && ck <= 64 && c_in_p % ck == 0, 2,
+  if (ck <= 0) ck = auto_ck(kind, c_in_p, is_merged(kind, c_out));
+  CAE_CHECK(ck % 16 == 0 && ck <= 128 && c_in_p % ck == 0, 2,
             "cae_pack_weights: ck=%d does not divide padded c_in=%d", ck, c_in_p);
   PackParams q;
   memset(&q, 0, sizeof(q));
@@ -830,8 +833,8 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   p.n_img = d->n;
   p.N = mma_n(kind, d->c_out);
   CAE_CHECK(p.N <= 256, 2, "cae_conv_igemm: c_out=%d too large", d->c_out);
-  p.ck = d->ck > 0 ? d->ck : auto_ck(kind, c_in_p);
-  CAE_CHECK(p.ck % 16 == 0 && p.ck <= 64 && c_in_p % p.ck == 0, 2, "cae_conv_igemm: bad ck=%d",
+  p.ck = d->ck > 0 ? d->ck : auto_ck(kind, c_in_p, merged);
+  CAE_CHECK(p.ck % 16 == 0 && p.ck <= 128 && c_in_p % p.ck == 0, 2, "cae_conv_igemm: bad ck=%d",
             p.ck);
   p.n_chunks = c_in_p / p.ck;
   TapDef taps[kMaxTaps];
@@ -973,12 +976,18 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
     else if (sa < 3 && (sa + 1) * p.a_stage_bytes + sb * p.b_stage_bytes <= budget) { ++sa; grew = true; }
     else if (sb < 4 && sa * p.a_stage_bytes + (sb + 1) * p.b_stage_bytes <= budget) { ++sb; grew = true; }
     else if (sa < 4 && (sa + 1) * p.a_stage_bytes + sb * p.b_stage_bytes <= budget) { ++sa; grew = true; }
+    else if (sa < kMaxSA && (sa + 1) * p.a_stage_bytes + sb * p.b_stage_bytes <= budget) { ++sa; grew = true; }
     else if (sb < kMaxSB && sa * p.a_stage_bytes + (sb + 1) * p.b_stage_bytes <= budget) { ++sb; grew = true; }
     if (!grew) break;
   }
   p.sa = sa;
   p.sb = sb;
   const int smem_bytes = sa * p.a_stage_bytes + sb * p.b_stage_bytes + 1024;
+  if (getenv("CAE_IGEMM_VERBOSE"))
+    fprintf(stderr, "cae_conv_igemm: kind %d %d->%d @%dx%d N=%d ck=%d mt=%d n_pass=%d n_acc=%d n_buf=%d "
+            "tpb=%d a_stage=%d x%d b_stage=%d x%d smem=%d tiles=%d\n", kind, d->c_in, d->c_out, d->h_in,
+            d->w_in, p.N, p.ck, p.mt, p.n_pass, p.n_acc, p.n_buf, p.tpb, p.a_stage_bytes, sa,
+            p.b_stage_bytes, sb, smem_bytes, p.n_tiles);
 
   p.tiles_x = (p.dom_w + 8 * mt - 1) / (8 * mt);
   const int tiles_y = (p.dom_h + 15) / 16;
