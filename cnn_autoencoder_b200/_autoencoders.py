@@ -279,9 +279,10 @@ class Analyzer(_Track):
     def _units(self):
         return [u for u in self.analysis_track if isinstance(u, _Unit)]
 
-    def forward(self, x):
+    def forward(self, x, quant=None):
         """x: fp32 N x C x H x W in [0,1] (or uint8 N x H x W x C, divided by 255 in the
-        first kernel) -> latent y, fp32 N x C_bn x H/2^L x W/2^L."""
+        first kernel) -> latent y, fp32 N x C_bn x H/2^L x W/2^L.  ``quant`` (eval only): an
+        ``EntropyBottleneck.quant_request()`` filled by the last layer's epilogue."""
         if self.training:
             if x.dtype == torch.uint8:
                 x = x.permute(0, 3, 1, 2).float() / 255.0
@@ -295,7 +296,7 @@ class Analyzer(_Track):
                 first = self._executor().steps[0]
                 fmt = C.FMT_F16_SPLIT if first.kind == C.CONV_S2 else C.FMT_F16_PLANAR
                 a = O.nchw_to_planar(a.t, fmt, C.HALO_REFLECT)
-            y, _, _ = self._executor().run(a, C.FMT_F32_NCHW)
+            y, _, _ = self._executor().run(a, C.FMT_F32_NCHW, quant=quant)
         return y.t
 
 
@@ -338,8 +339,9 @@ class Synthesizer(_Track):
             idx.append(k)
         return idx
 
-    def forward(self, x, as_uint8=False):
-        """y_q fp32 N x C_bn x h x w -> (x_r, fx_brg) exactly as R:442-455: x_r[0] is the
+    def forward(self, x, as_uint8=False, planar=None):
+        """y_q fp32 N x C_bn x h x w -> (x_r, fx_brg) exactly as R:442-455 (``planar``: the same
+        y_q already in the track's input layout, from the fused quantizer): x_r[0] is the
         full-resolution reconstruction, lower scales are None.  ``as_uint8`` (extension
         used by the codecs) additionally returns the N x H x W x C uint8 image produced
         by the last kernel's epilogue: ``(x_r, fx_brg, u8)``; ``as_uint8='only'`` skips the
@@ -356,8 +358,11 @@ class Synthesizer(_Track):
         if n_units == 0:
             return [x], [x]
         with self._lock, torch.no_grad():
-            a = O.nchw_to_planar(x, C.FMT_F16_PLANAR, C.HALO_KEEP) if x.shape[1] > 4 \
-                else O.wrap_nchw(x)
+            if planar is not None and x.shape[1] > 4:
+                a = planar
+            else:
+                a = O.nchw_to_planar(x, C.FMT_F16_PLANAR, C.HALO_KEEP) if x.shape[1] > 4 \
+                    else O.wrap_nchw(x)
             outs = self._unit_output_indices()
             keep = outs[:-1] if self.bridges else ()
             final = C.FMT_U8_HWC if as_uint8 else C.FMT_F32_NCHW

@@ -15,6 +15,7 @@ CSRC = os.path.join(_HERE, 'csrc')
 FMT_NONE, FMT_U8_HWC, FMT_F32_NCHW, FMT_F16_PLANAR, FMT_F16_SPLIT = 0, 1, 2, 3, 4
 HALO_KEEP, HALO_REFLECT = 0, 1
 ACT_NONE, ACT_LEAKY_RELU, ACT_RELU = 0, 1, 2
+ABI_VERSION = 2
 CONV_S1, CONV_S2, CONVT_S1, CONVT_S2 = 0, 1, 2, 3
 PAD_ZERO, PAD_REFLECT = 0, 1
 
@@ -38,7 +39,8 @@ class ConvDesc(ctypes.Structure):
                 ('weights', ctypes.c_void_p), ('bias', ctypes.c_void_p),
                 ('pre_act', ctypes.c_int32), ('post_act', ctypes.c_int32),
                 ('pad_mode', ctypes.c_int32), ('ck', ctypes.c_int32), ('mt', ctypes.c_int32),
-                ('grid', ctypes.c_int32), ('aux_out', ctypes.c_void_p)]
+                ('grid', ctypes.c_int32), ('aux_out', ctypes.c_void_p),
+                ('quant', ctypes.c_void_p)]
 
 
 class HeadDesc(ctypes.Structure):
@@ -57,6 +59,12 @@ class EbTables(ctypes.Structure):
                 ('mlp', ctypes.c_void_p), ('n_layers', ctypes.c_int32),
                 ('mlp_stride', ctypes.c_int32), ('dims', ctypes.c_int32 * 10),
                 ('hist_min', ctypes.c_int32), ('hist_bins', ctypes.c_int32)]
+
+
+class QuantFuse(ctypes.Structure):
+    _fields_ = [('tables', EbTables), ('y_q', ctypes.c_void_p), ('symbols', ctypes.c_void_p),
+                ('y_q_planar', Tensor), ('hist', ctypes.c_void_p), ('rate_bits', ctypes.c_void_p),
+                ('status', ctypes.c_void_p)]
 
 
 class CaeError(RuntimeError):
@@ -117,7 +125,7 @@ def lib():
         if name not in ('cae_abi_version', 'cae_last_error', 'cae_launch_count',
                         'cae_packed_weight_bytes'):
             getattr(L, name).restype = ctypes.c_int
-    if L.cae_abi_version() != 1:
+    if L.cae_abi_version() != ABI_VERSION:
         raise CaeError('libcae_b200.so ABI version mismatch')
     _lib = L
     return L

@@ -200,10 +200,12 @@ class TrackExecutor:
             self._buffers[key] = buf
         return buf[1]
 
-    def run(self, x, final_fmt, keep=(), aux_last=False):
+    def run(self, x, final_fmt, keep=(), aux_last=False, quant=None):
         """x: Act.  final_fmt: format of the last step's output (F32_NCHW, U8_HWC or
         planar).  keep: indices of intermediate tensors to return as well.
         aux_last: also return the last output as fp32 NCHW (alongside U8_HWC).
+        quant: a ``_entropy.QuantRequest``; when the last step is a tensor-core layer writing
+        the fp32 latent, the quantizer runs in its epilogue and ``quant.done`` is set.
         Returns (last Act or None, {index: Act}, aux tensor or None)."""
         tensors = {0: x}
         cur = x
@@ -279,10 +281,19 @@ class TrackExecutor:
                 if st.post_act is not None:
                     raise NotImplementedError('activation after a GDN residual add')
             else:
+                q = None
+                if (quant is not None and last and igemm and skip is None and out is not None
+                        and out.fmt == C.FMT_F32_NCHW and convert_after is None):
+                    q = quant.prepare(cur.n, st.c_out, ho, wo, cur.t.device)
                 call = ((st.kind, cur, wdev, st.c_out, out),
                         dict(igemm=igemm, bias=bias, skip=skip, pre_act=act_code(st.pre_act),
-                             post_act=act_code(st.post_act), pad_mode=st.pad_mode, aux=aux_t))
+                             post_act=act_code(st.post_act), pad_mode=st.pad_mode, aux=aux_t,
+                             quant=q))
                 O.conv(*call[0], **call[1])
+                if q is not None:
+                    quant.done = True
+                    # the recorded call must stay replayable after the request's tensors are gone
+                    call = (call[0], dict(call[1], quant=None))
             self.last_calls[k] = call
             if out is None:
                 out = O.Act(aux_t, C.FMT_F32_NCHW, cur.n, st.c_out, ho, wo)

@@ -43,6 +43,46 @@ class _LowerBound(torch.autograd.Function):
         return keep.type(grad.dtype) * grad, None
 
 
+class QuantRequest:
+    """Outputs of the quantizer when it runs inside the epilogue of the last analysis
+    convolution (``cae_conv_desc.quant``): ``y_q`` (fp32 NCHW), ``hist`` (C x bins),
+    ``rate`` (total bits, float64[1]), optionally ``sym`` (int32 NCHW) and ``planar`` (y_q in
+    the synthesis track's input layout).  ``done`` stays False when the track could not fuse
+    (tiny nets on the direct kernel, GDN / residual last layers): the caller then runs
+    ``EntropyBottleneck.quantize_rate`` on the latent as before."""
+
+    def __init__(self, eb, want_sym=False, want_planar=True):
+        self.eb, self.want_sym, self.want_planar = eb, want_sym, want_planar
+        self.done = False
+        self.y_q = self.sym = self.hist = self.rate = self.planar = self.status = None
+        self._struct = None
+
+    def prepare(self, n, c, h, w, device):
+        from . import _ops as O
+        eb = self.eb
+        if c != eb.channels:
+            raise ValueError(f'expected {eb.channels} channels, got {c}')
+        tb = eb._device_tables()
+        q = C.QuantFuse()
+        q.tables = eb._abi_tables(tb)
+        self.y_q = torch.empty((n, c, h, w), dtype=torch.float32, device=device)
+        self.hist = torch.zeros((c, tb['lut_len']), dtype=torch.int32, device=device)
+        self.rate = torch.zeros(1, dtype=torch.float64, device=device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        q.y_q, q.hist = self.y_q.data_ptr(), self.hist.data_ptr()
+        q.rate_bits, q.status = self.rate.data_ptr(), self.status.data_ptr()
+        if self.want_sym:
+            self.sym = torch.empty((n, c, h, w), dtype=torch.int32, device=device)
+            q.symbols = self.sym.data_ptr()
+        if self.want_planar:
+            self.planar = O.alloc_act(C.FMT_F16_PLANAR, n, c, h, w, C.HALO_KEEP, device=device)
+            q.y_q_planar = self.planar.desc()
+        else:
+            q.y_q_planar = C.Tensor(None, C.FMT_NONE, 0, 0, 0)
+        self._struct = q                      # keeps the table pointers alive until the launch
+        return q
+
+
 class EntropyBottleneck(nn.Module):
     def __init__(self, channels, *args, tail_mass=1e-9, init_scale=10, filters=(3, 3, 3, 3),
                  likelihood_bound=1e-9, entropy_coder_precision=16, **kwargs):
@@ -261,6 +301,11 @@ class EntropyBottleneck(nn.Module):
             return self._forward_torch(x, training=training)
         y_q, p_y, _, _, _ = self._quantize_cuda(x)
         return y_q, p_y
+
+    def quant_request(self, want_sym=False, want_planar=True):
+        """Request object for the quantizer fused into the latent layer's epilogue
+        (``Analyzer.forward(x, quant=req)``); see ``QuantRequest``."""
+        return QuantRequest(self, want_sym, want_planar)
 
     def quantize_rate(self, x):
         """(y_q, C x bins histogram, total bits) in one pass: what the encode+rate+decode

@@ -110,8 +110,9 @@ def pack_weights(kind, weight, scale=None, ck=0):
 
 
 def conv(kind, x, weights, c_out, out, *, igemm, bias=None, skip=None, pre_act=C.ACT_NONE,
-         post_act=C.ACT_NONE, pad_mode=C.PAD_REFLECT, aux=None, ck=0, mt=0, grid=0):
-    """out = post_act(pre_act(conv(x) + bias) + skip) through the C ABI."""
+         post_act=C.ACT_NONE, pad_mode=C.PAD_REFLECT, aux=None, ck=0, mt=0, grid=0, quant=None):
+    """out = post_act(pre_act(conv(x) + bias) + skip) through the C ABI.  ``quant``: a
+    ``_cabi.QuantFuse`` for the latent layer (igemm, fp32 NCHW output)."""
     d = C.ConvDesc()
     d.kind = kind
     d.n, d.h_in, d.w_in, d.c_in, d.c_out = x.n, x.h, x.w, x.c, c_out
@@ -123,6 +124,7 @@ def conv(kind, x, weights, c_out, out, *, igemm, bias=None, skip=None, pre_act=C
     d.pre_act, d.post_act, d.pad_mode = pre_act, post_act, pad_mode
     d.ck, d.mt, d.grid = ck, mt, grid
     d.aux_out = aux.data_ptr() if aux is not None else None
+    d.quant = ctypes.addressof(quant) if quant is not None else None
     L = C.lib()
     fn = L.cae_conv_igemm if igemm else L.cae_conv_direct
     C.check(fn(ctypes.byref(d), _stream_ptr()))

@@ -10,10 +10,9 @@
 // builds that table once with the model's own fp32 ops and the kernel looks it
 // up; symbols outside the table fall back to evaluating the density MLP here.
 #include "cae_common.cuh"
+#include "eb_device.cuh"
 
 namespace {
-
-constexpr int kMaxDim = 8;
 
 struct EbParams {
   const float *y;
@@ -24,42 +23,6 @@ struct EbParams {
   double *rate_bits;
   int32_t *status;
 };
-
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
-
-// logits_cumulative for one scalar input of channel c (A.1)
-__device__ float eb_logits(const cae_eb_tables &t, const float *mlp, float x) {
-  float v[kMaxDim], u[kMaxDim];
-  v[0] = x;
-  const float *q = mlp;
-  for (int i = 0; i < t.n_layers; ++i) {
-    const int din = t.dims[i], dout = t.dims[i + 1];
-    for (int o = 0; o < dout; ++o) {
-      float s = 0.f;
-      for (int k = 0; k < din; ++k) s += q[o * din + k] * v[k];
-      u[o] = s;
-    }
-    q += dout * din;
-    for (int o = 0; o < dout; ++o) u[o] += q[o];
-    q += dout;
-    if (i < t.n_layers - 1) {
-      for (int o = 0; o < dout; ++o) u[o] += q[o] * tanhf(u[o]);
-      q += dout;
-    }
-    for (int o = 0; o < dout; ++o) v[o] = u[o];
-  }
-  return v[0];
-}
-
-__device__ float eb_likelihood(const cae_eb_tables &t, int c, float v) {
-  const float *mlp = t.mlp + (size_t)c * t.mlp_stride;
-  const float lower = eb_logits(t, mlp, v - 0.5f);
-  const float upper = eb_logits(t, mlp, v + 0.5f);
-  const float s = lower + upper;
-  const float sign = s > 0.f ? -1.f : (s < 0.f ? 1.f : 0.f);
-  const float p = fabsf(sigmoidf_(sign * upper) - sigmoidf_(sign * lower));
-  return fmaxf(p, 1e-9f);
-}
 
 // grid = (N*C, blocks over hw); every block works inside one channel
 __global__ void __launch_bounds__(256) eb_quantize_kernel(const EbParams p) {
@@ -72,7 +35,6 @@ __global__ void __launch_bounds__(256) eb_quantize_kernel(const EbParams p) {
   __syncthreads();
 
   const float med = p.t.medians[c];
-  const float *lut = p.t.lut ? p.t.lut + (size_t)c * p.t.lut_len : nullptr;
   const size_t base = (size_t)nc * p.hw;
   float bits = 0.f;
   for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < p.hw; i += gridDim.y * blockDim.x) {
@@ -80,20 +42,11 @@ __global__ void __launch_bounds__(256) eb_quantize_kernel(const EbParams p) {
     const float r = rintf(y - med);  // torch.round: half to even
     const float yq = r + med;
     // saturate like a float->int32 cast of an in-range value; escapes stay exact up to 2^31
-    const int sym = (int)fminf(fmaxf(r, -2147483520.f), 2147483520.f);
+    const int sym = eb_symbol(r);
     if (p.y_q) p.y_q[base + i] = yq;
     if (p.symbols) p.symbols[base + i] = sym;
     if (p.p_y || p.rate_bits) {
-      float lik;
-      const int li = sym - p.t.lut_min;
-      if (lut && li >= 0 && li < p.t.lut_len) {
-        lik = lut[li];
-      } else if (p.t.mlp) {
-        lik = eb_likelihood(p.t, c, yq);
-      } else {
-        lik = 1e-9f;
-        if (p.status) atomicOr(p.status, 1);
-      }
+      const float lik = eb_lookup(p.t, c, sym, yq, p.status);
       if (p.p_y) p.p_y[base + i] = lik;
       bits -= log2f(lik);
     }
@@ -127,12 +80,7 @@ extern "C" int cae_eb_quantize(const float *y, int n, int c, int hw, const cae_e
                                double *rate_bits, int32_t *status, void *stream) {
   CAE_CHECK(y && t && t->medians, 2, "cae_eb_quantize: null argument");
   CAE_CHECK(n > 0 && c > 0 && hw > 0, 2, "cae_eb_quantize: bad shape");
-  if (t->mlp) {
-    CAE_CHECK(t->n_layers >= 1 && t->n_layers <= 9, 2, "cae_eb_quantize: bad n_layers");
-    for (int i = 0; i <= t->n_layers; ++i)
-      CAE_CHECK(t->dims[i] >= 1 && t->dims[i] <= kMaxDim, 2, "cae_eb_quantize: filter dim %d > %d",
-                t->dims[i], kMaxDim);
-  }
+  if (int rc = eb_check_tables(t, "cae_eb_quantize")) return rc;
   const int bins = hist ? t->hist_bins : 0;
   CAE_CHECK(bins >= 0 && bins <= 8192, 2, "cae_eb_quantize: hist_bins out of range");
   EbParams p;

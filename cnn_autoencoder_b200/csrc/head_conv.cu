@@ -27,10 +27,14 @@ constexpr int WPITCH = 72, SPITCH = SC + 1;       // window rows: 16-byte aligne
 constexpr int kLut = 260;                        // x/255 for a byte; entry 256 = 0 (zero padding)
 constexpr int PXT = 4;                           // stem pixels per thread
 constexpr int SG = (SC + PXT - 1) / PXT;         // pixel groups per patch row
-constexpr int kStemWarps = 11, kStemThreads = 32 * kStemWarps, kEpiWarps = 8;
-constexpr int kHeadThreads = kStemThreads + 32 + 32 * kEpiWarps;   // 11 + 1 (MMA) + 8 = 640
-static_assert(SR * SG <= kStemThreads && 2 * 128 <= kStemThreads, "stem group too small");
-static_assert((kStemWarps + 1) % 4 == 0, "epilogue warps must start at a TMEM quadrant 0");
+// The CUDA-core work is done by two independent groups of warps on alternating tiles (group g
+// fills A buffer g): their phases (window staging, stem arithmetic, gather) drift apart, so
+// one group's arithmetic overlaps the other's latency-bound phases and barriers.
+constexpr int kGroupWarps = 5, kGroupThreads = 32 * kGroupWarps;
+constexpr int kStemWarps = 2 * kGroupWarps, kStemThreads = 32 * kStemWarps;
+constexpr int kEpiWarps = 8;
+constexpr int kHeadThreads = kStemThreads + 32 + 32 * kEpiWarps;   // 10 + 1 (MMA) + 8 warps = 608
+// (any 8 consecutive warps cover the four TMEM lane quadrants twice: (m, quadrant) below)
 
 struct HeadParams {
   int n, h_in, w_in, h_out, w_out, c_out, N;
@@ -42,6 +46,7 @@ struct HeadParams {
   float s1, s2;
   uint32_t idesc;
   uint32_t tmem_cols;
+  unsigned long long *trace;   // CAE_HEAD_TRACE: per-tile phase timestamps of CTA 0 (ns)
   int debug;   // CAE_HEAD_DEBUG: 1 = no output stores, 2 = no stem compute / gather (timing only)
 };
 
@@ -51,7 +56,9 @@ __device__ __forceinline__ int reflect_i(int i, int n) {
   return i < 0 ? 0 : (i >= n ? n - 1 : i);
 }
 
-__device__ __forceinline__ void stem_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kStemThreads)); }
+__device__ __forceinline__ void stem_bar(int group) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(kGroupThreads));
+}
 
 template <int CI>
 struct HeadSmem {
@@ -71,9 +78,9 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t *sA = smem;                                   // [2][2][KG][128][16 B]
   uint8_t *sB = sA + 2 * L::A_BYTES;                    // [KG][N][16 B]
-  float *win = reinterpret_cast<float *>(sB + L::KG * p.N * 16);
-  __half *S = reinterpret_cast<__half *>(win + L::WIN_ELEMS);
-  float *lut = reinterpret_cast<float *>(S + ((L::S_ELEMS + 7) & ~7));
+  float *win0 = reinterpret_cast<float *>(sB + L::KG * p.N * 16);          // one window per group
+  __half *S0 = reinterpret_cast<__half *>(win0 + 2 * L::WIN_ELEMS);         // one stem patch per group
+  float *lut = reinterpret_cast<float *>(S0 + 2 * ((L::S_ELEMS + 7) & ~7));
   float *w1s = lut + kLut;                               // [ci][kh][co][4] + bias
   uint64_t *bars = reinterpret_cast<uint64_t *>(w1s + L::W1N);
   uint64_t *a_full = bars, *a_empty = bars + 2, *acc_full = bars + 4, *acc_empty = bars + 6;
@@ -110,7 +117,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
     }
     fence_barrier_init();
   }
-  if (warp == kStemThreads / 32) tmem_alloc(tmem_slot, p.tmem_cols);
+  if (warp == kStemWarps) tmem_alloc(tmem_slot, p.tmem_cols);
   fence_proxy_async();            // B operand written with generic stores, read by the MMA
   tc_fence_before();
   __syncthreads();
@@ -118,14 +125,18 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
 
-  if (warp < kStemThreads / 32) {
-    // =================================================== stem + im2col group
+  if (warp < 2 * kGroupWarps) {
+    // ================================================= stem + im2col groups
+    const int grp = warp / kGroupWarps, gwarp = warp - grp * kGroupWarps;
+    const int gtid = tid - grp * kGroupThreads;
+    float *win = win0 + grp * L::WIN_ELEMS;
+    __half *S = S0 + grp * ((L::S_ELEMS + 7) & ~7);
     // The window is read line by line: a line is one image row of the window (uint8 HWC:
     // WC * CI contiguous bytes) or one (channel, row) of an fp32 NCHW image (WC floats).
-    // Warp w owns lines w, w + 11, ...; a lane owns elements lane, lane + 32, ... of a line,
-    // so the element -> (column, channel) split is the same for every line and tile.
+    // Warp w of a group owns lines w, w + 5, ...; a lane owns elements lane, lane + 32, ... of
+    // a line, so the element -> (column, channel) split is the same for every line and tile.
     constexpr int LINES = U8 ? WR : WR * CI, ELEMS = U8 ? WC * CI : WC;
-    constexpr int LPW = (LINES + kStemWarps - 1) / kStemWarps, EPL = (ELEMS + 31) / 32;
+    constexpr int LPW = (LINES + kGroupWarps - 1) / kGroupWarps, EPL = (ELEMS + 31) / 32;
     float pf[LPW][EPL];
     int soff[EPL];                  // window offset of element lane + 32 i within its line
 #pragma unroll
@@ -142,7 +153,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
         // contiguous run at constant offsets; its row resolves the padding by itself
 #pragma unroll
         for (int l = 0; l < LPW; ++l) {
-          const int line = warp + l * kStemWarps;
+          const int line = gwarp + l * kGroupWarps;
           if (line < LINES) {
             const int r = U8 ? line : line % WR, c = U8 ? 0 : line / WR;
             const int gy = wy0 + r;
@@ -178,7 +189,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
       }
 #pragma unroll
       for (int l = 0; l < LPW; ++l) {
-        const int line = warp + l * kStemWarps;
+        const int line = gwarp + l * kGroupWarps;
         const int r = U8 ? line : line % WR, c = U8 ? 0 : line / WR;
         const int gy = wy0 + r;
         const bool yok = line < LINES && (p.pad_mode == CAE_PAD_REFLECT || (gy >= 0 && gy < p.h_in));
@@ -198,34 +209,40 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
         }
       }
     };
-    int tile = blockIdx.x;
+    // group g takes the CTA's tiles number g, g + 2, ... and always fills A buffer g
+    const int tstep = 2 * (int)gridDim.x;
+    int tile = blockIdx.x + grp * (int)gridDim.x;
     if (tile < p.n_tiles) prefetch(tile);
-    for (int it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
+    for (int k = 0; tile < p.n_tiles; tile += tstep, ++k) {
+      const int it = 2 * k + grp;
       const int rem = tile % tiles_per_img;
       const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
       const int oy0 = tyi * TH, ox0 = txi * TW;
       const int lo_y = 2 * oy0 - 1, lo_x = 2 * ox0 - 1;
+      const bool tr = p.trace && blockIdx.x == 0 && gtid == 0 && it < 64;
+      if (tr) p.trace[it * 8 + 0] = global_timer_ns();
       // 1. staged window -> shared memory (fp32, /255 through the exact table)
 #pragma unroll
       for (int l = 0; l < LPW; ++l) {
-        const int line = warp + l * kStemWarps;
+        const int line = gwarp + l * kGroupWarps;
         if (line >= LINES) break;
-        float *wl = win + (U8 ? line * WPITCH : ((line / WR) * WR + line % WR) * WPITCH);
+        float *wl = win + line * WPITCH;       // fp32 NCHW: line = c * WR + r
 #pragma unroll
         for (int i = 0; i < EPL; ++i) {
           if (lane + 32 * i >= ELEMS) break;
           wl[soff[i]] = U8 ? lut[__float_as_uint(pf[l][i])] : pf[l][i];
         }
       }
-      stem_bar();
+      stem_bar(grp);
+      if (tr) p.trace[it * 8 + 1] = global_timer_ns();
       // 2. next tile's window loads fly while this tile is computed
-      if (tile + (int)gridDim.x < p.n_tiles) prefetch(tile + gridDim.x);
-      // 3. stem convolution: thread = (patch row, 4 adjacent patch columns); the window row
+      if (tile + tstep < p.n_tiles) prefetch(tile + tstep);
+      // 3. stem convolution: work unit = (patch row, 4 adjacent patch columns); the window row
       //    segment is one 16-byte + one 8-byte shared load, the 3 x CI weights of a (ci, kh)
       //    are CI 16-byte broadcast loads
-      if (tid < SR * SG && !(p.debug & 2)) {
-        const int r = tid / SG, x0 = (tid - r * SG) * PXT;
+#pragma unroll 1
+      for (int u = gtid; u < SR * SG && !(p.debug & 2); u += kGroupThreads) {
+        const int r = u / SG, x0 = (u - r * SG) * PXT;
         float acc[PXT][CI];
 #pragma unroll
         for (int q = 0; q < PXT; ++q)
@@ -267,30 +284,33 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
           }
         }
       }
-      stem_bar();
-      // 4. im2col gather into the A buffer: thread = one output pixel (one M row)
-      mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1);
-      for (int px = tid; px < 2 * 128 && !(p.debug & 2); px += kStemThreads) {
+      stem_bar(grp);
+      if (tr) p.trace[it * 8 + 2] = global_timer_ns();
+      // 4. im2col gather into the A buffer: one output pixel (one M row) at a time
+      mbar_wait(&a_empty[grp], (k & 1) ^ 1);
+      if (tr) p.trace[it * 8 + 3] = global_timer_ns();
+#pragma unroll 1
+      for (int px = gtid; px < 2 * 128 && !(p.debug & 2); px += kGroupThreads) {
         const int m = px >> 7, row = px & 127;
         const int ty = m * 4 + (row >> 5), tx = row & 31;
         int ry[3], rx[3];
         bool vy[3], vx[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int gy = 2 * (oy0 + ty) - 1 + k, gx = 2 * (ox0 + tx) - 1 + k;
-          vy[k] = vx[k] = true;
+        for (int kk = 0; kk < 3; ++kk) {
+          const int gy = 2 * (oy0 + ty) - 1 + kk, gx = 2 * (ox0 + tx) - 1 + kk;
+          vy[kk] = vx[kk] = true;
           if (p.pad_mode != CAE_PAD_REFLECT) {
-            vy[k] = gy >= 0 && gy < p.h_in;
-            vx[k] = gx >= 0 && gx < p.w_in;
+            vy[kk] = gy >= 0 && gy < p.h_in;
+            vx[kk] = gx >= 0 && gx < p.w_in;
           }
           int ly = reflect_i(gy, p.h_in) - lo_y, lx = reflect_i(gx, p.w_in) - lo_x;
-          ry[k] = ly < 0 ? 0 : (ly >= SR ? SR - 1 : ly);   // rows of partial tiles: unused
-          rx[k] = lx < 0 ? 0 : (lx >= SC ? SC - 1 : lx);
+          ry[kk] = ly < 0 ? 0 : (ly >= SR ? SR - 1 : ly);   // rows of partial tiles: unused
+          rx[kk] = lx < 0 ? 0 : (lx >= SC ? SC - 1 : lx);
         }
         // k = (ci * 3 + kh) * 3 + kw, packed two halves per register
         uint32_t pk[L::KP / 2];
 #pragma unroll
-        for (int k = 0; k < L::KP / 2; ++k) pk[k] = 0u;
+        for (int kk = 0; kk < L::KP / 2; ++kk) pk[kk] = 0u;
         pk[L::K >> 1] |= 0x3C00u << ((L::K & 1) * 16);              // the two bias columns = 1.0
         pk[(L::K + 1) >> 1] |= 0x3C00u << (((L::K + 1) & 1) * 16);
         const unsigned short *S16 = reinterpret_cast<const unsigned short *>(S);
@@ -300,22 +320,23 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
           for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
-              const int k = (ci * 3 + kh) * 3 + kw;
+              const int kk = (ci * 3 + kh) * 3 + kw;
               uint32_t v = S16[(ci * SR + ry[kh]) * SPITCH + rx[kw]];
               if (!(vy[kh] && vx[kw])) v = 0u;
-              pk[k >> 1] |= v << ((k & 1) * 16);
+              pk[kk >> 1] |= v << ((kk & 1) * 16);
             }
-        uint8_t *dst = sA + (size_t)buf * L::A_BYTES + (size_t)m * L::KG * 2048 + row * 16;
+        uint8_t *dst = sA + (size_t)grp * L::A_BYTES + (size_t)m * L::KG * 2048 + row * 16;
 #pragma unroll
         for (int kg = 0; kg < L::KG; ++kg)
           *reinterpret_cast<uint4 *>(dst + kg * 2048) =
               make_uint4(pk[4 * kg], pk[4 * kg + 1], pk[4 * kg + 2], pk[4 * kg + 3]);
       }
       fence_proxy_async();
-      stem_bar();
-      if (tid == 0) mbar_arrive(&a_full[buf]);
+      stem_bar(grp);
+      if (gtid == 0) mbar_arrive(&a_full[grp]);
+      if (tr) p.trace[it * 8 + 4] = global_timer_ns();
     }
-  } else if (warp == kStemThreads / 32) {
+  } else if (warp == kStemWarps) {
     // ========================================================== MMA issuer
     const uint32_t sa_base = smem_u32(sA), sb_base = smem_u32(sB);
     int it = 0;
@@ -341,7 +362,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
       }
       __syncwarp();
     }
-  } else {
+  } else if (warp > kStemWarps) {
     // ============================================================ epilogue
     const int q = warp & 3;                       // TMEM lane quadrant this warp may read
     const int m_first = kEpiWarps == 8 ? (warp - kStemWarps - 1) >> 2 : 0;   // 8 warps: one M tile each
@@ -359,6 +380,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
       const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
       const int ox = txi * TW + tx;
       mbar_wait_backoff(&acc_full[buf], (it >> 1) & 1);
+      if (p.trace && blockIdx.x == 0 && warp == kStemWarps + 1 && lane == 0 && it < 64) p.trace[it * 8 + 5] = global_timer_ns();
       tc_fence_after();
 #pragma unroll 1
       for (int m = m_first; m < 2; m += m_step) {
@@ -428,19 +450,20 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (p.trace && blockIdx.x == 0 && warp == kStemWarps + 1 && lane == 0 && it < 64) p.trace[it * 8 + 6] = global_timer_ns();
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kStemThreads / 32) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (warp == kStemWarps) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 template <int CI>
 size_t head_smem_bytes(int N) {
   using L = HeadSmem<CI>;
-  size_t b = 2 * (size_t)L::A_BYTES + (size_t)L::KG * N * 16 + (size_t)L::WIN_ELEMS * 4 +
-             (size_t)((L::S_ELEMS + 7) & ~7) * 2 + kLut * 4 + L::W1N * 4 + 8 * 8 + 16;
+  size_t b = 2 * (size_t)L::A_BYTES + (size_t)L::KG * N * 16 + 2 * (size_t)L::WIN_ELEMS * 4 +
+             2 * (size_t)((L::S_ELEMS + 7) & ~7) * 2 + kLut * 4 + L::W1N * 4 + 8 * 8 + 16;
   return b;
 }
 
@@ -455,6 +478,27 @@ int launch_head(const HeadParams &p, cudaStream_t stream) {
   CAE_CUDA(cudaGetDevice(&dev));
   CAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.n_tiles < sms ? p.n_tiles : sms;
+  if (getenv("CAE_HEAD_TRACE")) {
+    // bring-up aid: phase timestamps of the first 64 tiles of CTA 0 (synchronous, prints to stderr)
+    HeadParams q = p;
+    unsigned long long *buf = nullptr, host[64 * 8];
+    CAE_CUDA(cudaMalloc(&buf, sizeof(host)));
+    CAE_CUDA(cudaMemset(buf, 0, sizeof(host)));
+    q.trace = buf;
+    kern<<<grid, kHeadThreads, smem, stream>>>(q);
+    CAE_CUDA(cudaStreamSynchronize(stream));
+    CAE_CUDA(cudaMemcpy(host, buf, sizeof(host), cudaMemcpyDeviceToHost));
+    cudaFree(buf);
+    fprintf(stderr, "head trace (ns, relative to tile start of the stem group):\n"
+                    " tile    start  win->smem  computed  a_empty  a_full | acc_full  epi_done  (abs since tile 0)\n");
+    for (int t = 0; t < 64 && host[t * 8]; ++t) {
+      const unsigned long long *h = host + t * 8, t0 = host[0];
+      fprintf(stderr, " %3d %9llu %9llu %9llu %8llu %7llu | %8llu %9llu\n", t, h[0] - t0, h[1] - h[0],
+              h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - t0, h[6] - t0);
+    }
+    cae_count_launch();
+    return 0;
+  }
   kern<<<grid, kHeadThreads, smem, stream>>>(p);
   cae_count_launch();
   CAE_CUDA(cudaGetLastError());

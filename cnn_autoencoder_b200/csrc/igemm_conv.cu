@@ -28,6 +28,7 @@
 #include <string.h>
 
 #include "cae_common.cuh"
+#include "eb_device.cuh"
 
 namespace {
 
@@ -86,6 +87,15 @@ struct IgParams {
   // 16-byte-unit strides of out / skip (32-bit: buffers are < 2^31 units)
   uint32_t out_pitch, out_ps, out_is, skip_pitch, skip_ps, skip_is;
   int pair_store;   // up == 2, planar output without reflect halo: 32-byte stores of pixel pairs
+  // quantizer fused into the latent layer's epilogue (EPI_LATENT only)
+  int quant;
+  int q_smem;        // 1: medians / likelihood table / histogram staged in shared memory
+  cae_eb_tables qt;
+  float *q_yq;
+  int32_t *q_sym, *q_hist, *q_status;
+  double *q_rate;
+  ActView q_pl;
+  uint32_t q_pitch, q_ps, q_is;
 };
 
 struct TapDef {
@@ -385,6 +395,82 @@ __device__ __forceinline__ void image_store(const IgParams &p, const uint32_t (&
   }
 }
 
+// Quantizer fused behind the latent layer (cae_quant_fuse): all 32 lanes call this with 16
+// consecutive channels of their pixel (valid = the pixel exists).  Same arithmetic as
+// eb_quantize_kernel.  The medians, the likelihood table and the histogram live in shared
+// memory when they fit (s_med != nullptr; the histogram is flushed once per CTA at the end),
+// the rate is accumulated in a register per thread and reduced once per warp at the end.
+struct QuantSmem {
+  const float *med, *lut;   // [c_out], [c_out][lut_len]
+  int *hist;                // [c_out][hist_bins]
+};
+
+__device__ __forceinline__ void quant_emit16(const IgParams &p, const QuantSmem &qs,
+                                             const float (&v)[16], int c0, int n, int oy, int ox,
+                                             bool valid, float &bits) {
+  const size_t cs = (size_t)p.out_h * p.out_w;
+  const int bins = p.q_hist ? p.qt.hist_bins : 0;
+  const int lane = (int)(threadIdx.x & 31);
+  uint4 *pl = nullptr;
+  if (p.q_pl.ptr && valid)
+    pl = reinterpret_cast<uint4 *>(p.q_pl.ptr) +
+         pixel_unit(p.q_pl.fmt, p.q_pitch, p.q_ps, p.q_is, p.q_pl.planes, n, oy + 1, ox + 1) +
+         (uint32_t)(c0 >> 3) * p.q_ps;
+  // eight channels (one planar unit) at a time keeps the live registers low
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int cb = c0 + 8 * h;
+    const size_t o0 = (((size_t)n * p.c_out + cb) * p.out_h + oy) * p.out_w + ox;
+    float yq[8];
+    int sym[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool on = valid && cb + i < p.c_out;
+      const float med = !on ? 0.f : (qs.med ? qs.med[cb + i] : __ldg(p.qt.medians + cb + i));
+      const float r = rintf(v[8 * h + i] - med);   // torch.round: half to even
+      yq[i] = on ? r + med : 0.f;
+      sym[i] = eb_symbol(r);
+    }
+    if (p.q_rate) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (valid && cb + i < p.c_out) {
+          const int li = sym[i] - p.qt.lut_min;
+          float lik;
+          if (qs.lut && li >= 0 && li < p.qt.lut_len) lik = qs.lut[(cb + i) * p.qt.lut_len + li];
+          else lik = eb_lookup(p.qt, cb + i, sym[i], yq[i], p.q_status);
+          bits -= log2f(lik);
+        }
+      }
+    }
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (cb + i < p.c_out) {
+          if (p.q_yq) p.q_yq[o0 + i * cs] = yq[i];
+          if (p.q_sym) p.q_sym[o0 + i * cs] = sym[i];
+        }
+      }
+    }
+    if (bins) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (cb + i < p.c_out) {                  // warp-uniform
+          int b = sym[i] - p.qt.hist_min;
+          b = b < 0 ? 0 : (b >= bins ? bins - 1 : b);
+          if (!valid) b = -1 - lane;             // lanes that do not count never match each other
+          const uint32_t peers = __match_any_sync(0xffffffffu, b);
+          if (b >= 0 && lane == __ffs(peers) - 1) {
+            if (qs.hist) atomicAdd(qs.hist + (cb + i) * bins + b, __popc(peers));
+            else atomicAdd(p.q_hist + (size_t)(cb + i) * bins + b, __popc(peers));
+          }
+        }
+      }
+    }
+    if (pl) pl[h * p.q_ps] = pack8(yq);
+  }
+}
+
 // One epilogue job = two 16-column TMEM loads in flight, then the math and stores.
 //  up == 1: columns [c0, c0+32) of accumulator m
 //  up == 2: columns [c0, c0+16) of the two horizontal output phases (py,0) and (py,1), i.e.
@@ -392,7 +478,8 @@ __device__ __forceinline__ void image_store(const IgParams &p, const uint32_t (&
 template <int EPI, int FAST>
 __device__ __forceinline__ void epilogue_job(const IgParams &p, uint32_t tmem_lane_base,
                                              int acc_base, int n, int y, int x, int job,
-                                             bool valid, float pre_s, float post_s, int pass) {
+                                             bool valid, float pre_s, float post_s, int pass,
+                                             const QuantSmem &qs, float &q_bits) {
   uint32_t r0[16], r1[16];
   if (EPI == EPI_IMAGE) {
     // merged final transposed layer: one 16-column accumulator, columns j = phase * c_out + c
@@ -452,7 +539,8 @@ __device__ __forceinline__ void epilogue_job(const IgParams &p, uint32_t tmem_la
     }
   }
   tmem_ld_wait();
-  if (!valid || (p.debug & 8)) return;
+  const bool fused_q = EPI == EPI_LATENT && p.quant;   // its warp collectives need every lane
+  if ((!valid && !fused_q) || (p.debug & 8)) return;
 
   if (FAST) {
     const __half2 pre2 = __float2half2_rn(pre_s), post2 = __float2half2_rn(post_s);
@@ -521,12 +609,15 @@ __device__ __forceinline__ void epilogue_job(const IgParams &p, uint32_t tmem_la
       for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * post_s);
     }
     if (EPI == EPI_LATENT) {
-      float *o = reinterpret_cast<float *>(p.out.ptr) +
-                 (((size_t)n * p.c_out + c0) * p.out_h + oy) * p.out_w + ox;
-      const size_t cs = (size_t)p.out_h * p.out_w;
+      if (valid) {
+        float *o = reinterpret_cast<float *>(p.out.ptr) +
+                   (((size_t)n * p.c_out + c0) * p.out_h + oy) * p.out_w + ox;
+        const size_t cs = (size_t)p.out_h * p.out_w;
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (c0 + i < p.c_out) o[i * cs] = v[i];
+        for (int i = 0; i < 16; ++i)
+          if (c0 + i < p.c_out) o[i * cs] = v[i];
+      }
+      if (fused_q) quant_emit16(p, qs, v, c0, n, oy, ox, valid, q_bits);
     } else {
       const uint4 lo = pack8(v), hi = pack8(v + 8);
       const uint32_t off = pixel_unit(p.out.fmt, p.out_pitch, p.out_ps, p.out_is, p.out.planes,
@@ -556,6 +647,19 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
   uint8_t *smem_a = smem;
   uint8_t *smem_b = smem + (size_t)p.sa * p.a_stage_bytes;
+  // fused quantizer: medians | likelihood table | histogram behind the rings
+  QuantSmem qs{nullptr, nullptr, nullptr};
+  if (EPI == EPI_LATENT && p.quant && p.q_smem) {
+    float *q0 = reinterpret_cast<float *>(smem_b + (size_t)p.sb * p.b_stage_bytes);
+    const int nl = p.c_out * p.qt.lut_len, nh = p.q_hist ? p.c_out * p.qt.hist_bins : 0;
+    for (int i = threadIdx.x; i < p.c_out; i += blockDim.x) q0[i] = p.qt.medians[i];
+    for (int i = threadIdx.x; i < nl; i += blockDim.x) q0[p.c_out + i] = p.qt.lut[i];
+    int *h0 = reinterpret_cast<int *>(q0 + p.c_out + nl);
+    for (int i = threadIdx.x; i < nh; i += blockDim.x) h0[i] = 0;
+    qs.med = q0;
+    qs.lut = q0 + p.c_out;
+    qs.hist = nh ? h0 : nullptr;
+  }
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.sa; ++i) {
@@ -704,6 +808,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     else jobs_per_m = (p.n_pass == 2 ? 1 : 2) * (p.N >> 4);
     const int n_jobs = p.mt * jobs_per_m;
     const float pre_s = act_slope(p.pre_act), post_s = act_slope(p.post_act);
+    float q_bits = 0.f;
     uint32_t j = 0;
     for (int vt = blockIdx.x; vt < p.n_tiles * p.n_pass; vt += gridDim.x, ++j) {
       const int tile = vt / p.n_pass, pass = vt - tile * p.n_pass;
@@ -734,16 +839,27 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int x = (txi * p.mt + m) * 8 + txl;
         const bool valid = y < p.dom_h && x < p.dom_w;
         epilogue_job<EPI, FAST>(p, lane_base, buf * acc_per_buf + m * p.n_acc, n, y, x, jj, valid,
-                                pre_s, post_s, pass);
+                                pre_s, post_s, pass, qs, q_bits);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
+    if (EPI == EPI_LATENT && p.quant && p.q_rate) {
+      for (int o = 16; o > 0; o >>= 1) q_bits += __shfl_xor_sync(0xffffffffu, q_bits, o);
+      if (lane == 0 && q_bits != 0.f) atomicAdd(p.q_rate, (double)q_bits);
+    }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (EPI == EPI_LATENT && qs.hist) {
+    const int nh = p.c_out * p.qt.hist_bins;
+    for (int i = threadIdx.x; i < nh; i += blockDim.x) {
+      const int v = qs.hist[i];
+      if (v) atomicAdd(p.q_hist + i, v);
+    }
+  }
   if (warp == 3) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
@@ -913,7 +1029,16 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   // warps one barrier round trip (~700 cycles), so a stage must carry well over that much
   // tensor work; tpb is the largest divisor of the tap count that leaves room for two stages
   // of each ring.
-  const int budget = 227 * 1024 - 2048;
+  int budget = 227 * 1024 - 2048;
+  // fused quantizer tables (medians, likelihoods, histogram) behind the rings when they fit
+  int q_bytes = 0;
+  if (d->quant && d->out.fmt == CAE_FMT_F32_NCHW && !merged && d->quant->tables.lut &&
+      !getenv("CAE_QUANT_NO_SMEM")) {
+    const cae_eb_tables &t = d->quant->tables;
+    const long long need = 4ll * d->c_out * (1 + t.lut_len + (d->quant->hist ? t.hist_bins : 0));
+    if (need > 0 && need <= 48 * 1024) q_bytes = round_up((int)need, 128);
+  }
+  budget -= q_bytes;
   p.b_tap_bytes = p.N * p.ck * 2;
   int pass_ntaps[2] = {p.n_taps, 0};
   p.pass_tap0[0] = p.pass_tap0[1] = 0;
@@ -982,7 +1107,8 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   }
   p.sa = sa;
   p.sb = sb;
-  const int smem_bytes = sa * p.a_stage_bytes + sb * p.b_stage_bytes + 1024;
+  const int smem_bytes = sa * p.a_stage_bytes + sb * p.b_stage_bytes + 1024 + q_bytes;
+  p.q_smem = q_bytes > 0;
   if (getenv("CAE_IGEMM_VERBOSE"))
     fprintf(stderr, "cae_conv_igemm: kind %d %d->%d @%dx%d N=%d ck=%d mt=%d n_pass=%d n_acc=%d n_buf=%d "
             "tpb=%d a_stage=%d x%d b_stage=%d x%d smem=%d tiles=%d\n", kind, d->c_in, d->c_out, d->h_in,
@@ -1012,6 +1138,29 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
     epi = EPI_LATENT;
     CAE_CHECK(p.up == 1 && d->out.ptr, 2, "cae_conv_igemm: fp32 NCHW output needs up==1");
     p.out.ptr = d->out.ptr;
+    if (d->quant) {
+      const cae_quant_fuse *q = d->quant;
+      CAE_CHECK(!d->skip.ptr, 2, "cae_conv_igemm: fused quantizer on a residual layer");
+      if (int rc = eb_check_tables(&q->tables, "cae_conv_igemm(quant)")) return rc;
+      CAE_CHECK(q->tables.hist_bins >= 0 && q->tables.hist_bins <= 8192, 2,
+                "cae_conv_igemm(quant): hist_bins out of range");
+      p.quant = 1;
+      p.qt = q->tables;
+      p.q_yq = q->y_q;
+      p.q_sym = q->symbols;
+      p.q_hist = q->hist;
+      p.q_rate = q->rate_bits;
+      p.q_status = q->status;
+      if (getenv("CAE_QUANT_NO_HIST")) p.q_hist = nullptr;     // bring-up timing knobs
+      if (getenv("CAE_QUANT_NO_RATE")) p.q_rate = nullptr;
+      if (getenv("CAE_QUANT_NO_YQ")) p.q_yq = nullptr;
+      if (q->y_q_planar.fmt != CAE_FMT_NONE && q->y_q_planar.ptr) {
+        CAE_CHECK(q->y_q_planar.fmt == CAE_FMT_F16_PLANAR && q->y_q_planar.planes * 8 == p.N, 2,
+                  "cae_conv_igemm(quant): planar y_q needs %d planes", p.N / 8);
+        p.q_pl = ActView{q->y_q_planar.ptr, q->y_q_planar.fmt, q->y_q_planar.planes,
+                         q->y_q_planar.halo, p.out_h, p.out_w};
+      }
+    }
   } else {
     epi = EPI_ACT;
     CAE_CHECK(d->out.ptr && (d->out.fmt == CAE_FMT_F16_PLANAR || d->out.fmt == CAE_FMT_F16_SPLIT),
@@ -1045,6 +1194,7 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
               "cae_conv_igemm: output tensor too large for 32-bit unit offsets; split the batch");
     strides(p.out.fmt, p.out.planes, p.out_h, p.out_w, p.out_pitch, p.out_ps, p.out_is);
   }
+  if (p.q_pl.ptr) strides(p.q_pl.fmt, p.q_pl.planes, p.out_h, p.out_w, p.q_pitch, p.q_ps, p.q_is);
   if (d->skip.fmt != CAE_FMT_NONE && d->skip.ptr) {
     CAE_CHECK(epi != EPI_IMAGE, 2, "cae_conv_igemm: skip unsupported on the final layer");
     CAE_CHECK((d->skip.fmt == CAE_FMT_F16_PLANAR || d->skip.fmt == CAE_FMT_F16_SPLIT) &&
@@ -1098,7 +1248,7 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   // add (12 warps: more registers), 0 = plain fp32 (bring-up / latent / image layers)
   int fast = 0;
   if (epi == EPI_ACT && !getenv("CAE_IGEMM_NO_FAST_EPILOGUE")) fast = p.skip.ptr ? 2 : 1;
-  if (!getenv("CAE_IGEMM_EPI_WARPS")) p.epi_warps = fast == 1 ? 16 : (fast == 2 ? 12 : 8);
+  if (!getenv("CAE_IGEMM_EPI_WARPS")) p.epi_warps = fast == 1 ? 16 : ((fast == 2 || p.quant) ? 12 : 8);
   if (fast != 1 && p.epi_warps > kMaxEpiWarps) p.epi_warps = kMaxEpiWarps;
   const int threads = 128 + 32 * p.epi_warps;
   void (*kern)(const CUtensorMap, const IgParams) =
@@ -1107,6 +1257,7 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
                                                : igemm_conv_kernel<EPI_ACT, 0>))
                      : (epi == EPI_LATENT ? igemm_conv_kernel<EPI_LATENT, 0>
                                           : igemm_conv_kernel<EPI_IMAGE, 0>);
+  static_assert(sizeof(IgParams) + sizeof(CUtensorMap) <= 4096, "kernel parameters exceed 4 KB");
   CAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   kern<<<grid, threads, smem_bytes, (cudaStream_t)stream>>>(tm, p);
   cae_count_launch();

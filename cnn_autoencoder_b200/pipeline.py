@@ -42,6 +42,7 @@ class CodecPipeline:
     def __init__(self, model):
         self.model = model
         self.level = len(model['decoder'].module.synthesis_track)
+        self.fuse_quantizer = True
 
     @torch.no_grad()
     def __call__(self, x_u8):
@@ -49,9 +50,16 @@ class CodecPipeline:
         bits, bpp): bpp is the estimated rate ``-sum(log2 p_y) / (N*H*W)``
         (``_ratedist.py:49-54``)."""
         n, h, w, _ = x_u8.shape
-        y = self.model['encoder'](x_u8)
-        y_q, hist, bits = self.model['fact_ent'].module.quantize_rate(y)
-        _, _, x_r_u8 = self.model['decoder'](y_q, as_uint8='only')
+        fact_ent = self.model['fact_ent'].module
+        req = fact_ent.quant_request() if self.fuse_quantizer else None
+        y = self.model['encoder'](x_u8, quant=req)
+        if req is not None and req.done:
+            # quantize + likelihood + histogram + rate ran in the last encoder layer's epilogue
+            y_q, hist, bits, planar = req.y_q, req.hist, req.rate, req.planar
+        else:
+            y_q, hist, bits = fact_ent.quantize_rate(y)
+            planar = None
+        _, _, x_r_u8 = self.model['decoder'](y_q, as_uint8='only', planar=planar)
         return dict(x_r_u8=x_r_u8, y=y, y_q=y_q, hist=hist, bits=bits,
                     bpp=bits / float(n * h * w))
 

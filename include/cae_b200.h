@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CAE_ABI_VERSION 1
+#define CAE_ABI_VERSION 2
 
 /* ---- tensor formats ------------------------------------------------------ */
 enum {
@@ -85,6 +85,8 @@ typedef struct {
   int32_t mt;              /* igemm: 16x8 M-tiles per CTA tile (1/2), 0 = auto           */
   int32_t grid;            /* igemm: CTAs, 0 = one per SM                                */
   void *aux_out;           /* optional second output (fp32 NCHW) or NULL                 */
+  const struct cae_quant_fuse *quant; /* igemm + fp32 NCHW output (the latent layer) only:
+                                         quantizer fused into the epilogue, or NULL      */
 } cae_conv_desc;
 
 /* ---- library ------------------------------------------------------------- */
@@ -161,7 +163,7 @@ int cae_planar_to_nchw(cae_tensor src, int n, int c, int h, int w, float *dst, v
  * rate_bits are ACCUMULATED into (zero them first).  Symbols outside the table
  * are evaluated with the density MLP; *status is set non-zero if that was needed
  * but no MLP was given.                                                        */
-typedef struct {
+typedef struct cae_eb_tables {
   const float *medians;     /* C */
   const float *lut;         /* C x lut_len likelihoods (already lower-bounded) */
   int32_t lut_min, lut_len;
@@ -178,6 +180,23 @@ typedef struct {
 int cae_eb_quantize(const float *y, int n, int c, int hw, const cae_eb_tables *t,
                     float *y_q, float *p_y, int32_t *symbols, int32_t *hist,
                     double *rate_bits, int32_t *status, void *stream);
+
+/* The same quantizer fused into the epilogue of the last analysis convolution
+ * (cae_conv_desc.quant; the layer whose output is the fp32 NCHW latent y, Analyzer.forward
+ * R:359-361 followed by fact_ent R:549 / _taskutils.py:97): while y is still in registers the
+ * epilogue also produces sym / y_q / the histogram / the rate exactly as cae_eb_quantize does
+ * from y, and can write y_q in the planar fp16 layout the synthesis track reads, so the
+ * latent makes one trip to HBM instead of three.  Every output may be NULL / CAE_FMT_NONE;
+ * hist and rate_bits are accumulated into.                                       */
+typedef struct cae_quant_fuse {
+  cae_eb_tables tables;
+  float *y_q;                /* fp32 NCHW                                          */
+  int32_t *symbols;          /* int32 NCHW                                         */
+  cae_tensor y_q_planar;     /* CAE_FMT_F16_PLANAR with planes = ceil(C/16)*2, zero halo */
+  int32_t *hist;             /* C x tables.hist_bins                                */
+  double *rate_bits;
+  int32_t *status;
+} cae_quant_fuse;
 
 /* ---- entropy coder (HOST, thread-safe, no globals) ------------------------ */
 /* compressai._CXX.pmf_to_quantized_cdf, reached from

@@ -382,3 +382,34 @@ def test_graphed_pipeline_matches_eager():
         assert torch.equal(got['y_q'], want['y_q'])
         assert torch.equal(got['hist'], want['hist'])
         assert got['bits'].item() == want['bits'].item()
+
+
+def test_fused_quantizer_matches_standalone():
+    """The quantizer fused into the latent layer's epilogue (cae_conv_desc.quant) against the
+    stand-alone cae_eb_quantize pass on the same latent: symbols, y_q, histogram and the
+    reconstruction are identical, the rate agrees to float summation order."""
+    from oracle import cae_oracle as O
+    from cnn_autoencoder_b200.pipeline import CodecPipeline
+    for arch, shape in (('A', (3, 64, 96)), ('A', (2, 40, 72)), ('B', (2, 64, 64))):
+        chk = O.make_checkpoint(O.NAMED_ARCHS[arch], seed=11)
+        model = _model(chk)
+        pipe = CodecPipeline(model)
+        n, h, w = shape
+        x = O.synth_natural(n, 3, h, w, seed=5).permute(0, 2, 3, 1).contiguous().cuda()
+        fused = pipe(x)
+        eb = model['fact_ent'].module
+        req = eb.quant_request(want_sym=True)
+        y = model['encoder'](x, quant=req)
+        assert req.done, 'the latent layer of the named nets is a tensor-core layer'
+        pipe.fuse_quantizer = False
+        plain = pipe(x)
+        sym_ref, hist_ref, rate_ref = eb.symbols_hist_rate(y)
+        torch.cuda.synchronize()
+        assert torch.equal(fused['y'], plain['y'])
+        assert torch.equal(fused['y_q'], plain['y_q'])
+        assert torch.equal(req.sym, sym_ref)
+        assert torch.equal(fused['hist'], plain['hist']) and torch.equal(req.hist, hist_ref)
+        assert int(fused['hist'].sum()) == fused['y'].numel()
+        assert abs(fused['bits'].item() - plain['bits'].item()) <= 1e-5 * abs(plain['bits'].item())
+        assert torch.equal(fused['x_r_u8'], plain['x_r_u8'])
+        assert int(req.status.item()) == 0
