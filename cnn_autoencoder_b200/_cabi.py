@@ -24,6 +24,7 @@ SYMBOLS = ['cae_abi_version', 'cae_last_error', 'cae_device_info', 'cae_launch_c
            'cae_conv_head',
            'cae_nchw_to_planar', 'cae_planar_to_nchw', 'cae_eb_quantize', 'cae_gdn',
            'cae_pmf_to_quantized_cdf', 'cae_rans_encode', 'cae_rans_decode',
+           'cae_rans_enc_table_bytes', 'cae_rans_build_enc_table',
            'cae_rans_encode_batch', 'cae_rans_compact', 'cae_rans_decode_batch']
 
 
@@ -58,7 +59,8 @@ class EbTables(ctypes.Structure):
                 ('lut_min', ctypes.c_int32), ('lut_len', ctypes.c_int32),
                 ('mlp', ctypes.c_void_p), ('n_layers', ctypes.c_int32),
                 ('mlp_stride', ctypes.c_int32), ('dims', ctypes.c_int32 * 10),
-                ('hist_min', ctypes.c_int32), ('hist_bins', ctypes.c_int32)]
+                ('hist_min', ctypes.c_int32), ('hist_bins', ctypes.c_int32),
+                ('tail_lik', ctypes.c_float), ('reserved', ctypes.c_int32)]
 
 
 class QuantFuse(ctypes.Structure):
@@ -116,14 +118,17 @@ def lib():
                                   sz, ctypes.POINTER(sz)]
     L.cae_rans_decode.argtypes = [vp, sz, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp, vp,
                                   vp]
+    L.cae_rans_enc_table_bytes.restype = sz
+    L.cae_rans_enc_table_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.cae_rans_build_enc_table.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp]
     L.cae_rans_encode_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp,
-                                        ctypes.c_int, vp, vp, vp, ctypes.c_int, vp, vp, vp]
+                                        ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, vp, vp, vp]
     L.cae_rans_compact.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
     L.cae_rans_decode_batch.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp,
                                         ctypes.c_int, vp, vp, vp, vp, vp]
     for name in SYMBOLS:
         if name not in ('cae_abi_version', 'cae_last_error', 'cae_launch_count',
-                        'cae_packed_weight_bytes'):
+                        'cae_packed_weight_bytes', 'cae_rans_enc_table_bytes'):
             getattr(L, name).restype = ctypes.c_int
     if L.cae_abi_version() != ABI_VERSION:
         raise CaeError('libcae_b200.so ABI version mismatch')

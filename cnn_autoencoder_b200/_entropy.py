@@ -17,6 +17,7 @@ coder behind the C ABI.  Training mode (additive-noise proxy, likelihood with
 gradients) stays on torch autograd ops on the device.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -26,6 +27,8 @@ import torch.nn.functional as F
 from . import _cabi as C
 
 _LUT_MARGIN = 32
+_LUT_EDGE = 8          # symbols per side that must sit on the likelihood bound
+_LUT_MAX = 2048        # widest half range of the likelihood table
 
 
 class _LowerBound(torch.autograd.Function):
@@ -51,8 +54,9 @@ class QuantRequest:
     (tiny nets on the direct kernel, GDN / residual last layers): the caller then runs
     ``EntropyBottleneck.quantize_rate`` on the latent as before."""
 
-    def __init__(self, eb, want_sym=False, want_planar=True):
+    def __init__(self, eb, want_sym=False, want_planar=True, want_yq=True, want_stats=True):
         self.eb, self.want_sym, self.want_planar = eb, want_sym, want_planar
+        self.want_yq, self.want_stats = want_yq, want_stats
         self.done = False
         self.y_q = self.sym = self.hist = self.rate = self.planar = self.status = None
         self._struct = None
@@ -65,12 +69,15 @@ class QuantRequest:
         tb = eb._device_tables()
         q = C.QuantFuse()
         q.tables = eb._abi_tables(tb)
-        self.y_q = torch.empty((n, c, h, w), dtype=torch.float32, device=device)
-        self.hist = torch.zeros((c, tb['lut_len']), dtype=torch.int32, device=device)
-        self.rate = torch.zeros(1, dtype=torch.float64, device=device)
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
-        q.y_q, q.hist = self.y_q.data_ptr(), self.hist.data_ptr()
-        q.rate_bits, q.status = self.rate.data_ptr(), self.status.data_ptr()
+        q.status = self.status.data_ptr()
+        if self.want_yq:
+            self.y_q = torch.empty((n, c, h, w), dtype=torch.float32, device=device)
+            q.y_q = self.y_q.data_ptr()
+        if self.want_stats:
+            self.hist = torch.zeros((c, tb['lut_len']), dtype=torch.int32, device=device)
+            self.rate = torch.zeros(1, dtype=torch.float64, device=device)
+            q.hist, q.rate_bits = self.hist.data_ptr(), self.rate.data_ptr()
         if self.want_sym:
             self.sym = torch.empty((n, c, h, w), dtype=torch.int32, device=device)
             q.symbols = self.sym.data_ptr()
@@ -231,12 +238,31 @@ class EntropyBottleneck(nn.Module):
             med = q[:, 0, 1]
             lo = int(torch.floor((q[:, 0, 0] - med).min()).item()) - _LUT_MARGIN
             hi = int(torch.ceil((q[:, 0, 2] - med).max()).item()) + _LUT_MARGIN
-            lo, hi = max(lo, -4096), min(hi, 4096)
-            syms = torch.arange(lo, hi + 1, device=q.device, dtype=torch.float32)
-            v = syms[None, None, :] + q[:, :, 1:2]
-            lik = self._likelihood(v)[:, 0, :]
-            if self.likelihood_bound > 0:
-                lik = torch.max(lik, self._bound(lik))
+            # Widen the table until both ends sit in the region where the likelihood is the
+            # lower bound (checked over a run of _LUT_EDGE symbols per side and channel): every
+            # symbol outside the table then has exactly the bound and needs no density
+            # evaluation on the device.  Give up (MLP fallback) beyond +-_LUT_MAX.
+            tail_lik = 0.0
+            while True:
+                lo, hi = max(lo, -_LUT_MAX), min(hi, _LUT_MAX)
+                syms = torch.arange(lo, hi + 1, device=q.device, dtype=torch.float32)
+                v = syms[None, None, :] + q[:, :, 1:2]
+                raw = self._likelihood(v)[:, 0, :]
+                lik = torch.max(raw, self._bound(raw)) if self.likelihood_bound > 0 else raw
+                if self.likelihood_bound <= 0:
+                    break
+                bound = float(self.likelihood_bound)
+                left_ok = bool((raw[:, :_LUT_EDGE] <= bound).all())
+                right_ok = bool((raw[:, -_LUT_EDGE:] <= bound).all())
+                if left_ok and right_ok:
+                    tail_lik = bound
+                    break
+                if (lo <= -_LUT_MAX or left_ok) and (hi >= _LUT_MAX or right_ok):
+                    break
+                if not left_ok:
+                    lo -= max(32, (hi - lo) // 2)
+                if not right_ok:
+                    hi += max(32, (hi - lo) // 2)
             blob = []
             K = len(self.filters)
             for i in range(K + 1):
@@ -246,7 +272,7 @@ class EntropyBottleneck(nn.Module):
                     blob.append(torch.tanh(getattr(self, f'_factor{i:d}').detach()).reshape(self.channels, -1))
             mlp = torch.cat(blob, dim=1).contiguous().float()
             tb = dict(medians=med.contiguous().float().clone(), lut=lik.contiguous().float(),
-                      lut_min=lo, lut_len=hi - lo + 1, mlp=mlp)
+                      lut_min=lo, lut_len=hi - lo + 1, mlp=mlp, tail_lik=tail_lik)
         if max((1,) + self.filters) > 8 or K + 1 > 9:
             tb['mlp'] = None
         self._tables, self._tables_key = tb, key
@@ -265,6 +291,7 @@ class EntropyBottleneck(nn.Module):
             for i, d in enumerate(dims):
                 t.dims[i] = d
         t.hist_min, t.hist_bins = tb['lut_min'], tb['lut_len']
+        t.tail_lik = tb.get('tail_lik', 0.0)
         return t
 
     def _quantize_cuda(self, x, want_yq=True, want_p=True, want_sym=False, want_hist=False,
@@ -302,10 +329,10 @@ class EntropyBottleneck(nn.Module):
         y_q, p_y, _, _, _ = self._quantize_cuda(x)
         return y_q, p_y
 
-    def quant_request(self, want_sym=False, want_planar=True):
+    def quant_request(self, want_sym=False, want_planar=True, want_yq=True, want_stats=True):
         """Request object for the quantizer fused into the latent layer's epilogue
         (``Analyzer.forward(x, quant=req)``); see ``QuantRequest``."""
-        return QuantRequest(self, want_sym, want_planar)
+        return QuantRequest(self, want_sym, want_planar, want_yq, want_stats)
 
     def quantize_rate(self, x):
         """(y_q, C x bins histogram, total bits) in one pass: what the encode+rate+decode
@@ -330,10 +357,11 @@ class EntropyBottleneck(nn.Module):
         return cdf, sizes, offs
 
     # Streams per call from which the batched device coder is used instead of the host thread
-    # pool.  One thread per stream is latency bound (~0.15 s for 196 608 symbols whatever the
-    # stream count), so it only wins with many hundreds of tiles in flight; measured on B200 +
-    # 16 host cores: 64 streams 132 MP/s, 128 streams 225 MP/s, host pool 415 MP/s.
-    GPU_CODER_MIN_STREAMS = 512
+    # pool.  One thread per stream is a dependent chain (~70 ms for the 196 608 symbols of a
+    # 512^2 tile whatever the stream count, tools/micro/coderbench.py), so it wins with a
+    # hundred or more tiles in flight: 128 streams 0.43 GP/s, 1024 streams 1.4 GP/s including
+    # the copy back (15 GP/s device side at 4096 streams); host pool of 16 cores 0.4 GP/s.
+    GPU_CODER_MIN_STREAMS = 128
 
     def compress(self, x):
         _, _, sym, _, _ = self._quantize_cuda(x, want_yq=False, want_p=False, want_sym=True)
@@ -343,40 +371,67 @@ class EntropyBottleneck(nn.Module):
         return [encode_symbols(sym_h[i], *self._host_tables()) for i in range(sym_h.shape[0])]
 
     def _dev_tables(self, device):
-        return (self._quantized_cdf.to(device=device, dtype=torch.int32).contiguous(),
-                self._cdf_length.to(device=device, dtype=torch.int32).reshape(-1).contiguous(),
-                self._offset.to(device=device, dtype=torch.int32).reshape(-1).contiguous())
+        """(cdf, sizes, offsets, encode table) on ``device``, rebuilt when ``update()`` changed
+        the CDFs.  The encode table is the division-free form of the state update
+        (``cae_rans_build_enc_table``)."""
+        key = (str(device), self._quantized_cdf.data_ptr(), self._quantized_cdf._version,
+               self._cdf_length._version, self._offset._version)
+        cache = getattr(self, '_dev_tables_cache', None)
+        if cache is not None and cache[0] == key:
+            return cache[1]
+        cdf = self._quantized_cdf.to(device=device, dtype=torch.int32).contiguous()
+        sizes = self._cdf_length.to(device=device, dtype=torch.int32).reshape(-1).contiguous()
+        offs = self._offset.to(device=device, dtype=torch.int32).reshape(-1).contiguous()
+        L = C.lib()
+        nbytes = L.cae_rans_enc_table_bytes(cdf.shape[0], cdf.shape[1])
+        table = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        C.check(L.cae_rans_build_enc_table(cdf.data_ptr(), cdf.shape[0], cdf.shape[1],
+                                           sizes.data_ptr(), table.data_ptr(), stream))
+        self._dev_tables_cache = (key, (cdf, sizes, offs, table))
+        return cdf, sizes, offs, table
 
-    def encode_symbols_gpu(self, sym):
-        """int32 symbols N x C x ... (device) -> list of N byte strings, all streams coded
-        concurrently on the device (one thread per stream, ``cae_rans_encode_batch``)."""
+    def encode_symbols_device(self, sym):
+        """int32 symbols N x C x ... (device) -> (packed uint8 device tensor holding the N
+        streams back to back, int64 host array of N + 1 byte offsets).  All streams are coded
+        concurrently (one thread per stream, ``cae_rans_encode_batch``); the only host
+        synchronisation is reading the N stream lengths."""
         if self._offset.numel() == 0:
             raise C.CaeError('EntropyBottleneck.update() must be called before compress/decompress')
         sym = sym.contiguous()
         n, c = sym.shape[0], sym.shape[1]
         hw = sym[0, 0].numel()
         dev = sym.device
-        cdf, sizes, offs = self._dev_tables(dev)
+        cdf, sizes, offs, table = self._dev_tables(dev)
         cap = c * hw + 64
         words = torch.empty((n, cap), dtype=torch.int32, device=dev)
         nwords = torch.empty(n, dtype=torch.int32, device=dev)
         status = torch.zeros(1, dtype=torch.int32, device=dev)
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         L = C.lib()
+        use_table = not os.environ.get('CAE_RANS_NO_TABLE')
         C.check(L.cae_rans_encode_batch(sym.data_ptr(), n, c, hw, cdf.data_ptr(), cdf.shape[1],
-                                        sizes.data_ptr(), offs.data_ptr(), words.data_ptr(), cap,
-                                        nwords.data_ptr(), status.data_ptr(), stream))
+                                        sizes.data_ptr(), offs.data_ptr(),
+                                        table.data_ptr() if use_table else None,
+                                        words.data_ptr(), cap, nwords.data_ptr(),
+                                        status.data_ptr(), stream))
         ends = torch.cumsum(nwords.long(), 0)
         starts = (ends - nwords.long()).contiguous()
-        total = int(ends[-1].item())                       # sync: stream lengths are data dependent
+        e = ends.cpu().numpy()                             # sync: stream lengths are data dependent
         if int(status.item()) & 1:
             raise C.CaeError('device entropy coder: a stream overflowed its staging buffer')
-        packed = torch.empty(total, dtype=torch.int32, device=dev)
+        packed = torch.empty(int(e[-1]), dtype=torch.int32, device=dev)
         C.check(L.cae_rans_compact(words.data_ptr(), n, cap, nwords.data_ptr(), starts.data_ptr(),
                                    packed.data_ptr(), stream))
-        host = packed.cpu().numpy().view(np.uint8)
-        e = ends.cpu().numpy()
-        return [host[4 * (int(e[i - 1]) if i else 0):4 * int(e[i])].tobytes() for i in range(n)]
+        off = np.zeros(n + 1, dtype=np.int64)
+        off[1:] = e * 4
+        return packed.view(torch.uint8), off
+
+    def encode_symbols_gpu(self, sym):
+        """int32 symbols N x C x ... (device) -> list of N byte strings."""
+        packed, off = self.encode_symbols_device(sym)
+        host = packed.cpu().numpy()
+        return [host[int(off[i]):int(off[i + 1])].tobytes() for i in range(len(off) - 1)]
 
     def decode_streams_gpu(self, strings, hw):
         """list of N byte strings -> int32 symbols N x C x hw on the device."""
@@ -392,7 +447,7 @@ class EntropyBottleneck(nn.Module):
         blob = torch.from_numpy(np.frombuffer(b''.join(bytes(s) for s in strings), dtype=np.int32).copy())
         words = blob.to(dev, non_blocking=True)
         off_d = torch.from_numpy(off).to(dev)
-        cdf, sizes, offs = self._dev_tables(dev)
+        cdf, sizes, offs, _ = self._dev_tables(dev)
         sym = torch.empty((n, c, hw), dtype=torch.int32, device=dev)
         status = torch.zeros(1, dtype=torch.int32, device=dev)
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)

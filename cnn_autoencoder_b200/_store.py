@@ -51,10 +51,12 @@ class DirArray:
                      for i, c, s in zip(idx, self.chunks, self.shape))
 
     # raw (already encoded) chunk bytes
-    def write_encoded(self, idx, data):
+    def write_encoded(self, idx, *parts):
+        """Write one chunk file from byte-like parts (header, payload, ...) without joining them."""
         tmp = self.chunk_file(idx) + '.partial'
         with open(tmp, 'wb') as f:
-            f.write(data)
+            for part in parts:
+                f.write(part)
         os.replace(tmp, self.chunk_file(idx))
 
     def read_encoded(self, idx):

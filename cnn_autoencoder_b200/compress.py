@@ -82,10 +82,11 @@ def open_source(input_filename, data_group='0/0'):
 def compress_image(codec, checkpoint, input_filename, output_filename, patch_size=512,
                    source_format='zarr', data_group='0/0', data_axes='TCZYX',
                    progress_bar=False, save_as_bottleneck=False, gpu=False, *,
-                   rank=None, world_size=None, batch_tiles=16, workers=None):
+                   rank=None, world_size=None, batch_tiles=16, workers=None, coder_tiles=1024):
     """Same positional signature as the reference (``compress.py:29-36``); the keyword-only
-    arguments select this process's shard and the GPU batch size.  Returns a dict of
-    counters (tiles, pixels, bytes, seconds) for the caller's throughput report."""
+    arguments select this process's shard, the GPU batch size and how many tiles are entropy
+    coded per device call.  Returns a dict of counters (tiles, pixels, bytes, seconds,
+    device_coded) for the caller's throughput report."""
     if 'CAE' not in codec:
         raise ValueError('Codec %s not supported' % codec)
     if not torch.cuda.is_available():
@@ -125,76 +126,149 @@ def compress_image(codec, checkpoint, input_filename, output_filename, patch_siz
 
     tiles = [(i, j) for i in range(gy) for j in range(gx)]
     mine = [tiles[k] for k in shard_range(len(tiles), rank, world_size)]
-    stats = dict(tiles=len(mine), pixels=0, bytes=0, seconds=0.0)
+    stats = dict(tiles=len(mine), pixels=0, bytes=0, seconds=0.0, device_coded=0,
+                 t_read=0.0, t_stage=0.0, t_gpu=0.0, t_code=0.0, t_write_wait=0.0)
     t_start = time.perf_counter()
     pool = ThreadPoolExecutor(max_workers=workers)
-    pending = []
+    writes = []                     # futures of chunk-file writes
+    acc = {}                        # latent shape -> dict(sym=[device tensors], meta=[(idx, h, w)])
+    coder = ThreadPoolExecutor(max_workers=1)      # entropy-codes one group while the transforms
+    coder_stream = torch.cuda.Stream()             # of the next group run on the main stream
+    coder_jobs = []
+    device = torch.cuda.current_device()
 
-    def flush(pending):
-        for fut, idx in pending:
-            data = fut.result()
-            dst.write_encoded(idx, data)
-            stats['bytes'] += len(data)
+    def write_stream(idx, h, w, data):
+        dst.write_encoded(idx, struct.pack('>QQ', h, w), data)
+        return 16 + len(data)
 
-    def code_tile(sym_chw, h, w):
-        return struct.pack('>QQ', h, w) + encode_symbols(sym_chw, cdf, sizes, offs)
+    def flush_group(key, final=False):
+        """Entropy-code the accumulated tiles of one latent shape.  With enough tiles in flight
+        every stream is coded concurrently on the device (the symbols never visit the host);
+        a small remainder goes to the host coder threads instead (one device call costs the
+        same ~70 ms whatever the stream count)."""
+        g = acc.pop(key, None)
+        if not g or not g['meta']:
+            return
+        t0 = time.perf_counter()
+        sym = g['sym'][0] if len(g['sym']) == 1 else torch.cat(g['sym'])
+        n = sym.shape[0]
+        if n >= fact_ent.GPU_CODER_MIN_STREAMS:
+            ready = torch.cuda.Event()
+            ready.record()                       # the symbols are complete at this point
+
+            def job(sym=sym, meta=g['meta'], ready=ready):
+                torch.cuda.set_device(device)
+                with torch.cuda.stream(coder_stream):
+                    coder_stream.wait_event(ready)
+                    packed, off = fact_ent.encode_symbols_device(sym)
+                    host = torch.empty(packed.numel(), dtype=torch.uint8, pin_memory=True)
+                    host.copy_(packed, non_blocking=True)
+                    coder_stream.synchronize()
+                view = memoryview(host.numpy())
+                return [pool.submit(write_stream, idx, h, w, view[int(off[k]):int(off[k + 1])])
+                        for k, (idx, h, w) in enumerate(meta)]
+            coder_jobs.append(coder.submit(job))
+            stats['device_coded'] += n
+        else:
+            sym_h = sym.reshape(n, sym.shape[1], -1).cpu().numpy()
+            for k, (idx, h, w) in enumerate(g['meta']):
+                writes.append(pool.submit(
+                    lambda k=k, idx=idx, h=h, w=w: write_stream(
+                        idx, h, w, encode_symbols(sym_h[k], cdf, sizes, offs))))
+        stats['t_code'] += time.perf_counter() - t0
 
     def run_batch(batch):
-        """batch: list of ((i, j), tile ndarray) with identical tile shapes."""
-        th, tw = batch[0][1].shape[:2]
-        pin = torch.empty((len(batch), th, tw, C), dtype=torch.uint8).pin_memory()
-        for k, (_, t) in enumerate(batch):
-            pin[k] = torch.from_numpy(t)
+        """batch: list of ((i, j), tile) with identical tile shapes; ``tile`` is an ndarray or
+        None (full ps x ps chunk, read from the source straight into the staging buffer)."""
+        th, tw = batch[0][1].shape[:2] if batch[0][1] is not None else (ps, ps)
+        t0 = time.perf_counter()
+        pin = _pinned((len(batch), th, tw, C))
+        if id(pin) in staged:
+            staged.pop(id(pin)).synchronize()          # its previous upload has been consumed
+        pin_np = pin.numpy()
+
+        def put(k):
+            (i, j), tile = batch[k]
+            if tile is not None:
+                pin_np[k] = tile
+                return
+            y0, x0 = i * ps, j * ps
+            part = src[y0:min(y0 + ps, H), x0:min(x0 + ps, W)]
+            if part.shape[0] != ps or part.shape[1] != ps:
+                pin_np[k] = 0                          # edge chunk: zero fill, as zarr pads
+            pin_np[k, :part.shape[0], :part.shape[1]] = part
+        list(pool.map(put, range(len(batch))))
         x = pin.cuda(non_blocking=True)
-        y = model['encoder'](x)
-        _, _, sym, _, _ = fact_ent._quantize_cuda(y, want_yq=False, want_p=False, want_sym=True)
+        t1 = time.perf_counter()
+        stats['t_stage'] += t1 - t0
+        req = None if os.environ.get('CAE_NO_FUSED_QUANT') else \
+            fact_ent.quant_request(want_sym=True, want_planar=False, want_yq=False, want_stats=False)
+        y = model['encoder'](x, quant=req)
+        if req is not None and req.done:
+            sym = req.sym                        # quantized in the last encoder layer's epilogue
+        else:
+            _, _, sym, _, _ = fact_ent._quantize_cuda(y, want_yq=False, want_p=False, want_sym=True)
         lh, lw = y.shape[2], y.shape[3]
         hh, ww = (lh, lw) if save_as_bottleneck else (th, tw)
         stats['pixels'] += len(batch) * th * tw
-        if len(batch) >= fact_ent.GPU_CODER_MIN_STREAMS:
-            # enough independent streams to fill the device coder: symbols never leave the GPU
-            header = struct.pack('>QQ', hh, ww)
-            streams = fact_ent.encode_symbols_gpu(sym)
-            return [(_Done(header + s), (idx[0], idx[1], 0)) for (idx, _), s in zip(batch, streams)]
-        sym_h = sym.reshape(sym.shape[0], sym.shape[1], -1).cpu().numpy()
-        out = []
-        for k, (idx, t) in enumerate(batch):
-            out.append((pool.submit(code_tile, sym_h[k], hh, ww), (idx[0], idx[1], 0)))
-        return out
+        g = acc.setdefault((lh, lw), dict(sym=[], meta=[]))
+        g['sym'].append(sym)
+        g['meta'] += [((idx[0], idx[1], 0), hh, ww) for idx, _ in batch]
+        staged[id(pin)] = torch.cuda.Event()
+        staged[id(pin)].record()                       # the staging buffer is free after this
+        stats['t_gpu'] += time.perf_counter() - t1
+        if len(g['meta']) >= coder_tiles:
+            flush_group((lh, lw))
+
+    def load(ij):
+        i, j = ij
+        if save_as_bottleneck:
+            return np.ascontiguousarray(src[i * ps:min((i + 1) * ps, H), j * ps:min((j + 1) * ps, W)])
+        return padded_tile(src, i * ps, j * ps, ps)
+
+    pinned, staged = {}, {}
+
+    def _pinned(shape):
+        # two reusable pinned staging buffers per batch shape, used alternately (page-locking
+        # per batch is slow; alternating lets batch k+1 be staged while batch k uploads)
+        ring = pinned.setdefault(shape, [])
+        if len(ring) < 2:
+            ring.append(torch.empty(shape, dtype=torch.uint8).pin_memory())
+            return ring[-1]
+        ring.append(ring.pop(0))
+        return ring[-1]
 
     groups = {}
-    for (i, j) in mine:
-        if save_as_bottleneck:
-            tile = np.ascontiguousarray(src[i * ps:min((i + 1) * ps, H), j * ps:min((j + 1) * ps, W)])
-        else:
-            tile = padded_tile(src, i * ps, j * ps, ps)
-        g = groups.setdefault(tile.shape, [])
-        g.append(((i, j), tile))
-        if len(g) == batch_tiles:
-            new = run_batch(g)
-            flush(pending)              # previous batch was coded while this one ran on the GPU
-            pending = new
-            groups[tile.shape] = []
+    for k0 in range(0, len(mine), batch_tiles):
+        part = mine[k0:k0 + batch_tiles]
+        if not save_as_bottleneck:
+            run_batch([(ij, None) for ij in part])            # one copy: source -> pinned buffer
+            continue
+        t0 = time.perf_counter()
+        loaded = list(pool.map(load, part))                   # tile reads in parallel
+        stats['t_read'] += time.perf_counter() - t0
+        for ij, tile in zip(part, loaded):
+            g = groups.setdefault(tile.shape, [])
+            g.append((ij, tile))
+            if len(g) == batch_tiles:
+                run_batch(g)
+                groups[tile.shape] = []
     for g in groups.values():
         if g:
-            new = run_batch(g)
-            flush(pending)
-            pending = new
-    flush(pending)
+            run_batch(g)
+    for key in list(acc):
+        flush_group(key, final=True)
+    t0 = time.perf_counter()
+    for j in coder_jobs:
+        writes += j.result()
+    for f in writes:
+        stats['bytes'] += f.result()
+    stats['t_write_wait'] = time.perf_counter() - t0
+    coder.shutdown()
     pool.shutdown()
     torch.cuda.synchronize()
     stats['seconds'] = time.perf_counter() - t_start
     return stats
-
-
-class _Done:
-    """A finished result with the Future interface the flush loop expects."""
-
-    def __init__(self, value):
-        self._value = value
-
-    def result(self):
-        return self._value
 
 
 class _CodecConfig:

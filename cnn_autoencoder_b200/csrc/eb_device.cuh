@@ -54,6 +54,7 @@ __device__ __forceinline__ float eb_lookup(const cae_eb_tables &t, int c, int sy
                                            int32_t *status) {
   const int li = sym - t.lut_min;
   if (t.lut && li >= 0 && li < t.lut_len) return __ldg(t.lut + (size_t)c * t.lut_len + li);
+  if (t.lut && t.tail_lik > 0.f) return t.tail_lik;   // the table ends where the bound begins
   if (t.mlp) return eb_likelihood(t, c, yq);
   if (status) atomicOr(status, 1);
   return 1e-9f;

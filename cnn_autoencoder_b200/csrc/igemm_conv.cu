@@ -89,7 +89,8 @@ struct IgParams {
   int pair_store;   // up == 2, planar output without reflect halo: 32-byte stores of pixel pairs
   // quantizer fused into the latent layer's epilogue (EPI_LATENT only)
   int quant;
-  int q_smem;        // 1: medians / likelihood table / histogram staged in shared memory
+  int q_smem;        // 1: medians and the core of the likelihood table / histogram in shared memory
+  int q_core_min, q_core_len;   // symbols [q_core_min, q_core_min + q_core_len) of every channel
   cae_eb_tables qt;
   float *q_yq;
   int32_t *q_sym, *q_hist, *q_status;
@@ -401,8 +402,8 @@ __device__ __forceinline__ void image_store(const IgParams &p, const uint32_t (&
 // memory when they fit (s_med != nullptr; the histogram is flushed once per CTA at the end),
 // the rate is accumulated in a register per thread and reduced once per warp at the end.
 struct QuantSmem {
-  const float *med, *lut;   // [c_out], [c_out][lut_len]
-  int *hist;                // [c_out][hist_bins]
+  const float *med, *lut;   // [c_out], [c_out][q_core_len]: the symbols around the median
+  int *hist;                // [c_out][q_core_len]
 };
 
 __device__ __forceinline__ void quant_emit16(const IgParams &p, const QuantSmem &qs,
@@ -435,10 +436,10 @@ __device__ __forceinline__ void quant_emit16(const IgParams &p, const QuantSmem 
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (valid && cb + i < p.c_out) {
-          const int li = sym[i] - p.qt.lut_min;
+          const int li = sym[i] - p.q_core_min;
           float lik;
-          if (qs.lut && li >= 0 && li < p.qt.lut_len) lik = qs.lut[(cb + i) * p.qt.lut_len + li];
-          else lik = eb_lookup(p.qt, cb + i, sym[i], yq[i], p.q_status);
+          if (qs.lut && li >= 0 && li < p.q_core_len) lik = qs.lut[(cb + i) * p.q_core_len + li];
+          else lik = eb_lookup(p.qt, cb + i, sym[i], yq[i], p.q_status);   // rare: global table
           bits -= log2f(lik);
         }
       }
@@ -461,8 +462,11 @@ __device__ __forceinline__ void quant_emit16(const IgParams &p, const QuantSmem 
           if (!valid) b = -1 - lane;             // lanes that do not count never match each other
           const uint32_t peers = __match_any_sync(0xffffffffu, b);
           if (b >= 0 && lane == __ffs(peers) - 1) {
-            if (qs.hist) atomicAdd(qs.hist + (cb + i) * bins + b, __popc(peers));
-            else atomicAdd(p.q_hist + (size_t)(cb + i) * bins + b, __popc(peers));
+            const int lc = sym[i] - p.q_core_min;
+            if (qs.hist && lc >= 0 && lc < p.q_core_len)
+              atomicAdd(qs.hist + (cb + i) * p.q_core_len + lc, __popc(peers));
+            else
+              atomicAdd(p.q_hist + (size_t)(cb + i) * bins + b, __popc(peers));
           }
         }
       }
@@ -651,9 +655,12 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   QuantSmem qs{nullptr, nullptr, nullptr};
   if (EPI == EPI_LATENT && p.quant && p.q_smem) {
     float *q0 = reinterpret_cast<float *>(smem_b + (size_t)p.sb * p.b_stage_bytes);
-    const int nl = p.c_out * p.qt.lut_len, nh = p.q_hist ? p.c_out * p.qt.hist_bins : 0;
+    const int nl = p.c_out * p.q_core_len, nh = p.q_hist ? nl : 0;
     for (int i = threadIdx.x; i < p.c_out; i += blockDim.x) q0[i] = p.qt.medians[i];
-    for (int i = threadIdx.x; i < nl; i += blockDim.x) q0[p.c_out + i] = p.qt.lut[i];
+    for (int i = threadIdx.x; i < nl; i += blockDim.x) {
+      const int c = i / p.q_core_len, k = i - c * p.q_core_len;
+      q0[p.c_out + i] = p.qt.lut[(size_t)c * p.qt.lut_len + (p.q_core_min - p.qt.lut_min) + k];
+    }
     int *h0 = reinterpret_cast<int *>(q0 + p.c_out + nl);
     for (int i = threadIdx.x; i < nh; i += blockDim.x) h0[i] = 0;
     qs.med = q0;
@@ -854,10 +861,16 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (EPI == EPI_LATENT && qs.hist) {
-    const int nh = p.c_out * p.qt.hist_bins;
+    // core bins of this CTA -> the global histogram (same clamping as the direct path)
+    const int nh = p.c_out * p.q_core_len, bins = p.qt.hist_bins;
     for (int i = threadIdx.x; i < nh; i += blockDim.x) {
       const int v = qs.hist[i];
-      if (v) atomicAdd(p.q_hist + i, v);
+      if (v) {
+        const int c = i / p.q_core_len;
+        int b = p.q_core_min + (i - c * p.q_core_len) - p.qt.hist_min;
+        b = b < 0 ? 0 : (b >= bins ? bins - 1 : b);
+        atomicAdd(p.q_hist + (size_t)c * bins + b, v);
+      }
     }
   }
   if (warp == 3) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -1034,9 +1047,19 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   int q_bytes = 0;
   if (d->quant && d->out.fmt == CAE_FMT_F32_NCHW && !merged && d->quant->tables.lut &&
       !getenv("CAE_QUANT_NO_SMEM")) {
+    // as many symbols around the median as fit 40 KB (likelihoods + histogram); the rest of
+    // the table stays in global memory (rare symbols)
     const cae_eb_tables &t = d->quant->tables;
-    const long long need = 4ll * d->c_out * (1 + t.lut_len + (d->quant->hist ? t.hist_bins : 0));
-    if (need > 0 && need <= 48 * 1024) q_bytes = round_up((int)need, 128);
+    int core = (40 * 1024 / (4 * d->c_out) - 1) / 2;
+    if (core > t.lut_len) core = t.lut_len;
+    if (core >= 16) {
+      int cmin = -(core / 2);
+      if (cmin < t.lut_min) cmin = t.lut_min;
+      if (cmin + core > t.lut_min + t.lut_len) cmin = t.lut_min + t.lut_len - core;
+      p.q_core_min = cmin;
+      p.q_core_len = core;
+      q_bytes = round_up(4 * d->c_out * (1 + 2 * core), 128);
+    }
   }
   budget -= q_bytes;
   p.b_tap_bytes = p.N * p.ck * 2;

@@ -28,9 +28,9 @@ from .compress import _dist_info, shard_range
 def decompress_image(input_filename, output_filename, destination_format='zarr',
                      data_group='0/0', decomp_group='decompressed', checkpoint=None,
                      progress_bar=False, gpu=False, *, rank=None, world_size=None,
-                     batch_tiles=16, workers=None):
+                     batch_tiles=16, workers=None, coder_tiles=1024):
     """Same positional signature as the reference (``decompress.py:40-47``).  Returns a
-    dict of counters (tiles, pixels, seconds)."""
+    dict of counters (tiles, pixels, seconds, device_decoded)."""
     if not torch.cuda.is_available():
         raise RuntimeError('decompress_image needs a CUDA device (no CPU fallback)')
     if checkpoint is None or (isinstance(checkpoint, str) and not len(checkpoint)):
@@ -78,7 +78,8 @@ def decompress_image(input_filename, output_filename, destination_format='zarr',
 
     tiles = [(i, j) for i in range(gy) for j in range(gx)]
     mine = [tiles[k] for k in shard_range(len(tiles), rank, world_size)]
-    stats = dict(tiles=len(mine), pixels=0, seconds=0.0)
+    stats = dict(tiles=len(mine), pixels=0, seconds=0.0, device_decoded=0,
+                 t_read=0.0, t_decode=0.0, t_gpu=0.0, t_write_wait=0.0)
     t_start = time.perf_counter()
     pool = ThreadPoolExecutor(max_workers=workers)
 
@@ -92,36 +93,71 @@ def decompress_image(input_filename, output_filename, destination_format='zarr',
         idx, (lh, lw), stream = item
         return decode_symbols(stream, C_bn, lh * lw, cdf, sizes, offs).reshape(C_bn, lh, lw)
 
-    def run_batch(batch):
-        """batch: list of (idx, (lh, lw), stream bytes) with one latent shape."""
+    writes = []
+
+    def put_tile(idx, tile):
+        y0, x0 = idx[0] * ps, idx[1] * ps
+        tile = tile[:min(ps, H - y0), :min(ps, W - x0)]
+        if want_png:
+            canvas[y0:y0 + tile.shape[0], x0:x0 + tile.shape[1]] = tile
+        else:
+            dst.write_chunk((idx[0], idx[1], 0), tile)
+        return tile.shape[0] * tile.shape[1]
+
+    def run_group(batch):
+        """batch: up to ``coder_tiles`` items (idx, (lh, lw), stream bytes) of one latent shape.
+        All streams are entropy-decoded in one device call when there are enough of them (a
+        small remainder goes to the host coder threads), then the synthesis transform runs
+        over ``batch_tiles`` tiles at a time and the chunk writes go to the thread pool."""
         lh, lw = batch[0][1]
+        t0 = time.perf_counter()
         if len(batch) >= fact_ent.GPU_CODER_MIN_STREAMS:
             sym = fact_ent.decode_streams_gpu([b[2] for b in batch], lh * lw)
-            y_q = sym.reshape(len(batch), C_bn, lh, lw).float() + med
+            stats['device_decoded'] += len(batch)
         else:
-            sym = np.stack(list(pool.map(decode_tile, batch)))
-            y_q = torch.from_numpy(sym).pin_memory().cuda(non_blocking=True).float() + med
-        _, _, u8 = decoder(y_q, as_uint8='only')
-        img = u8.cpu().numpy()
-        for k, (idx, _, _) in enumerate(batch):
-            y0, x0 = idx[0] * ps, idx[1] * ps
-            tile = img[k][:min(ps, H - y0), :min(ps, W - x0)]
-            if want_png:
-                canvas[y0:y0 + tile.shape[0], x0:x0 + tile.shape[1]] = tile
-            else:
-                dst.write_chunk((idx[0], idx[1], 0), tile)
-            stats['pixels'] += tile.shape[0] * tile.shape[1]
+            sym = torch.from_numpy(np.stack(list(pool.map(decode_tile, batch)))).pin_memory()
+            sym = sym.cuda(non_blocking=True)
+        sym = sym.reshape(len(batch), C_bn, lh, lw)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        stats['t_decode'] += t1 - t0
+        prev = None
+        for k0 in range(0, len(batch) + batch_tiles, batch_tiles):
+            cur = None
+            if k0 < len(batch):
+                y_q = sym[k0:k0 + batch_tiles].float() + med
+                _, _, u8 = decoder(y_q, as_uint8='only')
+                host = torch.empty(u8.shape, dtype=torch.uint8, pin_memory=True)
+                host.copy_(u8, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record()
+                cur = (k0, host, done)
+            if prev is not None:                 # hand batch k-1 to the writers while k runs
+                p0, phost, pdone = prev
+                pdone.synchronize()
+                img = phost.numpy()
+                for k in range(img.shape[0]):
+                    writes.append(pool.submit(put_tile, batch[p0 + k][0], img[k]))
+            prev = cur
+        stats['t_gpu'] += time.perf_counter() - t1
 
     groups = {}
-    for item in pool.map(read_tile, mine):
+    t0 = time.perf_counter()
+    items = list(pool.map(read_tile, mine))
+    stats['t_read'] = time.perf_counter() - t0
+    for item in items:
         g = groups.setdefault(item[1], [])
         g.append(item)
-        if len(g) == batch_tiles:
-            run_batch(g)
+        if len(g) == coder_tiles:
+            run_group(g)
             groups[item[1]] = []
     for g in groups.values():
         if g:
-            run_batch(g)
+            run_group(g)
+    t0 = time.perf_counter()
+    for f in writes:
+        stats['pixels'] += f.result()
+    stats['t_write_wait'] = time.perf_counter() - t0
     pool.shutdown()
     torch.cuda.synchronize()
     if want_png:

@@ -6,6 +6,8 @@ encode/decode``, ``/root/reference/src/models/tasks/_autoencoders.py:539-584``,
 and ``forward_func``, ``_taskutils.py:95-108``) for a BATCH of tiles, with the
 entropy coder left out (it is host code; see ``compress.py``).
 """
+import os
+
 import torch
 
 from . import _cabi
@@ -42,7 +44,7 @@ class CodecPipeline:
     def __init__(self, model):
         self.model = model
         self.level = len(model['decoder'].module.synthesis_track)
-        self.fuse_quantizer = True
+        self.fuse_quantizer = not os.environ.get('CAE_NO_FUSED_QUANT')
 
     @torch.no_grad()
     def __call__(self, x_u8):

@@ -175,6 +175,11 @@ typedef struct cae_eb_tables {
   int32_t n_layers, mlp_stride;
   int32_t dims[10];
   int32_t hist_min, hist_bins;
+  /* > 0: the table reaches, on both sides, the symbols whose likelihood is the lower bound
+   * (1e-9, CompressAI likelihood_bound), so every symbol outside the table has exactly this
+   * likelihood and the MLP is never evaluated.  0: unknown, fall back to the MLP.            */
+  float tail_lik;
+  int32_t reserved;
 } cae_eb_tables;
 
 int cae_eb_quantize(const float *y, int n, int c, int hw, const cae_eb_tables *t,
@@ -223,10 +228,16 @@ int cae_rans_decode(const uint8_t *enc /*HOST*/, size_t nbytes, int c, int hw,
  * exclusive prefix sum of nwords, in words).  Decoding reads stream k from
  * words[word_offsets[k] .. word_offsets[k+1]) (bit 1 of *status: a stream was truncated).
  * All pointers are device pointers; tables as in the host entry points.                   */
+/* Optional per-(channel, symbol) encode table (16 bytes per entry, C x cdf_stride entries on the
+ * device) that replaces the 64-bit division of the state update by an exact reciprocal
+ * multiply; built once per set of CDFs.  enc_table == NULL encodes with the plain division.   */
+size_t cae_rans_enc_table_bytes(int c, int cdf_stride);
+int cae_rans_build_enc_table(const int32_t *cdfs, int c, int cdf_stride, const int32_t *cdf_sizes,
+                             void *table, void *stream);
 int cae_rans_encode_batch(const int32_t *symbols, int n, int c, int hw, const int32_t *cdfs,
                           int cdf_stride, const int32_t *cdf_sizes, const int32_t *offsets,
-                          uint32_t *words, int cap_words, int32_t *nwords, int32_t *status,
-                          void *stream);
+                          const void *enc_table, uint32_t *words, int cap_words, int32_t *nwords,
+                          int32_t *status, void *stream);
 int cae_rans_compact(const uint32_t *words, int n, int cap_words, const int32_t *nwords,
                      const int64_t *out_offsets, uint32_t *out, void *stream);
 int cae_rans_decode_batch(const uint32_t *words, const int64_t *word_offsets, int n, int c, int hw,

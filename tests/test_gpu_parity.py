@@ -345,10 +345,15 @@ def test_device_entropy_coder_is_byte_identical_to_host_coder():
     sym.view(-1)[idx] = torch.randint(-90000, 90000, (400,), generator=g, dtype=torch.int32)
     sym[3, 0, 0] = 2 ** 27
     sym[3, 47, hw - 1] = -(2 ** 27)
-    streams = fe.encode_symbols_gpu(sym.cuda())
+    streams = fe.encode_symbols_gpu(sym.cuda())           # reciprocal-multiply table path
     cdf, sizes, offs = fe._host_tables()
-    for k in (0, 3, 33, 69):
-        assert streams[k] == E.encode_symbols(sym[k].numpy(), cdf, sizes, offs)
+    for k in range(n):
+        assert streams[k] == E.encode_symbols(sym[k].numpy(), cdf, sizes, offs), k
+    os.environ['CAE_RANS_NO_TABLE'] = '1'                  # plain 64-bit division path
+    try:
+        assert fe.encode_symbols_gpu(sym.cuda()) == streams
+    finally:
+        del os.environ['CAE_RANS_NO_TABLE']
     back = fe.decode_streams_gpu(streams, hw).cpu()
     assert torch.equal(back, sym)
     # through the module API (>= GPU_CODER_MIN_STREAMS tiles): compress / decompress

@@ -30,6 +30,7 @@ def main():
     ap.add_argument('--arch', default='A')
     ap.add_argument('--batch-tiles', type=int, default=32)
     ap.add_argument('--workers', type=int, default=None)
+    ap.add_argument('--coder-tiles', type=int, default=1024)
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -47,7 +48,8 @@ def main():
     chk = O.make_checkpoint(O.NAMED_ARCHS[args.arch], seed=1234)
     base = os.environ.get('SLIDEBENCH_DIR') or tempfile.mkdtemp(prefix='slide_')
     comp, rec = os.path.join(base, 'c.zarr'), os.path.join(base, 'r.zarr')
-    kw = dict(rank=rank, world_size=world, batch_tiles=args.batch_tiles, workers=args.workers)
+    kw = dict(rank=rank, world_size=world, batch_tiles=args.batch_tiles, workers=args.workers,
+              coder_tiles=args.coder_tiles)
     compress.compress_image('CAE', chk, slide[:args.ps * 2, :args.ps * 2], os.path.join(base, 'w.zarr'),
                             patch_size=args.ps, rank=0, world_size=1, batch_tiles=4)   # warm-up
     t0 = time.perf_counter()
@@ -59,6 +61,9 @@ def main():
                compress_MPps=round(cs['pixels'] / 1e6 / (t1 - t0), 1),
                decompress_MPps=round(ds['pixels'] / 1e6 / (t2 - t1), 1),
                both_MPps=round(cs['pixels'] / 1e6 / (t2 - t0), 1),
+               device_coded=cs.get('device_coded'), device_decoded=ds.get('device_decoded'),
+               compress_phases={k: round(v, 3) for k, v in cs.items() if k.startswith('t_')},
+               decompress_phases={k: round(v, 3) for k, v in ds.items() if k.startswith('t_')},
                bytes=cs['bytes'], bpp=round(8 * cs['bytes'] / max(cs['pixels'], 1), 4),
                host_cores=os.cpu_count())
     if world == 1:
