@@ -60,3 +60,14 @@ def test_error_text_is_reported():
     d.kind = 99
     rc = C.lib().cae_conv_igemm(ctypes.byref(d), None)
     assert rc != 0 and b'bad kind' in C.lib().cae_last_error()
+
+
+def test_graft_entry_build_runs():
+    """The driver's build check: __graft_entry__.build() compiles (incrementally) and imports."""
+    import importlib
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    g = importlib.import_module('__graft_entry__')
+    g.build()
