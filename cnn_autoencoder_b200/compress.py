@@ -201,8 +201,9 @@ def compress_image(codec, checkpoint, input_filename, output_filename, patch_siz
         x = pin.cuda(non_blocking=True)
         t1 = time.perf_counter()
         stats['t_stage'] += t1 - t0
-        req = None if os.environ.get('CAE_NO_FUSED_QUANT') else \
-            fact_ent.quant_request(want_sym=True, want_planar=False, want_yq=False, want_stats=False)
+        # stand-alone quantizer by default (see pipeline.CodecPipeline for the measurement)
+        req = fact_ent.quant_request(want_sym=True, want_planar=False, want_yq=False,
+                                     want_stats=False) if os.environ.get('CAE_FUSED_QUANT') else None
         y = model['encoder'](x, quant=req)
         if req is not None and req.done:
             sym = req.sym                        # quantized in the last encoder layer's epilogue

@@ -401,6 +401,7 @@ def test_fused_quantizer_matches_standalone():
         pipe = CodecPipeline(model)
         n, h, w = shape
         x = O.synth_natural(n, 3, h, w, seed=5).permute(0, 2, 3, 1).contiguous().cuda()
+        pipe.fuse_quantizer = True
         fused = pipe(x)
         eb = model['fact_ent'].module
         req = eb.quant_request(want_sym=True)
