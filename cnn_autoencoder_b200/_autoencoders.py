@@ -321,9 +321,19 @@ class Synthesizer(_Track):
             track.append(nn.Identity())
         self.synthesis_track = nn.Sequential(*track)
         if multiscale_analysis:
-            raise NotImplementedError('multiscale_analysis colour heads are scheduled: SURVEY.md 8f-3')
-        layers = [nn.Sequential(NoneColorLayer()) for _ in range(compression_level - 1)]
+            # R:417-429: a reflect-padded 3x3 colour head on every intermediate scale
+            if groups:
+                raise NotImplementedError('only dense 3x3 convolutions have CUDA kernels '
+                                          '(groups=True is scheduled: SURVEY.md 8f-3)')
+            layers = [nn.Sequential(nn.Conv2d(channels_net * channels_expansion ** i, channels_org,
+                                              kernel_size=kernel_size, stride=1,
+                                              padding=kernel_size // 2, bias=bias,
+                                              padding_mode='reflect'))
+                      for i in reversed(range(compression_level - 1))]
+        else:
+            layers = [nn.Sequential(NoneColorLayer()) for _ in range(compression_level - 1)]
         layers.append(nn.Identity())
+        self.multiscale = bool(multiscale_analysis)
         self.color_layers = nn.ModuleList(layers)
         self.rec_level = compression_level
         self.bridges = False       # set True to get fx_brg as fp32 tensors in eval mode
@@ -364,7 +374,7 @@ class Synthesizer(_Track):
                 a = O.nchw_to_planar(x, C.FMT_F16_PLANAR, C.HALO_KEEP) if x.shape[1] > 4 \
                     else O.wrap_nchw(x)
             outs = self._unit_output_indices()
-            keep = outs[:-1] if self.bridges else ()
+            keep = outs[:-1] if (self.bridges or self.multiscale) else ()
             final = C.FMT_U8_HWC if as_uint8 else C.FMT_F32_NCHW
             only_u8 = as_uint8 == 'only'
             last, kept, aux = self._executor().run(a, final, keep=keep, aux_last=not only_u8)
@@ -372,9 +382,24 @@ class Synthesizer(_Track):
                 return [None] * n_units, [None] * n_units, last.t
             x_full = aux if aux is not None else last.t
             u8 = last.t if (as_uint8 and last.fmt == C.FMT_U8_HWC) else None
-            fx_brg = [O.planar_to_nchw(kept[i]) if i in kept else None for i in outs[:-1]]
+            fx_brg = [O.planar_to_nchw(kept[i]) if (self.bridges and i in kept) else None
+                      for i in outs[:-1]]
             fx_brg.append(x_full)
-        x_r = [None] * (n_units - 1)
+            x_r = [None] * (n_units - 1)
+            if self.multiscale:
+                # colour heads read the kept intermediate tensors (zero halo: their consumer is
+                # a transposed conv), so they run on the direct kernel, which resolves the
+                # reflect padding by index arithmetic on the interior
+                for u, i in enumerate(outs[:-1]):
+                    conv = self.color_layers[u][0]
+                    a_in = kept[i]
+                    out = O.alloc_act(C.FMT_F32_NCHW, a_in.n, conv.out_channels, a_in.h, a_in.w,
+                                      device=a_in.t.device)
+                    O.conv(C.CONV_S1, a_in, conv.weight.detach().float().contiguous(),
+                           conv.out_channels, out, igemm=False,
+                           bias=conv.bias.detach().float().contiguous() if conv.bias is not None else None,
+                           pad_mode=C.PAD_REFLECT)
+                    x_r[n_units - 2 - u] = out.t
         x_r.insert(0, x_full)
         if as_uint8:
             if u8 is None:

@@ -433,20 +433,15 @@ class EntropyBottleneck(nn.Module):
         host = packed.cpu().numpy()
         return [host[int(off[i]):int(off[i + 1])].tobytes() for i in range(len(off) - 1)]
 
-    def decode_streams_gpu(self, strings, hw):
-        """list of N byte strings -> int32 symbols N x C x hw on the device."""
+    def decode_streams_device(self, words, word_off, hw):
+        """``words``: int32 device tensor holding N streams back to back, ``word_off``: N + 1
+        word offsets (host array) -> int32 symbols N x C x hw on the device, all streams decoded
+        concurrently (``cae_rans_decode_batch``)."""
         if self._offset.numel() == 0:
             raise C.CaeError('EntropyBottleneck.update() must be called before compress/decompress')
-        dev = self.quantiles.device
-        n, c = len(strings), self.channels
-        lens = np.array([len(s) for s in strings], dtype=np.int64)
-        if (lens % 4).any() or (lens < 8).any():
-            raise C.CaeError('entropy-coded stream is not a whole number of words >= 2')
-        off = np.zeros(n + 1, dtype=np.int64)
-        np.cumsum(lens // 4, out=off[1:])
-        blob = torch.from_numpy(np.frombuffer(b''.join(bytes(s) for s in strings), dtype=np.int32).copy())
-        words = blob.to(dev, non_blocking=True)
-        off_d = torch.from_numpy(off).to(dev)
+        dev = words.device
+        n, c = len(word_off) - 1, self.channels
+        off_d = torch.from_numpy(np.ascontiguousarray(word_off, dtype=np.int64)).to(dev)
         cdf, sizes, offs, _ = self._dev_tables(dev)
         sym = torch.empty((n, c, hw), dtype=torch.int32, device=dev)
         status = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -457,6 +452,17 @@ class EntropyBottleneck(nn.Module):
         if int(status.item()) & 2:
             raise C.CaeError('device entropy decoder: a stream is truncated')
         return sym
+
+    def decode_streams_gpu(self, strings, hw):
+        """list of N byte strings -> int32 symbols N x C x hw on the device."""
+        dev = self.quantiles.device
+        lens = np.array([len(s) for s in strings], dtype=np.int64)
+        if (lens % 4).any() or (lens < 8).any():
+            raise C.CaeError('entropy-coded stream is not a whole number of words >= 2')
+        off = np.zeros(len(strings) + 1, dtype=np.int64)
+        np.cumsum(lens // 4, out=off[1:])
+        blob = torch.from_numpy(np.frombuffer(b''.join(bytes(s) for s in strings), dtype=np.int32).copy())
+        return self.decode_streams_device(blob.to(dev, non_blocking=True), off, hw)
 
     def decompress(self, strings, size):
         hw = int(np.prod(size))

@@ -90,3 +90,59 @@ def padded_tile(src, y0, x0, ps, fill_value=0):
     out = np.full((ps, ps, c), fill_value, dtype=tile.dtype)
     out[:tile.shape[0], :tile.shape[1]] = tile
     return out
+
+
+# --------------------------------------------------------------------------
+# Native batch I/O of the tile loops (csrc/host_io.cpp through the C ABI)
+# --------------------------------------------------------------------------
+
+def _paths_blob(paths):
+    return b''.join(os.fsencode(p) + b'\0' for p in paths)
+
+
+def native_gather(src, ps, tile_yx, dst, threads):
+    """dst[k] = ps x ps x C tile tile_yx[k] of the C-contiguous uint8 H x W x C ndarray ``src``
+    (edge tiles zero filled), by native threads (``cae_tiles_gather_u8``)."""
+    from . import _cabi as C
+    tile_yx = np.ascontiguousarray(tile_yx, dtype=np.int32)
+    h, w, c = src.shape
+    C.check(C.lib().cae_tiles_gather_u8(src.ctypes.data, h, w, c, ps, tile_yx.ctypes.data,
+                                        tile_yx.shape[0], dst.ctypes.data, threads))
+
+
+def can_native_gather(src):
+    return (isinstance(src, np.ndarray) and src.dtype == np.uint8 and src.ndim == 3
+            and src.flags.c_contiguous)
+
+
+def native_write(paths, headers, payload, payload_off, threads):
+    """File k = headers[k] (uint8 n x hdr_len, or None) + payload[payload_off[k]:payload_off[k+1]]
+    (``cae_files_write``: written as .partial, then renamed)."""
+    from . import _cabi as C
+    off = np.ascontiguousarray(payload_off, dtype=np.int64)
+    hdr_len = 0 if headers is None else headers.shape[1]
+    if headers is not None:
+        headers = np.ascontiguousarray(headers, dtype=np.uint8)
+    C.check(C.lib().cae_files_write(_paths_blob(paths), len(paths),
+                                    headers.ctypes.data if headers is not None else None, hdr_len,
+                                    payload.ctypes.data, off.ctypes.data, threads))
+
+
+def native_read(paths, hdr_len, threads, alloc=None):
+    """Read files whole: returns (headers uint8 n x hdr_len, payload uint8 1-D, int64 offsets
+    n + 1).  ``alloc(nbytes)`` provides the payload buffer (a pinned one for uploads)."""
+    from . import _cabi as C
+    n = len(paths)
+    blob = _paths_blob(paths)
+    sizes = np.empty(n, dtype=np.int64)
+    C.check(C.lib().cae_files_stat(blob, n, sizes.ctypes.data, threads))
+    if (sizes < hdr_len).any():
+        bad = paths[int(np.argmax(sizes < hdr_len))]
+        raise FileNotFoundError('chunk file %s is missing or truncated' % bad)
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(sizes - hdr_len, out=off[1:])
+    headers = np.empty((n, max(hdr_len, 1)), dtype=np.uint8)
+    payload = alloc(int(off[-1])) if alloc is not None else np.empty(int(off[-1]), dtype=np.uint8)
+    C.check(C.lib().cae_files_read(blob, n, headers.ctypes.data, hdr_len, payload.ctypes.data,
+                                   off.ctypes.data, threads))
+    return headers[:, :hdr_len], payload, off

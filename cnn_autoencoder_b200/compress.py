@@ -24,7 +24,7 @@ import torch
 
 from . import _autoencoders as AE
 from ._entropy import encode_symbols
-from ._store import DirArray, padded_tile
+from ._store import DirArray, can_native_gather, native_gather, native_write, padded_tile
 
 
 def shard_range(n_items, rank, world_size):
@@ -135,6 +135,7 @@ def compress_image(codec, checkpoint, input_filename, output_filename, patch_siz
     coder = ThreadPoolExecutor(max_workers=1)      # entropy-codes one group while the transforms
     coder_stream = torch.cuda.Stream()             # of the next group run on the main stream
     coder_jobs = []
+    out_pin = [None]                               # reused pinned buffer of the coder thread
     device = torch.cuda.current_device()
 
     def write_stream(idx, h, w, data):
@@ -161,12 +162,21 @@ def compress_image(codec, checkpoint, input_filename, output_filename, patch_siz
                 with torch.cuda.stream(coder_stream):
                     coder_stream.wait_event(ready)
                     packed, off = fact_ent.encode_symbols_device(sym)
-                    host = torch.empty(packed.numel(), dtype=torch.uint8, pin_memory=True)
+                    # page-locked allocations stall every other CUDA call of the process: keep
+                    # one buffer for all groups and only grow it
+                    if out_pin[0] is None or out_pin[0].numel() < packed.numel():
+                        out_pin[0] = torch.empty(int(packed.numel() * 1.25) + 4096,
+                                                 dtype=torch.uint8, pin_memory=True)
+                    host = out_pin[0][:packed.numel()]
                     host.copy_(packed, non_blocking=True)
                     coder_stream.synchronize()
-                view = memoryview(host.numpy())
-                return [pool.submit(write_stream, idx, h, w, view[int(off[k]):int(off[k + 1])])
-                        for k, (idx, h, w) in enumerate(meta)]
+                # one native call writes the group's chunk files (16-byte header + stream each)
+                hdr = np.frombuffer(b''.join(struct.pack('>QQ', h, w) for _, h, w in meta),
+                                    dtype=np.uint8).reshape(len(meta), 16)
+                native_write([dst.chunk_file(idx) for idx, _, _ in meta], hdr, host.numpy(), off,
+                             workers)
+                stats['bytes'] += int(off[-1]) + 16 * len(meta)
+                return []
             coder_jobs.append(coder.submit(job))
             stats['device_coded'] += n
         else:
@@ -186,6 +196,11 @@ def compress_image(codec, checkpoint, input_filename, output_filename, patch_siz
         if id(pin) in staged:
             staged.pop(id(pin)).synchronize()          # its previous upload has been consumed
         pin_np = pin.numpy()
+        if native_src and batch[0][1] is None:
+            native_gather(src, ps, np.array([ij for ij, _ in batch], dtype=np.int32), pin_np, workers)
+            batch_done = True
+        else:
+            batch_done = False
 
         def put(k):
             (i, j), tile = batch[k]
@@ -197,7 +212,8 @@ def compress_image(codec, checkpoint, input_filename, output_filename, patch_siz
             if part.shape[0] != ps or part.shape[1] != ps:
                 pin_np[k] = 0                          # edge chunk: zero fill, as zarr pads
             pin_np[k, :part.shape[0], :part.shape[1]] = part
-        list(pool.map(put, range(len(batch))))
+        if not batch_done:
+            list(pool.map(put, range(len(batch))))
         x = pin.cuda(non_blocking=True)
         t1 = time.perf_counter()
         stats['t_stage'] += t1 - t0
@@ -228,6 +244,7 @@ def compress_image(codec, checkpoint, input_filename, output_filename, patch_siz
         return padded_tile(src, i * ps, j * ps, ps)
 
     pinned, staged = {}, {}
+    native_src = can_native_gather(src)      # in-memory / memory-mapped slide: native tile gather
 
     def _pinned(shape):
         # two reusable pinned staging buffers per batch shape, used alternately (page-locking

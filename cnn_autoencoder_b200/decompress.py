@@ -21,7 +21,7 @@ import torch
 
 from . import _autoencoders as AE
 from ._entropy import decode_symbols
-from ._store import DirArray
+from ._store import DirArray, native_read, native_write
 from .compress import _dist_info, shard_range
 
 
@@ -141,16 +141,94 @@ def decompress_image(input_filename, output_filename, destination_format='zarr',
             prev = cur
         stats['t_gpu'] += time.perf_counter() - t1
 
+    pins = {}
+
+    def out_pin(shape, slot):
+        # two alternating page-locked output buffers per shape (allocating them per batch would
+        # stall the other CUDA calls of the process)
+        key = (shape, slot)
+        if key not in pins:
+            pins[key] = torch.empty(shape, dtype=torch.uint8, pin_memory=True)
+        return pins[key]
+
+    read_pin = [None]
+
+    def read_alloc(nbytes):
+        if read_pin[0] is None or read_pin[0].numel() < nbytes:
+            read_pin[0] = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
+        return read_pin[0][:nbytes].numpy()
+
+    def run_native(part):
+        """The fast path for one read batch: chunk files -> pinned buffer (native threads) ->
+        device -> all streams decoded in one call -> synthesis transform per ``batch_tiles`` ->
+        pinned buffer -> chunk files (native threads).  Returns False when the batch does not
+        qualify (mixed tile shapes, too few streams): the caller then takes the general path."""
+        n = len(part)
+        if n < fact_ent.GPU_CODER_MIN_STREAMS or want_png:
+            return False
+        t0 = time.perf_counter()
+        paths = [src.chunk_file((i, j, 0)) for i, j in part]
+        hdr, payload, off = native_read(paths, 16, workers, alloc=read_alloc)
+        hw = hdr.copy().view('>u8').reshape(n, 2).astype(np.int64)
+        if (hw != hw[0]).any() or (off % 4).any():
+            return False
+        h, w = int(hw[0, 0]), int(hw[0, 1])
+        lh, lw = (h // 2 ** level, w // 2 ** level) if codec_id == 'cae' else (h, w)
+        stats['t_read'] += time.perf_counter() - t0
+        t1 = time.perf_counter()
+        words = torch.from_numpy(payload).view(torch.int32).cuda(non_blocking=True)
+        sym = fact_ent.decode_streams_device(words, off // 4, lh * lw).reshape(n, C_bn, lh, lw)
+        stats['device_decoded'] += n
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        stats['t_decode'] += t2 - t1
+        tile_bytes = ps * ps * c_img
+        prev = None
+        for k0 in range(0, n + batch_tiles, batch_tiles):
+            cur = None
+            if k0 < n:
+                y_q = sym[k0:k0 + batch_tiles].float() + med
+                _, _, u8 = decoder(y_q, as_uint8='only')
+                host = out_pin(tuple(u8.shape), (k0 // batch_tiles) & 1)
+                host.copy_(u8, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record()
+                cur = (k0, host, done)
+            if prev is not None:                 # write batch k-1 while batch k runs on the GPU
+                p0, phost, pdone = prev
+                pdone.synchronize()
+                img = phost.numpy()
+                m = img.shape[0]
+                if img.shape[1] != ps or img.shape[2] != ps:
+                    return False                 # (cannot happen for the 'cae' codec: full chunks)
+                for k in range(m):               # zero what lies beyond the image (edge chunks)
+                    i, j = part[p0 + k]
+                    vh, vw = min(ps, H - i * ps), min(ps, W - j * ps)
+                    if vh < ps:
+                        img[k, vh:] = 0
+                    if vw < ps:
+                        img[k, :, vw:] = 0
+                    stats['pixels'] += vh * vw
+                native_write([dst.chunk_file((i, j, 0)) for i, j in part[p0:p0 + m]], None,
+                             img.reshape(-1), np.arange(m + 1, dtype=np.int64) * tile_bytes, workers)
+            prev = cur
+        stats['t_gpu'] += time.perf_counter() - t2
+        return True
+
     groups = {}
-    t0 = time.perf_counter()
-    items = list(pool.map(read_tile, mine))
-    stats['t_read'] = time.perf_counter() - t0
-    for item in items:
-        g = groups.setdefault(item[1], [])
-        g.append(item)
-        if len(g) == coder_tiles:
-            run_group(g)
-            groups[item[1]] = []
+    for r0 in range(0, len(mine), coder_tiles):
+        part = mine[r0:r0 + coder_tiles]
+        if codec_id == 'cae' and run_native(part):
+            continue
+        t0 = time.perf_counter()
+        items = list(pool.map(read_tile, part))
+        stats['t_read'] += time.perf_counter() - t0
+        for item in items:
+            g = groups.setdefault(item[1], [])
+            g.append(item)
+            if len(g) == coder_tiles:
+                run_group(g)
+                groups[item[1]] = []
     for g in groups.values():
         if g:
             run_group(g)

@@ -244,6 +244,24 @@ int cae_rans_decode_batch(const uint32_t *words, const int64_t *word_offsets, in
                           const int32_t *cdfs, int cdf_stride, const int32_t *cdf_sizes,
                           const int32_t *offsets, int32_t *symbols, int32_t *status, void *stream);
 
+/* ---- tile-loop front end (HOST, native threads) ------------------------------- */
+/* What the reference leaves to dask's threaded scheduler and zarr's chunk store
+ * (compress.py:101-128, decompress.py:72-96), on whole batches of tiles so that a Python loop
+ * does not bound the GPU.  All pointers are host pointers; `threads` native threads per call.
+ *  cae_tiles_gather_u8: dst[k] = ps x ps x c tile (tile_yx[2k], tile_yx[2k+1]) of the row-major
+ *    H x W x c uint8 image, edge tiles zero filled (zarr's chunk padding).
+ *  cae_files_write: file k = headers[k*hdr_len ..][hdr_len] + payload[payload_off[k] ..
+ *    payload_off[k+1]); paths = n NUL-terminated strings back to back; written as
+ *    <path>.partial then renamed.
+ *  cae_files_stat / cae_files_read: sizes, then header / payload split back the same way.   */
+int cae_tiles_gather_u8(const uint8_t *src, int64_t H, int64_t W, int c, int ps,
+                        const int32_t *tile_yx, int n, uint8_t *dst, int threads);
+int cae_files_write(const char *paths, int n, const uint8_t *headers, int hdr_len,
+                    const uint8_t *payload, const int64_t *payload_off, int threads);
+int cae_files_stat(const char *paths, int n, int64_t *sizes, int threads);
+int cae_files_read(const char *paths, int n, uint8_t *headers, int hdr_len, uint8_t *payload,
+                   const int64_t *payload_off, int threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -307,7 +307,19 @@ def init_transform_state(arch, seed):
                     sd[key + '.gamma'] = gamma
         return sd
 
-    return fill(analysis_plan(a), False), fill(synthesis_plan(a), True)
+    enc_sd, dec_sd = fill(analysis_plan(a), False), fill(synthesis_plan(a), True)
+    if a['multiscale_analysis']:
+        # colour heads, R:417-429: Conv2d(channels_net * e^i -> channels_org), i reversed
+        L, e = a['compression_level'], a['channels_expansion']
+        for u, i in enumerate(reversed(range(L - 1))):
+            cin, cout = a['channels_net'] * e ** i, a['channels_org']
+            grp = cout if a['groups'] else 1
+            shape = (cout, cin // grp, 3, 3)
+            bound = gain * math.sqrt(6.0 / (shape[1] * 9 + shape[0] * 9))
+            dec_sd[f'color_layers.{u}.0.weight'] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+            if a['bias']:
+                dec_sd[f'color_layers.{u}.0.bias'] = torch.full((cout,), 0.01)
+    return enc_sd, dec_sd
 
 
 # --------------------------------------------------------------------------

@@ -419,3 +419,25 @@ def test_fused_quantizer_matches_standalone():
         assert abs(fused['bits'].item() - plain['bits'].item()) <= 1e-5 * abs(plain['bits'].item())
         assert torch.equal(fused['x_r_u8'], plain['x_r_u8'])
         assert int(req.status.item()) == 0
+
+
+def test_multiscale_colour_heads_match_oracle():
+    """multiscale_analysis=True (R:417-429): the reflect-padded colour heads on the intermediate
+    scales, run on the kept planar tensors, against the oracle (pinned to the reference for this
+    switch in tests/test_oracle_vs_reference.py)."""
+    from oracle import cae_oracle as O
+    arch = dict(channels_org=3, channels_net=32, channels_bn=16, compression_level=3,
+                act_layer_type='LeakyReLU', multiscale_analysis=True, bias=True)
+    chk = O.make_checkpoint(arch, seed=5)
+    model = _model(chk)
+    om = O.OracleModel(chk)
+    y_q = torch.round(torch.randn(2, 16, 8, 12, generator=torch.Generator().manual_seed(2)) * 4)
+    x_r, fx_brg = model['decoder'](y_q.cuda())
+    ref, _ = om.decoder(y_q)
+    assert len(x_r) == 3 and all(t is not None for t in x_r)
+    for got, want in zip(x_r, ref):
+        assert got.shape == want.shape
+        assert torch.allclose(got.cpu(), want, atol=2e-2, rtol=2e-2), (got.cpu() - want).abs().max()
+    # the codec path is unchanged by the switch
+    _, _, u8 = model['decoder'](y_q.cuda(), as_uint8='only')
+    assert u8.shape == (2, 64, 96, 3)

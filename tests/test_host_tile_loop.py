@@ -126,3 +126,22 @@ def test_model_mirror_builds_on_cpu_and_refuses_to_run():
                         act_layer_type='LeakyReLU', groups=True)
     with pytest.raises(ValueError):
         M.Analyzer(act_layer_type='LeakyRelU')      # the reference's own typo default is rejected
+
+
+def test_multiscale_synthesizer_train_mode_equals_oracle():
+    """The colour heads of multiscale_analysis=True exist with the reference's state-dict keys
+    and the train()-mode (torch) forward reproduces the oracle on CPU."""
+    import torch
+    import cnn_autoencoder_b200 as M
+    from oracle import cae_oracle as O
+    arch = dict(channels_org=3, channels_net=16, channels_bn=8, compression_level=3,
+                act_layer_type='LeakyReLU', multiscale_analysis=True, bias=True)
+    chk = O.make_checkpoint(arch, seed=6)
+    assert 'color_layers.0.0.weight' in chk['decoder'] and 'color_layers.1.0.bias' in chk['decoder']
+    model = M.autoencoder_from_state_dict(chk, gpu=False, train=True)
+    y = torch.randn(1, 8, 4, 6)
+    with torch.no_grad():
+        x_r, _ = model['decoder'](y)
+        ref, _ = O.OracleModel(chk).decoder(y)
+    for a, b in zip(x_r, ref):
+        assert torch.equal(a, b)
