@@ -28,15 +28,17 @@ struct EbParams {
 __global__ void __launch_bounds__(256) eb_quantize_kernel(const EbParams p) {
   extern __shared__ int32_t s_hist[];
   __shared__ float s_red[8];
-  const int nc = blockIdx.x;
-  const int c = nc % p.c;
+  // block = (channel c, image group g, hw slice): it walks images n = g, g + groups, ... of one
+  // channel, so the shared histogram is zeroed and flushed once per many thousand symbols
+  const int c = blockIdx.x % p.c, g = blockIdx.x / p.c, groups = gridDim.x / p.c;
   const int bins = p.hist ? p.t.hist_bins : 0;
   for (int i = threadIdx.x; i < bins; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
 
   const float med = p.t.medians[c];
-  const size_t base = (size_t)nc * p.hw;
   float bits = 0.f;
+  for (int n = g; n < p.n; n += groups) {
+  const size_t base = ((size_t)n * p.c + c) * p.hw;
   for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < p.hw; i += gridDim.y * blockDim.x) {
     const float y = p.y[base + i];
     const float r = rintf(y - med);  // torch.round: half to even
@@ -55,6 +57,7 @@ __global__ void __launch_bounds__(256) eb_quantize_kernel(const EbParams p) {
       b = b < 0 ? 0 : (b >= bins ? bins - 1 : b);
       atomicAdd(&s_hist[b], 1);
     }
+  }
   }
 
   if (p.rate_bits) {
@@ -90,7 +93,11 @@ extern "C" int cae_eb_quantize(const float *y, int n, int c, int hw, const cae_e
   int bx = (hw + 256 * 4 - 1) / (256 * 4);
   if (bx < 1) bx = 1;
   if (bx > 64) bx = 64;
-  dim3 grid((unsigned)(n * c), (unsigned)bx);
+  // about eight blocks per SM in total: images are grouped per channel to reach that
+  int groups = (8 * 148) / (c * bx);
+  if (groups < 1) groups = 1;
+  if (groups > n) groups = n;
+  dim3 grid((unsigned)(groups * c), (unsigned)bx);
   eb_quantize_kernel<<<grid, 256, bins * sizeof(int32_t), (cudaStream_t)stream>>>(p);
   cae_count_launch();
   CAE_CUDA(cudaGetLastError());
