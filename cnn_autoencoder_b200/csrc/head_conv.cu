@@ -8,12 +8,14 @@
 // Unfused, the stem writes a 16-channel-padded fp16 tensor at full image resolution that
 // the tensor-core layer reads straight back (2 x 268 MB at 128 x 256^2, for 3 real
 // channels) and the stride-2 layer spends 9 K=16 MMAs per tile on 3 channels.  Here the
-// stem result never leaves the SM: per 8 x 32 output tile a group of CUDA-core warps
+// stem result never leaves the SM: per 8 x 32 output tile a group of six CUDA-core warps
 // computes the 17 x 65 stem patch from the uint8 window into shared memory, gathers it as
-// an im2col A operand with K = 9 * c_in (27 -> 32) in the UMMA K-major core-matrix layout,
-// and one thread issues K/16 tcgen05 MMAs per 128 pixels into a double-buffered TMEM
-// accumulator that the epilogue warps drain (bias, activation, fp16 planar stores with the
-// consumer's reflect halo).  The kernel is bound by its output stores.
+// an im2col A operand with K = 9 * c_in taps + 2 bias columns (29 -> 32) in the UMMA K-major
+// core-matrix layout, and issues K/16 tcgen05 MMAs per 128 pixels into its TMEM accumulator;
+// two such groups work on alternating tiles, eight epilogue warps drain the accumulators
+// (activation, fp16 planar stores with the consumer's reflect halo).  Measured per tile and SM:
+// ~2.2 us of stem arithmetic, ~1.2 us window staging, ~1.2 us gather + MMA issue per group
+// (two tiles in flight), ~2 us epilogue; 221 us for 128 x 256^2 (504 us unfused).
 #include <stdlib.h>
 
 #include "cae_common.cuh"
@@ -25,15 +27,16 @@ constexpr int SR = 2 * TH + 1, SC = 2 * TW + 1;  // stem patch
 constexpr int WR = SR + 2, WC = SC + 2;          // image window
 constexpr int WPITCH = 72, SPITCH = SC + 1;       // window rows: 16-byte aligned, 4-px groups
 constexpr int kLut = 260;                        // x/255 for a byte; entry 256 = 0 (zero padding)
-constexpr int PXT = 4;                           // stem pixels per thread
+constexpr int PXT = 6;                           // stem pixels per thread: 11 x 17 = 187 work units
 constexpr int SG = (SC + PXT - 1) / PXT;         // pixel groups per patch row
 // The CUDA-core work is done by two independent groups of warps on alternating tiles (group g
-// fills A buffer g): their phases (window staging, stem arithmetic, gather) drift apart, so
-// one group's arithmetic overlaps the other's latency-bound phases and barriers.
-constexpr int kGroupWarps = 5, kGroupThreads = 32 * kGroupWarps;
+// fills A buffer g and accumulator g, and issues its own MMAs): two tiles are in flight per SM,
+// so one group's arithmetic overlaps the other's latency-bound phases and barriers.
+constexpr int kGroupWarps = 6, kGroupThreads = 32 * kGroupWarps;   // >= SR * SG: one pass per tile
 constexpr int kStemWarps = 2 * kGroupWarps, kStemThreads = 32 * kStemWarps;
 constexpr int kEpiWarps = 8;
-constexpr int kHeadThreads = kStemThreads + 32 + 32 * kEpiWarps;   // 10 + 1 (MMA) + 8 warps = 608
+constexpr int kHeadThreads = kStemThreads + 32 * kEpiWarps;   // 12 + 8 warps = 640
+static_assert(SR * SG <= kGroupThreads, "the stem arithmetic is one pass of a group");
 // (any 8 consecutive warps cover the four TMEM lane quadrants twice: (m, quadrant) below)
 
 struct HeadParams {
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
   float *lut = reinterpret_cast<float *>(S0 + 2 * ((L::S_ELEMS + 7) & ~7));
   float *w1s = lut + kLut;                               // [ci][kh][co][4] + bias
   uint64_t *bars = reinterpret_cast<uint64_t *>(w1s + L::W1N);
-  uint64_t *a_full = bars, *a_empty = bars + 2, *acc_full = bars + 4, *acc_empty = bars + 6;
+  uint64_t *a_empty = bars + 2, *acc_full = bars + 4, *acc_empty = bars + 6;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -110,14 +113,13 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
   }
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&a_full[b], 1);
       mbar_init(&a_empty[b], 1);
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], kEpiWarps);
     }
     fence_barrier_init();
   }
-  if (warp == kStemWarps) tmem_alloc(tmem_slot, p.tmem_cols);
+  if (warp == 0) tmem_alloc(tmem_slot, p.tmem_cols);
   fence_proxy_async();            // B operand written with generic stores, read by the MMA
   tc_fence_before();
   __syncthreads();
@@ -237,8 +239,8 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
       if (tr) p.trace[it * 8 + 1] = global_timer_ns();
       // 2. next tile's window loads fly while this tile is computed
       if (tile + tstep < p.n_tiles) prefetch(tile + tstep);
-      // 3. stem convolution: work unit = (patch row, 4 adjacent patch columns); the window row
-      //    segment is one 16-byte + one 8-byte shared load, the 3 x CI weights of a (ci, kh)
+      // 3. stem convolution: work unit = (patch row, 6 adjacent patch columns), one per thread;
+      //    the window row segment is four 8-byte shared loads, the 3 x CI weights of a (ci, kh)
       //    are CI 16-byte broadcast loads
 #pragma unroll 1
       for (int u = gtid; u < SR * SG && !(p.debug & 2); u += kGroupThreads) {
@@ -252,10 +254,14 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
         for (int ci = 0; ci < CI; ++ci)
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
-            const float *wrow = win + (ci * WR + r + kh) * WPITCH + x0;
-            const float4 a4 = *reinterpret_cast<const float4 *>(wrow);
-            const float2 a2 = *reinterpret_cast<const float2 *>(wrow + 4);
-            const float w6[PXT + 2] = {a4.x, a4.y, a4.z, a4.w, a2.x, a2.y};
+            const float *wrow = win + (ci * WR + r + kh) * WPITCH + x0;     // 8-byte aligned
+            float w6[PXT + 2];
+#pragma unroll
+            for (int j = 0; j < PXT + 2; j += 2) {
+              const float2 a2 = *reinterpret_cast<const float2 *>(wrow + j);
+              w6[j] = a2.x;
+              w6[j + 1] = a2.y;
+            }
 #pragma unroll
             for (int co = 0; co < CI; ++co) {
               const float4 wv = *reinterpret_cast<const float4 *>(w1s + ((ci * 3 + kh) * CI + co) * 4);
@@ -333,39 +339,35 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
       }
       fence_proxy_async();
       stem_bar(grp);
-      if (gtid == 0) mbar_arrive(&a_full[grp]);
+      // 5. the group's first warp issues the tile's MMAs itself (K / 16 per 128 pixels: there is
+      //    nothing to gain from a dedicated issuing warp, and the warp slot buys registers)
+      if (gwarp == 0) {
+        mbar_wait(&acc_empty[grp], (k & 1) ^ 1);       // the epilogue has drained accumulator g
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa_base = smem_u32(sA), sb_base = smem_u32(sB);
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            const uint32_t d = tmem_base + (uint32_t)((grp * 2 + m) * p.N);
+#pragma unroll
+            for (int ks = 0; ks < L::KP / 16; ++ks) {
+              const uint64_t da = make_smem_desc(
+                  sa_base + grp * L::A_BYTES + m * L::KG * 2048 + ks * 2 * 2048, 2048, 128);
+              const uint64_t db = make_smem_desc(sb_base + ks * 2 * p.N * 16, p.N * 16, 128);
+              umma_f16(d, da, db, p.idesc, ks > 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&a_empty[grp]);
+          umma_commit(&acc_full[grp]);
+        }
+        __syncwarp();
+      }
       if (tr) p.trace[it * 8 + 4] = global_timer_ns();
     }
-  } else if (warp == kStemWarps) {
-    // ========================================================== MMA issuer
-    const uint32_t sa_base = smem_u32(sA), sb_base = smem_u32(sB);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
-      mbar_wait_backoff(&a_full[buf], (it >> 1) & 1);
-      mbar_wait_backoff(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          const uint32_t d = tmem_base + (uint32_t)((buf * 2 + m) * p.N);
-#pragma unroll
-          for (int ks = 0; ks < L::KP / 16; ++ks) {
-            const uint64_t da = make_smem_desc(
-                sa_base + buf * L::A_BYTES + m * L::KG * 2048 + ks * 2 * 2048, 2048, 128);
-            const uint64_t db = make_smem_desc(sb_base + ks * 2 * p.N * 16, p.N * 16, 128);
-            umma_f16(d, da, db, p.idesc, ks > 0 ? 1u : 0u);
-          }
-        }
-        umma_commit(&a_empty[buf]);
-        umma_commit(&acc_full[buf]);
-      }
-      __syncwarp();
-    }
-  } else if (warp > kStemWarps) {
+  } else {
     // ============================================================ epilogue
     const int q = warp & 3;                       // TMEM lane quadrant this warp may read
-    const int m_first = kEpiWarps == 8 ? (warp - kStemWarps - 1) >> 2 : 0;   // 8 warps: one M tile each
+    const int m_first = kEpiWarps == 8 ? (warp - kStemWarps) >> 2 : 0;   // 8 warps: one M tile each
     const int m_step = kEpiWarps == 8 ? 2 : 1;
     const int tx = lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -380,7 +382,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
       const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
       const int ox = txi * TW + tx;
       mbar_wait_backoff(&acc_full[buf], (it >> 1) & 1);
-      if (p.trace && blockIdx.x == 0 && warp == kStemWarps + 1 && lane == 0 && it < 64) p.trace[it * 8 + 5] = global_timer_ns();
+      if (p.trace && blockIdx.x == 0 && warp == kStemWarps && lane == 0 && it < 64) p.trace[it * 8 + 5] = global_timer_ns();
       tc_fence_after();
 #pragma unroll 1
       for (int m = m_first; m < 2; m += m_step) {
@@ -450,13 +452,13 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
-      if (p.trace && blockIdx.x == 0 && warp == kStemWarps + 1 && lane == 0 && it < 64) p.trace[it * 8 + 6] = global_timer_ns();
+      if (p.trace && blockIdx.x == 0 && warp == kStemWarps && lane == 0 && it < 64) p.trace[it * 8 + 6] = global_timer_ns();
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kStemWarps) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (warp == 0) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 template <int CI>
