@@ -340,7 +340,7 @@ def main():
                 # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed
                 # ncu --set full capture (profiles/r01_ncu_full_enc2_128to128_s1_batch128.json);
                 # only meaningful for the default batch
-                'traffic': 1061193984 if (B == BATCH and args.arch == ARCH_NAME) else None,
+                'traffic': 1113868800 if (B == BATCH and args.arch == ARCH_NAME) else None,
                 'kernel': 'igemm_conv_kernel<EPI_ACT> conv3x3 s1 %d->%d @%dx%d x%d' % (
                     st.c_in, st.c_out, x_in.h, x_in.w, x_in.n),
                 'ms': round(t_ms, 4), 'ms_median': round(t_med, 4), 'ms_min': round(times[0], 4),
