@@ -134,7 +134,8 @@ def run_reference(args, rank, world):
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': round(dt / args.steps * 1e3, 3), 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'net {ARCH_NAME}, {BATCH}x3x{SIZE}x{SIZE} uint8 patches, '
+        'config': {'workload': f'net {ARCH_NAME} (3->128->128->48 L3 LeakyReLU), '
+                               f'{BATCH}x3x{SIZE}x{SIZE} uint8 patches per GPU, '
                                'encode+quantize+rate+decode', 'sample': sample},
         'cpu_baseline': {'value': round(val, 4), 'unit': 'MP/s', 'cores': cores, 'kind': 'port',
                          'sample': sample},
