@@ -441,3 +441,30 @@ def test_multiscale_colour_heads_match_oracle():
     # the codec path is unchanged by the switch
     _, _, u8 = model['decoder'](y_q.cuda(), as_uint8='only')
     assert u8.shape == (2, 64, 96, 3)
+
+
+@pytest.mark.parametrize('shape,c_org', [((2, 64, 96), 3), ((1, 40, 56), 1), ((2, 40, 72), 4),
+                                         ((1, 256, 256), 3)])
+def test_fused_head_matches_the_two_kernel_path(shape, c_org):
+    """cae_conv_head (stem + first stride-2 layer in one launch) against the unfused pair of
+    kernels on the same weights: same fp16 rounding points, so the latents agree to fp16
+    accumulation-order noise and both sit within the oracle tolerance."""
+    from oracle import cae_oracle as O
+    arch = dict(channels_org=c_org, channels_net=32, channels_bn=16, compression_level=3,
+                act_layer_type='LeakyReLU', bias=True)
+    chk = O.make_checkpoint(arch, seed=21)
+    model = _model(chk)
+    n, h, w = shape
+    x = O.synth_natural(n, c_org, h, w, seed=9)
+    x_in = x.permute(0, 2, 3, 1).contiguous().cuda() if c_org == 3 else (x.float() / 255.0).cuda()
+    enc = model['encoder']
+    ex = enc.module._executor()
+    ex.fuse_head = True
+    y_fused = enc(x_in).clone()
+    assert ex.last_calls[0][0] == 'head'
+    ex.fuse_head = False
+    y_plain = enc(x_in).clone()
+    assert ex.last_calls[0][0] != 'head'
+    ref = O.OracleModel(chk).encoder(x.float() / 255.0)
+    assert torch.allclose(y_fused.cpu(), ref, atol=2e-2, rtol=2e-2)
+    assert torch.allclose(y_fused, y_plain, atol=1e-2, rtol=1e-2)

@@ -145,3 +145,33 @@ def test_multiscale_synthesizer_train_mode_equals_oracle():
         ref, _ = O.OracleModel(chk).decoder(y)
     for a, b in zip(x_r, ref):
         assert torch.equal(a, b)
+
+
+def test_native_tile_gather_and_chunk_files(tmp_path):
+    """csrc/host_io.cpp through the C ABI (no GPU): tiles cut out of a slide with zero-filled
+    edges equal ``padded_tile``; chunk files written / read back by native threads keep the
+    header / payload split byte for byte."""
+    import numpy as np
+    from cnn_autoencoder_b200 import _store as S
+    rng = np.random.default_rng(0)
+    src = rng.integers(0, 255, (700, 900, 3), dtype=np.uint8)
+    ps = 256
+    yx = np.array([[0, 0], [2, 3], [1, 2], [2, 0], [0, 3]], dtype=np.int32)
+    dst = np.full((len(yx), ps, ps, 3), 7, np.uint8)
+    assert S.can_native_gather(src) and not S.can_native_gather(src[:, ::2])
+    S.native_gather(src, ps, yx, dst, 4)
+    for k, (ty, tx) in enumerate(yx):
+        assert np.array_equal(dst[k], S.padded_tile(src, ty * ps, tx * ps, ps)), k
+    paths = [str(tmp_path / f'c.{k}') for k in range(6)]
+    payload = rng.integers(0, 255, 4000, dtype=np.uint8)
+    off = np.array([0, 16, 16, 900, 2777, 3999, 4000])          # includes an empty payload
+    hdr = rng.integers(0, 255, (6, 16), dtype=np.uint8)
+    S.native_write(paths, hdr, payload, off, 3)
+    assert not list(tmp_path.glob('*.partial'))
+    h2, p2, o2 = S.native_read(paths, 16, 3)
+    assert np.array_equal(h2, hdr) and np.array_equal(p2, payload) and np.array_equal(o2, off)
+    with open(paths[3], 'rb') as f:
+        assert f.read() == hdr[3].tobytes() + payload[900:2777].tobytes()
+    import pytest
+    with pytest.raises(FileNotFoundError):
+        S.native_read(paths + [str(tmp_path / 'missing')], 16, 2)
