@@ -52,7 +52,9 @@ class HeadDesc(ctypes.Structure):
                 ('w_stem', ctypes.c_void_p), ('b_stem', ctypes.c_void_p),
                 ('w_down', ctypes.c_void_p), ('b_down', ctypes.c_void_p),
                 ('act_stem', ctypes.c_int32), ('act_down', ctypes.c_int32),
-                ('pad_mode', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+                ('pad_mode', ctypes.c_int32), ('residual', ctypes.c_int32),
+                ('w_stem2', ctypes.c_void_p), ('b_stem2', ctypes.c_void_p),
+                ('act_mid', ctypes.c_int32), ('reserved', ctypes.c_int32)]
 
 
 class EbTables(ctypes.Structure):

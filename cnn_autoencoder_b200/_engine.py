@@ -173,22 +173,34 @@ class TrackExecutor:
         halo = C.HALO_REFLECT if (not nxt.transposed and nxt.pad_mode == C.PAD_REFLECT) else C.HALO_KEEP
         return fmt, halo
 
-    def _head_pair(self, k, cur, keep, final_fmt):
-        """True when steps k, k+1 are the stem + stride-2 pair of the first downsampling unit
-        reading the raw image, and the fused kernel covers them."""
-        if not self.fuse_head or k + 2 > len(self.steps) - 1 or (k + 1) in keep:
-            return False
-        a, b = self.steps[k], self.steps[k + 1]
-        if cur.fmt not in (C.FMT_U8_HWC, C.FMT_F32_NCHW):
-            return False
-        plain = lambda s: (s.skip is None and s.gdn is None and s.post_act is None
-                           and not s.transposed)
-        if not (plain(a) and plain(b) and a.kind == C.CONV_S1 and b.kind == C.CONV_S2):
-            return False
-        if not (a.c_in <= 4 and a.c_out == a.c_in and b.c_in == a.c_in and b.c_out <= 128):
-            return False
-        fmt, _ = self._consumer_layout(k + 2, final_fmt)
-        return a.pad_mode == b.pad_mode and fmt == C.FMT_F16_PLANAR
+    def _head_match(self, k, cur, keep, final_fmt):
+        """Number of steps (2: plain unit, 3: residual unit, 0: none) starting at k that form the
+        first downsampling unit reading the raw image and that the fused kernel covers."""
+        if not self.fuse_head or cur.fmt not in (C.FMT_U8_HWC, C.FMT_F32_NCHW):
+            return 0
+        for span in (2, 3):
+            if k + span > len(self.steps) - 1 or any((k + j) in keep for j in range(1, span)):
+                continue
+            steps = self.steps[k:k + span]
+            if any(s.gdn is not None or s.transposed or s.pad_mode != steps[0].pad_mode
+                   for s in steps):
+                continue
+            a, down = steps[0], steps[-1]
+            stems_ok = all(s.kind == C.CONV_S1 and s.c_in <= 4 and s.c_out == s.c_in
+                           for s in steps[:-1])
+            if not (stems_ok and down.kind == C.CONV_S2 and down.c_in == a.c_in and
+                    down.c_out <= 128 and down.skip is None and down.post_act is None):
+                continue
+            if a.skip is not None or a.post_act is not None:
+                continue
+            if span == 3:
+                b = steps[1]
+                if not (b.skip == k and b.pre_act is None):     # res + x, then the activation
+                    continue
+            fmt, _ = self._consumer_layout(k + span, final_fmt)
+            if fmt == C.FMT_F16_PLANAR:
+                return span
+        return 0
 
     def _buffer(self, key, fmt, n, c, h, w, halo, device):
         full = (key, fmt, n, c, h, w, halo, str(device))
@@ -212,26 +224,31 @@ class TrackExecutor:
         aux = None
         n_steps = len(self.steps)
         self.last_calls = {}
-        fused = False
+        skip_steps = 0
         for k, st in enumerate(self.steps):
-            if fused:                     # consumed by the fused head launched at k - 1
-                fused = False
+            if skip_steps:                # consumed by the fused head launched before
+                skip_steps -= 1
                 continue
-            if self._head_pair(k, cur, keep, final_fmt):
-                nxt = self.steps[k + 1]
+            span = self._head_match(k, cur, keep, final_fmt)
+            if span:
+                down = self.steps[k + span - 1]
                 w1, b1 = st.materialise(False)
-                w2, b2 = nxt.materialise(False)
-                ho, wo = O.KIND_OUT[nxt.kind](cur.h, cur.w)
-                fmt, halo = self._consumer_layout(k + 2, final_fmt)
-                out = self._buffer(k + 1, fmt, cur.n, nxt.c_out, ho, wo, halo, cur.t.device)
-                call = ('head', (cur, w1, b1, w2, b2, nxt.c_out, out),
-                        dict(act_stem=act_code(st.pre_act), act_down=act_code(nxt.pre_act),
-                             pad_mode=st.pad_mode))
+                w2, b2 = down.materialise(False)
+                ho, wo = O.KIND_OUT[down.kind](cur.h, cur.w)
+                fmt, halo = self._consumer_layout(k + span, final_fmt)
+                out = self._buffer(k + span - 1, fmt, cur.n, down.c_out, ho, wo, halo, cur.t.device)
+                kw = dict(act_stem=act_code(st.pre_act), act_down=act_code(down.pre_act),
+                          pad_mode=st.pad_mode)
+                if span == 3:
+                    mid = self.steps[k + 1]
+                    kw['w_stem2'], kw['b_stem2'] = mid.materialise(False)
+                    kw['act_mid'] = act_code(mid.post_act)
+                call = ('head', (cur, w1, b1, w2, b2, down.c_out, out), kw)
                 O.conv_head(*call[1], **call[2])
                 self.last_calls[k] = call
-                tensors[k + 2] = out
+                tensors[k + span] = out
                 cur = out
-                fused = True
+                skip_steps = span - 1
                 continue
             igemm = self._use_igemm(st, cur)
             if igemm and cur.fmt not in (C.FMT_F16_PLANAR, C.FMT_F16_SPLIT):

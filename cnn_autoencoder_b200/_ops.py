@@ -132,9 +132,12 @@ def conv(kind, x, weights, c_out, out, *, igemm, bias=None, skip=None, pre_act=C
 
 
 def conv_head(x, w_stem, b_stem, w_down, b_down, c_out, out, *, act_stem=C.ACT_NONE,
-              act_down=C.ACT_NONE, pad_mode=C.PAD_REFLECT):
+              act_down=C.ACT_NONE, pad_mode=C.PAD_REFLECT, w_stem2=None, b_stem2=None,
+              act_mid=C.ACT_NONE):
     """out = act_down(conv_s2(act_stem(conv_s1(x) + b_stem)) + b_down): the fused first
-    downsampling unit (``cae_conv_head``).  x: U8_HWC / F32_NCHW Act, out: planar Act."""
+    downsampling unit (``cae_conv_head``).  x: U8_HWC / F32_NCHW Act, out: planar Act.
+    With ``w_stem2`` the residual form: the stride-2 convolution reads
+    ``act_mid(conv_s1_b(act_stem(conv_s1_a(x) + b_stem)) + b_stem2 + x)``."""
     d = C.HeadDesc()
     d.n, d.h_in, d.w_in, d.c_in, d.c_out = x.n, x.h, x.w, x.c, c_out
     d.inp = x.desc()
@@ -142,6 +145,11 @@ def conv_head(x, w_stem, b_stem, w_down, b_down, c_out, out, *, act_stem=C.ACT_N
     d.w_stem, d.b_stem = w_stem.data_ptr(), (b_stem.data_ptr() if b_stem is not None else None)
     d.w_down, d.b_down = w_down.data_ptr(), (b_down.data_ptr() if b_down is not None else None)
     d.act_stem, d.act_down, d.pad_mode = act_stem, act_down, pad_mode
+    if w_stem2 is not None:
+        d.residual = 1
+        d.w_stem2 = w_stem2.data_ptr()
+        d.b_stem2 = b_stem2.data_ptr() if b_stem2 is not None else None
+        d.act_mid = act_mid
     C.check(C.lib().cae_conv_head(ctypes.byref(d), _stream_ptr()))
     return out
 

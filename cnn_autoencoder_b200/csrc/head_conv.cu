@@ -24,8 +24,18 @@ namespace {
 
 constexpr int TH = 8, TW = 32;                 // output tile (two M=128 accumulators)
 constexpr int SR = 2 * TH + 1, SC = 2 * TW + 1;  // stem patch
-constexpr int WR = SR + 2, WC = SC + 2;          // image window
-constexpr int WPITCH = 72, SPITCH = SC + 1;       // window rows: 16-byte aligned, 4-px groups
+constexpr int SPITCH = SC + 1;
+// image window: one halo ring for the plain unit, two for the residual unit (two stacked
+// stride-1 convolutions); rows are 16-byte aligned and long enough for the widest work unit
+template <bool RES>
+struct Win {
+  static constexpr int HALO = RES ? 2 : 1;
+  static constexpr int WR = SR + 2 * HALO, WC = SC + 2 * HALO;
+  static constexpr int WPITCH = RES ? 76 : 72;
+  // residual unit: first convolution's output (fp32), one ring larger than the stem patch
+  static constexpr int R1 = SR + 2, C1 = SC + 2, P1 = 72;
+  static constexpr int PX1 = 8, G1 = (C1 + PX1 - 1) / PX1;     // 9 x 19 = 171 work units
+};
 constexpr int kLut = 260;                        // x/255 for a byte; entry 256 = 0 (zero padding)
 constexpr int PXT = 6;                           // stem pixels per thread: 11 x 17 = 187 work units
 constexpr int SG = (SC + PXT - 1) / PXT;         // pixel groups per patch row
@@ -36,7 +46,8 @@ constexpr int kGroupWarps = 6, kGroupThreads = 32 * kGroupWarps;   // >= SR * SG
 constexpr int kStemWarps = 2 * kGroupWarps, kStemThreads = 32 * kStemWarps;
 constexpr int kEpiWarps = 8;
 constexpr int kHeadThreads = kStemThreads + 32 * kEpiWarps;   // 12 + 8 warps = 640
-static_assert(SR * SG <= kGroupThreads, "the stem arithmetic is one pass of a group");
+static_assert(SR * SG <= kGroupThreads && Win<true>::R1 * Win<true>::G1 <= kGroupThreads,
+              "each stem stage is one pass of a group");
 // (any 8 consecutive warps cover the four TMEM lane quadrants twice: (m, quadrant) below)
 
 struct HeadParams {
@@ -46,7 +57,8 @@ struct HeadParams {
   const void *in;
   ActView out;
   const float *w1, *b1, *w2, *b2;
-  float s1, s2;
+  const float *w1b, *b1b;      // residual unit: second stride-1 convolution
+  float s1, s2, sm;            // activation slopes: stem, down, (residual) after the add
   uint32_t idesc;
   uint32_t tmem_cols;
   unsigned long long *trace;   // CAE_HEAD_TRACE: per-tile phase timestamps of CTA 0 (ns)
@@ -63,26 +75,31 @@ __device__ __forceinline__ void stem_bar(int group) {
   asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(kGroupThreads));
 }
 
-template <int CI>
+template <int CI, bool RES>
 struct HeadSmem {
+  using W = Win<RES>;
   // K columns: 9 * CI taps, then two columns of ones that carry the bias as an fp16 hi + lo
   // pair (exact to ~2^-22 relative), so the epilogue has no bias add
   static constexpr int K = 9 * CI, KB = K + 2, KP = (KB + 15) / 16 * 16, KG = KP / 8;
   static constexpr int A_BYTES = 2 * KG * 2048;              // one buffer: two M tiles
-  static constexpr int WIN_ELEMS = CI * WR * WPITCH;
+  static constexpr int WIN_ELEMS = CI * W::WR * W::WPITCH;
+  static constexpr int S1_ELEMS = RES ? CI * W::R1 * W::P1 : 0;
   static constexpr int S_ELEMS = CI * SR * SPITCH;
-  static constexpr int W1N = CI * 3 * CI * 4 + 4;            // [ci][kh][co][4] stem weights + bias
+  static constexpr int W1N = (RES ? 2 : 1) * (CI * 3 * CI * 4 + 4);   // [ci][kh][co][4] weights + bias, per stem conv
 
 };
 
-template <int CI, bool U8>
+template <int CI, bool U8, bool RES>
 __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadParams p) {
-  using L = HeadSmem<CI>;
+  using L = HeadSmem<CI, RES>;
+  using W = Win<RES>;
+  constexpr int WR = W::WR, WC = W::WC, WPITCH = W::WPITCH, HALO = W::HALO;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t *sA = smem;                                   // [2][2][KG][128][16 B]
   uint8_t *sB = sA + 2 * L::A_BYTES;                    // [KG][N][16 B]
   float *win0 = reinterpret_cast<float *>(sB + L::KG * p.N * 16);          // one window per group
-  __half *S0 = reinterpret_cast<__half *>(win0 + 2 * L::WIN_ELEMS);         // one stem patch per group
+  float *s1_0 = win0 + 2 * L::WIN_ELEMS;                                     // residual: first conv's output
+  __half *S0 = reinterpret_cast<__half *>(s1_0 + 2 * L::S1_ELEMS);          // one stem patch per group
   float *lut = reinterpret_cast<float *>(S0 + 2 * ((L::S_ELEMS + 7) & ~7));
   float *w1s = lut + kLut;                               // [ci][kh][co][4] + bias
   uint64_t *bars = reinterpret_cast<uint64_t *>(w1s + L::W1N);
@@ -99,6 +116,14 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
     w1s[i] = kw < 3 ? p.w1[((co * CI + ci) * 3 + kh) * 3 + kw] : 0.f;
   }
   if (tid < 4) w1s[CI * 3 * CI * 4 + tid] = (p.b1 && tid < CI) ? p.b1[tid] : 0.f;
+  constexpr int WSET = CI * 3 * CI * 4 + 4;
+  if (RES) {
+    for (int i = tid; i < CI * 3 * CI * 4; i += kHeadThreads) {
+      const int kw = i & 3, co = (i >> 2) % CI, kh = ((i >> 2) / CI) % 3, ci = (i >> 2) / (3 * CI);
+      w1s[WSET + i] = kw < 3 ? p.w1b[((co * CI + ci) * 3 + kh) * 3 + kw] : 0.f;
+    }
+    if (tid < 4) w1s[WSET + CI * 3 * CI * 4 + tid] = (p.b1b && tid < CI) ? p.b1b[tid] : 0.f;
+  }
   for (int i = tid; i < p.N * L::KP; i += kHeadThreads) {
     const int nn = i / L::KP, k = i - nn * L::KP;
     __half hv = __float2half_rn(0.f);
@@ -132,6 +157,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
     const int grp = warp / kGroupWarps, gwarp = warp - grp * kGroupWarps;
     const int gtid = tid - grp * kGroupThreads;
     float *win = win0 + grp * L::WIN_ELEMS;
+    float *s1 = s1_0 + grp * L::S1_ELEMS;
     __half *S = S0 + grp * ((L::S_ELEMS + 7) & ~7);
     // The window is read line by line: a line is one image row of the window (uint8 HWC:
     // WC * CI contiguous bytes) or one (channel, row) of an fp32 NCHW image (WC floats).
@@ -149,7 +175,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
     auto prefetch = [&](int tile) {
       const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
       const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
-      const int wy0 = 2 * tyi * TH - 2, wx0 = 2 * txi * TW - 2;
+      const int wy0 = 2 * tyi * TH - 1 - HALO, wx0 = 2 * txi * TW - 1 - HALO;
       if (wx0 >= 0 && wx0 + WC <= p.w_in) {
         // no column of the window leaves the image (the common case): a line is one
         // contiguous run at constant offsets; its row resolves the padding by itself
@@ -239,22 +265,92 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
       if (tr) p.trace[it * 8 + 1] = global_timer_ns();
       // 2. next tile's window loads fly while this tile is computed
       if (tile + tstep < p.n_tiles) prefetch(tile + tstep);
-      // 3. stem convolution: work unit = (patch row, 6 adjacent patch columns), one per thread;
-      //    the window row segment is four 8-byte shared loads, the 3 x CI weights of a (ci, kh)
-      //    are CI 16-byte broadcast loads
-#pragma unroll 1
-      for (int u = gtid; u < SR * SG && !(p.debug & 2); u += kGroupThreads) {
-        const int r = u / SG, x0 = (u - r * SG) * PXT;
+      // 3. stem arithmetic.  A work unit = (patch row, PX adjacent patch columns), one per
+      //    thread; a source row segment is a few 8-byte shared loads, the 3 x CI weights of a
+      //    (ci, kh) are CI 16-byte broadcast loads.
+      const float *src2 = win;             // what the convolution feeding the patch reads
+      int src2_rows = WR, src2_pitch = WPITCH;
+      const float *wset2 = w1s;
+      if (RES) {
+        // 3a. residual unit, first convolution (R:114-124): S1 = act(conv_a(x) + b_a) in fp32 on
+        //     the patch grown by one ring
+        constexpr int PX1 = W::PX1;
+        if (gtid < W::R1 * W::G1 && !(p.debug & 2)) {
+          const int r = gtid / W::G1, x0 = (gtid - r * W::G1) * PX1;
+          float acc[PX1][CI];
+#pragma unroll
+          for (int q = 0; q < PX1; ++q)
+#pragma unroll
+            for (int co = 0; co < CI; ++co) acc[q][co] = w1s[CI * 3 * CI * 4 + co];
+#pragma unroll
+          for (int ci = 0; ci < CI; ++ci)
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+              const float *wrow = win + (ci * WR + r + kh) * WPITCH + x0;     // 16-byte aligned
+              float w10[PX1 + 2];
+#pragma unroll
+              for (int j = 0; j < PX1 + 2; j += 2) {
+                const float2 a2 = *reinterpret_cast<const float2 *>(wrow + j);
+                w10[j] = a2.x;
+                w10[j + 1] = a2.y;
+              }
+#pragma unroll
+              for (int co = 0; co < CI; ++co) {
+                const float4 wv = *reinterpret_cast<const float4 *>(w1s + ((ci * 3 + kh) * CI + co) * 4);
+#pragma unroll
+                for (int q = 0; q < PX1; ++q) {
+                  acc[q][co] = fmaf(w10[q], wv.x, acc[q][co]);
+                  acc[q][co] = fmaf(w10[q + 1], wv.y, acc[q][co]);
+                  acc[q][co] = fmaf(w10[q + 2], wv.z, acc[q][co]);
+                }
+              }
+            }
+#pragma unroll
+          for (int q = 0; q < PX1; ++q)
+            if (x0 + q < W::C1) {
+#pragma unroll
+              for (int co = 0; co < CI; ++co) {
+                const float v = acc[q][co];
+                s1[(co * W::R1 + r) * W::P1 + x0 + q] = fmaxf(v, v * p.s1);
+              }
+            }
+        }
+        stem_bar(grp);
+        // 3b. the second convolution pads S1 by itself (R:125-137): positions of the ring that lie
+        //     outside the image take the mirrored (or zero) value -- border tiles only
+        const int g1y = lo_y - 1, g1x = lo_x - 1;
+        if (g1y < 0 || g1y + W::R1 > p.h_in || g1x < 0 || g1x + W::C1 > p.w_in) {
+          for (int e = gtid; e < W::R1 * W::C1; e += kGroupThreads) {
+            const int r = e / W::C1, c = e - r * W::C1;
+            const int gy = g1y + r, gx = g1x + c;
+            if (gy >= 0 && gy < p.h_in && gx >= 0 && gx < p.w_in) continue;
+            int sr = reflect_i(gy, p.h_in) - g1y, sc = reflect_i(gx, p.w_in) - g1x;
+            const bool inside = sr >= 0 && sr < W::R1 && sc >= 0 && sc < W::C1 &&
+                                p.pad_mode == CAE_PAD_REFLECT;
+#pragma unroll
+            for (int co = 0; co < CI; ++co)
+              s1[(co * W::R1 + r) * W::P1 + c] = inside ? s1[(co * W::R1 + sr) * W::P1 + sc] : 0.f;
+          }
+          stem_bar(grp);
+        }
+        src2 = s1;
+        src2_rows = W::R1;
+        src2_pitch = W::P1;
+        wset2 = w1s + WSET;
+      }
+      // 3c. the convolution that produces the stem patch (plain unit: the only one)
+      if (gtid < SR * SG && !(p.debug & 2)) {
+        const int r = gtid / SG, x0 = (gtid - r * SG) * PXT;
         float acc[PXT][CI];
 #pragma unroll
         for (int q = 0; q < PXT; ++q)
 #pragma unroll
-          for (int co = 0; co < CI; ++co) acc[q][co] = w1s[CI * 3 * CI * 4 + co];
+          for (int co = 0; co < CI; ++co) acc[q][co] = wset2[CI * 3 * CI * 4 + co];
 #pragma unroll
         for (int ci = 0; ci < CI; ++ci)
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
-            const float *wrow = win + (ci * WR + r + kh) * WPITCH + x0;     // 8-byte aligned
+            const float *wrow = src2 + (ci * src2_rows + r + kh) * src2_pitch + x0;     // 8-byte aligned
             float w6[PXT + 2];
 #pragma unroll
             for (int j = 0; j < PXT + 2; j += 2) {
@@ -264,7 +360,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
             }
 #pragma unroll
             for (int co = 0; co < CI; ++co) {
-              const float4 wv = *reinterpret_cast<const float4 *>(w1s + ((ci * 3 + kh) * CI + co) * 4);
+              const float4 wv = *reinterpret_cast<const float4 *>(wset2 + ((ci * 3 + kh) * CI + co) * 4);
 #pragma unroll
               for (int q = 0; q < PXT; ++q) {
                 acc[q][co] = fmaf(w6[q], wv.x, acc[q][co]);
@@ -284,7 +380,13 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
 #pragma unroll
             for (int co = 0; co < CI; ++co) {
               float v = acc[q][co];
-              v = fmaxf(v, v * p.s1);
+              if (RES) {
+                // fx = conv_b(S1) + b_b + x, then the unit's activation (R:172 and :139-141)
+                v += win[(co * WR + r + HALO) * WPITCH + x0 + q + HALO];
+                v = fmaxf(v, v * p.sm);
+              } else {
+                v = fmaxf(v, v * p.s1);
+              }
               S[(co * SR + r) * SPITCH + x0 + q] = __float2half_rn(in ? v : 0.f);
             }
           }
@@ -461,20 +563,21 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_conv_kernel(const HeadPa
   if (warp == 0) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-template <int CI>
+template <int CI, bool RES>
 size_t head_smem_bytes(int N) {
-  using L = HeadSmem<CI>;
+  using L = HeadSmem<CI, RES>;
   size_t b = 2 * (size_t)L::A_BYTES + (size_t)L::KG * N * 16 + 2 * (size_t)L::WIN_ELEMS * 4 +
-             2 * (size_t)((L::S_ELEMS + 7) & ~7) * 2 + kLut * 4 + L::W1N * 4 + 8 * 8 + 16;
+             2 * (size_t)L::S1_ELEMS * 4 + 2 * (size_t)((L::S_ELEMS + 7) & ~7) * 2 + kLut * 4 +
+             L::W1N * 4 + 8 * 8 + 16;
   return b;
 }
 
-template <int CI, bool U8>
+template <int CI, bool U8, bool RES = false>
 int launch_head(const HeadParams &p, cudaStream_t stream) {
   // one CTA per SM by construction (the TMEM allocation must never wait on a neighbour)
-  size_t smem = head_smem_bytes<CI>(p.N);
+  size_t smem = head_smem_bytes<CI, RES>(p.N);
   if (smem < 120 * 1024) smem = 120 * 1024;
-  auto kern = head_conv_kernel<CI, U8>;
+  auto kern = head_conv_kernel<CI, U8, RES>;
   CAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
   CAE_CUDA(cudaGetDevice(&dev));
@@ -549,6 +652,14 @@ extern "C" int cae_conv_head(const cae_head_desc *d, void *stream) {
                 d->act_down <= CAE_ACT_RELU, 2, "cae_conv_head: bad activation");
   p.s1 = slope(d->act_stem);
   p.s2 = slope(d->act_down);
+  if (d->residual) {
+    CAE_CHECK(d->w_stem2, 2, "cae_conv_head: residual unit without its second convolution");
+    CAE_CHECK(d->act_mid >= CAE_ACT_NONE && d->act_mid <= CAE_ACT_RELU, 2,
+              "cae_conv_head: bad activation");
+    p.w1b = d->w_stem2;
+    p.b1b = d->b_stem2;
+    p.sm = slope(d->act_mid);
+  }
   p.idesc = make_idesc_f16(128, p.N);
   uint32_t cols = 32;
   while ((int)cols < 4 * p.N) cols <<= 1;
@@ -556,6 +667,14 @@ extern "C" int cae_conv_head(const cae_head_desc *d, void *stream) {
   if (const char *e = getenv("CAE_HEAD_DEBUG")) p.debug = atoi(e);
   cudaStream_t s = (cudaStream_t)stream;
   const bool u8 = d->in.fmt == CAE_FMT_U8_HWC;
+  if (d->residual) {
+    switch (d->c_in) {
+      case 1: return u8 ? launch_head<1, true, true>(p, s) : launch_head<1, false, true>(p, s);
+      case 2: return u8 ? launch_head<2, true, true>(p, s) : launch_head<2, false, true>(p, s);
+      case 3: return u8 ? launch_head<3, true, true>(p, s) : launch_head<3, false, true>(p, s);
+      default: return u8 ? launch_head<4, true, true>(p, s) : launch_head<4, false, true>(p, s);
+    }
+  }
   switch (d->c_in) {
     case 1: return u8 ? launch_head<1, true>(p, s) : launch_head<1, false>(p, s);
     case 2: return u8 ? launch_head<2, true>(p, s) : launch_head<2, false>(p, s);

@@ -135,6 +135,13 @@ typedef struct cae_head_desc {
   const float *b_down;     /* [c_out] or NULL                                       */
   int32_t act_stem, act_down; /* CAE_ACT_*                                         */
   int32_t pad_mode;        /* CAE_PAD_*                                             */
+  /* ResidualDownsamplingUnit (R:104-174) with a plain activation: the stem is
+   *   fx = act_mid( conv_s1_b( act_stem( conv_s1_a(in) + b_stem ) ) + b_stem2 + in )
+   * before the stride-2 convolution; residual = 0 selects the plain unit above.     */
+  int32_t residual;
+  const float *w_stem2;    /* [c_in][c_in][3][3] second stride-1 convolution, or NULL */
+  const float *b_stem2;    /* [c_in] or NULL                                        */
+  int32_t act_mid;         /* activation after the residual add                     */
   int32_t reserved;
 } cae_head_desc;
 int cae_conv_head(const cae_head_desc *d, void *stream);

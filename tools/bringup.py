@@ -181,7 +181,7 @@ def _igemm_case(kind_name, n, ci, co, h, w, *, out_fmt=None, halo_out=None, mt=0
 
 
 def case_head(n, ci, co, h, w, *, u8=True, pad_name='reflect', halo_out=None, act1=1, act2=1,
-              tol=3e-3):
+              tol=3e-3, residual=False):
     """cae_conv_head against conv_s2(fp16(act(conv_s1(x)))) in torch fp32."""
     torch, F, C, O = _mods()
     g = torch.Generator(device='cuda').manual_seed(11)
@@ -198,12 +198,19 @@ def case_head(n, ci, co, h, w, *, u8=True, pad_name='reflect', halo_out=None, ac
     w2 = fp16_vals((co, ci, 3, 3), g, scale=0.3)
     b2 = torch.randn((co,), generator=g, device='cuda') * 0.1
     act = {0: lambda t: t, 1: lambda t: F.leaky_relu(t, 0.01), 2: torch.relu}
-    s = act[act1](ref_conv(C.CONV_S1, x, w1, pad) + b1.view(1, -1, 1, 1)).half().float()
+    s = act[act1](ref_conv(C.CONV_S1, x, w1, pad) + b1.view(1, -1, 1, 1))
+    extra = {}
+    if residual:
+        w1b = torch.randn((ci, ci, 3, 3), generator=g, device='cuda') * 0.4
+        b1b = torch.randn((ci,), generator=g, device='cuda') * 0.1
+        s = act[act1](ref_conv(C.CONV_S1, s, w1b, pad) + b1b.view(1, -1, 1, 1) + x)
+        extra = dict(w_stem2=w1b, b_stem2=b1b, act_mid=act1)
+    s = s.half().float()
     want = act[act2](ref_conv(C.CONV_S2, s, w2, pad) + b2.view(1, -1, 1, 1))
     ho, wo = O.KIND_OUT[C.CONV_S2](h, w)
     halo = halo_out if halo_out is not None else C.HALO_REFLECT
     out = O.alloc_act(C.FMT_F16_PLANAR, n, co, ho, wo, halo=halo)
-    O.conv_head(xin, w1, b1, w2, b2, co, out, act_stem=act1, act_down=act2, pad_mode=pad)
+    O.conv_head(xin, w1, b1, w2, b2, co, out, act_stem=act1, act_down=act2, pad_mode=pad, **extra)
     pv = padded_view(out)
     ok = check('interior', pv[:, :co, 1:-1, 1:-1], want, tol)
     mode = 'reflect' if halo == C.HALO_REFLECT else 'constant'
@@ -266,6 +273,11 @@ CASES = {
     'head_odd_c1': lambda: case_head(2, 1, 24, 37, 51, u8=False, act2=0),
     'head_c4_zero_pad': lambda: case_head(1, 4, 64, 40, 72, pad_name='zero', halo_out=0, act1=2),
     'head_small': lambda: case_head(1, 3, 48, 6, 10, u8=False),
+    'head_res_u8': lambda: case_head(2, 3, 128, 64, 96, residual=True),
+    'head_res_multi_tile': lambda: case_head(2, 3, 128, 256, 256, residual=True),
+    'head_res_odd_c1': lambda: case_head(2, 1, 24, 37, 51, u8=False, act2=0, residual=True),
+    'head_res_zero_pad': lambda: case_head(1, 4, 64, 40, 72, pad_name='zero', halo_out=0, act1=2, residual=True),
+    'head_res_small': lambda: case_head(1, 3, 48, 6, 10, u8=False, residual=True),
     'eb': case_eb,
 }
 
