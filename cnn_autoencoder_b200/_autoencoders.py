@@ -370,9 +370,15 @@ class Synthesizer(_Track):
         with self._lock, torch.no_grad():
             if planar is not None and x.shape[1] > 4:
                 a = planar
+            elif x.shape[1] > 4:
+                # the planar copy of the latent lives in a buffer kept per shape (the zero halo
+                # is written once at allocation)
+                key = (tuple(x.shape), str(x.device))
+                buf = self._in_planar if getattr(self, '_in_planar_key', None) == key else None
+                a = O.nchw_to_planar(x, C.FMT_F16_PLANAR, C.HALO_KEEP, out=buf)
+                self._in_planar, self._in_planar_key = a, key
             else:
-                a = O.nchw_to_planar(x, C.FMT_F16_PLANAR, C.HALO_KEEP) if x.shape[1] > 4 \
-                    else O.wrap_nchw(x)
+                a = O.wrap_nchw(x)
             outs = self._unit_output_indices()
             keep = outs[:-1] if (self.bridges or self.multiscale) else ()
             final = C.FMT_U8_HWC if as_uint8 else C.FMT_F32_NCHW

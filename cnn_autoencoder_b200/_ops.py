@@ -161,9 +161,12 @@ def replay(call):
     return conv(*call[0], **call[1])
 
 
-def nchw_to_planar(x, fmt=C.FMT_F16_PLANAR, halo=C.HALO_KEEP):
+def nchw_to_planar(x, fmt=C.FMT_F16_PLANAR, halo=C.HALO_KEEP, out=None):
+    """fp32 NCHW -> internal layout.  ``out``: a buffer of the right shape to reuse (its zero
+    halo persists: only the interior, and the reflect halo if asked for, are rewritten)."""
     a = wrap_nchw(x)
-    out = alloc_act(fmt, a.n, a.c, a.h, a.w, halo, device=x.device)
+    if out is None:
+        out = alloc_act(fmt, a.n, a.c, a.h, a.w, halo, device=x.device)
     C.check(C.lib().cae_nchw_to_planar(a.t.data_ptr(), a.n, a.c, a.h, a.w, out.desc(),
                                        _stream_ptr()))
     return out

@@ -9,6 +9,8 @@
 // integer, so the likelihood takes one value per (channel, symbol): the host
 // builds that table once with the model's own fp32 ops and the kernel looks it
 // up; symbols outside the table fall back to evaluating the density MLP here.
+#include <stdlib.h>
+
 #include "cae_common.cuh"
 #include "eb_device.cuh"
 
@@ -37,27 +39,60 @@ __global__ void __launch_bounds__(256) eb_quantize_kernel(const EbParams p) {
 
   const float med = p.t.medians[c];
   float bits = 0.f;
-  for (int n = g; n < p.n; n += groups) {
-  const size_t base = ((size_t)n * p.c + c) * p.hw;
-  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < p.hw; i += gridDim.y * blockDim.x) {
-    const float y = p.y[base + i];
-    const float r = rintf(y - med);  // torch.round: half to even
-    const float yq = r + med;
-    // saturate like a float->int32 cast of an in-range value; escapes stay exact up to 2^31
-    const int sym = eb_symbol(r);
-    if (p.y_q) p.y_q[base + i] = yq;
-    if (p.symbols) p.symbols[base + i] = sym;
+  const float *lut = p.t.lut ? p.t.lut + (size_t)c * p.t.lut_len : nullptr;
+  // one symbol: everything eb_quantize produces for it; returns the histogram bin (or -1)
+  auto one = [&](float y, float &yq, int &sym, float &lik) -> int {
+    const float r = rintf(y - med);            // torch.round: half to even
+    yq = r + med;
+    sym = eb_symbol(r);                        // saturating float -> int32, escapes stay exact
     if (p.p_y || p.rate_bits) {
-      const float lik = eb_lookup(p.t, c, sym, yq, p.status);
-      if (p.p_y) p.p_y[base + i] = lik;
-      bits -= log2f(lik);
+      const int li = sym - p.t.lut_min;
+      lik = (lut && li >= 0 && li < p.t.lut_len) ? __ldg(lut + li)
+                                                 : eb_lookup(p.t, c, sym, yq, p.status);
+      bits -= __log2f(lik);
     }
-    if (bins) {
-      int b = sym - p.t.hist_min;
-      b = b < 0 ? 0 : (b >= bins ? bins - 1 : b);
-      atomicAdd(&s_hist[b], 1);
+    if (!bins) return -1;
+    const int b = sym - p.t.hist_min;
+    return b < 0 ? 0 : (b >= bins ? bins - 1 : b);
+  };
+  const bool vec4 = (p.hw & 3) == 0;           // rows of four symbols: 16-byte loads and stores
+  for (int n = g; n < p.n; n += groups) {
+    const size_t base = ((size_t)n * p.c + c) * p.hw;
+    if (vec4) {
+      const int hw4 = p.hw >> 2;
+      for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < hw4; i += gridDim.y * blockDim.x) {
+        const float4 y4 = *reinterpret_cast<const float4 *>(p.y + base + 4 * (size_t)i);
+        float4 q4, l4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        int4 s4;
+        const int b0 = one(y4.x, q4.x, s4.x, l4.x), b1 = one(y4.y, q4.y, s4.y, l4.y);
+        const int b2 = one(y4.z, q4.z, s4.z, l4.z), b3 = one(y4.w, q4.w, s4.w, l4.w);
+        if (p.y_q) *reinterpret_cast<float4 *>(p.y_q + base + 4 * (size_t)i) = q4;
+        if (p.symbols) *reinterpret_cast<int4 *>(p.symbols + base + 4 * (size_t)i) = s4;
+        if (p.p_y) *reinterpret_cast<float4 *>(p.p_y + base + 4 * (size_t)i) = l4;
+        if (bins) {
+          // neighbouring symbols often share a bin: merge equal bins before the atomics
+          int cnt0 = 1, cnt1 = 1, cnt2 = 1, cnt3 = 1;
+          if (b1 == b0) { cnt0 += 1; cnt1 = 0; }
+          if (b2 == b0) { cnt0 += 1; cnt2 = 0; } else if (b2 == b1 && cnt1) { cnt1 += 1; cnt2 = 0; }
+          if (b3 == b0) { cnt0 += 1; cnt3 = 0; } else if (b3 == b1 && cnt1) { cnt1 += 1; cnt3 = 0; }
+          else if (b3 == b2 && cnt2) { cnt2 += 1; cnt3 = 0; }
+          atomicAdd(&s_hist[b0], cnt0);
+          if (cnt1) atomicAdd(&s_hist[b1], cnt1);
+          if (cnt2) atomicAdd(&s_hist[b2], cnt2);
+          if (cnt3) atomicAdd(&s_hist[b3], cnt3);
+        }
+      }
+    } else {
+      for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < p.hw; i += gridDim.y * blockDim.x) {
+        float yq, lik = 0.f;
+        int sym;
+        const int bb = one(p.y[base + i], yq, sym, lik);
+        if (p.y_q) p.y_q[base + i] = yq;
+        if (p.symbols) p.symbols[base + i] = sym;
+        if (p.p_y) p.p_y[base + i] = lik;
+        if (bins) atomicAdd(&s_hist[bb], 1);
+      }
     }
-  }
   }
 
   if (p.rate_bits) {
@@ -90,7 +125,7 @@ extern "C" int cae_eb_quantize(const float *y, int n, int c, int hw, const cae_e
   p.y = y; p.n = n; p.c = c; p.hw = hw; p.t = *t;
   p.y_q = y_q; p.p_y = p_y; p.symbols = symbols; p.hist = hist;
   p.rate_bits = rate_bits; p.status = status;
-  int bx = (hw + 256 * 4 - 1) / (256 * 4);
+  int bx = (hw + 256 * 16 - 1) / (256 * 16);
   if (bx < 1) bx = 1;
   if (bx > 64) bx = 64;
   // about eight blocks per SM in total: images are grouped per channel to reach that
