@@ -3,10 +3,13 @@ reference (``compress_image`` :29-168, ``compress`` :171-209) for the CAE codecs
 
 The reference hands every ``patch_size`` chunk to the codec one at a time from
 dask's threaded scheduler (``z.rechunk(...)`` :101, ``to_zarr(compressor=codec)``
-:121-128).  Here the same chunks are processed B200-first: tiles are gathered
-into pinned batches, the analysis transform + quantizer run once per batch on the
-GPU, the integer symbols come back in one copy and are entropy coded by a pool of
-host threads (the C++ coder releases the GIL) while the next batch is on the GPU.
+:121-128).  Here the same chunks are processed B200-first: native threads cut
+``batch_tiles`` tiles out of the slide into a pinned buffer, the analysis transform +
+quantizer run once per batch on the GPU, and the integer symbols of up to ``coder_tiles``
+tiles stay on the device, where every tile's rANS stream is coded concurrently on a second
+CUDA stream while the transforms of the next tiles run; the packed streams come back in one
+copy and native threads write the chunk files.  (Below 128 tiles per call the C++ host
+coder, on a thread pool, is faster and is used instead.)
 Tiles are independent (no halo between chunks), so ``world_size`` processes -- one
 per GPU -- each take a contiguous range of the chunk grid and write their own chunk
 files; there is no collective.  The output is a zarr-v2 directory array whose

@@ -2,9 +2,11 @@
 reference (``decompress_fn_impl`` :24-37, ``decompress_image`` :40-140,
 ``decompress`` :143-180).
 
-Chunks are entropy decoded by a pool of host threads (C++ coder, GIL released),
-stacked into batches, and the synthesis transform with its fused
-``*255 -> clip -> uint8 -> HWC`` epilogue runs once per batch on the GPU.  As in
+Native threads read up to ``coder_tiles`` chunk files into one pinned buffer, all their
+rANS streams are decoded concurrently on the device, and the synthesis transform with its
+fused ``*255 -> clip -> uint8 -> HWC`` epilogue runs over ``batch_tiles`` tiles at a time
+while native threads write the previous batch.  (Few or irregular chunks take the general
+path: host C++ coder on a thread pool.)  As in
 ``compress.py`` the chunk grid is sharded across processes by contiguous range;
 no collective.  The reconstruction goes to ``<output>/<decomp_group>/<group>/0``
 like the reference (:81-96); chunks are stored raw (the reference's Blosc-zlib
