@@ -34,6 +34,10 @@ class GraphedPipeline:
         with torch.cuda.graph(self.graph):
             self.out = pipe(x_static)
         self.launches = _cabi.launch_count() - n0   # kernels of this library per replay
+        # the graph holds raw pointers into the executors' intermediate buffers: keep those
+        # tensors alive for as long as the graph, whatever the executors cache later
+        self._keep = [dict(pipe.model[k].module._executor()._buffers)
+                      for k in ('encoder', 'decoder') if k in pipe.model]
 
     def replay(self):
         self.graph.replay()
