@@ -38,6 +38,7 @@ class GraphedPipeline:
         # tensors alive for as long as the graph, whatever the executors cache later
         self._keep = [dict(pipe.model[k].module._executor()._buffers)
                       for k in ('encoder', 'decoder') if k in pipe.model]
+        self._keep.append(getattr(pipe.model['decoder'].module, '_in_planar', None))
 
     def replay(self):
         self.graph.replay()
