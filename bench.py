@@ -60,7 +60,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                 '-i', str(self.index), '-lms', '100'], stdout=subprocess.PIPE, text=True)
+                 '-i', str(self.index), '-lms', '25'], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
