@@ -595,7 +595,7 @@ int launch_head(const HeadParams &p, cudaStream_t stream) {
     CAE_CUDA(cudaMemcpy(host, buf, sizeof(host), cudaMemcpyDeviceToHost));
     cudaFree(buf);
     fprintf(stderr, "head trace (ns, relative to tile start of the stem group):\n"
-                    " tile    start  win->smem  computed  a_empty  a_full | acc_full  epi_done  (abs since tile 0)\n");
+                    " tile    start  win->smem  computed  a_empty  mma_issued | acc_full  epi_done  (abs since tile 0)\n");
     for (int t = 0; t < 64 && host[t * 8]; ++t) {
       const unsigned long long *h = host + t * 8, t0 = host[0];
       fprintf(stderr, " %3d %9llu %9llu %9llu %8llu %7llu | %8llu %9llu\n", t, h[0] - t0, h[1] - h[0],
