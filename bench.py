@@ -206,9 +206,17 @@ def main():
         run_dev = lambda: pipe(x_dev)
         launches_per_step = None
     else:
-        g_dev = pipe.graphed(x_dev, warmup=warmup)
-        run_dev = g_dev.replay
-        launches_per_step = g_dev.launches
+        try:
+            g_dev = pipe.graphed(x_dev, warmup=warmup)
+            run_dev = g_dev.replay
+            launches_per_step = g_dev.launches
+        except RuntimeError as exc:            # capture refused: time the eager launches instead
+            print(f'bench.py: CUDA graph capture failed ({exc}); timing eager launches',
+                  file=sys.stderr)
+            args.no_graph = True
+            torch.cuda.synchronize()
+            run_dev = lambda: pipe(x_dev)
+            launches_per_step = None
     for _ in range(warmup):
         out = run_dev()
     barrier()
