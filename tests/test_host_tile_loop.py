@@ -175,3 +175,31 @@ def test_native_tile_gather_and_chunk_files(tmp_path):
     import pytest
     with pytest.raises(FileNotFoundError):
         S.native_read(paths + [str(tmp_path / 'missing')], 16, 2)
+
+
+def test_engine_plans_the_fused_head_where_it_applies():
+    """Host-side planning only (no kernels): the first unit is handed to the fused head kernel
+    for plain and residual nets reading a raw image, and not where its conditions fail."""
+    import torch
+    import cnn_autoencoder_b200 as M
+    from cnn_autoencoder_b200 import _cabi as C, _ops
+    from oracle import cae_oracle as O
+
+    def span(arch, fmt=C.FMT_U8_HWC, keep=()):
+        chk = O.make_checkpoint(dict(channels_org=3, channels_net=32, channels_bn=16, **arch), seed=1)
+        model = M.autoencoder_from_state_dict(chk, gpu=False, train=False)
+        ex = model['encoder'].module._executor()
+        t = torch.zeros(1, 8, 8, 3, dtype=torch.uint8)
+        x = _ops.Act(t, fmt, 1, 3, 8, 8)
+        return ex._head_match(0, x, keep, C.FMT_F32_NCHW), len(ex.steps)
+
+    assert span(dict(compression_level=3, act_layer_type='LeakyReLU'))[0] == 2
+    assert span(dict(compression_level=3, act_layer_type='LeakyReLU', use_residual=True))[0] == 3
+    assert span(dict(compression_level=3, act_layer_type='ReLU', batch_norm=True))[0] == 2
+    # stride-2 consumer wants the parity-split layout: not covered by the head kernel
+    assert span(dict(compression_level=2, act_layer_type='LeakyReLU'))[0] == 0
+    # GDN units have no stride-1 stem; planar (already converted) inputs are not raw images
+    assert span(dict(compression_level=3, act_layer_type='GDN'))[0] == 0
+    assert span(dict(compression_level=3, act_layer_type='LeakyReLU'), fmt=C.FMT_F16_PLANAR)[0] == 0
+    # a caller that wants the stem's output kept gets the separate kernels
+    assert span(dict(compression_level=3, act_layer_type='LeakyReLU'), keep=(1,))[0] == 0
