@@ -202,6 +202,12 @@ def main():
     # ---------------- device-resident throughput ----------------
     # One step = one replay of the pipeline captured in a CUDA graph (the same kernels, in the
     # same order, as the eager call; --no-graph issues them one by one from Python).
+    if not args.no_graph and any(k in os.environ for k in (
+            'CUDA_INJECTION64_PATH', 'NV_COMPUTE_PROFILER_PERFWORKS_DIR', 'NV_NSIGHT_INJECTION_PORT_BASE')):
+        # a profiler is attached: ncu --set full cannot replay the tensor-map kernels as graph
+        # nodes (LaunchFailed on its second pass, profiles/README.md), so launch them one by one
+        print('bench.py: profiler detected, launching kernels eagerly (no CUDA graph)', file=sys.stderr)
+        args.no_graph = True
     if args.no_graph:
         run_dev = lambda: pipe(x_dev)
         launches_per_step = None
