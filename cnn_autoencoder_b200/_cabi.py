@@ -15,7 +15,7 @@ CSRC = os.path.join(_HERE, 'csrc')
 FMT_NONE, FMT_U8_HWC, FMT_F32_NCHW, FMT_F16_PLANAR, FMT_F16_SPLIT = 0, 1, 2, 3, 4
 HALO_KEEP, HALO_REFLECT = 0, 1
 ACT_NONE, ACT_LEAKY_RELU, ACT_RELU = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 CONV_S1, CONV_S2, CONVT_S1, CONVT_S2 = 0, 1, 2, 3
 PAD_ZERO, PAD_REFLECT = 0, 1
 
@@ -63,7 +63,7 @@ class EbTables(ctypes.Structure):
                 ('mlp', ctypes.c_void_p), ('n_layers', ctypes.c_int32),
                 ('mlp_stride', ctypes.c_int32), ('dims', ctypes.c_int32 * 10),
                 ('hist_min', ctypes.c_int32), ('hist_bins', ctypes.c_int32),
-                ('tail_lik', ctypes.c_float), ('reserved', ctypes.c_int32)]
+                ('tail_lik', ctypes.c_float), ('lik_bound', ctypes.c_float)]
 
 
 class QuantFuse(ctypes.Structure):

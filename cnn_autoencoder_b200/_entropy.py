@@ -46,6 +46,19 @@ class _LowerBound(torch.autograd.Function):
         return keep.type(grad.dtype) * grad, None
 
 
+class _LikelihoodLowerBound(nn.Module):
+    """State-dict shell of CompressAI's ``LowerBound`` submodule: every genuine
+    EntropyBottleneck checkpoint carries ``likelihood_lower_bound.bound``
+    (``scripts/transfer_weights.py`` of the reference lists it)."""
+
+    def __init__(self, bound):
+        super().__init__()
+        self.register_buffer('bound', torch.tensor([float(bound)]))
+
+    def forward(self, x):
+        return _LowerBound.apply(x, self.bound.to(x.dtype))
+
+
 class QuantRequest:
     """Outputs of the quantizer when it runs inside the epilogue of the last analysis
     convolution (``cae_conv_desc.quant``): ``y_q`` (fp32 NCHW), ``hist`` (C x bins),
@@ -99,7 +112,9 @@ class EntropyBottleneck(nn.Module):
         self.init_scale = float(init_scale)
         self.tail_mass = float(tail_mass)
         self.entropy_coder_precision = int(entropy_coder_precision)
-        self.likelihood_bound = float(likelihood_bound)
+        self.use_likelihood_bound = float(likelihood_bound) > 0
+        if self.use_likelihood_bound:
+            self.likelihood_lower_bound = _LikelihoodLowerBound(likelihood_bound)
 
         dims = (1,) + self.filters + (1,)
         scale = self.init_scale ** (1 / (len(self.filters) + 1))
@@ -147,8 +162,28 @@ class EntropyBottleneck(nn.Module):
     def _medians(self):
         return self.quantiles[:, 0, 1].detach()
 
+    @property
+    def likelihood_bound(self):
+        """The bound in force: the loaded ``likelihood_lower_bound.bound`` buffer."""
+        return float(self.likelihood_lower_bound.bound.item()) if self.use_likelihood_bound else 0.0
+
     def _bound(self, ref):
-        return torch.tensor([self.likelihood_bound], dtype=ref.dtype, device=ref.device)
+        return self.likelihood_lower_bound.bound.to(device=ref.device, dtype=ref.dtype)
+
+    # CompressAI >= 1.2.5 stores the density parameters as ParameterLists
+    _NEW_KEYS = (('matrices.', '_matrix'), ('biases.', '_bias'), ('factors.', '_factor'))
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        for new, old in self._NEW_KEYS:
+            for k in [k for k in state_dict if k.startswith(prefix + new)]:
+                idx = k[len(prefix + new):]
+                if idx.isdigit():
+                    state_dict[prefix + old + idx] = state_dict.pop(k)
+        if self.use_likelihood_bound:
+            # fixtures written by this repo before the buffer existed lack the key
+            state_dict.setdefault(prefix + 'likelihood_lower_bound.bound',
+                                  self.likelihood_lower_bound.bound.clone())
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
     def _forward_torch(self, x, training=False):
         """The model written with torch ops (training path; also what the tables
@@ -169,8 +204,8 @@ class EntropyBottleneck(nn.Module):
             med = self.quantiles[:, :, 1:2]
             v = torch.round(v - med) + med
         lik = self._likelihood(v)
-        if self.likelihood_bound > 0:
-            lik = _LowerBound.apply(lik, self._bound(lik))
+        if self.use_likelihood_bound:
+            lik = self.likelihood_lower_bound(lik)
         out = v.reshape(shape).permute(*perm).contiguous()
         lik = lik.reshape(shape).permute(*perm).contiguous()
         return out, lik
@@ -180,6 +215,18 @@ class EntropyBottleneck(nn.Module):
         return torch.abs(logits - self.target).sum()
 
     # -------------------------------------------------------------- tables
+    def _host_clone(self):
+        """Parameter-only copy on the CPU in fp32: every table (integer CDFs, likelihood
+        LUT) is computed with CPU fp32 ops whatever device the module lives on, so that
+        whoever decodes the stream or checks the rate can reproduce it."""
+        host = EntropyBottleneck.__new__(EntropyBottleneck)
+        nn.Module.__init__(host)
+        host.filters = self.filters
+        for name, prm in self.named_parameters():
+            host.register_parameter(name, nn.Parameter(prm.detach().float().cpu(),
+                                                       requires_grad=False))
+        return host
+
     def update(self, force=False):
         if self._offset.numel() > 0 and not force:
             return False
@@ -187,12 +234,7 @@ class EntropyBottleneck(nn.Module):
         # the integer CDF must be reproducible by whoever decodes the stream.
         dev = self.quantiles.device
         with torch.no_grad():
-            host = EntropyBottleneck.__new__(EntropyBottleneck)
-            nn.Module.__init__(host)
-            host.filters = self.filters
-            for name, prm in self.named_parameters():
-                host.register_parameter(name, nn.Parameter(prm.detach().float().cpu(),
-                                                           requires_grad=False))
+            host = self._host_clone()
             q = host.quantiles
             med = q[:, 0, 1]
             minima = torch.clamp(torch.ceil(med - q[:, 0, 0]).int(), min=0)
@@ -233,8 +275,11 @@ class EntropyBottleneck(nn.Module):
         key = self._param_key()
         if self._tables is not None and self._tables_key == key:
             return self._tables
+        dev = self.quantiles.device
+        bound = self.likelihood_bound
         with torch.no_grad():
-            q = self.quantiles.detach()
+            host = self._host_clone()
+            q = host.quantiles
             med = q[:, 0, 1]
             lo = int(torch.floor((q[:, 0, 0] - med).min()).item()) - _LUT_MARGIN
             hi = int(torch.ceil((q[:, 0, 2] - med).max()).item()) + _LUT_MARGIN
@@ -245,13 +290,12 @@ class EntropyBottleneck(nn.Module):
             tail_lik = 0.0
             while True:
                 lo, hi = max(lo, -_LUT_MAX), min(hi, _LUT_MAX)
-                syms = torch.arange(lo, hi + 1, device=q.device, dtype=torch.float32)
+                syms = torch.arange(lo, hi + 1, dtype=torch.float32)
                 v = syms[None, None, :] + q[:, :, 1:2]
-                raw = self._likelihood(v)[:, 0, :]
-                lik = torch.max(raw, self._bound(raw)) if self.likelihood_bound > 0 else raw
-                if self.likelihood_bound <= 0:
+                raw = host._likelihood(v)[:, 0, :]
+                lik = torch.clamp(raw, min=bound) if bound > 0 else raw
+                if bound <= 0:
                     break
-                bound = float(self.likelihood_bound)
                 left_ok = bool((raw[:, :_LUT_EDGE] <= bound).all())
                 right_ok = bool((raw[:, -_LUT_EDGE:] <= bound).all())
                 if left_ok and right_ok:
@@ -266,13 +310,14 @@ class EntropyBottleneck(nn.Module):
             blob = []
             K = len(self.filters)
             for i in range(K + 1):
-                blob.append(F.softplus(getattr(self, f'_matrix{i:d}').detach()).reshape(self.channels, -1))
-                blob.append(getattr(self, f'_bias{i:d}').detach().reshape(self.channels, -1))
+                blob.append(F.softplus(getattr(host, f'_matrix{i:d}')).reshape(self.channels, -1))
+                blob.append(getattr(host, f'_bias{i:d}').reshape(self.channels, -1))
                 if i < K:
-                    blob.append(torch.tanh(getattr(self, f'_factor{i:d}').detach()).reshape(self.channels, -1))
+                    blob.append(torch.tanh(getattr(host, f'_factor{i:d}')).reshape(self.channels, -1))
             mlp = torch.cat(blob, dim=1).contiguous().float()
-            tb = dict(medians=med.contiguous().float().clone(), lut=lik.contiguous().float(),
-                      lut_min=lo, lut_len=hi - lo + 1, mlp=mlp, tail_lik=tail_lik)
+            tb = dict(medians=med.contiguous().float().clone().to(dev),
+                      lut=lik.contiguous().float().to(dev), lut_min=lo, lut_len=hi - lo + 1,
+                      mlp=mlp.to(dev), tail_lik=tail_lik, lik_bound=bound)
         if max((1,) + self.filters) > 8 or K + 1 > 9:
             tb['mlp'] = None
         self._tables, self._tables_key = tb, key
@@ -292,6 +337,7 @@ class EntropyBottleneck(nn.Module):
                 t.dims[i] = d
         t.hist_min, t.hist_bins = tb['lut_min'], tb['lut_len']
         t.tail_lik = tb.get('tail_lik', 0.0)
+        t.lik_bound = tb.get('lik_bound', 0.0)
         return t
 
     def _quantize_cuda(self, x, want_yq=True, want_p=True, want_sym=False, want_hist=False,

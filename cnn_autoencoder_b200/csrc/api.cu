@@ -1,6 +1,9 @@
 // Library-level entry points of the C ABI: error text, device probe, launch counter.
 #include <atomic>
+#include <mutex>
 #include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "cae_common.cuh"
 
@@ -14,6 +17,44 @@ void cae_set_error(const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+namespace {
+const char *g_knob_val[CAE_KNOB_COUNT];
+std::once_flag g_knob_once;
+
+void read_knobs() {
+  static const char *names[CAE_KNOB_COUNT] = {
+#define X(n) "CAE_" #n,
+      CAE_KNOB_LIST(X)
+#undef X
+  };
+  const char *dbg = getenv("CAE_DEBUG");
+  const bool on = dbg && strcmp(dbg, "1") == 0;
+  for (int i = 0; i < CAE_KNOB_COUNT; ++i) {
+    const char *v = getenv(names[i]);
+    g_knob_val[i] = nullptr;
+    if (!v) continue;
+    if (on) g_knob_val[i] = strdup(v);
+    else fprintf(stderr, "cae_b200: ignoring bring-up knob %s (set CAE_DEBUG=1 to enable it)\n", names[i]);
+  }
+}
+}  // namespace
+
+const char *cae_knob(CaeKnob k) {
+  std::call_once(g_knob_once, read_knobs);
+  return g_knob_val[k];
+}
+
+int cae_sm_count() {
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int v = cached[dev].load(std::memory_order_relaxed);
+  if (v > 0) return v;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+  cached[dev].store(v, std::memory_order_relaxed);
+  return v;
 }
 
 void cae_count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }

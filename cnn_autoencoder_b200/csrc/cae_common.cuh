@@ -13,6 +13,25 @@
 // ------------------------------------------------------------------ errors
 void cae_set_error(const char *fmt, ...);
 void cae_count_launch(int n = 1);
+int cae_sm_count();   // SMs of the current device (cached per device)
+
+// Bring-up / experiment knobs (environment variables CAE_<NAME>).  The environment is read ONCE,
+// at the first call, and a knob is only honoured when CAE_DEBUG=1 is set as well: several of
+// them produce wrong output on purpose (loads / MMAs / stores switched off), so a stray variable
+// in a production environment must not reach the kernels.  Returns the value or nullptr.
+#define CAE_KNOB_LIST(X)                                                                      \
+  X(HEAD_TRACE) X(HEAD_DEBUG) X(IGEMM_MERGED_CK64) X(IGEMM_CK_S2) X(IGEMM_TWO_PASS)           \
+  X(IGEMM_ONE_PASS) X(IGEMM_MT) X(IGEMM_SWAP_LBO_SBO) X(QUANT_NO_SMEM) X(IGEMM_TPB)           \
+  X(IGEMM_VERBOSE) X(QUANT_NO_HIST) X(QUANT_NO_RATE) X(QUANT_NO_YQ) X(IGEMM_DEBUG)            \
+  X(IGEMM_NO_PAIR_STORE) X(IGEMM_EPI_WARPS) X(IGEMM_NO_FAST_EPILOGUE) X(IGEMM_NO_TMA_STORE)   \
+  X(IGEMM_NO_PAIR_MMA) X(RANS_V1)
+enum CaeKnob {
+#define X(n) CAE_KNOB_##n,
+  CAE_KNOB_LIST(X)
+#undef X
+  CAE_KNOB_COUNT
+};
+const char *cae_knob(CaeKnob k);
 
 #define CAE_CHECK(cond, code, ...)            \
   do {                                        \

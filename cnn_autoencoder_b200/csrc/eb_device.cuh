@@ -41,7 +41,7 @@ static __device__ __noinline__ float eb_likelihood(const cae_eb_tables &t, int c
   const float s = lower + upper;
   const float sign = s > 0.f ? -1.f : (s < 0.f ? 1.f : 0.f);
   const float p = fabsf(eb_sigmoid(sign * upper) - eb_sigmoid(sign * lower));
-  return fmaxf(p, 1e-9f);
+  return fmaxf(p, t.lik_bound);
 }
 
 // sym = rint(y - median) saturated like an in-range float -> int32 cast
@@ -57,7 +57,7 @@ __device__ __forceinline__ float eb_lookup(const cae_eb_tables &t, int c, int sy
   if (t.lut && t.tail_lik > 0.f) return t.tail_lik;   // the table ends where the bound begins
   if (t.mlp) return eb_likelihood(t, c, yq);
   if (status) atomicOr(status, 1);
-  return 1e-9f;
+  return t.lik_bound;
 }
 
 inline int eb_check_tables(const cae_eb_tables *t, const char *who) {

@@ -129,7 +129,7 @@ extern "C" int cae_eb_quantize(const float *y, int n, int c, int hw, const cae_e
   if (bx < 1) bx = 1;
   if (bx > 64) bx = 64;
   // about eight blocks per SM in total: images are grouped per channel to reach that
-  int groups = (8 * 148) / (c * bx);
+  int groups = (8 * cae_sm_count()) / (c * bx);
   if (groups < 1) groups = 1;
   if (groups > n) groups = n;
   dim3 grid((unsigned)(groups * c), (unsigned)bx);

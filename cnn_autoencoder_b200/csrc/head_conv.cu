@@ -583,7 +583,7 @@ int launch_head(const HeadParams &p, cudaStream_t stream) {
   CAE_CUDA(cudaGetDevice(&dev));
   CAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.n_tiles < sms ? p.n_tiles : sms;
-  if (getenv("CAE_HEAD_TRACE")) {
+  if (cae_knob(CAE_KNOB_HEAD_TRACE)) {
     // bring-up aid: phase timestamps of the first 64 tiles of CTA 0 (synchronous, prints to stderr)
     HeadParams q = p;
     unsigned long long *buf = nullptr, host[64 * 8];
@@ -664,7 +664,7 @@ extern "C" int cae_conv_head(const cae_head_desc *d, void *stream) {
   uint32_t cols = 32;
   while ((int)cols < 4 * p.N) cols <<= 1;
   p.tmem_cols = cols;
-  if (const char *e = getenv("CAE_HEAD_DEBUG")) p.debug = atoi(e);
+  if (const char *e = cae_knob(CAE_KNOB_HEAD_DEBUG)) p.debug = atoi(e);
   cudaStream_t s = (cudaStream_t)stream;
   const bool u8 = d->in.fmt == CAE_FMT_U8_HWC;
   if (d->residual) {

@@ -147,9 +147,9 @@ inline int mma_n(int kind, int c_out) {
 inline int auto_ck(int kind, int c_in_p, bool merged = false) {
   // final image layer (N = 16): the MMAs are tiny and the layer is bound by the barrier round
   // trips per stage, so take the whole K = 128 in one stage
-  if (merged && c_in_p % 128 == 0 && !getenv("CAE_IGEMM_MERGED_CK64")) return 128;
+  if (merged && c_in_p % 128 == 0 && !cae_knob(CAE_KNOB_IGEMM_MERGED_CK64)) return 128;
   if (kind == CAE_CONV_S2) {
-    if (const char *e = getenv("CAE_IGEMM_CK_S2")) {      // experiment knob (pack and launch agree)
+    if (const char *e = cae_knob(CAE_KNOB_IGEMM_CK_S2)) {      // experiment knob (pack and launch agree)
       const int v = atoi(e);
       if ((v == 16 || v == 32) && c_in_p % v == 0) return v;
     }
@@ -974,7 +974,7 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   // (measured with the 256-bit pair stores: 128->128 @64x64 209 -> 199 us, 48->128 43 -> 37 us)
   const bool convt2 = kind == CAE_CONVT_S2 && !merged;
   p.n_pass = 1;
-  if (convt2 && (getenv("CAE_IGEMM_TWO_PASS") || (4 * p.N > 256 && !getenv("CAE_IGEMM_ONE_PASS"))))
+  if (convt2 && (cae_knob(CAE_KNOB_IGEMM_TWO_PASS) || (4 * p.N > 256 && !cae_knob(CAE_KNOB_IGEMM_ONE_PASS))))
     p.n_pass = 2;
   p.n_acc = (kind == CAE_CONVT_S2 && !merged) ? (p.n_pass == 2 ? 2 : 4) : 1;
   p.up = (kind == CAE_CONVT_S2) ? 2 : 1;
@@ -992,7 +992,7 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
 
   int mt = d->mt > 0 ? d->mt : 2;
   if (d->mt <= 0)
-    if (const char *e = getenv("CAE_IGEMM_MT")) mt = atoi(e) == 1 ? 1 : 2;
+    if (const char *e = cae_knob(CAE_KNOB_IGEMM_MT)) mt = atoi(e) == 1 ? 1 : 2;
   if (p.dom_w <= 8) mt = 1;
   if (p.n_acc * p.N * mt > 512) mt = 1;
   if (p.n_pass == 2 && p.n_acc * p.N * mt > 256) mt = 1;   // keep the accumulators double buffered
@@ -1028,7 +1028,7 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   p.sbo_a = (uint32_t)(p.PW * 16);
   p.lbo_b = (uint32_t)(p.N * 16);
   p.sbo_b = 128;
-  if (getenv("CAE_IGEMM_SWAP_LBO_SBO")) {  // bring-up knob, see DESIGN.md
+  if (cae_knob(CAE_KNOB_IGEMM_SWAP_LBO_SBO)) {  // bring-up knob, see DESIGN.md
     uint32_t t = p.lbo_a; p.lbo_a = p.sbo_a; p.sbo_a = t;
     t = p.lbo_b; p.lbo_b = p.sbo_b; p.sbo_b = t;
   }
@@ -1046,7 +1046,7 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   // fused quantizer tables (medians, likelihoods, histogram) behind the rings when they fit
   int q_bytes = 0;
   if (d->quant && d->out.fmt == CAE_FMT_F32_NCHW && !merged && d->quant->tables.lut &&
-      !getenv("CAE_QUANT_NO_SMEM")) {
+      !cae_knob(CAE_KNOB_QUANT_NO_SMEM)) {
     // as many symbols around the median as fit 40 KB (likelihoods + histogram); the rest of
     // the table stays in global memory (rare symbols)
     const cae_eb_tables &t = d->quant->tables;
@@ -1081,7 +1081,7 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
       break;
     }
   }
-  if (const char *e = getenv("CAE_IGEMM_TPB")) {
+  if (const char *e = cae_knob(CAE_KNOB_IGEMM_TPB)) {
     const int v = atoi(e);
     if (v >= 1 && divides(v) && 2 * p.a_stage_bytes + 2 * v * p.b_tap_bytes <= budget) tpb = v;
   }
@@ -1132,7 +1132,7 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   p.sb = sb;
   const int smem_bytes = sa * p.a_stage_bytes + sb * p.b_stage_bytes + 1024 + q_bytes;
   p.q_smem = q_bytes > 0;
-  if (getenv("CAE_IGEMM_VERBOSE"))
+  if (cae_knob(CAE_KNOB_IGEMM_VERBOSE))
     fprintf(stderr, "cae_conv_igemm: kind %d %d->%d @%dx%d N=%d ck=%d mt=%d n_pass=%d n_acc=%d n_buf=%d "
             "tpb=%d a_stage=%d x%d b_stage=%d x%d smem=%d tiles=%d\n", kind, d->c_in, d->c_out, d->h_in,
             d->w_in, p.N, p.ck, p.mt, p.n_pass, p.n_acc, p.n_buf, p.tpb, p.a_stage_bytes, sa,
@@ -1174,9 +1174,9 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
       p.q_hist = q->hist;
       p.q_rate = q->rate_bits;
       p.q_status = q->status;
-      if (getenv("CAE_QUANT_NO_HIST")) p.q_hist = nullptr;     // bring-up timing knobs
-      if (getenv("CAE_QUANT_NO_RATE")) p.q_rate = nullptr;
-      if (getenv("CAE_QUANT_NO_YQ")) p.q_yq = nullptr;
+      if (cae_knob(CAE_KNOB_QUANT_NO_HIST)) p.q_hist = nullptr;     // bring-up timing knobs
+      if (cae_knob(CAE_KNOB_QUANT_NO_RATE)) p.q_rate = nullptr;
+      if (cae_knob(CAE_KNOB_QUANT_NO_YQ)) p.q_yq = nullptr;
       if (q->y_q_planar.fmt != CAE_FMT_NONE && q->y_q_planar.ptr) {
         CAE_CHECK(q->y_q_planar.fmt == CAE_FMT_F16_PLANAR && q->y_q_planar.planes * 8 == p.N, 2,
                   "cae_conv_igemm(quant): planar y_q needs %d planes", p.N / 8);
@@ -1252,26 +1252,24 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CAE_CHECK(cr == CUDA_SUCCESS, 3, "cae_conv_igemm: cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
-  int sm_count = 0, dev = 0;
-  CAE_CUDA(cudaGetDevice(&dev));
-  CAE_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  const int sm_count = cae_sm_count();
   int grid = d->grid > 0 ? d->grid : sm_count;
   if (grid > p.n_tiles * p.n_pass) grid = p.n_tiles * p.n_pass;
 
   p.debug = 0;
-  if (const char *e = getenv("CAE_IGEMM_DEBUG")) p.debug = atoi(e);
+  if (const char *e = cae_knob(CAE_KNOB_IGEMM_DEBUG)) p.debug = atoi(e);
   p.pair_store = epi == EPI_ACT && p.up == 2 && p.out.fmt == CAE_FMT_F16_PLANAR &&
-                 p.out.halo != CAE_HALO_REFLECT && !(p.debug & 16) && !getenv("CAE_IGEMM_NO_PAIR_STORE");
+                 p.out.halo != CAE_HALO_REFLECT && !(p.debug & 16) && !cae_knob(CAE_KNOB_IGEMM_NO_PAIR_STORE);
   p.epi_warps = 8;
-  if (const char *e = getenv("CAE_IGEMM_EPI_WARPS")) {
+  if (const char *e = cae_knob(CAE_KNOB_IGEMM_EPI_WARPS)) {
     const int v = atoi(e);
     if (v == 4 || v == 8 || v == 12 || v == 16) p.epi_warps = v;
   }
   // epilogue variant: 1 = packed half2 (16 epilogue warps), 2 = the same after an fp32 residual
   // add (12 warps: more registers), 0 = plain fp32 (bring-up / latent / image layers)
   int fast = 0;
-  if (epi == EPI_ACT && !getenv("CAE_IGEMM_NO_FAST_EPILOGUE")) fast = p.skip.ptr ? 2 : 1;
-  if (!getenv("CAE_IGEMM_EPI_WARPS")) p.epi_warps = fast == 1 ? 16 : ((fast == 2 || p.quant) ? 12 : 8);
+  if (epi == EPI_ACT && !cae_knob(CAE_KNOB_IGEMM_NO_FAST_EPILOGUE)) fast = p.skip.ptr ? 2 : 1;
+  if (!cae_knob(CAE_KNOB_IGEMM_EPI_WARPS)) p.epi_warps = fast == 1 ? 16 : ((fast == 2 || p.quant) ? 12 : 8);
   if (fast != 1 && p.epi_warps > kMaxEpiWarps) p.epi_warps = kMaxEpiWarps;
   const int threads = 128 + 32 * p.epi_warps;
   void (*kern)(const CUtensorMap, const IgParams) =

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CAE_ABI_VERSION 2
+#define CAE_ABI_VERSION 3
 
 /* ---- tensor formats ------------------------------------------------------ */
 enum {
@@ -186,7 +186,9 @@ typedef struct cae_eb_tables {
    * (1e-9, CompressAI likelihood_bound), so every symbol outside the table has exactly this
    * likelihood and the MLP is never evaluated.  0: unknown, fall back to the MLP.            */
   float tail_lik;
-  int32_t reserved;
+  /* CompressAI's likelihood_lower_bound.bound (1e-9 unless the checkpoint says otherwise):
+   * the floor applied to likelihoods evaluated on the device.                                */
+  float lik_bound;
 } cae_eb_tables;
 
 int cae_eb_quantize(const float *y, int n, int c, int hw, const cae_eb_tables *t,

@@ -342,6 +342,12 @@ class _LowerBoundFn(torch.autograd.Function):
         return pass_through.type(g.dtype) * g, None
 
 
+class _LowerBoundModule(nn.Module):
+    def __init__(self, bound):
+        super().__init__()
+        self.register_buffer('bound', torch.tensor([float(bound)]))
+
+
 class EntropyBottleneck(nn.Module):
     """Restated factorized-prior entropy model.  Call sites in the reference:
     ctor R:476-477, R:607-608; forward ``_taskutils.py:97``; compress R:549-551,
@@ -356,7 +362,9 @@ class EntropyBottleneck(nn.Module):
         self.init_scale = float(init_scale)
         self.tail_mass = float(tail_mass)
         self.entropy_coder_precision = int(entropy_coder_precision)
-        self.register_buffer('_lik_bound', torch.tensor([float(likelihood_bound)]), persistent=False)
+        # CompressAI keeps the bound in a LowerBound submodule whose buffer is part of every
+        # state dict (key ``likelihood_lower_bound.bound``; scripts/transfer_weights.py lists it)
+        self.likelihood_lower_bound = _LowerBoundModule(likelihood_bound)
 
         F_ = (1,) + self.filters + (1,)
         scale = self.init_scale ** (1 / (len(self.filters) + 1))
@@ -377,6 +385,12 @@ class EntropyBottleneck(nn.Module):
         self.register_buffer('_offset', torch.IntTensor())
         self.register_buffer('_quantized_cdf', torch.IntTensor())
         self.register_buffer('_cdf_length', torch.IntTensor())
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # fixtures written before the bound buffer was restated lack its key
+        state_dict.setdefault(prefix + 'likelihood_lower_bound.bound',
+                              self.likelihood_lower_bound.bound.clone())
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
     # -- density model ------------------------------------------------------
     def _logits_cumulative(self, v, stop_gradient):
@@ -418,7 +432,7 @@ class EntropyBottleneck(nn.Module):
             med = self._medians()
             v = torch.round(v - med) + med
         lik = self._likelihood(v)
-        lik = _LowerBoundFn.apply(lik, self._lik_bound)
+        lik = _LowerBoundFn.apply(lik, self.likelihood_lower_bound.bound)
         out = v.reshape(shape).permute(*perm).contiguous()
         lik = lik.reshape(shape).permute(*perm).contiguous()
         return out, lik

@@ -60,6 +60,9 @@ def state_sha256(chk):
     h = hashlib.sha256()
     for part in ('encoder', 'decoder', 'fact_ent'):
         for k in sorted(chk[part]):
+            if k == 'likelihood_lower_bound.bound':
+                continue      # constant buffer added to the state dict in round 2; the committed
+                              # fixtures' hashes cover the weights, which did not change
             h.update(k.encode())
             h.update(chk[part][k].detach().cpu().contiguous().numpy().tobytes())
     return h.hexdigest()
