@@ -364,8 +364,7 @@ class Synthesizer(_Track):
                 fx_brg.append(fx)
             return x_r, fx_brg
         self._check_input(x)
-        n_units = len(self._units())
-        if n_units == 0:
+        if len(self._units()) == 0:
             return [x], [x]
         with self._lock, torch.no_grad():
             if planar is not None and x.shape[1] > 4:
@@ -379,6 +378,17 @@ class Synthesizer(_Track):
                 self._in_planar, self._in_planar_key = a, key
             else:
                 a = O.wrap_nchw(x)
+            return self._run(a, as_uint8)
+
+    def forward_planar(self, a, as_uint8=False):
+        """``forward`` on a latent that is already in the track's input layout (an ``_ops.Act``
+        in planar fp16 with a zero halo, e.g. written by ``cae_eb_dequantize_planar``)."""
+        with self._lock, torch.no_grad():
+            return self._run(a, as_uint8)
+
+    def _run(self, a, as_uint8):
+        n_units = len(self._units())
+        if True:
             outs = self._unit_output_indices()
             keep = outs[:-1] if (self.bridges or self.multiscale) else ()
             final = C.FMT_U8_HWC if as_uint8 else C.FMT_F32_NCHW

@@ -455,23 +455,21 @@ class EntropyBottleneck(nn.Module):
         status = torch.zeros(1, dtype=torch.int32, device=dev)
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         L = C.lib()
-        use_table = not os.environ.get('CAE_RANS_NO_TABLE')
+        use_table = True
         C.check(L.cae_rans_encode_batch(sym.data_ptr(), n, c, hw, cdf.data_ptr(), cdf.shape[1],
                                         sizes.data_ptr(), offs.data_ptr(),
                                         table.data_ptr() if use_table else None,
                                         words.data_ptr(), cap, nwords.data_ptr(),
                                         status.data_ptr(), stream))
-        ends = torch.cumsum(nwords.long(), 0)
-        starts = (ends - nwords.long()).contiguous()
-        e = ends.cpu().numpy()                             # sync: stream lengths are data dependent
+        off_d = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        C.check(L.cae_rans_scan(nwords.data_ptr(), n, off_d.data_ptr(), stream))
+        e = off_d.cpu().numpy()                            # sync: stream lengths are data dependent
         if int(status.item()) & 1:
             raise C.CaeError('device entropy coder: a stream overflowed its staging buffer')
         packed = torch.empty(int(e[-1]), dtype=torch.int32, device=dev)
-        C.check(L.cae_rans_compact(words.data_ptr(), n, cap, nwords.data_ptr(), starts.data_ptr(),
+        C.check(L.cae_rans_compact(words.data_ptr(), n, cap, nwords.data_ptr(), off_d.data_ptr(),
                                    packed.data_ptr(), stream))
-        off = np.zeros(n + 1, dtype=np.int64)
-        off[1:] = e * 4
-        return packed.view(torch.uint8), off
+        return packed.view(torch.uint8), e * 4
 
     def encode_symbols_gpu(self, sym):
         """int32 symbols N x C x ... (device) -> list of N byte strings."""

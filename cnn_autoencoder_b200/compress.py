@@ -27,7 +27,32 @@ import torch
 
 from . import _autoencoders as AE
 from ._entropy import encode_symbols
+from . import _slide
 from ._store import DirArray, can_native_gather, native_gather, native_write, padded_tile
+
+_models = {}
+
+
+def load_model(checkpoint):
+    """``autoencoder_from_state_dict(checkpoint, gpu=True, train=False)`` (R:505-527), kept for
+    the next call on the same checkpoint: a slide is usually one of many compressed with one
+    model, and the packed weights / CUDA graphs hang off the model objects."""
+    if isinstance(checkpoint, str):
+        key = ('path', checkpoint, os.path.getmtime(checkpoint), torch.cuda.current_device())
+    else:
+        # (the three table buffers of fact_ent are shared with the module while loading and
+        # rewritten by update(): not part of the identity of a checkpoint)
+        sig = tuple((k, v.data_ptr(), v._version) for part in ('encoder', 'decoder', 'fact_ent')
+                    for k, v in sorted((checkpoint.get(part) or {}).items())
+                    if k not in ('_quantized_cdf', '_offset', '_cdf_length'))
+        key = ('dict', id(checkpoint), hash(sig), torch.cuda.current_device())
+    m = _models.get(key)
+    if m is None:
+        if len(_models) >= 4:
+            _models.clear()
+        m = _models[key] = AE.autoencoder_from_state_dict(checkpoint=checkpoint, gpu=True,
+                                                          train=False)
+    return m
 
 
 def shard_range(n_items, rank, world_size):
@@ -100,7 +125,7 @@ def compress_image(codec, checkpoint, input_filename, output_filename, patch_siz
     H, W, C = src.shape
     ps = patch_size
 
-    model = AE.autoencoder_from_state_dict(checkpoint=checkpoint, gpu=True, train=False)
+    model = load_model(checkpoint)
     fact_ent = model['fact_ent'].module
     channels_bn = fact_ent.channels
     level = len(model['encoder'].module.analysis_track)
@@ -132,6 +157,20 @@ def compress_image(codec, checkpoint, input_filename, output_filename, patch_siz
     stats = dict(tiles=len(mine), pixels=0, bytes=0, seconds=0.0, device_coded=0,
                  t_read=0.0, t_stage=0.0, t_gpu=0.0, t_code=0.0, t_write_wait=0.0)
     t_start = time.perf_counter()
+    if (not save_as_bottleneck and can_native_gather(src) and ps % (2 ** level) == 0
+            and len(mine) >= fact_ent.GPU_CODER_MIN_STREAMS and not os.environ.get('CAE_NO_SLIDE_ENGINE')):
+        # the batched engine: strided DMA out of the slide, one CUDA-graph replay per batch, all
+        # streams of a group coded on the device (see _slide.py)
+        tc = _slide.tile_codec(model, ps, C, batch_tiles)
+        if len(mine) >= batch_tiles:
+            tc.warm(encode=True, decode=False)
+        t_start = time.perf_counter()
+        st = _slide._Stats()
+        _slide.compress_tiles(tc, src, mine, dst.chunk_file, (ps, ps), workers, coder_tiles, st)
+        stats.update(st)
+        stats['engine'] = 'slide'
+        stats['seconds'] = time.perf_counter() - t_start
+        return stats
     pool = ThreadPoolExecutor(max_workers=workers)
     writes = []                     # futures of chunk-file writes
     acc = {}                        # latent shape -> dict(sym=[device tensors], meta=[(idx, h, w)])

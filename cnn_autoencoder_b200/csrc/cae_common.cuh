@@ -24,7 +24,7 @@ int cae_sm_count();   // SMs of the current device (cached per device)
   X(IGEMM_ONE_PASS) X(IGEMM_MT) X(IGEMM_SWAP_LBO_SBO) X(QUANT_NO_SMEM) X(IGEMM_TPB)           \
   X(IGEMM_VERBOSE) X(QUANT_NO_HIST) X(QUANT_NO_RATE) X(QUANT_NO_YQ) X(IGEMM_DEBUG)            \
   X(IGEMM_NO_PAIR_STORE) X(IGEMM_EPI_WARPS) X(IGEMM_NO_FAST_EPILOGUE) X(IGEMM_NO_TMA_STORE)   \
-  X(IGEMM_NO_PAIR_MMA) X(RANS_V1)
+  X(IGEMM_NO_PAIR_MMA) X(RANS_V1) X(RANS_V2)
 enum CaeKnob {
 #define X(n) CAE_KNOB_##n,
   CAE_KNOB_LIST(X)

@@ -111,7 +111,51 @@ __global__ void __launch_bounds__(256) eb_quantize_kernel(const EbParams p) {
   }
 }
 
+// int32 symbols (N x C x h x w) -> y_q = sym + median_c in the synthesis track's input layout
+// (planar fp16, zero halo untouched): the de-quantisation of EntropyBottleneck.decompress
+// ("symbols + medians"; reached from _autoencoders.py:568-572) fused with the
+// layout conversion, one pass.  Thread = one pixel x one 8-channel plane.
+__global__ void __launch_bounds__(256) eb_dequantize_planar_kernel(
+    const int32_t *__restrict__ sym, const float *__restrict__ medians, int n_img, int c, int h,
+    int w, ActView dst) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t hw = (size_t)h * w, total = (size_t)n_img * dst.planes * hw;
+  if (idx >= total) return;
+  const int x = (int)(idx % w);
+  const int y = (int)((idx / w) % h);
+  const int plane = (int)((idx / hw) % dst.planes);
+  const int n = (int)(idx / (hw * dst.planes));
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ch = plane * 8 + i;
+    v[i] = ch < c ? (float)__ldg(sym + ((size_t)n * c + ch) * hw + (size_t)y * w + x) + __ldg(medians + ch)
+                  : 0.f;
+  }
+  __half2 hv[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) hv[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+  reinterpret_cast<uint4 *>(dst.ptr)[act_unit_offset(dst, n, plane, y + 1, x + 1)] =
+      *reinterpret_cast<uint4 *>(hv);
+}
+
 }  // namespace
+
+extern "C" int cae_eb_dequantize_planar(const int32_t *symbols, const float *medians, int n, int c,
+                                        int h, int w, cae_tensor dst, void *stream) {
+  CAE_CHECK(symbols && medians && dst.ptr && dst.fmt == CAE_FMT_F16_PLANAR, 2,
+            "cae_eb_dequantize_planar: bad argument");
+  CAE_CHECK(n > 0 && c > 0 && h > 0 && w > 0 && dst.planes * 8 >= c, 2,
+            "cae_eb_dequantize_planar: bad shape");
+  ActView v;
+  v.ptr = dst.ptr; v.fmt = dst.fmt; v.planes = dst.planes; v.halo = dst.halo; v.H = h; v.W = w;
+  const size_t total = (size_t)n * dst.planes * h * w;
+  eb_dequantize_planar_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      symbols, medians, n, c, h, w, v);
+  cae_count_launch();
+  CAE_CUDA(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int cae_eb_quantize(const float *y, int n, int c, int hw, const cae_eb_tables *t,
                                float *y_q, float *p_y, int32_t *symbols, int32_t *hist,

@@ -258,6 +258,452 @@ __global__ void __launch_bounds__(64) rans_decode_kernel(const RansDecParams p) 
   if (bad) atomicOr(p.status, 2);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Warp-staged coders (the default).  One thread still owns one stream -- a range-coder state is
+// a dependent chain -- but the 32 streams of a warp move their symbols through shared memory in
+// 32 x 32 chunks: the warp reads (writes) 32 symbols of each of its streams as one coalesced
+// 128-byte access, software-pipelined one chunk ahead, and every lane then walks its own row of
+// the chunk (row pitch 33 words: conflict free both ways).  The one-thread-per-stream kernels
+// above issue one dependent, uncoalesced 4-byte global access per symbol (~330 ns each: 65 ms
+// per call whatever the stream count); here the per-symbol chain is shared memory only.
+// ------------------------------------------------------------------------------------------
+constexpr int kChunk = 32;
+constexpr int kPitch = kChunk + 1;
+
+// Hot-path pieces of the warp-staged encoder.  The 32 lanes of a warp code 32 different streams,
+// so any branch on the state (renormalise or not) diverges at almost every symbol; both the word
+// emission and the state update are therefore predicated, and only the escape path (rare by
+// construction of the tables) is a real, out-of-line branch.
+__device__ __forceinline__ void st_global_if(uint32_t *ptr, uint32_t w, bool p) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.b32 [%0], %1;\n\t}"
+               ::"l"(ptr), "r"(w), "r"((uint32_t)p)
+               : "memory");
+}
+
+struct PredEmitter {
+  uint32_t *base;
+  int pos;        // words still free below the written tail; may go negative (= overflow)
+  __device__ __forceinline__ void put_if(bool p, uint32_t w) {
+    st_global_if(base + (pos - 1), w, p && pos > 0);
+    pos -= p ? 1 : 0;
+  }
+};
+
+__device__ __forceinline__ void enc_step(uint64_t &x, PredEmitter &e, const EncEntry &t) {
+  const uint32_t freq = (1u << kPrecision) - (uint32_t)t.cmpl_freq;
+  const bool p = (uint32_t)(x >> 47) >= freq;          // x >= ((L >> 16) << 32) * freq
+  e.put_if(p, (uint32_t)x);
+  x = p ? (x >> 32) : x;
+  const uint64_t q = __umul64hi(x, t.rcp_freq) >> t.rcp_shift;
+  x = x + t.bias + q * t.cmpl_freq;
+}
+
+struct EncState {
+  uint64_t x;
+  int pos;
+};
+
+// by value in, by value out: nothing of the hot loop's state has its address taken
+static __device__ __noinline__ EncState enc_escape(uint64_t x, uint32_t *base, int pos, long long vv,
+                                                   int max_value) {
+  // sign-folded raw value as 4-bit groups, their count in unary-of-15 -- emitted last to first
+  // (the decoder reads them in the forward order); the sentinel code follows in the caller
+  PredEmitter e{base, pos};
+  const uint32_t raw = vv < 0 ? (uint32_t)(-2 * vv - 1) : (uint32_t)(2 * (vv - max_value));
+  int groups = 0;
+  while (groups < 8 && (raw >> (groups * kBypassBits)) != 0) ++groups;
+  auto nibble = [&](uint32_t val) {
+    const bool p = (uint32_t)(x >> 47) >= (1u << (16 - kBypassBits));
+    e.put_if(p, (uint32_t)x);
+    x = p ? (x >> 32) : x;
+    x = (x << kBypassBits) | val;
+  };
+  for (int g = groups - 1; g >= 0; --g) nibble((raw >> (g * kBypassBits)) & 15u);
+  nibble((uint32_t)(groups % kMaxBypass));
+  for (int q = 0; q < groups / kMaxBypass; ++q) nibble((uint32_t)kMaxBypass);
+  return EncState{x, e.pos};
+}
+
+__global__ void __launch_bounds__(32) rans_encode_warp_kernel(const RansEncParams p) {
+  extern __shared__ __align__(16) uint8_t enc_smem[];
+  const int lane = threadIdx.x;
+  int32_t *stage = reinterpret_cast<int32_t *>(enc_smem);                 // [32][33]
+  EncEntry *tab = reinterpret_cast<EncEntry *>(enc_smem + kChunk * kPitch * 4 + 32);
+  const EncEntry *table = p.table;
+  if (p.table_in_smem) {
+    for (int i = lane; i < p.c * p.stride; i += 32) tab[i] = p.table[i];
+    table = tab;
+  }
+  __syncwarp();
+  const int k0 = blockIdx.x * 32;
+  const int k = k0 + lane;
+  const bool live = k < p.n;
+  const int n_here = min(32, p.n - k0);
+  PredEmitter e{p.words + (size_t)(live ? k : k0) * p.cap, p.cap};
+  uint64_t x = kRansL;
+  const size_t per_stream = (size_t)p.c * p.hw;
+  const int32_t *sym0 = p.symbols + (size_t)k0 * per_stream;
+  const int chunks = (p.hw + kChunk - 1) / kChunk;
+  const int total = p.c * chunks;
+
+  int32_t pre[kChunk];
+  auto fetch = [&](int t) {       // chunk t of every stream of the warp: 32 coalesced loads
+    const int ch = t / chunks, j = t - ch * chunks;
+    const int i = j * kChunk + lane;
+    const int32_t *src = sym0 + (size_t)ch * p.hw + i;
+    const bool ok = i < p.hw;
+#pragma unroll
+    for (int s = 0; s < kChunk; ++s)
+      pre[s] = (ok && s < n_here) ? __ldg(src + (size_t)s * per_stream) : 0;
+  };
+  fetch(total - 1);
+  for (int t = total - 1; t >= 0; --t) {
+    const int ch = t / chunks, j = t - ch * chunks;
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < kChunk; ++s) stage[s * kPitch + lane] = pre[s];
+    __syncwarp();
+    if (t > 0) fetch(t - 1);
+    if (!live) continue;
+    const EncEntry *row = table + (size_t)ch * p.stride;
+    const int max_value = p.sizes[ch] - 2;
+    const int offset = p.offsets[ch];
+    const int m = min(kChunk, p.hw - j * kChunk);
+    const int32_t *mine = stage + lane * kPitch;
+    // The state update is a dependent chain (compare, 64-bit multiply-high, shift, multiply,
+    // add); everything else of a symbol -- its load, the range test, the 16-byte table entry --
+    // does not depend on the state, so it is fetched one symbol ahead and overlaps the chain.
+    int value = mine[m - 1] - offset;
+    bool esc = (unsigned)value >= (unsigned)max_value;
+    EncEntry ent = row[esc ? max_value : value];
+#pragma unroll 4
+    for (int i = m - 1; i >= 0; --i) {
+      const int v_cur = value;
+      const bool esc_cur = esc;
+      const EncEntry cur = ent;
+      if (i > 0) {
+        value = mine[i - 1] - offset;
+        esc = (unsigned)value >= (unsigned)max_value;
+        ent = row[esc ? max_value : value];
+      }
+      if (esc_cur) {
+        const EncState st = enc_escape(x, e.base, e.pos, (long long)v_cur, max_value);
+        x = st.x;
+        e.pos = st.pos;
+      }
+      enc_step(x, e, cur);
+    }
+  }
+  if (!live) return;
+  e.put_if(true, (uint32_t)(x >> 32));
+  e.put_if(true, (uint32_t)x);
+  const bool overflow = e.pos < 0;
+  p.nwords[k] = overflow ? 0 : p.cap - e.pos;
+  if (overflow) atomicOr(p.status, 1);
+}
+
+// exclusive prefix sum of the stream lengths (one block; n is a few thousand at most)
+__global__ void __launch_bounds__(1024) rans_scan_kernel(const int32_t *__restrict__ nwords, int n,
+                                                         int64_t *__restrict__ off) {
+  __shared__ long long part[1024];
+  const int per = (n + 1023) / 1024;
+  const int b = threadIdx.x * per, e = min(n, b + per);
+  long long s = 0;
+  for (int i = b; i < e; ++i) s += nwords[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long run = 0;
+    for (int i = 0; i < 1024; ++i) { const long long v = part[i]; part[i] = run; run += v; }
+    off[n] = run;
+  }
+  __syncthreads();
+  long long run = part[threadIdx.x];
+  for (int i = b; i < e; ++i) { off[i] = run; run += nwords[i]; }
+}
+
+struct WordReader {          // forward reader with one word of look-ahead
+  const uint32_t *ptr, *end;
+  uint32_t nxt;
+  bool bad;
+  __device__ __forceinline__ void init(const uint32_t *b, const uint32_t *e) {
+    ptr = b; end = e; bad = false;
+    nxt = ptr < end ? __ldg(ptr) : 0u;
+  }
+  __device__ __forceinline__ uint32_t take() {
+    if (ptr >= end) { bad = true; return 0u; }
+    const uint32_t w = nxt;
+    ++ptr;
+    if (ptr < end) nxt = __ldg(ptr);
+    return w;
+  }
+};
+
+__device__ __forceinline__ uint32_t dec_nibble_w(uint64_t &x, WordReader &r) {
+  const uint32_t val = (uint32_t)(x & 15u);
+  x >>= kBypassBits;
+  if (x < kRansL) x = (x << 32) | r.take();
+  return val;
+}
+
+// Decoder with a direct look-up: for the channel being decoded a 4096-entry table maps the top
+// 12 bits of the cumulative frequency to (first symbol whose range reaches into that bucket, its
+// start and frequency), so the symbol search on the state's dependent chain is ONE 8-byte
+// shared-memory load (plus a rare step forward for buckets that straddle a boundary).  All
+// streams of a warp move through the channels together, so one table (32 KB) serves the warp
+// and is rebuilt at every channel switch (128 entries per lane, ~0.3 % of the channel's work).
+constexpr int kFineBits = 12;
+constexpr int kFine = 1 << kFineBits;
+
+__device__ __forceinline__ void ld_global_if(uint32_t &dst, const uint32_t *ptr, bool p) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.nc.b32 %0, [%1];\n\t}"
+               : "+r"(dst)
+               : "l"(ptr), "r"((uint32_t)p)
+               : "memory");
+}
+
+struct PredReader {          // forward reader, one word of look-ahead, no branch on the hot path
+  const uint32_t *ptr, *end; // ptr: the word held in nxt; ptr > end at the end = read past the stream
+  uint32_t nxt;
+  __device__ __forceinline__ void init(const uint32_t *b, const uint32_t *e) {
+    ptr = b; end = e;
+    nxt = ptr < end ? __ldg(ptr) : 0u;
+  }
+  __device__ __forceinline__ uint32_t take_if(bool need) {
+    const uint32_t w = nxt;
+    ptr += need ? 1 : 0;
+    ld_global_if(nxt, ptr, need && ptr < end);
+    return w;
+  }
+};
+
+__device__ __forceinline__ void dec_renorm(uint64_t &x, PredReader &r) {
+  const bool need = x < kRansL;
+  const uint32_t w = r.take_if(need);
+  x = need ? ((x << 32) | w) : x;
+}
+
+struct DecState {
+  uint64_t x;
+  const uint32_t *ptr;
+  uint32_t nxt;
+  int value;
+};
+
+static __device__ __noinline__ DecState dec_escape(uint64_t x, const uint32_t *ptr, const uint32_t *end,
+                                                   uint32_t nxt, int max_value) {
+  PredReader r{ptr, end, nxt};
+  auto nibble = [&]() {
+    const uint32_t val = (uint32_t)(x & 15u);
+    x >>= kBypassBits;
+    dec_renorm(x, r);
+    return val;
+  };
+  int v = (int)nibble(), groups = v;
+  while (v == kMaxBypass && groups < 64) { v = (int)nibble(); groups += v; }
+  uint32_t raw = 0;
+  for (int g = 0; g < groups; ++g) {
+    const uint32_t nib = nibble();
+    if (g < 8) raw |= nib << (g * kBypassBits);
+  }
+  const int value = (int)(raw >> 1);
+  return DecState{x, r.ptr, r.nxt, (raw & 1u) ? -value - 1 : value + max_value};
+}
+
+// the bucket of the fine table straddles a symbol boundary and cf lies beyond the first symbol:
+// returns (lo << 32) | start of the symbol that holds cf
+static __device__ __noinline__ uint64_t dec_walk(const int32_t *cdf, uint32_t cf, int lo) {
+  uint32_t start;
+  do {
+    ++lo;
+    start = (uint32_t)cdf[lo];
+  } while (cf >= (uint32_t)cdf[lo + 1]);
+  return ((uint64_t)(uint32_t)lo << 32) | start;
+}
+
+__global__ void __launch_bounds__(32) rans_decode_fine_kernel(const RansDecParams p) {
+  extern __shared__ __align__(16) uint8_t dec_smem[];
+  const int lane = threadIdx.x;
+  uint2 *fine = reinterpret_cast<uint2 *>(dec_smem);                       // [4096]
+  int32_t *stage = reinterpret_cast<int32_t *>(dec_smem + kFine * 8);      // [32][33]
+  int32_t *scdf = stage + kChunk * kPitch + 8;                             // [c][stride]
+  for (int i = lane; i < p.c * p.stride; i += 32) scdf[i] = p.cdfs[i];
+  __syncwarp();
+  const int k0 = blockIdx.x * 32;
+  const int k = k0 + lane;
+  const bool live = k < p.n;
+  const int n_here = min(32, p.n - k0);
+  PredReader r;
+  uint64_t x = kRansL;
+  if (live) {
+    r.init(p.words + p.off[k], p.words + p.off[k + 1]);
+    const uint32_t w0 = r.take_if(true), w1 = r.take_if(true);
+    x = (uint64_t)w0 | ((uint64_t)w1 << 32);
+  } else {
+    r.init(nullptr, nullptr);
+  }
+  const size_t per_stream = (size_t)p.c * p.hw;
+  int32_t *out0 = p.symbols + (size_t)k0 * per_stream;
+  const int chunks = (p.hw + kChunk - 1) / kChunk;
+  for (int ch = 0; ch < p.c; ++ch) {
+    const int32_t *cdf = scdf + (size_t)ch * p.stride;
+    const int size = p.sizes[ch], max_value = size - 2, offset = p.offsets[ch];
+    __syncwarp();
+    {
+      // buckets [128 lane, 128 lane + 128): s = last symbol with cdf[s] <= 16 b
+      const int b0 = lane * (kFine / 32);
+      int s = 0, hi = size - 1;
+      const uint32_t c0 = (uint32_t)b0 << (kPrecision - kFineBits);
+      while (hi - s > 1) {
+        const int mid = (s + hi) >> 1;
+        if ((uint32_t)cdf[mid] <= c0) s = mid; else hi = mid;
+      }
+      for (int b = b0; b < b0 + kFine / 32; ++b) {
+        const uint32_t cb = (uint32_t)b << (kPrecision - kFineBits);
+        while ((uint32_t)cdf[s + 1] <= cb) ++s;
+        const uint32_t start = (uint32_t)cdf[s];
+        fine[b] = make_uint2(start | ((uint32_t)s << 16), (uint32_t)cdf[s + 1] - start);
+      }
+    }
+    __syncwarp();
+    for (int j = 0; j < chunks; ++j) {
+      const int m = min(kChunk, p.hw - j * kChunk);
+      if (live) {
+        int32_t *mine = stage + lane * kPitch;
+#pragma unroll 4
+        for (int i = 0; i < m; ++i) {
+          const uint32_t cf = (uint32_t)x & 0xffffu;
+          const uint2 fe = fine[cf >> (kPrecision - kFineBits)];
+          uint32_t start = fe.x & 0xffffu, freq = fe.y;
+          int lo = (int)(fe.x >> 16);
+          if (cf - start >= freq) {                                            // rare
+            const uint64_t w = dec_walk(cdf, cf, lo);
+            lo = (int)(w >> 32);
+            start = (uint32_t)w;
+            freq = (uint32_t)cdf[lo + 1] - start;
+          }
+          x = (uint64_t)freq * (x >> kPrecision) + (cf - start);
+          dec_renorm(x, r);
+          int value = lo;
+          if (lo == max_value) {                                               // rare
+            const DecState st = dec_escape(x, r.ptr, r.end, r.nxt, max_value);
+            x = st.x;
+            r.ptr = st.ptr;
+            r.nxt = st.nxt;
+            value = st.value;
+          }
+          mine[i] = value + offset;
+        }
+      }
+      __syncwarp();
+      const int i = j * kChunk + lane;
+      if (i < p.hw) {
+        int32_t *dst = out0 + (size_t)ch * p.hw + i;
+#pragma unroll 8
+        for (int s = 0; s < n_here; ++s) dst[(size_t)s * per_stream] = stage[s * kPitch + lane];
+      }
+      __syncwarp();
+    }
+  }
+  if (live && r.ptr > r.end) atomicOr(p.status, 2);
+}
+
+__global__ void __launch_bounds__(32) rans_decode_warp_kernel(const RansDecParams p, int coarse) {
+  extern __shared__ __align__(16) uint8_t dec_smem[];
+  const int lane = threadIdx.x;
+  int32_t *stage = reinterpret_cast<int32_t *>(dec_smem);                 // [32][33]
+  int32_t *scdf = stage + kChunk * kPitch + 8;
+  uint8_t *first = reinterpret_cast<uint8_t *>(scdf + (p.cdf_in_smem ? p.c * p.stride : 0));
+  const int32_t *cdfs = p.cdfs;
+  if (p.cdf_in_smem) {
+    for (int i = lane; i < p.c * p.stride; i += 32) scdf[i] = p.cdfs[i];
+    cdfs = scdf;
+  }
+  __syncwarp();
+  if (coarse) {
+    // first[ch][b] = last symbol whose cumulative count is <= 256 b: the search for a
+    // cumulative frequency cf starts there and walks forward (peaked densities: 0-2 steps)
+    for (int ch = lane; ch < p.c; ch += 32) {
+      const int32_t *cdf = cdfs + (size_t)ch * p.stride;
+      const int size = p.sizes[ch];
+      for (int s = 0; s + 1 < size; ++s) {
+        const int b0 = (cdf[s] + 255) >> 8, b1 = (cdf[s + 1] + 255) >> 8;
+        for (int b = b0; b < b1 && b < 256; ++b) first[ch * 256 + b] = (uint8_t)s;
+      }
+    }
+  }
+  __syncwarp();
+  const int k0 = blockIdx.x * 32;
+  const int k = k0 + lane;
+  const bool live = k < p.n;
+  const int n_here = min(32, p.n - k0);
+  WordReader r;
+  uint64_t x = kRansL;
+  if (live) {
+    const uint32_t *b = p.words + p.off[k], *e = p.words + p.off[k + 1];
+    r.init(b, e);
+    const uint32_t w0 = r.take(), w1 = r.take();
+    x = (uint64_t)w0 | ((uint64_t)w1 << 32);
+  } else {
+    r.init(nullptr, nullptr);
+  }
+  const size_t per_stream = (size_t)p.c * p.hw;
+  int32_t *out0 = p.symbols + (size_t)k0 * per_stream;
+  const int chunks = (p.hw + kChunk - 1) / kChunk;
+  for (int ch = 0; ch < p.c; ++ch) {
+    const int32_t *cdf = cdfs + (size_t)ch * p.stride;
+    const uint8_t *fst = first + ch * 256;
+    const int size = p.sizes[ch], max_value = size - 2, offset = p.offsets[ch];
+    for (int j = 0; j < chunks; ++j) {
+      const int m = min(kChunk, p.hw - j * kChunk);
+      if (live) {
+        int32_t *mine = stage + lane * kPitch;
+        for (int i = 0; i < m; ++i) {
+          const uint32_t cf = (uint32_t)(x & 0xffffu);
+          int lo;
+          if (coarse) {
+            lo = fst[cf >> 8];
+            while ((uint32_t)cdf[lo + 1] <= cf) ++lo;
+          } else {
+            lo = 0;
+            int hi = size - 1;          // last entry with cdf[s] <= cf
+            while (hi - lo > 1) {
+              const int mid = (lo + hi) >> 1;
+              if ((uint32_t)cdf[mid] <= cf) lo = mid; else hi = mid;
+            }
+          }
+          const uint32_t start = (uint32_t)cdf[lo], freq = (uint32_t)cdf[lo + 1] - start;
+          x = (uint64_t)freq * (x >> kPrecision) + cf - start;
+          if (x < kRansL) x = (x << 32) | r.take();
+          int value = lo;
+          if (lo == max_value) {
+            int v = (int)dec_nibble_w(x, r), groups = v;
+            while (v == kMaxBypass && !r.bad) { v = (int)dec_nibble_w(x, r); groups += v; }
+            uint32_t raw = 0;
+            for (int g = 0; g < groups; ++g) {
+              const uint32_t nib = dec_nibble_w(x, r);
+              if (g < 8) raw |= nib << (g * kBypassBits);
+            }
+            value = (int)(raw >> 1);
+            value = (raw & 1u) ? -value - 1 : value + max_value;
+          }
+          mine[i] = value + offset;
+        }
+      }
+      __syncwarp();
+      const int i = j * kChunk + lane;
+      if (i < p.hw) {
+        int32_t *dst = out0 + (size_t)ch * p.hw + i;
+#pragma unroll 8
+        for (int s = 0; s < n_here; ++s) dst[(size_t)s * per_stream] = stage[s * kPitch + lane];
+      }
+      __syncwarp();
+    }
+  }
+  if (live && r.bad) atomicOr(p.status, 2);
+}
+
 }  // namespace
 
 extern "C" size_t cae_rans_enc_table_bytes(int c, int cdf_stride) {
@@ -285,6 +731,18 @@ extern "C" int cae_rans_encode_batch(const int32_t *symbols, int n, int c, int h
   CAE_CHECK(n > 0 && c > 0 && hw > 0 && cap_words >= 4, 2, "cae_rans_encode_batch: bad shape");
   RansEncParams p{reinterpret_cast<const EncEntry *>(enc_table), 0, symbols, n, c, hw, cdfs,
                   cdf_stride, cdf_sizes, offsets, words, cap_words, nwords, status};
+  if (enc_table && !cae_knob(CAE_KNOB_RANS_V1)) {
+    const size_t tbytes = cae_rans_enc_table_bytes(c, cdf_stride);
+    p.table_in_smem = tbytes <= 160 * 1024;
+    const size_t smem = kChunk * kPitch * 4 + 32 + (p.table_in_smem ? tbytes : 0);
+    if (smem > 48 * 1024)
+      CAE_CUDA(cudaFuncSetAttribute(rans_encode_warp_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rans_encode_warp_kernel<<<(n + 31) / 32, 32, smem, (cudaStream_t)stream>>>(p);
+    cae_count_launch();
+    CAE_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (enc_table) {
     const size_t tbytes = cae_rans_enc_table_bytes(c, cdf_stride);
     p.table_in_smem = tbytes <= 96 * 1024;
@@ -321,12 +779,45 @@ extern "C" int cae_rans_decode_batch(const uint32_t *words, const int64_t *word_
   CAE_CHECK(n > 0 && c > 0 && hw > 0, 2, "cae_rans_decode_batch: bad shape");
   RansDecParams p{words, word_offsets, n, c, hw, cdfs, cdf_stride, cdf_sizes, offsets, symbols, status, 0};
   const size_t cbytes = (size_t)c * cdf_stride * sizeof(int32_t);
+  if (!cae_knob(CAE_KNOB_RANS_V1) && !cae_knob(CAE_KNOB_RANS_V2) && cdf_stride <= 65535 &&
+      cbytes <= 160 * 1024) {
+    const size_t smem = kFine * 8 + (kChunk * kPitch + 8) * 4 + cbytes + 16;
+    if (smem > 48 * 1024)
+      CAE_CUDA(cudaFuncSetAttribute(rans_decode_fine_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rans_decode_fine_kernel<<<(n + 31) / 32, 32, smem, (cudaStream_t)stream>>>(p);
+    cae_count_launch();
+    CAE_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (!cae_knob(CAE_KNOB_RANS_V1)) {
+    // coarse start table (uint8 symbol indices): every table must have <= 256 entries
+    const int coarse = cdf_stride <= 256 && cbytes + (size_t)c * 256 <= 160 * 1024;
+    p.cdf_in_smem = coarse || cbytes <= 160 * 1024;
+    const size_t smem = (kChunk * kPitch + 8) * 4 + (p.cdf_in_smem ? cbytes : 0) +
+                        (coarse ? (size_t)c * 256 : 0) + 16;
+    if (smem > 48 * 1024)
+      CAE_CUDA(cudaFuncSetAttribute(rans_decode_warp_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rans_decode_warp_kernel<<<(n + 31) / 32, 32, smem, (cudaStream_t)stream>>>(p, coarse);
+    cae_count_launch();
+    CAE_CUDA(cudaGetLastError());
+    return 0;
+  }
   p.cdf_in_smem = cbytes <= 96 * 1024;
   const size_t smem = p.cdf_in_smem ? cbytes : 0;
   if (smem > 48 * 1024)
     CAE_CUDA(cudaFuncSetAttribute(rans_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
   rans_decode_kernel<<<(n + 63) / 64, 64, smem, (cudaStream_t)stream>>>(p);
+  cae_count_launch();
+  CAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int cae_rans_scan(const int32_t *nwords, int n, int64_t *out_offsets, void *stream) {
+  CAE_CHECK(nwords && out_offsets && n > 0, 2, "cae_rans_scan: bad argument");
+  rans_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nwords, n, out_offsets);
   cae_count_launch();
   CAE_CUDA(cudaGetLastError());
   return 0;

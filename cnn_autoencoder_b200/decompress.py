@@ -24,7 +24,8 @@ import torch
 from . import _autoencoders as AE
 from ._entropy import decode_symbols
 from ._store import DirArray, native_read, native_write
-from .compress import _dist_info, shard_range
+from . import _slide
+from .compress import _dist_info, load_model, shard_range
 
 
 def decompress_image(input_filename, output_filename, destination_format='zarr',
@@ -46,7 +47,7 @@ def decompress_image(input_filename, output_filename, destination_format='zarr',
     if codec_id not in ('cae', 'cae_bn'):
         raise ValueError('array compressor %r is not a CAE codec' % codec_id)
 
-    model = AE.autoencoder_from_state_dict(checkpoint=checkpoint, gpu=True, train=False)
+    model = load_model(checkpoint)
     fact_ent = model['fact_ent'].module
     decoder = model['decoder']
     level = decoder.module.rec_level
@@ -66,9 +67,16 @@ def decompress_image(input_filename, output_filename, destination_format='zarr',
 
     component = '%s/%s' % (decomp_group, data_group) if len(decomp_group) else data_group
     comp_r = '/'.join(component.split('/')[:-1]) + '/0'
-    out_path = os.path.join(output_filename, comp_r)
-    want_png = 'zarr' not in destination_format
-    if want_png:
+    in_memory = isinstance(output_filename, np.ndarray)
+    out_path = None if in_memory else os.path.join(output_filename, comp_r)
+    want_png = in_memory or 'zarr' not in destination_format
+    if in_memory:
+        # extension: reconstruct straight into a caller-owned H x W x c uint8 array (page-locked
+        # memory makes the device -> host tile copies asynchronous, see _slide.pin_array)
+        if output_filename.shape != (H, W, c_img) or output_filename.dtype != np.uint8:
+            raise ValueError('destination array must be uint8 of shape %r' % ((H, W, c_img),))
+        canvas = output_filename
+    elif want_png:
         canvas = np.zeros((H, W, c_img), dtype=np.uint8)
     elif rank == 0:
         dst = DirArray(out_path, shape=(H, W, c_img), chunks=(ps, ps, c_img), dtype=np.uint8,
@@ -83,6 +91,22 @@ def decompress_image(input_filename, output_filename, destination_format='zarr',
     stats = dict(tiles=len(mine), pixels=0, seconds=0.0, device_decoded=0,
                  t_read=0.0, t_decode=0.0, t_gpu=0.0, t_write_wait=0.0)
     t_start = time.perf_counter()
+    out_image = output_filename if isinstance(output_filename, np.ndarray) else None
+    if (codec_id == 'cae' and ps % (2 ** level) == 0 and (not want_png or out_image is not None)
+            and len(mine) >= fact_ent.GPU_CODER_MIN_STREAMS
+            and not os.environ.get('CAE_NO_SLIDE_ENGINE')):
+        tc = _slide.tile_codec(model, ps, c_img, batch_tiles)
+        if len(mine) >= batch_tiles:
+            tc.warm(encode=False, decode=True)
+        t_start = time.perf_counter()
+        st = _slide._Stats()
+        _slide.decompress_tiles(tc, mine, src.chunk_file, workers, coder_tiles, st, H, W,
+                                out_chunk_path=None if out_image is not None else dst.chunk_file,
+                                out_image=out_image)
+        stats.update(st)
+        stats['engine'] = 'slide'
+        stats['seconds'] = time.perf_counter() - t_start
+        return stats
     pool = ThreadPoolExecutor(max_workers=workers)
 
     def read_tile(idx):
@@ -240,7 +264,7 @@ def decompress_image(input_filename, output_filename, destination_format='zarr',
     stats['t_write_wait'] = time.perf_counter() - t0
     pool.shutdown()
     torch.cuda.synchronize()
-    if want_png:
+    if want_png and not in_memory:
         from PIL import Image
         fn_out = output_filename.split(destination_format)[0] + destination_format
         Image.fromarray(canvas if c_img != 1 else canvas[..., 0]).save(fn_out)

@@ -195,6 +195,12 @@ int cae_eb_quantize(const float *y, int n, int c, int hw, const cae_eb_tables *t
                     float *y_q, float *p_y, int32_t *symbols, int32_t *hist,
                     double *rate_bits, int32_t *status, void *stream);
 
+/* EntropyBottleneck.decompress's de-quantisation ("symbols + medians"; reached from
+ * R:568-572) written straight into the synthesis track's input layout: symbols int32
+ * N x C x h x w -> dst planar fp16 (zero halo untouched), y_q = (float)sym + median_c.          */
+int cae_eb_dequantize_planar(const int32_t *symbols, const float *medians, int n, int c, int h,
+                             int w, cae_tensor dst, void *stream);
+
 /* The same quantizer fused into the epilogue of the last analysis convolution
  * (cae_conv_desc.quant; the layer whose output is the fp32 NCHW latent y, Analyzer.forward
  * R:359-361 followed by fact_ent R:549 / _taskutils.py:97): while y is still in registers the
@@ -228,7 +234,7 @@ int cae_rans_decode(const uint8_t *enc /*HOST*/, size_t nbytes, int c, int hw,
                     const int32_t *cdfs, int cdf_stride, const int32_t *cdf_sizes,
                     const int32_t *offsets, int32_t *symbols /*HOST*/);
 
-/* ---- entropy coder (DEVICE, batched: one thread per tile stream) ------------ */
+/* ---- entropy coder (DEVICE, batched: one thread per tile stream, symbols staged per warp) ------------ */
 /* Same stream format as cae_rans_encode / cae_rans_decode, for n independent streams at once
  * (the tiles of a slide).  symbols: n x C x hw int32.  Encoding writes stream k
  * into the TAIL of words[k*cap_words .. (k+1)*cap_words) and its length into nwords[k]
@@ -247,6 +253,9 @@ int cae_rans_encode_batch(const int32_t *symbols, int n, int c, int hw, const in
                           int cdf_stride, const int32_t *cdf_sizes, const int32_t *offsets,
                           const void *enc_table, uint32_t *words, int cap_words, int32_t *nwords,
                           int32_t *status, void *stream);
+/* out_offsets[0..n] = exclusive prefix sum of nwords (out_offsets[n] = total words), on the
+ * device, so that packing needs no host round trip.                                        */
+int cae_rans_scan(const int32_t *nwords, int n, int64_t *out_offsets, void *stream);
 int cae_rans_compact(const uint32_t *words, int n, int cap_words, const int32_t *nwords,
                      const int64_t *out_offsets, uint32_t *out, void *stream);
 int cae_rans_decode_batch(const uint32_t *words, const int64_t *word_offsets, int n, int c, int hw,
@@ -270,6 +279,25 @@ int cae_files_write(const char *paths, int n, const uint8_t *headers, int hdr_le
 int cae_files_stat(const char *paths, int n, int64_t *sizes, int threads);
 int cae_files_read(const char *paths, int n, uint8_t *headers, int hdr_len, uint8_t *payload,
                    const int64_t *payload_off, int threads);
+
+/* ---- tile movement between the host slide and the device (strided DMA) ---------------------- */
+/* The chunk loop of compress.py:101-128 / decompress.py:72-96 without a host-side gather: tile k
+ * = (tile_yx[2k], tile_yx[2k+1]) of the row-major H x W x c uint8 slide in HOST memory (page-locked
+ * for the copies to be asynchronous) <-> slot k of a tile-major DEVICE buffer n x ps x ps x c,
+ * enqueued on `stream`.  Upload zero-fills the part of an edge tile beyond the image (zarr's
+ * chunk padding), download crops it.  tile_yx is a HOST array.                                */
+int cae_tiles_upload_u8(const uint8_t *src /*HOST*/, int64_t H, int64_t W, int c, int ps,
+                        const int32_t *tile_yx /*HOST*/, int n, uint8_t *dst, void *stream);
+int cae_tiles_download_u8(const uint8_t *src, int n, int ps, int c, const int32_t *tile_yx /*HOST*/,
+                          uint8_t *dst /*HOST*/, int64_t H, int64_t W, void *stream);
+
+/* ---- evaluation sums on the device ------------------------------------------ */
+/* sse[i] += sum over the per_image uint8 values of image i of (a - b)^2: the numerator of
+ * compute_rmse / compute_psnr (src/test_cae.py:57-63, computed there on the host after a full
+ * download) and of DistMSELoss in uint8 units (_ratedist.py:57-63).  a, b: n_images x per_image
+ * uint8 on the device; sse: n_images uint64 on the device, accumulated into.                   */
+int cae_sse_u8(const uint8_t *a, const uint8_t *b, int n_images, int64_t per_image,
+               uint64_t *sse, void *stream);
 
 #ifdef __cplusplus
 }

@@ -584,6 +584,34 @@ class OracleModel:
         return to_uint8_hwc(x_r[0][0])
 
 
+def _codec_trace(self, buf):
+    """Everything the parity gates of a throughput run compare for one uint8 HWC chunk: the
+    oracle's latent relative to the medians, its integer symbols (C x h x w) and its uint8
+    reconstruction (the 'cae' codec flow R:539-584 without the byte stream)."""
+    with torch.no_grad():
+        x = to_float_chw(buf)
+        y = self.encoder(x)
+        med = self.fact_ent._medians().detach().reshape(1, -1, 1, 1)
+        sym = self.fact_ent.symbols(y)
+        x_r, _ = self.decoder(sym.type_as(med) + med)
+        return dict(y_minus_median=(y - med)[0], symbols=sym[0], x_r_u8=to_uint8_hwc(x_r[0][0]))
+
+
+def _symbol_bits(self, sym):
+    """-sum log2 p of the given integer symbols (C x h x w) under the oracle's density: the
+    numerator of the estimated rate (``_ratedist.py:51-52``) for ANY symbol array, so that two
+    implementations' symbols are priced by the same model."""
+    with torch.no_grad():
+        med = self.fact_ent._medians().detach().reshape(1, -1, 1, 1)
+        y_q = sym.reshape(1, *sym.shape).type_as(med) + med
+        _, p = self.fact_ent(y_q)            # eval: round(y_q - med) + med == y_q
+        return float(-torch.log2(p).sum())
+
+
+OracleModel.codec_trace = _codec_trace
+OracleModel.symbol_bits = _symbol_bits
+
+
 def to_float_chw(buf_u8_hwc):
     """u8 HWC -> fp32 1xCxHxW, true division by 255 (R:542-545, compress.py:53-55)."""
     h, w, c = buf_u8_hwc.shape

@@ -1,0 +1,132 @@
+"""The batched whole-slide engine (``_slide.py``) behind compress_image / decompress_image:
+config 3 in miniature -- a synthetic tissue slide with ragged edge chunks, enough chunks for the
+device coder, through the public tile loops; checked chunk by chunk against the oracle codec."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ARCH = dict(channels_org=3, channels_net=32, channels_bn=16, compression_level=3,
+            act_layer_type='LeakyReLU')
+PS = 64
+
+
+def _slide(gy, gx, crop):
+    from oracle import cae_oracle as O
+    s = np.concatenate([np.concatenate([O.synth_tissue_tile(i, j, ps=PS, seed=2) for j in range(gx)],
+                                       axis=1) for i in range(gy)], axis=0)
+    return np.ascontiguousarray(s[:s.shape[0] - crop[0], :s.shape[1] - crop[1]])
+
+
+@pytest.mark.parametrize('pinned', [True, False])
+def test_slide_engine_roundtrip_against_oracle(tmp_path, pinned):
+    from oracle import cae_oracle as O
+    from cnn_autoencoder_b200 import compress, decompress, _store, _slide as S
+    chk = O.make_checkpoint(ARCH, seed=31)
+    oracle = O.OracleModel(chk)
+    slide = _slide(12, 13, (24, 40))                # 156 chunks, edge chunks of 40 and 24 px
+    handle = None
+    if pinned:
+        pin = torch.empty(slide.shape, dtype=torch.uint8).pin_memory()
+        pin.numpy()[:] = slide
+        slide = pin.numpy()
+        assert S.is_pinned_array(slide)
+    out = str(tmp_path / 'slide.zarr')
+    st = compress.compress_image('CAE', chk, slide, out, patch_size=PS, batch_tiles=16, coder_tiles=96)
+    assert st['engine'] == 'slide' and st['tiles'] == 156 and st['device_coded'] == 156
+    arr = _store.DirArray(os.path.join(out, '0/0'), mode='r')
+    assert arr.compressor_config['id'] == 'cae' and arr.grid == (12, 13, 1)
+    lh = PS // 8
+    agree = total = 0
+    for (i, j) in [(0, 0), (3, 7), (11, 12), (11, 0), (0, 12), (5, 5)]:
+        tile = _store.padded_tile(slide, i * PS, j * PS, PS)
+        ref = oracle.codec_encode(tile)
+        got = arr.read_encoded((i, j, 0))
+        assert got[:16] == ref[:16]                  # '>QQ' (ps, ps): zarr pads edge chunks
+        s_ref = oracle.fact_ent.decompress([ref[16:]], (lh, lh))
+        s_got = oracle.fact_ent.decompress([got[16:]], (lh, lh))
+        agree += int((s_ref == s_got).sum()); total += s_ref.numel()
+        if torch.equal(s_ref, s_got):
+            assert got == ref                        # identical symbols => identical bytes
+    assert agree / total >= 0.999
+    # decompress: chunk files, and straight into a caller-owned array
+    rec_dir = str(tmp_path / 'rec.zarr')
+    ds = decompress.decompress_image(out, rec_dir, checkpoint=chk, batch_tiles=16, coder_tiles=96)
+    assert ds['engine'] == 'slide' and ds['device_decoded'] == 156
+    assert ds['pixels'] == slide.shape[0] * slide.shape[1]
+    rec = _store.DirArray(os.path.join(rec_dir, 'decompressed/0/0'), mode='r')
+    full = np.zeros_like(slide)
+    for i in range(12):
+        for j in range(13):
+            full[rec.chunk_slices((i, j, 0))[:2]] = rec.read_chunk((i, j, 0))
+    canvas = torch.zeros(slide.shape, dtype=torch.uint8).pin_memory().numpy()
+    decompress.decompress_image(out, canvas, checkpoint=chk, batch_tiles=16, coder_tiles=96)
+    assert np.array_equal(canvas, full)
+    ref_full = np.zeros_like(slide)
+    for i in range(12):
+        for j in range(13):
+            tile = _store.padded_tile(slide, i * PS, j * PS, PS)
+            r_tile = oracle.codec_decode(oracle.codec_encode(tile))
+            sl = rec.chunk_slices((i, j, 0))
+            ref_full[sl[:2]] = r_tile[:sl[0].stop - sl[0].start, :sl[1].stop - sl[1].start]
+    assert abs(O.psnr_u8(slide, full) - O.psnr_u8(slide, ref_full)) <= 0.05
+    # the raw chunk files of edge chunks are zero beyond the image, like zarr's fill value
+    edge = np.frombuffer(rec.read_encoded((11, 12, 0)), dtype=np.uint8).reshape(PS, PS, 3)
+    assert not edge[40:].any() and not edge[:, 24:].any()
+
+
+def test_slide_engine_matches_the_general_tile_loop(tmp_path, monkeypatch):
+    """Same chunk files from the batched engine and from the per-batch general path."""
+    from oracle import cae_oracle as O
+    from cnn_autoencoder_b200 import compress, _store
+    chk = O.make_checkpoint(ARCH, seed=5)
+    slide = _slide(12, 12, (0, 0))
+    a, b = str(tmp_path / 'a.zarr'), str(tmp_path / 'b.zarr')
+    sa = compress.compress_image('CAE', chk, slide, a, patch_size=PS, batch_tiles=16)
+    monkeypatch.setenv('CAE_NO_SLIDE_ENGINE', '1')
+    sb = compress.compress_image('CAE', chk, slide, b, patch_size=PS, batch_tiles=16)
+    assert sa.get('engine') == 'slide' and sb.get('engine') is None
+    A, B = (_store.DirArray(os.path.join(p, '0/0'), mode='r') for p in (a, b))
+    for i in range(12):
+        for j in range(12):
+            assert A.read_encoded((i, j, 0)) == B.read_encoded((i, j, 0))
+
+
+def test_device_roundtrip_and_phase_record():
+    from oracle import cae_oracle as O
+    import cnn_autoencoder_b200 as M
+    from cnn_autoencoder_b200 import _slide as S
+    chk = O.make_checkpoint(ARCH, seed=9)
+    model = M.autoencoder_from_state_dict(chk, gpu=True, train=False)
+    tc = S.TileCodec(model, PS, 3, batch=16)
+    x = torch.from_numpy(np.stack([O.synth_tissue_tile(0, j, ps=PS, seed=4) for j in range(40)])).cuda()
+    out = torch.empty_like(x)
+    nbytes = S.device_roundtrip(tc, x, out, coder_tiles=32)
+    torch.cuda.synchronize()
+    # against the eager kernels run batch by batch
+    ref = tc.decode_eager(tc.encode_eager(x))
+    assert torch.equal(out, ref) and nbytes > 40 * 16
+    rec = S.phase_times(tc, x, 32)
+    assert rec['roundtrip_exact'] and rec['chunks'] == 32
+
+
+def test_sse_kernel_gives_the_psnr_numerator():
+    import ctypes
+    from cnn_autoencoder_b200 import _cabi as C
+    g = torch.Generator().manual_seed(3)
+    a = torch.randint(0, 256, (5, 3 * 100 * 77), dtype=torch.uint8, generator=g)
+    b = torch.randint(0, 256, (5, 3 * 100 * 77), dtype=torch.uint8, generator=g)
+    want = ((a.double() - b.double()) ** 2).sum(1)
+    sse = torch.zeros(5, dtype=torch.int64, device='cuda')
+    ad, bd = a.cuda(), b.cuda()
+    C.check(C.lib().cae_sse_u8(ad.data_ptr(), bd.data_ptr(), 5, a.shape[1], sse.data_ptr(),
+                               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    assert torch.equal(sse.cpu().double(), want)
+    # unaligned views take the scalar path
+    sse.zero_()
+    C.check(C.lib().cae_sse_u8(ad[0, 1:].data_ptr(), bd[0, 1:].data_ptr(), 1, a.shape[1] - 1,
+                               sse.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    assert sse[0].item() == int(((a[0, 1:].double() - b[0, 1:].double()) ** 2).sum().item())
