@@ -456,44 +456,63 @@ __device__ __forceinline__ uint32_t dec_nibble_w(uint64_t &x, WordReader &r) {
 constexpr int kFineBits = 12;
 constexpr int kFine = 1 << kFineBits;
 
-__device__ __forceinline__ void ld_global_if(uint32_t &dst, const uint32_t *ptr, bool p) {
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.nc.b32 %0, [%1];\n\t}"
-               : "+r"(dst)
-               : "l"(ptr), "r"((uint32_t)p)
-               : "memory");
-}
+// Stream words reach the decoding lane through a per-lane ring in shared memory filled with
+// 4-byte cp.async copies issued a whole chunk ahead.  A register look-ahead does not work here:
+// the 32 lanes consume words at data-dependent moments, so almost every symbol step has SOME lane
+// loading, and the next step's read of the look-ahead register then stalls the whole warp on
+// that load's latency (measured: 470 cycles per symbol).  cp.async has no destination register,
+// hence no scoreboard dependency; the word is picked up later with a shared-memory load.
+constexpr int kRing = 128;              // words per lane; a chunk consumes at most 32 * 4
 
-struct PredReader {          // forward reader, one word of look-ahead, no branch on the hot path
-  const uint32_t *ptr, *end; // ptr: the word held in nxt; ptr > end at the end = read past the stream
-  uint32_t nxt;
-  __device__ __forceinline__ void init(const uint32_t *b, const uint32_t *e) {
-    ptr = b; end = e;
-    nxt = ptr < end ? __ldg(ptr) : 0u;
+struct RingReader {
+  const uint32_t *gbase;    // first word of this lane's stream
+  uint32_t ring;            // shared-memory byte address of this lane's ring
+  int n_words;              // stream length
+  int rd, fl, safe;         // words consumed / copies issued / copies known to have landed
+
+  __device__ __forceinline__ void issue() {      // top the ring up to rd + kRing, one group
+    const int lim = min(rd + kRing, n_words);
+    while (fl < lim) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring + (uint32_t)((fl & (kRing - 1)) << 2)),
+                   "l"(gbase + fl)
+                   : "memory");
+      ++fl;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  __device__ __forceinline__ uint32_t take_if(bool need) {
-    const uint32_t w = nxt;
-    ptr += need ? 1 : 0;
-    ld_global_if(nxt, ptr, need && ptr < end);
+  // chunk boundary: refill, then make sure at least `need` unread words have landed
+  __device__ __forceinline__ void chunk_begin(int need) {
+    const int fl_prev = fl;
+    issue();
+    asm volatile("cp.async.wait_group 1;" ::: "memory");      // all but the group just issued
+    safe = fl_prev;
+    if (safe - rd < need && safe < n_words) {                  // rare (escape-heavy chunk)
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      safe = fl;
+    }
+  }
+  __device__ __forceinline__ uint32_t peek() const {
+    uint32_t w;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(ring + (uint32_t)((rd & (kRing - 1)) << 2)));
     return w;
   }
 };
 
-__device__ __forceinline__ void dec_renorm(uint64_t &x, PredReader &r) {
+__device__ __forceinline__ void dec_renorm(uint64_t &x, RingReader &r) {
+  const uint32_t w = r.peek();              // address known early: off the state's chain
   const bool need = x < kRansL;
-  const uint32_t w = r.take_if(need);
   x = need ? ((x << 32) | w) : x;
+  r.rd += need ? 1 : 0;
 }
 
 struct DecState {
   uint64_t x;
-  const uint32_t *ptr;
-  uint32_t nxt;
+  int rd;
   int value;
 };
 
-static __device__ __noinline__ DecState dec_escape(uint64_t x, const uint32_t *ptr, const uint32_t *end,
-                                                   uint32_t nxt, int max_value) {
-  PredReader r{ptr, end, nxt};
+static __device__ __noinline__ DecState dec_escape(uint64_t x, RingReader r, int max_value) {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");        // everything issued has landed
   auto nibble = [&]() {
     const uint32_t val = (uint32_t)(x & 15u);
     x >>= kBypassBits;
@@ -508,7 +527,7 @@ static __device__ __noinline__ DecState dec_escape(uint64_t x, const uint32_t *p
     if (g < 8) raw |= nib << (g * kBypassBits);
   }
   const int value = (int)(raw >> 1);
-  return DecState{x, r.ptr, r.nxt, (raw & 1u) ? -value - 1 : value + max_value};
+  return DecState{x, r.rd, (raw & 1u) ? -value - 1 : value + max_value};
 }
 
 // the bucket of the fine table straddles a symbol boundary and cf lies beyond the first symbol:
@@ -526,7 +545,8 @@ __global__ void __launch_bounds__(32) rans_decode_fine_kernel(const RansDecParam
   extern __shared__ __align__(16) uint8_t dec_smem[];
   const int lane = threadIdx.x;
   uint2 *fine = reinterpret_cast<uint2 *>(dec_smem);                       // [4096]
-  int32_t *stage = reinterpret_cast<int32_t *>(dec_smem + kFine * 8);      // [32][33]
+  uint32_t *rings = reinterpret_cast<uint32_t *>(dec_smem + kFine * 8);    // [32][kRing]
+  int32_t *stage = reinterpret_cast<int32_t *>(rings + 32 * kRing);        // [32][33]
   int32_t *scdf = stage + kChunk * kPitch + 8;                             // [c][stride]
   for (int i = lane; i < p.c * p.stride; i += 32) scdf[i] = p.cdfs[i];
   __syncwarp();
@@ -534,14 +554,23 @@ __global__ void __launch_bounds__(32) rans_decode_fine_kernel(const RansDecParam
   const int k = k0 + lane;
   const bool live = k < p.n;
   const int n_here = min(32, p.n - k0);
-  PredReader r;
+  RingReader r;
+  r.ring = smem_u32(rings + lane * kRing);
+  r.rd = r.fl = r.safe = 0;
+  r.gbase = p.words;
+  r.n_words = 0;
   uint64_t x = kRansL;
   if (live) {
-    r.init(p.words + p.off[k], p.words + p.off[k + 1]);
-    const uint32_t w0 = r.take_if(true), w1 = r.take_if(true);
+    r.gbase = p.words + p.off[k];
+    r.n_words = (int)(p.off[k + 1] - p.off[k]);
+    r.issue();
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    r.safe = r.fl;
+    const uint32_t w0 = r.peek();
+    r.rd = 1;
+    const uint32_t w1 = r.peek();
+    r.rd = 2;
     x = (uint64_t)w0 | ((uint64_t)w1 << 32);
-  } else {
-    r.init(nullptr, nullptr);
   }
   const size_t per_stream = (size_t)p.c * p.hw;
   int32_t *out0 = p.symbols + (size_t)k0 * per_stream;
@@ -570,6 +599,7 @@ __global__ void __launch_bounds__(32) rans_decode_fine_kernel(const RansDecParam
     for (int j = 0; j < chunks; ++j) {
       const int m = min(kChunk, p.hw - j * kChunk);
       if (live) {
+        r.chunk_begin(kChunk);
         int32_t *mine = stage + lane * kPitch;
 #pragma unroll 4
         for (int i = 0; i < m; ++i) {
@@ -587,10 +617,9 @@ __global__ void __launch_bounds__(32) rans_decode_fine_kernel(const RansDecParam
           dec_renorm(x, r);
           int value = lo;
           if (lo == max_value) {                                               // rare
-            const DecState st = dec_escape(x, r.ptr, r.end, r.nxt, max_value);
+            const DecState st = dec_escape(x, r, max_value);
             x = st.x;
-            r.ptr = st.ptr;
-            r.nxt = st.nxt;
+            r.rd = st.rd;
             value = st.value;
           }
           mine[i] = value + offset;
@@ -606,7 +635,7 @@ __global__ void __launch_bounds__(32) rans_decode_fine_kernel(const RansDecParam
       __syncwarp();
     }
   }
-  if (live && r.ptr > r.end) atomicOr(p.status, 2);
+  if (live && r.rd > r.n_words) atomicOr(p.status, 2);
 }
 
 __global__ void __launch_bounds__(32) rans_decode_warp_kernel(const RansDecParams p, int coarse) {
@@ -781,7 +810,7 @@ extern "C" int cae_rans_decode_batch(const uint32_t *words, const int64_t *word_
   const size_t cbytes = (size_t)c * cdf_stride * sizeof(int32_t);
   if (!cae_knob(CAE_KNOB_RANS_V1) && !cae_knob(CAE_KNOB_RANS_V2) && cdf_stride <= 65535 &&
       cbytes <= 160 * 1024) {
-    const size_t smem = kFine * 8 + (kChunk * kPitch + 8) * 4 + cbytes + 16;
+    const size_t smem = kFine * 8 + 32 * kRing * 4 + (kChunk * kPitch + 8) * 4 + cbytes + 16;
     if (smem > 48 * 1024)
       CAE_CUDA(cudaFuncSetAttribute(rans_decode_fine_kernel,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
