@@ -103,6 +103,10 @@ class TileCodec:
         self.launches_enc = self.launches_dec = 0
         self.replays_enc = self.replays_dec = 0
         self._pins = {}              # page-locked staging buffers, kept across calls
+        # streams live as long as the codec: the caching allocator pools memory per stream, so a
+        # fresh stream per call would cudaMalloc its gigabyte-sized scratch again every time
+        self.s_in, self.s_out, self.s_code = (torch.cuda.Stream(self.dev) for _ in range(3))
+        self._bufs = {}
 
     # ---- the per-batch work, eager form (also what the graphs capture) ----
     @torch.no_grad()
@@ -172,6 +176,13 @@ class TileCodec:
             return out
         return self.decode_eager(self.sym_in[slot][:n])
 
+    def buffer(self, name, shape, dtype):
+        """A device tensor kept under ``name`` (reallocated when the shape changes)."""
+        t = self._bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = self._bufs[name] = torch.empty(shape, dtype=dtype, device=self.dev)
+        return t
+
     def pinned(self, name, nbytes):
         """A page-locked uint8 buffer of at least ``nbytes`` kept under ``name`` (page-locking
         is slow and stalls other CUDA calls: allocate once, grow rarely)."""
@@ -234,7 +245,7 @@ def compress_tiles(tc, src, tiles, chunk_path, header_hw, workers, coder_tiles, 
     pinned_src = device_source is None and _tiles_pinned(src, tile_yx, ps)
     L = C.lib()
     main = torch.cuda.current_stream(dev)
-    s_in, s_code = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    s_in, s_code = tc.s_in, tc.s_code
     ev_up = [torch.cuda.Event() for _ in range(tc.slots)]
     ev_free = [None] * tc.slots
     stage = None
@@ -243,17 +254,28 @@ def compress_tiles(tc, src, tiles, chunk_path, header_hw, workers, coder_tiles, 
         stage_ev = [None, None]
     G = max(B, min(coder_tiles, n_tiles))
     G = -(-G // B) * B
-    sym_all = [torch.empty((G, tc.cb, tc.lh * tc.lw), dtype=torch.int32, device=dev)
-               for _ in range(2 if n_tiles > G else 1)]
+    sym_all = [tc.buffer('sym_group%d' % k, (G, tc.cb, tc.lh * tc.lw), torch.int32)
+               for k in range(2 if n_tiles > G else 1)]
     coded = [None] * len(sym_all)       # per group buffer: (threading.Event, [cuda event]) of its job
     coder = ThreadPoolExecutor(max_workers=1)
     jobs = []
     hdr1 = np.frombuffer(struct.pack('>QQ', *header_hw), dtype=np.uint8)
 
+    import time as _t
+    t00 = _t.perf_counter()
+    trace = stats.setdefault('trace', {}) if stats.get('want_trace') else None
+
+    def mark(name):
+        if trace is not None:
+            trace[name] = round(_t.perf_counter() - t00, 4)
+
     def code_group(gi, lo, n, ready, launched, holder):
         torch.cuda.set_device(dev)
         with torch.cuda.stream(s_code):
             s_code.wait_event(ready)
+            if trace is not None:
+                ready.synchronize()
+                mark('c_symbols_ready_g%d' % gi)
             try:
                 packed, off = fe.encode_symbols_device(sym_all[gi][:n])
                 done = torch.cuda.Event()
@@ -261,12 +283,15 @@ def compress_tiles(tc, src, tiles, chunk_path, header_hw, workers, coder_tiles, 
                 holder.append(done)          # the coder kernels have read the group buffer
             finally:
                 launched.set()
+            mark('c_coded')
             host = tc.pinned('streams_out', packed.numel())
             host.copy_(packed, non_blocking=True)
             s_code.synchronize()
+            mark('c_streams_on_host')
         hdr = np.broadcast_to(hdr1, (n, 16))
         native_write([chunk_path((int(i), int(j), 0)) for i, j in tile_yx[lo:lo + n]], hdr,
                      host.numpy(), off, workers)
+        mark('c_files_written')
         stats.add('bytes', int(off[-1]) + 16 * n)
         stats.add('device_coded', n)
 
@@ -319,10 +344,12 @@ def compress_tiles(tc, src, tiles, chunk_path, header_hw, workers, coder_tiles, 
             glo += gpos
             gpos = 0
             gi = (gi + 1) % len(sym_all)
+    mark('c_all_batches_issued')
     for j in jobs:
         j.result()
     coder.shutdown()
     torch.cuda.synchronize(dev)
+    mark('c_done')
 
 
 def decompress_tiles(tc, tiles, chunk_path, workers, coder_tiles, stats, H, W, out_chunk_path=None,
@@ -337,7 +364,7 @@ def decompress_tiles(tc, tiles, chunk_path, workers, coder_tiles, stats, H, W, o
     tile_yx = np.ascontiguousarray(np.array(tiles, dtype=np.int32).reshape(-1, 2))
     L = C.lib()
     main = torch.cuda.current_stream(dev)
-    s_out, s_code = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    s_out, s_code = tc.s_out, tc.s_code
     G = max(B, min(coder_tiles, n_tiles))
     G = -(-G // B) * B
     groups = [(lo, min(G, n_tiles - lo)) for lo in range(0, n_tiles, G)]
@@ -349,6 +376,13 @@ def decompress_tiles(tc, tiles, chunk_path, workers, coder_tiles, stats, H, W, o
     slot_busy = [None] * tc.slots          # D2H (and file write) still reading the slot's output
     wjobs = []
     expect_hdr = struct.pack('>QQ', ps, ps)
+    import time as _t
+    t00 = _t.perf_counter()
+    trace = stats.setdefault('trace', {}) if stats.get('want_trace') else None
+
+    def mark(name):
+        if trace is not None:
+            trace[name] = round(_t.perf_counter() - t00, 4)
 
     def load_group(gk):
         """chunk files -> pinned buffer -> device -> symbols (on the coder stream)."""
@@ -359,6 +393,7 @@ def decompress_tiles(tc, tiles, chunk_path, workers, coder_tiles, stats, H, W, o
         def alloc(nbytes):
             return tc.pinned('streams_in%d' % (gk & 1), nbytes).numpy()
         hdr, payload, off = native_read(paths, 16, workers, alloc=alloc)
+        mark('d_files_read_g%d' % gk)
         if (off % 4).any() or bytes(hdr[0]) != expect_hdr or (hdr != hdr[0]).any():
             raise C.CaeError('chunk headers differ from the (patch, patch) the codec wrote')
         with torch.cuda.stream(s_code):
@@ -366,6 +401,9 @@ def decompress_tiles(tc, tiles, chunk_path, workers, coder_tiles, stats, H, W, o
             sym = fe.decode_streams_device(words, off // 4, tc.lh * tc.lw)
             done = torch.cuda.Event()
             done.record(s_code)
+            if trace is not None:
+                done.synchronize()
+                mark('d_symbols_decoded_g%d' % gk)
         stats.add('device_decoded', n)
         return sym.reshape(n, tc.cb, tc.lh, tc.lw), done
 
@@ -431,8 +469,13 @@ def decompress_tiles(tc, tiles, chunk_path, workers, coder_tiles, stats, H, W, o
                     slot_busy[slot] = job
             if not (n == B and tc.graphs):
                 u8.record_stream(s_out)
+    mark('d_all_batches_issued')
+    if trace is not None:
+        torch.cuda.synchronize(dev)
+        mark('d_gpu_done')
     for j in list(wjobs):
         j.result()
+    mark('d_files_written')
     reader.shutdown()
     if writer is not None:
         writer.shutdown()
@@ -448,11 +491,7 @@ def device_roundtrip(tc, x_dev, out_dev, coder_tiles):
     n_tiles = x_dev.shape[0]
     G = max(B, min(coder_tiles, n_tiles))
     G = -(-G // B) * B
-    key = ('rt', G)
-    sym_all = tc.__dict__.get('_rt_sym', {}).get(key)
-    if sym_all is None:
-        sym_all = torch.empty((G, tc.cb, tc.lh * tc.lw), dtype=torch.int32, device=dev)
-        tc.__dict__.setdefault('_rt_sym', {})[key] = sym_all
+    sym_all = tc.buffer('sym_group0', (G, tc.cb, tc.lh * tc.lw), torch.int32)
     total = 0
     b = 0
     for lo in range(0, n_tiles, G):

@@ -165,7 +165,7 @@ def compress_image(codec, checkpoint, input_filename, output_filename, patch_siz
         if len(mine) >= batch_tiles:
             tc.warm(encode=True, decode=False)
         t_start = time.perf_counter()
-        st = _slide._Stats()
+        st = _slide._Stats(want_trace=bool(os.environ.get('CAE_SLIDE_TRACE')))
         _slide.compress_tiles(tc, src, mine, dst.chunk_file, (ps, ps), workers, coder_tiles, st)
         stats.update(st)
         stats['engine'] = 'slide'

@@ -99,7 +99,7 @@ def decompress_image(input_filename, output_filename, destination_format='zarr',
         if len(mine) >= batch_tiles:
             tc.warm(encode=False, decode=True)
         t_start = time.perf_counter()
-        st = _slide._Stats()
+        st = _slide._Stats(want_trace=bool(os.environ.get('CAE_SLIDE_TRACE')))
         _slide.decompress_tiles(tc, mine, src.chunk_file, workers, coder_tiles, st, H, W,
                                 out_chunk_path=None if out_image is not None else dst.chunk_file,
                                 out_image=out_image)

@@ -22,7 +22,7 @@ def step():
     cs = CMP.compress_image('CAE', chk, slide, work + '/s.zarr', patch_size=512, gpu=True, **kw)
     ds = DEC.decompress_image(work + '/s.zarr', work + '/r.zarr', checkpoint=chk, gpu=True, **kw)
     return cs, ds
-step(); step()
+step(); step(); step()
 torch.cuda.synchronize()
 t0 = time.perf_counter(); cs, ds = step(); torch.cuda.synchronize(); print('step wall', time.perf_counter() - t0, cs, ds)
 pr = cProfile.Profile(); pr.enable(); step(); pr.disable()
