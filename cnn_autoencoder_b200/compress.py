@@ -134,7 +134,15 @@ def compress_image(codec, checkpoint, input_filename, output_filename, patch_siz
     gy, gx = -(-H // ps), -(-W // ps)
     out_path = os.path.join(output_filename, data_group) if data_group else output_filename
     if save_as_bottleneck:
-        # '-sbn': the stored array is the latent; chunks ceil(cs / 2^L) (compress.py:103-109)
+        # '-sbn': the stored array is the latent; chunks ceil(cs / 2^L) (compress.py:103-109).
+        # The reference runs the analysis transform on the edge tiles at their true size
+        # (map_blocks, :111-113); the stride-2 kernels here need even sizes at every level, so a
+        # slide whose edge tiles are not multiples of 2^L is refused before any work is done.
+        for name, size in (('height', H), ('width', W)):
+            edge = size % ps
+            if edge % (2 ** level):
+                raise ValueError('save_as_bottleneck: the edge tiles of this slide are %d px in %s, '
+                                 'not a multiple of 2^%d; pad or crop the slide' % (edge, name, level))
         comp = AE.ConvolutionalAutoencoderBottleneck(channels_bn=channels_bn, fact_ent=fact_ent,
                                                      gpu=True)
         lat = lambda v: int(math.ceil(v / 2 ** level))
@@ -263,6 +271,12 @@ def compress_image(codec, checkpoint, input_filename, output_filename, patch_siz
         req = fact_ent.quant_request(want_sym=True, want_planar=False, want_yq=False,
                                      want_stats=False) if os.environ.get('CAE_FUSED_QUANT') else None
         y = model['encoder'](x, quant=req)
+        if save_as_bottleneck and (y.shape[2] != lat(ps) or y.shape[3] != lat(ps)):
+            # edge chunk of the latent array: zarr pads it to the full chunk with the fill value 0
+            # before the codec sees it (compress.py:121-128 -> R:637-651), header = full chunk
+            full = torch.zeros((y.shape[0], y.shape[1], lat(ps), lat(ps)), dtype=y.dtype, device=y.device)
+            full[:, :, :y.shape[2], :y.shape[3]] = y
+            y, req = full, None
         if req is not None and req.done:
             sym = req.sym                        # quantized in the last encoder layer's epilogue
         else:

@@ -113,10 +113,17 @@ def decompress_image(input_filename, output_filename, destination_format='zarr',
         buf = src.read_encoded((idx[0], idx[1], 0))
         h, w = struct.unpack('>QQ', buf[:16])
         lh, lw = (h // 2 ** level, w // 2 ** level) if codec_id == 'cae' else (h, w)
-        return idx, (lh, lw), buf[16:]
+        if codec_id == 'cae_bn':
+            # zarr hands the caller only the part of an edge chunk that lies inside the array
+            # (decompress.py:51-58): the synthesis transform runs on the cropped latent
+            vh = min(lh, src.shape[0] - idx[0] * src.chunks[0])
+            vw = min(lw, src.shape[1] - idx[1] * src.chunks[1])
+        else:
+            vh, vw = lh, lw
+        return idx, (lh, lw, vh, vw), buf[16:]
 
     def decode_tile(item):
-        idx, (lh, lw), stream = item
+        idx, (lh, lw, vh, vw), stream = item
         return decode_symbols(stream, C_bn, lh * lw, cdf, sizes, offs).reshape(C_bn, lh, lw)
 
     writes = []
@@ -135,7 +142,7 @@ def decompress_image(input_filename, output_filename, destination_format='zarr',
         All streams are entropy-decoded in one device call when there are enough of them (a
         small remainder goes to the host coder threads), then the synthesis transform runs
         over ``batch_tiles`` tiles at a time and the chunk writes go to the thread pool."""
-        lh, lw = batch[0][1]
+        lh, lw, vh, vw = batch[0][1]
         t0 = time.perf_counter()
         if len(batch) >= fact_ent.GPU_CODER_MIN_STREAMS:
             sym = fact_ent.decode_streams_gpu([b[2] for b in batch], lh * lw)
@@ -143,7 +150,7 @@ def decompress_image(input_filename, output_filename, destination_format='zarr',
         else:
             sym = torch.from_numpy(np.stack(list(pool.map(decode_tile, batch)))).pin_memory()
             sym = sym.cuda(non_blocking=True)
-        sym = sym.reshape(len(batch), C_bn, lh, lw)
+        sym = sym.reshape(len(batch), C_bn, lh, lw)[:, :, :vh, :vw]
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         stats['t_decode'] += t1 - t0

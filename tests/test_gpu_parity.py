@@ -99,8 +99,11 @@ def test_named_archs_against_reference_outputs(path):
     assert d <= 0.05, d
 
 
+PARITY_LOG = os.environ.get('CAE_PARITY_LOG')     # measured gate values, one JSON line per case
+
+
 @pytest.mark.parametrize('name,n,size', [('A', 4, 256), ('A_res', 2, 256), ('B', 2, 256),
-                                         ('A', 1, 512)])
+                                         ('A', 1, 512), ('A_res', 1, 512), ('B', 1, 512)])
 def test_full_size_pipeline_against_oracle(name, n, size):
     """configs[1]/[2] shapes: whole pipeline vs the oracle on the same seeded inputs."""
     from oracle import cae_oracle as O
@@ -121,6 +124,15 @@ def test_full_size_pipeline_against_oracle(name, n, size):
     d_psnr = abs(_psnr(img, out['x_r_u8'].cpu().numpy()) - _psnr(img, ref_u8))
     assert d_psnr <= 0.05, d_psnr
     bpp_ref = O.rate_loss(x_u8.float(), ref['p_y']).item()
+    if PARITY_LOG:
+        import json
+        with open(PARITY_LOG, 'a') as f:
+            f.write(json.dumps(dict(net=name, n=n, size=size, symbols=int(out['y'].numel()),
+                                    flipped=nflip, flip_pct=round(100 * (1 - agree), 5),
+                                    max_flip_distance_from_boundary=round(boundary, 6),
+                                    abs_dpsnr_db=round(d_psnr, 6), est_bpp=round(out['bpp'].item(), 5),
+                                    abs_dbpp_pct=round(100 * abs(out['bpp'].item() - bpp_ref) / bpp_ref, 6),
+                                    gates='flip_pct <= 0.1, boundary < 0.02, dPSNR <= 0.05 dB, dbpp <= 0.5 %')) + '\n')
     assert abs(out['bpp'].item() - bpp_ref) <= 0.005 * bpp_ref
     # histogram == bincount of the symbols the kernel itself produced (integer work: exact)
     sym, hist, bits = model['fact_ent'].module.symbols_hist_rate(out['y'])

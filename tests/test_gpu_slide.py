@@ -130,3 +130,64 @@ def test_sse_kernel_gives_the_psnr_numerator():
     C.check(C.lib().cae_sse_u8(ad[0, 1:].data_ptr(), bd[0, 1:].data_ptr(), 1, a.shape[1] - 1,
                                sse.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
     assert sse[0].item() == int(((a[0, 1:].double() - b[0, 1:].double()) ** 2).sum().item())
+
+
+def test_save_as_bottleneck_tile_loop_with_ragged_edges(tmp_path):
+    """'-sbn' (compress.py:50-62, 103-113 of the reference; 'cae_bn' decode R:653-673): the stored
+    array is the latent, edge chunks zero-padded to the full latent chunk as zarr does before the
+    codec sees them, header = full chunk.  Checked chunk by chunk against the oracle."""
+    from oracle import cae_oracle as O
+    from cnn_autoencoder_b200 import compress, decompress, _store
+    chk = O.make_checkpoint(ARCH, seed=17)
+    oracle = O.OracleModel(chk)
+    ps = 128
+    slide = np.concatenate([np.concatenate([O.synth_tissue_tile(i, j, ps=ps, seed=6) for j in range(3)],
+                                           axis=1) for i in range(2)], axis=0)
+    slide = np.ascontiguousarray(slide[:200, :304])          # edge chunks of 72 and 48 px (multiples of 8)
+    out = str(tmp_path / 'lat.zarr')
+    st = compress.compress_image('CAE', chk, slide, out, patch_size=ps, save_as_bottleneck=True, batch_tiles=4)
+    assert st['tiles'] == 6
+    arr = _store.DirArray(os.path.join(out, '0/0'), mode='r')
+    assert arr.compressor_config['id'] == 'cae_bn'
+    assert arr.shape == (16 + 9, 16 + 16 + 6, 16) and arr.chunks == (16, 16, 16) and arr.dtype == np.float32
+    agree = total = 0
+    for i in range(2):
+        for j in range(3):
+            tile = slide[i * ps:(i + 1) * ps, j * ps:(j + 1) * ps]
+            y = oracle.encoder(O.to_float_chw(tile))                  # true-size edge tile (map_blocks)
+            full = torch.zeros(1, 16, 16, 16)
+            full[:, :, :y.shape[2], :y.shape[3]] = y                  # zarr's chunk padding, fill 0
+            ref = oracle.fact_ent.compress(full)[0]
+            got = arr.read_encoded((i, j, 0))
+            assert got[:16] == (16).to_bytes(8, 'big') * 2
+            s_ref = oracle.fact_ent.decompress([ref], (16, 16))
+            s_got = oracle.fact_ent.decompress([got[16:]], (16, 16))
+            agree += int((s_ref == s_got).sum()); total += s_ref.numel()
+    assert agree / total >= 0.999
+    rec_dir = str(tmp_path / 'rec.zarr')
+    ds = decompress.decompress_image(out, rec_dir, checkpoint=chk, batch_tiles=4)
+    assert ds['pixels'] == 200 * 304
+    rec = _store.DirArray(os.path.join(rec_dir, 'decompressed/0/0'), mode='r')
+    assert rec.shape == (200, 304, 3)
+    full_img, ref_img = np.zeros_like(slide), np.zeros_like(slide)
+    for i in range(2):
+        for j in range(3):
+            sl = rec.chunk_slices((i, j, 0))
+            full_img[sl[:2]] = rec.read_chunk((i, j, 0))
+            tile = slide[sl[:2]]
+            y = oracle.encoder(O.to_float_chw(tile))
+            y_q, _ = oracle.fact_ent(y)
+            x_r, _ = oracle.decoder(y_q)
+            ref_img[sl[:2]] = O.to_uint8_hwc(x_r[0][0])
+    assert abs(O.psnr_u8(slide, full_img) - O.psnr_u8(slide, ref_img)) <= 0.05
+
+
+def test_save_as_bottleneck_refuses_unsupported_edges_up_front(tmp_path):
+    from oracle import cae_oracle as O
+    from cnn_autoencoder_b200 import compress
+    chk = O.make_checkpoint(ARCH, seed=17)
+    slide = np.zeros((200, 300, 3), dtype=np.uint8)            # 300 - 256 = 44: not a multiple of 8
+    with pytest.raises(ValueError, match='edge tiles'):
+        compress.compress_image('CAE', chk, slide, str(tmp_path / 'x.zarr'), patch_size=128,
+                                save_as_bottleneck=True)
+    assert not os.path.exists(str(tmp_path / 'x.zarr' / '0' / '0' / '0.0.0'))
