@@ -157,8 +157,6 @@ class _Unit(nn.Module):
         if kernel_size != 3:
             raise NotImplementedError('the CUDA kernels implement kernel_size=3 '
                                       '(the only value the reference uses)')
-        if groups:
-            raise NotImplementedError('groups=True (depthwise) is scheduled: SURVEY.md 8f-3')
         if act_layer_type not in _SUPPORTED_ACTS:
             raise ValueError(f'Activation layer {act_layer_type} not supported')
         track = 'synthesis' if self.transposed else 'analysis'
@@ -169,11 +167,15 @@ class _Unit(nn.Module):
 
         def conv(seq, cin, cout, stride):
             if self.transposed:
+                # groups=True: every layer is built with groups=channels_in (R:68, 83, 119, 135,
+                # 153, 195, 210, 247); torch refuses channel counts the groups do not divide,
+                # exactly as in the reference
                 m = nn.ConvTranspose2d(cin, cout, 3, stride=stride, padding=1,
-                                       output_padding=stride - 1, bias=bias)
+                                       output_padding=stride - 1, bias=bias,
+                                       groups=cin if groups else 1)
             else:
                 m = nn.Conv2d(cin, cout, 3, stride=stride, padding=1, bias=bias,
-                              padding_mode='reflect')
+                              padding_mode='reflect', groups=cin if groups else 1)
             layout.append(('conv', seq, len(seqs[seq])))
             seqs[seq].append(m)
             if batch_norm:
@@ -322,12 +324,10 @@ class Synthesizer(_Track):
         self.synthesis_track = nn.Sequential(*track)
         if multiscale_analysis:
             # R:417-429: a reflect-padded 3x3 colour head on every intermediate scale
-            if groups:
-                raise NotImplementedError('only dense 3x3 convolutions have CUDA kernels '
-                                          '(groups=True is scheduled: SURVEY.md 8f-3)')
             layers = [nn.Sequential(nn.Conv2d(channels_net * channels_expansion ** i, channels_org,
                                               kernel_size=kernel_size, stride=1,
                                               padding=kernel_size // 2, bias=bias,
+                                              groups=channels_org if groups else 1,
                                               padding_mode='reflect'))
                       for i in reversed(range(compression_level - 1))]
         else:
@@ -414,7 +414,7 @@ class Synthesizer(_Track):
                     O.conv(C.CONV_S1, a_in, conv.weight.detach().float().contiguous(),
                            conv.out_channels, out, igemm=False,
                            bias=conv.bias.detach().float().contiguous() if conv.bias is not None else None,
-                           pad_mode=C.PAD_REFLECT)
+                           pad_mode=C.PAD_REFLECT, groups=conv.groups)
                     x_r[n_units - 2 - u] = out.t
         x_r.insert(0, x_full)
         if as_uint8:

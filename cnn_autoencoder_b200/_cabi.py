@@ -42,7 +42,8 @@ class ConvDesc(ctypes.Structure):
                 ('pre_act', ctypes.c_int32), ('post_act', ctypes.c_int32),
                 ('pad_mode', ctypes.c_int32), ('ck', ctypes.c_int32), ('mt', ctypes.c_int32),
                 ('grid', ctypes.c_int32), ('aux_out', ctypes.c_void_p),
-                ('quant', ctypes.c_void_p)]
+                ('quant', ctypes.c_void_p), ('groups', ctypes.c_int32),
+                ('reserved', ctypes.c_int32)]
 
 
 class HeadDesc(ctypes.Structure):

@@ -49,9 +49,9 @@ class Step:
         self.gdn = None             # GDN module applied to the conv output before the skip add
         self.transposed = isinstance(conv, nn.ConvTranspose2d)
         stride = conv.stride[0]
-        if conv.kernel_size != (3, 3) or conv.groups != 1 or conv.dilation != (1, 1):
-            raise NotImplementedError('only dense 3x3 convolutions have CUDA kernels '
-                                      '(groups=True is scheduled: SURVEY.md 8f-3)')
+        if conv.kernel_size != (3, 3) or conv.dilation != (1, 1):
+            raise NotImplementedError('only 3x3 convolutions have CUDA kernels')
+        self.groups = conv.groups     # > 1: depthwise-style layers of groups=True nets (direct kernel)
         self.kind = ({1: C.CONVT_S1, 2: C.CONVT_S2} if self.transposed
                      else {1: C.CONV_S1, 2: C.CONV_S2})[stride]
         self.c_in = conv.in_channels
@@ -85,7 +85,11 @@ class Step:
                 wdev = O.pack_weights(self.kind, w, scale=scale)
             else:
                 if scale is not None:
-                    w = w * (scale.view(1, -1, 1, 1) if self.transposed else scale.view(-1, 1, 1, 1))
+                    if self.transposed and self.groups > 1:      # (c_in, c_out / G, 3, 3)
+                        g = self.groups
+                        w = (w.view(g, -1, w.shape[1], 3, 3) * scale.view(g, 1, -1, 1, 1)).view_as(w)
+                    else:
+                        w = w * (scale.view(1, -1, 1, 1) if self.transposed else scale.view(-1, 1, 1, 1))
                 wdev = w.contiguous()
             self._cache = (wdev, b.contiguous() if b is not None else None)
         self._cache_key = key
@@ -158,6 +162,8 @@ class TrackExecutor:
 
     @staticmethod
     def _use_igemm(step, x):
+        if step.groups != 1:
+            return False                      # grouped layers: HBM-bound, CUDA-core direct kernel
         if x.fmt in (C.FMT_F32_NCHW, C.FMT_U8_HWC):
             return False                      # raw image / latent from the caller: direct kernel
         return not (step.c_in <= 4 and step.c_out <= 4)
@@ -183,7 +189,7 @@ class TrackExecutor:
                 continue
             steps = self.steps[k:k + span]
             if any(s.gdn is not None or s.transposed or s.pad_mode != steps[0].pad_mode
-                   for s in steps):
+                   or s.groups != 1 for s in steps):
                 continue
             a, down = steps[0], steps[-1]
             stems_ok = all(s.kind == C.CONV_S1 and s.c_in <= 4 and s.c_out == s.c_in
@@ -291,7 +297,7 @@ class TrackExecutor:
                                    C.HALO_KEEP, cur.t.device)
                 call = ((st.kind, cur, wdev, st.c_out, tmp),
                         dict(igemm=igemm, bias=bias, skip=None, pre_act=C.ACT_NONE,
-                             post_act=C.ACT_NONE, pad_mode=st.pad_mode, aux=None))
+                             post_act=C.ACT_NONE, pad_mode=st.pad_mode, aux=None, groups=st.groups))
                 O.conv(*call[0], **call[1])
                 beta, gamma = st.gdn.effective()
                 O.gdn(tmp, out, beta, gamma, st.gdn.inverse, skip=skip)
@@ -305,7 +311,7 @@ class TrackExecutor:
                 call = ((st.kind, cur, wdev, st.c_out, out),
                         dict(igemm=igemm, bias=bias, skip=skip, pre_act=act_code(st.pre_act),
                              post_act=act_code(st.post_act), pad_mode=st.pad_mode, aux=aux_t,
-                             quant=q))
+                             quant=q, groups=st.groups))
                 O.conv(*call[0], **call[1])
                 if q is not None:
                     quant.done = True

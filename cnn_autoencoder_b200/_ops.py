@@ -110,7 +110,8 @@ def pack_weights(kind, weight, scale=None, ck=0):
 
 
 def conv(kind, x, weights, c_out, out, *, igemm, bias=None, skip=None, pre_act=C.ACT_NONE,
-         post_act=C.ACT_NONE, pad_mode=C.PAD_REFLECT, aux=None, ck=0, mt=0, grid=0, quant=None):
+         post_act=C.ACT_NONE, pad_mode=C.PAD_REFLECT, aux=None, ck=0, mt=0, grid=0, quant=None,
+         groups=1):
     """out = post_act(pre_act(conv(x) + bias) + skip) through the C ABI.  ``quant``: a
     ``_cabi.QuantFuse`` for the latent layer (igemm, fp32 NCHW output)."""
     d = C.ConvDesc()
@@ -125,6 +126,7 @@ def conv(kind, x, weights, c_out, out, *, igemm, bias=None, skip=None, pre_act=C
     d.ck, d.mt, d.grid = ck, mt, grid
     d.aux_out = aux.data_ptr() if aux is not None else None
     d.quant = ctypes.addressof(quant) if quant is not None else None
+    d.groups = groups
     L = C.lib()
     fn = L.cae_conv_igemm if igemm else L.cae_conv_direct
     C.check(fn(ctypes.byref(d), _stream_ptr()))

@@ -21,6 +21,7 @@ struct DcParams {
   int pre_act, post_act;
   float *aux;
   int out_channels_padded;  // planar outputs: planes * 8
+  int groups, cin_pg, cout_pg;   // grouped convolution (groups=channels_in in the reference)
 };
 
 __device__ __forceinline__ float load_in(const DcParams &p, int n, int c, int y, int x) {
@@ -76,6 +77,24 @@ __global__ void __launch_bounds__(128) direct_conv_kernel(const DcParams p) {
         iy = ty / p.stride;
         ix = tx / p.stride;
         if (iy >= p.h_in || ix >= p.w_in) continue;
+      }
+      if (p.groups > 1) {
+        // nn.Conv2d(groups=G): weight (c_out, c_in/G, 3, 3); nn.ConvTranspose2d(groups=G): weight
+        // (c_in, c_out/G, 3, 3); output channel co belongs to group co / (c_out/G) and only sees
+        // that group's c_in/G input channels (R:68, 83, 119, 135, 153: groups=channels_in)
+#pragma unroll
+        for (int i = 0; i < CO_BLK; ++i) {
+          const int co = co0 + i;
+          if (co >= p.c_out) continue;
+          const int g = co / p.cout_pg, col = co - g * p.cout_pg;
+          for (int cl = 0; cl < p.cin_pg; ++cl) {
+            const int ci = g * p.cin_pg + cl;
+            const size_t wi = p.transposed ? (((size_t)ci * p.cout_pg + col) * 3 + kh) * 3 + kw
+                                           : (((size_t)co * p.cin_pg + cl) * 3 + kh) * 3 + kw;
+            acc[i] = fmaf(load_in(p, n, ci, iy, ix), __ldg(p.w + wi), acc[i]);
+          }
+        }
+        continue;
       }
       for (int ci = 0; ci < p.c_in; ++ci) {
         const float v = load_in(p, n, ci, iy, ix);
@@ -448,7 +467,12 @@ extern "C" int cae_conv_direct(const cae_conv_desc *d, void *stream) {
   p.pre_act = d->pre_act;
   p.post_act = d->post_act;
   p.aux = (float *)d->aux_out;
-  if (d->kind == CAE_CONV_S1 && d->c_in <= 4 && d->c_out <= 4 && p.n <= 65535) {
+  p.groups = d->groups > 1 ? d->groups : 1;
+  CAE_CHECK(d->c_in % p.groups == 0 && d->c_out % p.groups == 0, 2,
+            "cae_conv_direct: groups=%d does not divide c_in=%d / c_out=%d", p.groups, d->c_in, d->c_out);
+  p.cin_pg = d->c_in / p.groups;
+  p.cout_pg = d->c_out / p.groups;
+  if (p.groups == 1 && d->kind == CAE_CONV_S1 && d->c_in <= 4 && d->c_out <= 4 && p.n <= 65535) {
     dim3 grid((unsigned)((p.w_out + ST_W - 1) / ST_W), (unsigned)((p.h_out + ST_H - 1) / ST_H),
               (unsigned)p.n);
     const dim3 blk(ST_TX, ST_H);

@@ -944,6 +944,7 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   const int kind = d->kind;
   CAE_CHECK(kind >= CAE_CONV_S1 && kind <= CAE_CONVT_S2, 2, "cae_conv_igemm: bad kind %d", kind);
   CAE_CHECK(d->in.ptr && d->weights, 2, "cae_conv_igemm: null input or weights");
+  CAE_CHECK(d->groups <= 1, 2, "cae_conv_igemm: grouped convolutions run on cae_conv_direct");
   CAE_CHECK(d->n > 0 && d->h_in > 0 && d->w_in > 0, 2, "cae_conv_igemm: bad shape");
   const int c_in_p = round_up(d->c_in, 16);
   CAE_CHECK(d->in.planes * 8 == c_in_p, 2,

@@ -87,6 +87,12 @@ typedef struct {
   void *aux_out;           /* optional second output (fp32 NCHW) or NULL                 */
   const struct cae_quant_fuse *quant; /* igemm + fp32 NCHW output (the latent layer) only:
                                          quantizer fused into the epilogue, or NULL      */
+  int32_t groups;          /* direct kernel only: nn.Conv2d / nn.ConvTranspose2d `groups`
+                              (the reference's groups=True builds every layer with
+                              groups=channels_in, R:68, 83, 119, 135, 153); 0 or 1 = dense;
+                              weights stay in torch layout (c_out, c_in/groups, 3, 3) resp.
+                              (c_in, c_out/groups, 3, 3)                                 */
+  int32_t reserved;
 } cae_conv_desc;
 
 /* ---- library ------------------------------------------------------------- */

@@ -51,6 +51,12 @@ SMALL_ARCHS = {
                        act_layer_type='LeakyReLU', batch_norm=True, use_residual=True),
     'rgb_exp2': dict(channels_org=3, channels_net=8, channels_bn=8, compression_level=3,
                      channels_expansion=2, act_layer_type='LeakyReLU'),
+    # groups=True builds every layer with groups=channels_in (R:68, 83, 119, 135, 153): torch
+    # only accepts it when every layer's output channels are a multiple of its input channels
+    'c4_groups': dict(channels_org=4, channels_net=4, channels_bn=4, compression_level=2,
+                      act_layer_type='LeakyReLU', groups=True, bias=True),
+    'c8_groups_res': dict(channels_org=8, channels_net=8, channels_bn=8, compression_level=2,
+                          act_layer_type='LeakyReLU', groups=True, use_residual=True),
 }
 
 NAMED_INPUT = dict(A=(2, 64, 64), A_res=(1, 64, 64), B=(1, 64, 64))
@@ -79,13 +85,16 @@ def run_reference(chk, x_u8):
     return dict(y=y, y_q=y_q, p_y=p_y, x_r=x_r[0])
 
 
-def main():
+def main(only=None):
+    """``only``: iterable of SMALL_ARCHS names to (re)generate; default = every fixture."""
     if not R.available():
         sys.exit('reference tree not found; fixtures can only be generated in the build container')
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(1)          # deterministic accumulation order
 
     for name, arch in SMALL_ARCHS.items():
+        if only is not None and name not in only:
+            continue
         chk = R.reference_checkpoint(arch, seed=1234)
         if arch.get('batch_norm'):
             g = torch.Generator().manual_seed(7)
@@ -103,6 +112,8 @@ def main():
                    os.path.join(GOLDEN_DIR, f'transforms_{name}.pt'))
         print(name, 'y', tuple(out['y'].shape), 'x_r', tuple(out['x_r'].shape))
 
+    if only is not None:
+        return
     for name, (n, h, w) in NAMED_INPUT.items():
         arch = O.NAMED_ARCHS[name]
         chk = O.make_checkpoint(arch, seed=1234)
@@ -142,4 +153,4 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    main(only=sys.argv[1:] or None)

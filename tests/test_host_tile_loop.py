@@ -121,9 +121,12 @@ def test_model_mirror_builds_on_cpu_and_refuses_to_run():
     assert {'analysis_track.0.model.1.beta', 'analysis_track.0.model.1.gamma',
             'analysis_track.0.model.1.beta_reparam.pedestal',
             'analysis_track.0.model.1.gamma_reparam.lower_bound.bound'} <= gk
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):      # 16 is not a multiple of groups=3: torch refuses, as in the reference
         M.setup_modules(channels_org=3, channels_net=16, channels_bn=8, compression_level=2,
                         act_layer_type='LeakyReLU', groups=True)
+    d = M.setup_modules(channels_org=4, channels_net=4, channels_bn=4, compression_level=2,
+                        act_layer_type='LeakyReLU', groups=True)
+    assert d['encoder'].analysis_track[0].model[0].groups == 4
     with pytest.raises(ValueError):
         M.Analyzer(act_layer_type='LeakyRelU')      # the reference's own typo default is rejected
 
