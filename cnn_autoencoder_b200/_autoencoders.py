@@ -294,7 +294,9 @@ class Analyzer(_Track):
             return x
         with self._lock, torch.no_grad():
             a = O.wrap_u8_hwc(x) if x.dtype == torch.uint8 else O.wrap_nchw(x)
-            if a.c > 4 and a.fmt == C.FMT_F32_NCHW:
+            if a.c > 4 and a.fmt == C.FMT_F32_NCHW and self._executor().steps[0].groups == 1:
+                # wide dense first layer: tensor-core path, input rounded to fp16 here (a grouped
+                # first layer reads the fp32 image itself on the direct kernel)
                 first = self._executor().steps[0]
                 fmt = C.FMT_F16_SPLIT if first.kind == C.CONV_S2 else C.FMT_F16_PLANAR
                 a = O.nchw_to_planar(a.t, fmt, C.HALO_REFLECT)

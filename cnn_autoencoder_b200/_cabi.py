@@ -22,7 +22,8 @@ PAD_ZERO, PAD_REFLECT = 0, 1
 SYMBOLS = ['cae_abi_version', 'cae_last_error', 'cae_device_info', 'cae_launch_count',
            'cae_packed_weight_bytes', 'cae_pack_weights', 'cae_conv_igemm', 'cae_conv_direct',
            'cae_conv_head',
-           'cae_nchw_to_planar', 'cae_planar_to_nchw', 'cae_eb_quantize', 'cae_eb_dequantize_planar', 'cae_gdn',
+           'cae_nchw_to_planar', 'cae_planar_to_nchw', 'cae_eb_quantize', 'cae_eb_dequantize_planar',
+           'cae_eb_train_blob_size', 'cae_eb_train_fwd', 'cae_eb_train_bwd', 'cae_gdn',
            'cae_pmf_to_quantized_cdf', 'cae_rans_encode', 'cae_rans_decode',
            'cae_rans_enc_table_bytes', 'cae_rans_build_enc_table',
            'cae_rans_encode_batch', 'cae_rans_scan', 'cae_rans_compact', 'cae_rans_decode_batch',
@@ -134,6 +135,11 @@ def lib():
     i64 = ctypes.c_int64
     L.cae_eb_dequantize_planar.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, Tensor, vp]
+    L.cae_eb_train_blob_size.argtypes = []
+    L.cae_eb_train_fwd.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_float, vp, vp, vp]
+    L.cae_eb_train_bwd.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                   vp, vp, vp, vp, vp]
     L.cae_tiles_upload_u8.argtypes = [vp, i64, i64, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int,
                                       vp, vp]
     L.cae_tiles_download_u8.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, i64,

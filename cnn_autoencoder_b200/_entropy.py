@@ -59,6 +59,45 @@ class _LikelihoodLowerBound(nn.Module):
         return _LowerBound.apply(x, self.bound.to(x.dtype))
 
 
+class _EbTrainFn(torch.autograd.Function):
+    """Training-mode forward / backward of the bottleneck as the two fused kernels
+    ``cae_eb_train_fwd`` / ``cae_eb_train_bwd``.  ``blob`` (C x 58) holds the effective
+    parameters softplus(_matrix_i), _bias_i, tanh(_factor_i); it is built with torch ops from the
+    module's parameters, so autograd carries the kernel's ``d/d blob`` through those (tiny)
+    Jacobians into ``_matrix*`` / ``_bias*`` / ``_factor*``."""
+
+    @staticmethod
+    def forward(ctx, y, noise, blob, bound):
+        y = y.contiguous().float()
+        n, c = y.shape[0], y.shape[1]
+        hw = y[0, 0].numel()
+        y_hat, lik = torch.empty_like(y), torch.empty_like(y)
+        blob = blob.contiguous().float()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(y.device).cuda_stream)
+        C.check(C.lib().cae_eb_train_fwd(y.data_ptr(), noise.data_ptr() if noise is not None else None,
+                                         blob.data_ptr(), n, c, hw, bound, y_hat.data_ptr(),
+                                         lik.data_ptr(), stream))
+        ctx.save_for_backward(y_hat, blob)
+        ctx.bound = bound
+        return y_hat, lik
+
+    @staticmethod
+    def backward(ctx, g_yhat, g_lik):
+        y_hat, blob = ctx.saved_tensors
+        n, c = y_hat.shape[0], y_hat.shape[1]
+        hw = y_hat[0, 0].numel()
+        g_y = torch.empty_like(y_hat)
+        g_blob = torch.zeros_like(blob)
+        g_yhat = g_yhat.contiguous().float() if g_yhat is not None else None
+        g_lik = g_lik.contiguous().float() if g_lik is not None else None
+        stream = ctypes.c_void_p(torch.cuda.current_stream(y_hat.device).cuda_stream)
+        C.check(C.lib().cae_eb_train_bwd(y_hat.data_ptr(), blob.data_ptr(), n, c, hw, ctx.bound,
+                                         g_yhat.data_ptr() if g_yhat is not None else None,
+                                         g_lik.data_ptr() if g_lik is not None else None,
+                                         g_y.data_ptr(), g_blob.data_ptr(), stream))
+        return g_y, None, g_blob, None
+
+
 class QuantRequest:
     """Outputs of the quantizer when it runs inside the epilogue of the last analysis
     convolution (``cae_conv_desc.quant``): ``y_q`` (fp32 NCHW), ``hist`` (C x bins),
@@ -184,6 +223,38 @@ class EntropyBottleneck(nn.Module):
             state_dict.setdefault(prefix + 'likelihood_lower_bound.bound',
                                   self.likelihood_lower_bound.bound.clone())
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    def _effective_blob(self):
+        """C x 58 effective parameters in the layout ``cae_eb_train_fwd`` documents, as a
+        differentiable function of the module's parameters."""
+        parts = []
+        K = len(self.filters)
+        for i in range(K + 1):
+            parts.append(F.softplus(getattr(self, f'_matrix{i:d}')).reshape(self.channels, -1))
+            parts.append(getattr(self, f'_bias{i:d}').reshape(self.channels, -1))
+            if i < K:
+                parts.append(torch.tanh(getattr(self, f'_factor{i:d}')).reshape(self.channels, -1))
+        return torch.cat(parts, dim=1)
+
+    def _forward_train_cuda(self, x):
+        """Training-mode forward on the fused kernels (filters (3, 3, 3, 3) on a CUDA device)."""
+        if self.noise_fn is not None:
+            # reproducible runs supply the noise in CompressAI's C x 1 x M layout
+            nd = x.dim()
+            perm = [1, 0] + list(range(2, nd))
+            shape = x.permute(*perm).shape
+            noise = self.noise_fn(x.permute(*perm).reshape(shape[0], 1, -1))
+            noise = noise.reshape(shape).permute(*perm).contiguous().to(x.device, torch.float32)
+        else:
+            noise = torch.empty_like(x, dtype=torch.float32).uniform_(-0.5, 0.5)
+        return _EbTrainFn.apply(x, noise, self._effective_blob(), self.likelihood_bound_const)
+
+    @property
+    def likelihood_bound_const(self):
+        # the bound as a Python float without a device synchronisation per step
+        if getattr(self, '_bound_cache', None) is None or self._bound_cache[0] != self.likelihood_lower_bound.bound._version:
+            self._bound_cache = (self.likelihood_lower_bound.bound._version, self.likelihood_bound)
+        return self._bound_cache[1]
 
     def _forward_torch(self, x, training=False):
         """The model written with torch ops (training path; also what the tables
@@ -370,6 +441,9 @@ class EntropyBottleneck(nn.Module):
     def forward(self, x, training=None):
         if training is None:
             training = self.training
+        if training and x.is_cuda and self.filters == (3, 3, 3, 3) and self.use_likelihood_bound \
+                and not os.environ.get('CAE_EB_TRAIN_TORCH'):
+            return self._forward_train_cuda(x)
         if training or torch.is_grad_enabled() and x.requires_grad:
             return self._forward_torch(x, training=training)
         y_q, p_y, _, _, _ = self._quantize_cuda(x)

@@ -207,6 +207,24 @@ int cae_eb_quantize(const float *y, int n, int c, int hw, const cae_eb_tables *t
 int cae_eb_dequantize_planar(const int32_t *symbols, const float *medians, int n, int c, int h,
                              int w, cae_tensor dst, void *stream);
 
+/* EntropyBottleneck.forward in TRAINING mode (additive-noise proxy + likelihood with gradients;
+ * CompressAI, reached from _taskutils.py:97 inside the train step train_cae_ms.py:209-219;
+ * SURVEY.md A.1), one fused kernel per direction instead of ~60 ATen launches:
+ *   y_hat = y + noise;  l,u = logits_c(y_hat -+ 1/2);  s = -sign(l+u);
+ *   lik = max(|sigmoid(s u) - sigmoid(s l)|, bound).
+ * `blob` holds the EFFECTIVE per-channel parameters, C x cae_eb_train_blob_size() floats: for each
+ * of the 5 layers of filters (3,3,3,3): softplus(_matrix_i) [dout x din], _bias_i [dout],
+ * tanh(_factor_i) [dout] (none for the last layer) -- the caller keeps the softplus / tanh
+ * Jacobians (tiny tensors).  Backward: given d/d y_hat and d/d lik (either may be NULL) writes
+ * g_y = d/d y and ACCUMULATES d/d blob (zero it first); LowerBound passes the gradient where
+ * the raw likelihood >= bound or the incoming gradient is negative.  noise may be NULL (0).   */
+int cae_eb_train_blob_size(void);
+int cae_eb_train_fwd(const float *y, const float *noise, const float *blob, int n, int c, int hw,
+                     float bound, float *y_hat, float *lik, void *stream);
+int cae_eb_train_bwd(const float *y_hat, const float *blob, int n, int c, int hw, float bound,
+                     const float *g_yhat, const float *g_lik, float *g_y, float *g_blob,
+                     void *stream);
+
 /* The same quantizer fused into the epilogue of the last analysis convolution
  * (cae_conv_desc.quant; the layer whose output is the fp32 NCHW latent y, Analyzer.forward
  * R:359-361 followed by fact_ent R:549 / _taskutils.py:97): while y is still in registers the

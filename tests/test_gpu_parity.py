@@ -480,3 +480,43 @@ def test_fused_head_matches_the_two_kernel_path(shape, c_org):
     ref = O.OracleModel(chk).encoder(x.float() / 255.0)
     assert torch.allclose(y_fused.cpu(), ref, atol=2e-2, rtol=2e-2)
     assert torch.allclose(y_fused, y_plain, atol=1e-2, rtol=1e-2)
+
+
+def test_training_mode_bottleneck_kernels_match_autograd():
+    """``cae_eb_train_fwd`` / ``cae_eb_train_bwd`` against the same model written with torch
+    autograd ops (CompressAI's formulation): outputs, d/dy and the gradient of
+    every density parameter, with noise fixed through ``noise_fn``."""
+    from cnn_autoencoder_b200._entropy import EntropyBottleneck
+    torch.manual_seed(11)
+    eb = EntropyBottleneck(6).cuda().train()
+    with torch.no_grad():
+        eb._factor1.add_(torch.randn_like(eb._factor1) * 0.4)
+        eb._factor2.add_(torch.randn_like(eb._factor2) * 0.4)
+        eb._matrix2.add_(torch.randn_like(eb._matrix2) * 0.3)
+    y0 = (torch.randn(3, 6, 9, 7, device='cuda') * 6)
+    y0[0, 0, 0, 0] = 400.0                       # far tail: likelihood on the bound
+    noise = (torch.rand(6, 1, 3 * 63, device='cuda') - 0.5)
+    eb.noise_fn = lambda v: noise
+    w_lik = torch.randn(3, 6, 9, 7, device='cuda')
+    w_hat = torch.randn(3, 6, 9, 7, device='cuda')
+
+    def run(kernel):
+        eb.zero_grad()
+        y = y0.clone().requires_grad_(True)
+        if kernel:
+            y_hat, lik = eb(y)
+        else:
+            y_hat, lik = eb._forward_torch(y, training=True)
+        loss = (torch.log2(lik) * w_lik).sum() + (y_hat * w_hat).sum()
+        loss.backward()
+        return y_hat.detach(), lik.detach(), y.grad.clone(), {n: p.grad.clone() for n, p in eb.named_parameters()
+                                                             if p.grad is not None}
+    a = run(True)
+    b = run(False)
+    assert torch.allclose(a[0], b[0], atol=1e-6)
+    assert torch.allclose(a[1], b[1], rtol=2e-5, atol=1e-12)
+    assert torch.allclose(a[2], b[2], rtol=2e-4, atol=1e-6)
+    assert set(a[3]) == set(b[3]) and len(a[3]) >= 14
+    for k in a[3]:
+        scale = b[3][k].abs().max().item() + 1e-12
+        assert (a[3][k] - b[3][k]).abs().max().item() <= 2e-4 * scale + 1e-7, k

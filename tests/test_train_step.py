@@ -32,13 +32,17 @@ def _noise_for(shard, total):
     return fn
 
 
-def _step(model, x, shard, total, group=None):
+def _step(model, x, shard, total, group=None, bucket=False, steps=1, acc=None):
     model['fact_ent'].module.noise_fn = _noise_for(shard, total)
     fwd = M.decorate_trainable_modules(trainable_modules=['encoder', 'decoder', 'fact_ent'],
                                        enabled_modules=['encoder', 'decoder', 'fact_ent'])
     crit = M.setup_loss('RateMSE', distortion_lambda=0.01)
     opts = M.setup_optimizers(model, lr=1e-3, aux_lr=1e-2)
-    return M.train_step(x, model, crit, opts, fwd, group=group)
+    b = M.GradBucket(model) if bucket else None
+    for s in range(steps):
+        out = M.train_step(x, model, crit, opts, fwd, group=group, bucket=b, step=s,
+                           mod_grad_accumulate=acc)
+    return out
 
 
 def _worker(rank, world, port, out):
@@ -49,7 +53,7 @@ def _worker(rank, world, port, out):
     _, model = _build()
     x = O.synth_natural(4, 3, 32, 32, seed=9).float() / 255.0
     shard = slice(rank * 2, rank * 2 + 2)
-    _step(model, x[shard], shard, 4)
+    _step(model, x[shard], shard, 4, bucket=True)      # persistent bucket, overlapped all-reduce
     if rank == 0:
         torch.save({k: v.state_dict() for k, v in model.items()}, out)
     dist.destroy_process_group()
@@ -96,3 +100,46 @@ def test_train_mode_loss_terms_match_oracle():
 def test_allreduce_is_a_noop_without_a_process_group():
     _, model = _build()
     assert M.allreduce_gradients(model) == 0
+
+
+def test_persistent_bucket_equals_the_gathered_bucket():
+    torch.set_num_threads(1)
+    x = O.synth_natural(4, 3, 32, 32, seed=9).float() / 255.0
+    _, a = _build()
+    _, b = _build()
+    _step(a, x, slice(0, 4), 4, bucket=False, steps=2)
+    _step(b, x, slice(0, 4), 4, bucket=True, steps=2)
+    for k in a:
+        for (n, p), (_, q) in zip(a[k].named_parameters(), b[k].named_parameters()):
+            assert torch.equal(p, q), (k, n)
+    bucket = M.GradBucket(b)
+    assert bucket.attached() and bucket.numel() == sum(p.numel() for k in b for p in b[k].parameters())
+    assert list(bucket.ranges) == ['decoder', 'encoder', 'fact_ent', 'fact_ent_aux']
+
+
+def test_mod_grad_accumulate_gates_the_optimizers():
+    """train_cae_ms.py:221-222: an optimizer clips / steps / zeroes only when step % period == 0,
+    its gradients accumulating in between."""
+    torch.set_num_threads(1)
+    x = O.synth_natural(2, 3, 32, 32, seed=2).float() / 255.0
+    _, m = _build()
+    before = {k: [p.detach().clone() for p in v.parameters()] for k, v in m.items()}
+    fwd = M.decorate_trainable_modules(trainable_modules=['encoder', 'decoder', 'fact_ent'],
+                                       enabled_modules=['encoder', 'decoder', 'fact_ent'])
+    crit = M.setup_loss('RateMSE', distortion_lambda=0.01)
+    opts = M.setup_optimizers(m, lr=1e-3, aux_lr=1e-2)
+    bucket = M.GradBucket(m)
+    m['fact_ent'].module.noise_fn = _noise_for(slice(0, 2), 2)
+    acc = {'encoder': 2, 'decoder': 1, 'fact_ent': 1, 'fact_ent_aux': 1}
+    M.train_step(x, m, crit, opts, fwd, bucket=bucket, step=1, mod_grad_accumulate=acc)
+    enc_same = all(torch.equal(p, q) for p, q in zip(m['encoder'].parameters(), before['encoder']))
+    dec_moved = any(not torch.equal(p, q) for p, q in zip(m['decoder'].parameters(), before['decoder']))
+    assert enc_same and dec_moved
+    a, b = bucket.ranges['encoder']
+    g1 = bucket.flat[a:b].clone()
+    assert g1.abs().sum() > 0                                   # kept for the next step
+    a2, b2 = bucket.ranges['decoder']
+    assert bucket.flat[a2:b2].abs().sum() == 0                  # zeroed after its step
+    M.train_step(x, m, crit, opts, fwd, bucket=bucket, step=2, mod_grad_accumulate=acc)
+    assert any(not torch.equal(p, q) for p, q in zip(m['encoder'].parameters(), before['encoder']))
+    assert bucket.flat[a:b].abs().sum() == 0

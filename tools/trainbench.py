@@ -1,35 +1,34 @@
-"""Config 5 of BASELINE.json on real GPUs: the train_cae_ms rate-distortion step, batch 16 per
-GPU of 3 x 256 x 256 patches, data parallel with ONE flat-bucket NCCL all-reduce per step.
+"""Config 5 of BASELINE.json on real GPUs: the train_cae_ms rate-distortion step
+(/root/reference/src/train_cae_ms.py:209-230), batch 16 per GPU of 3 x 256 x 256 patches, data
+parallel over one process per GPU with the persistent flat gradient bucket of
+``cnn_autoencoder_b200.train_step`` (NCCL all-reduce, the synthesis half overlapped with the
+analysis transform's backward).
 
-    python tools/trainbench.py --steps 10
-    torchrun --nproc-per-node 8 --master-addr 127.0.0.1 tools/trainbench.py --steps 10
+    python bench.py --workload train [--steps K]            (1 GPU)
+    torchrun --nproc-per-node 8 --master-addr 127.0.0.1 bench.py --workload train --gpus 8
 
-Reports per-step time (CUDA events, max over ranks), samples/s of the whole job, the size of the
-gradient bucket, the loss trajectory, and checks that every rank holds bit-identical parameters
-after the last step (the replicas must not drift).  The transforms' train()-mode forward and
-backward are torch autograd ops on the device for now."""
-import argparse
+Prints the bench.py JSON line: ``value`` = samples/s of the whole job with the batch resident in
+HBM (CUDA events, max over ranks), ``e2e`` = the same with each step's batch copied from pinned
+host memory and the loss read back, plus the gradient-bucket size, the all-reduce's share, the
+loss trajectory and whether every rank holds bit-identical parameters after the last step.
+Kernels: the training-mode bottleneck runs on this repo's fused kernels; the transforms'
+train()-mode forward / backward are torch autograd (cuDNN) -- see DESIGN.md."""
 import json
 import os
 import sys
+import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-import torch  # noqa: E402
-import torch.distributed as dist  # noqa: E402
 
-import cnn_autoencoder_b200 as M  # noqa: E402
-from oracle import cae_oracle as O  # noqa: E402  (random-init checkpoint + synthetic patches only)
+def run(args):
+    import torch
+    import torch.distributed as dist
+    import cnn_autoencoder_b200 as M
+    from cnn_autoencoder_b200 import _cabi
+    from oracle import cae_oracle as O     # random-init checkpoint + synthetic patches only
 
-
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--batch', type=int, default=16)
-    ap.add_argument('--arch', default='A')
-    args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -37,50 +36,108 @@ def main():
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    batch = 16
+    warmup = max(args.warmup, 3)
     chk = O.make_checkpoint(O.NAMED_ARCHS[args.arch], seed=1234)
     model = M.autoencoder_from_state_dict(chk, gpu=True, train=True)
     fwd = M.decorate_trainable_modules(trainable_modules=['encoder', 'decoder', 'fact_ent'],
                                        enabled_modules=['encoder', 'decoder', 'fact_ent'])
     crit = M.setup_loss('RateMSE', distortion_lambda=0.01)
     opts = M.setup_optimizers(model, lr=1e-4, aux_lr=1e-3)
-    x = (O.synth_natural(args.batch, 3, 256, 256, seed=100 + rank).float() / 255.0).cuda()
-    losses = []
-    for _ in range(args.warmup):
-        out = M.train_step(x, model, crit, opts, fwd)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    bucket = M.GradBucket(model)
+    x_pin = (O.synth_natural(batch, 3, 256, 256, seed=100 + rank).float() / 255.0).pin_memory()
+    x = x_pin.cuda(non_blocking=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step = [0]
+
+    def one(xb):
+        out = M.train_step(xb, model, crit, opts, fwd, bucket=bucket, step=step[0])
+        step[0] += 1
+        return out
+
+    for _ in range(warmup):
+        out = one(x)
+    barrier()
+    launches0 = _cabi.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
+    losses = []
     for s, e in ev:
         s.record()
-        out = M.train_step(x, model, crit, opts, fwd)
+        out = one(x)
         e.record()
-        losses.append(out['loss'] if isinstance(out, dict) and 'loss' in out else None)
-    torch.cuda.synchronize()
+        losses.append(out['loss'].detach())
+    barrier()
+    launches = _cabi.launch_count() - launches0
     ms = torch.tensor([sum(s.elapsed_time(e) for s, e in ev)], dtype=torch.float64, device='cuda')
+    # e2e: the step's batch from pinned host memory, the loss back to the host
+    x_stage = torch.empty_like(x)
+    loss_host = torch.empty(1).pin_memory()
+    barrier()
+    s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(args.steps):
+        x_stage.copy_(x_pin, non_blocking=True)
+        out = one(x_stage)
+        loss_host.copy_(torch.mean(out['loss']).detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e0.record()
+    barrier()
+    e2e_ms = torch.tensor([s0.elapsed_time(e0)], dtype=torch.float64, device='cuda')
+    # all-reduce alone (the same spans, no compute to hide under)
+    ar_ms = 0.0
+    if world > 1:
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a0.record()
+        for _ in range(10):
+            dist.all_reduce(bucket.flat)
+        a1.record()
+        barrier()
+        ar_ms = a0.elapsed_time(a1) / 10
+        bucket.flat.zero_()
     flat = torch.cat([p.detach().reshape(-1).double() for k in sorted(model)
                       for p in model[k].parameters()])
     lo, hi = flat.clone(), flat.clone()
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     if rank == 0:
         step_ms = ms.item() / args.steps
-        loss_vals = [None if v is None else float(torch.as_tensor(v).float().mean().item())
-                     for v in losses]
-        print(json.dumps(dict(config='train_cae_ms step, net %s, batch %d x 3 x 256 x 256 per GPU' %
-                              (args.arch, args.batch), n_gpus=world, steps=args.steps,
-                              ms_per_step=round(step_ms, 3),
-                              samples_per_s=round(world * args.batch / (step_ms / 1e3), 1),
-                              grad_bucket_elems=int(flat.numel()),
-                              replicas_identical=bool(torch.equal(lo, hi)),
-                              loss_first=loss_vals[0], loss_last=loss_vals[-1],
-                              finite=all(v is None or v == v for v in loss_vals))))
+        lv = [float(torch.mean(v).item()) for v in losses]
+        print(json.dumps({
+            'metric': 'train_step_samples_per_sec', 'value': round(world * batch / (step_ms / 1e3), 1),
+            'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': warmup,
+            'ms_per_step': round(step_ms, 3), 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'train_cae_ms rate-distortion step, net %s, batch %d x 3 x 256 x 256 per GPU, '
+                                   'RateMSE lambda 0.01, Adam 1e-4 / aux 1e-3, clip 1.0' % (args.arch, batch),
+                       'kernels': 'bottleneck fwd/bwd: cae_eb_train_fwd / cae_eb_train_bwd (this repo); '
+                                  'transforms fwd/bwd: torch autograd (cuDNN)',
+                       'parallelism': 'dp%d, one persistent flat fp32 gradient bucket, NCCL all-reduce, '
+                                      'synthesis half launched under the analysis backward' % world},
+            'e2e': {'value': round(world * batch * args.steps / (e2e_ms.item() / 1e3), 1), 'unit': 'samples/s',
+                    'h2d_bytes_per_step': int(x_pin.numel() * 4), 'd2h_bytes_per_step': 4},
+            'gpu_launches': int(launches),
+            'grad_bucket_elems': int(bucket.numel()), 'allreduce_alone_ms': round(ar_ms, 4),
+            'replicas_identical': bool(torch.equal(lo, hi)),
+            'loss_first': lv[0], 'loss_last': lv[-1], 'finite': all(v == v for v in lv)}))
     if world > 1:
         dist.destroy_process_group()
 
 
 if __name__ == '__main__':
-    main()
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--arch', default='A')
+    run(ap.parse_args())
