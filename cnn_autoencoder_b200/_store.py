@@ -27,8 +27,12 @@ class DirArray:
                         dtype=self.dtype.str, fill_value=fill_value, order='C', filters=None,
                         compressor=compressor.get_config() if compressor is not None else None,
                         dimension_separator='.')
-            with open(meta_file, 'w') as f:
+            # written aside and renamed: the other ranks of a sharded job open the array while
+            # rank 0 (re)creates it and must never see a half-written file
+            tmp = meta_file + '.%d.tmp' % os.getpid()
+            with open(tmp, 'w') as f:
                 json.dump(meta, f, indent=1, default=str)
+            os.replace(tmp, meta_file)
         else:
             with open(meta_file) as f:
                 meta = json.load(f)

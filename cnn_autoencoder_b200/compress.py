@@ -68,6 +68,13 @@ def _dist_info(rank, world_size):
     return rank, world_size
 
 
+def default_workers():
+    """Native I/O threads of one rank: the host cores are shared by the ranks of the box
+    (torchrun exports LOCAL_WORLD_SIZE), oversubscribing them slows every rank."""
+    local = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', 1)))
+    return max(2, min(32, (os.cpu_count() or 4) // local))
+
+
 def open_source(input_filename, data_group='0/0'):
     """H x W x C uint8 array-like from: an ndarray, a ``.npy`` path (memory mapped), a
     directory array written by ``_store.DirArray`` (``<path>/<data_group>``), or -- when
@@ -120,7 +127,7 @@ def compress_image(codec, checkpoint, input_filename, output_filename, patch_siz
     if not torch.cuda.is_available():
         raise RuntimeError('compress_image needs a CUDA device (no CPU fallback)')
     rank, world_size = _dist_info(rank, world_size)
-    workers = workers or min(32, os.cpu_count() or 4)
+    workers = workers or default_workers()
     src = open_source(input_filename, data_group)
     H, W, C = src.shape
     ps = patch_size

@@ -25,7 +25,7 @@ from . import _autoencoders as AE
 from ._entropy import decode_symbols
 from ._store import DirArray, native_read, native_write
 from . import _slide
-from .compress import _dist_info, load_model, shard_range
+from .compress import _dist_info, default_workers, load_model, shard_range
 
 
 def decompress_image(input_filename, output_filename, destination_format='zarr',
@@ -39,7 +39,7 @@ def decompress_image(input_filename, output_filename, destination_format='zarr',
     if checkpoint is None or (isinstance(checkpoint, str) and not len(checkpoint)):
         raise ValueError('a checkpoint is required to run the synthesis transform')
     rank, world_size = _dist_info(rank, world_size)
-    workers = workers or min(32, os.cpu_count() or 4)
+    workers = workers or default_workers()
     src = DirArray(os.path.join(input_filename, data_group) if data_group else input_filename,
                    mode='r')
     cfg = src.compressor_config or {}
