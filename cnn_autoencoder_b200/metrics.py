@@ -1,0 +1,75 @@
+"""Evaluation metrics of the reference's ``src/test_cae.py`` for the codec path, with the sums
+computed on the device:
+
+* ``rmse`` / ``psnr``: ``compute_rmse`` :57-58, ``compute_psnr`` :60-63 —
+  ``20 log10(255) - 10 log10(mean((x - x_r)^2))``.  The reference subtracts two uint8 arrays
+  without widening (the differences wrap); here the squared differences are
+  summed exactly in 64-bit integers by ``cae_sse_u8``.
+* ``bpp``: ``compute_rate`` :71-73 — ``8 * bytes_stored / (H * W)``.
+
+The reference computes these on the host after downloading the whole reconstruction; here the
+reconstruction can stay where the synthesis transform left it.  Inputs are uint8 CUDA tensors
+(or ndarrays, which are uploaded); there is no CPU implementation.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _cabi as C
+
+
+def _as_cuda_u8(a, device):
+    if isinstance(a, np.ndarray):
+        a = torch.from_numpy(np.ascontiguousarray(a))
+    if a.dtype != torch.uint8:
+        raise TypeError('expected uint8 images')
+    if not a.is_cuda:
+        if device is None:
+            if not torch.cuda.is_available():
+                raise C.CaeError('metrics run on the GPU only (no CPU fallback)')
+            device = torch.device('cuda', torch.cuda.current_device())
+        a = a.to(device, non_blocking=True)
+    return a.contiguous()
+
+
+def sse_u8(x, x_r, per_image=False):
+    """Sum of squared differences of two uint8 arrays of the same shape (exact, int64).
+    ``per_image``: one sum per leading index (N x ... inputs) instead of the total."""
+    dev = x.device if isinstance(x, torch.Tensor) and x.is_cuda else (
+        x_r.device if isinstance(x_r, torch.Tensor) and x_r.is_cuda else None)
+    a, b = _as_cuda_u8(x, dev), _as_cuda_u8(x_r, dev)
+    if a.shape != b.shape:
+        raise ValueError('shape mismatch %r vs %r' % (tuple(a.shape), tuple(b.shape)))
+    n = a.shape[0] if per_image else 1
+    per = a.numel() // max(n, 1)
+    out = torch.zeros(n, dtype=torch.int64, device=a.device)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
+    with torch.cuda.device(a.device):
+        for n0 in range(0, n, 65535):
+            m = min(65535, n - n0)
+            C.check(C.lib().cae_sse_u8(a.data_ptr() + n0 * per, b.data_ptr() + n0 * per, m, per,
+                                       out[n0:].data_ptr(), stream))
+    return out if per_image else out[0]
+
+
+def mse(x, x_r):
+    n = x.numel() if isinstance(x, torch.Tensor) else x.size
+    return float(sse_u8(x, x_r).item()) / n
+
+
+def rmse(x, x_r):
+    """``compute_rmse`` (test_cae.py:57-58)."""
+    return math.sqrt(mse(x, x_r))
+
+
+def psnr(x, x_r, max_val=255.0):
+    """``compute_psnr`` (test_cae.py:60-63), with the widening the reference lacks."""
+    m = mse(x, x_r)
+    return float('inf') if m == 0 else 20.0 * math.log10(max_val) - 10.0 * math.log10(m)
+
+
+def bpp(nbytes_stored, height, width):
+    """``compute_rate`` (test_cae.py:71-73)."""
+    return 8.0 * float(nbytes_stored) / (height * width)

@@ -113,6 +113,22 @@ def test_device_roundtrip_and_phase_record():
     assert rec['roundtrip_exact'] and rec['chunks'] == 32
 
 
+def test_metrics_match_the_reference_definitions():
+    """PSNR / RMSE / bpp as src/test_cae.py:57-73 defines them (with a widening cast), on the GPU."""
+    from oracle import cae_oracle as O
+    from cnn_autoencoder_b200 import metrics
+    g = np.random.default_rng(4)
+    x = g.integers(0, 256, size=(3, 70, 50, 3), dtype=np.uint8)
+    x_r = np.clip(x.astype(np.int32) + g.integers(-9, 10, size=x.shape), 0, 255).astype(np.uint8)
+    assert abs(metrics.psnr(x, x_r) - O.psnr_u8(x, x_r)) < 1e-9
+    d = x.astype(np.float64) - x_r.astype(np.float64)
+    assert abs(metrics.rmse(torch.from_numpy(x).cuda(), torch.from_numpy(x_r).cuda()) - np.sqrt((d ** 2).mean())) < 1e-9
+    per = metrics.sse_u8(x, x_r, per_image=True).cpu().numpy()
+    assert per.tolist() == [(d[i] ** 2).sum() for i in range(3)]
+    assert metrics.psnr(x, x) == float('inf')
+    assert metrics.bpp(1000, 100, 80) == O.bpp(1000, 100, 80)
+
+
 def test_sse_kernel_gives_the_psnr_numerator():
     import ctypes
     from cnn_autoencoder_b200 import _cabi as C

@@ -24,12 +24,29 @@ dev_out = torch.empty_like(dev_in)
 yx = np.array([(i, j) for i in range(T // GX) for j in range(GX)], dtype=np.int32)
 L = C.lib()
 s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-def step():
+def up():
     for k0 in range(0, T, 32):
         C.check(L.cae_tiles_upload_u8(src.numpy().ctypes.data, H, W, 3, PS, yx[k0:k0 + 32].ctypes.data, 32,
                                       dev_in[k0:].data_ptr(), ctypes.c_void_p(s_in.cuda_stream)))
+def down():
+    for k0 in range(0, T, 32):
         C.check(L.cae_tiles_download_u8(dev_out[k0:].data_ptr(), 32, PS, 3, yx[k0:k0 + 32].ctypes.data,
                                         dst.numpy().ctypes.data, H, W, ctypes.c_void_p(s_out.cuda_stream)))
+SEQ = '--sequential' in sys.argv
+def step():
+    if SEQ:
+        # the order of compress_image -> decompress_image: tiles up + streams down, THEN streams
+        # up + tiles down (the two directions of a step are not in flight together)
+        up()
+        with torch.cuda.stream(s_out):
+            streams_h.copy_(streams_d, non_blocking=True)
+        s_in.synchronize(); s_out.synchronize()
+        with torch.cuda.stream(s_in):
+            streams_d.copy_(streams_h, non_blocking=True)
+        down()
+        s_in.synchronize(); s_out.synchronize()
+        return
+    up(); down()
     with torch.cuda.stream(s_in):
         streams_d.copy_(streams_h, non_blocking=True)
     with torch.cuda.stream(s_out):
@@ -52,7 +69,7 @@ if world > 1:
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
 if rank == 0:
     nbytes = 2 * (T * PS * PS * 3 + streams_h.numel())
-    print(json.dumps(dict(what='copy-only ceiling of the WSI step', n_gpus=world, s_per_step=round(dt.item() / K, 4),
+    print(json.dumps(dict(what='copy-only ceiling of the WSI step, directions ' + ('one after the other (as compress -> decompress)' if SEQ else 'concurrent'), n_gpus=world, s_per_step=round(dt.item() / K, 4),
                           aggregate_gb_s=round(world * nbytes * K / dt.item() / 1e9, 1),
                           per_gpu_gb_s_each_way=round(nbytes / 2 * K / dt.item() / 1e9, 1),
                           ceiling_mp_s=round(world * T * PS * PS * K / dt.item() / 1e6, 1),

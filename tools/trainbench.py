@@ -94,6 +94,8 @@ def run(args):
     ar_ms = 0.0
     if world > 1:
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            dist.all_reduce(bucket.flat)
         barrier()
         a0.record()
         for _ in range(10):
