@@ -15,13 +15,14 @@ CSRC = os.path.join(_HERE, 'csrc')
 FMT_NONE, FMT_U8_HWC, FMT_F32_NCHW, FMT_F16_PLANAR, FMT_F16_SPLIT = 0, 1, 2, 3, 4
 HALO_KEEP, HALO_REFLECT = 0, 1
 ACT_NONE, ACT_LEAKY_RELU, ACT_RELU = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 CONV_S1, CONV_S2, CONVT_S1, CONVT_S2 = 0, 1, 2, 3
 PAD_ZERO, PAD_REFLECT = 0, 1
 
 SYMBOLS = ['cae_abi_version', 'cae_last_error', 'cae_device_info', 'cae_launch_count',
            'cae_packed_weight_bytes', 'cae_pack_weights', 'cae_conv_igemm', 'cae_conv_direct',
-           'cae_conv_head',
+           'cae_conv_head', 'cae_proj_weight_bytes', 'cae_proj_bytes', 'cae_pack_proj_weights',
+           'cae_image_from_proj',
            'cae_nchw_to_planar', 'cae_planar_to_nchw', 'cae_eb_quantize', 'cae_eb_dequantize_planar',
            'cae_eb_train_blob_size', 'cae_eb_train_fwd', 'cae_eb_train_bwd', 'cae_gdn',
            'cae_pmf_to_quantized_cdf', 'cae_rans_encode', 'cae_rans_decode',
@@ -44,7 +45,11 @@ class ConvDesc(ctypes.Structure):
                 ('pad_mode', ctypes.c_int32), ('ck', ctypes.c_int32), ('mt', ctypes.c_int32),
                 ('grid', ctypes.c_int32), ('aux_out', ctypes.c_void_p),
                 ('quant', ctypes.c_void_p), ('groups', ctypes.c_int32),
-                ('reserved', ctypes.c_int32)]
+                ('reserved', ctypes.c_int32), ('proj', ctypes.c_void_p)]
+
+
+class ProjFuse(ctypes.Structure):
+    _fields_ = [('weights', ctypes.c_void_p), ('proj', ctypes.c_void_p)]
 
 
 class HeadDesc(ctypes.Structure):
@@ -110,6 +115,13 @@ def lib():
     L.cae_conv_igemm.argtypes = [ctypes.POINTER(ConvDesc), vp]
     L.cae_conv_direct.argtypes = [ctypes.POINTER(ConvDesc), vp]
     L.cae_conv_head.argtypes = [ctypes.POINTER(HeadDesc), vp]
+    L.cae_proj_weight_bytes.restype = sz
+    L.cae_proj_weight_bytes.argtypes = []
+    L.cae_proj_bytes.restype = sz
+    L.cae_proj_bytes.argtypes = [ctypes.c_int] * 3
+    L.cae_pack_proj_weights.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
+    L.cae_image_from_proj.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp,
+                                      ctypes.c_int, ctypes.c_int, vp, vp, vp]
     L.cae_nchw_to_planar.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      Tensor, vp]
     L.cae_planar_to_nchw.argtypes = [Tensor, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -152,7 +164,8 @@ def lib():
     L.cae_files_read.argtypes = [ctypes.c_char_p, ctypes.c_int, vp, ctypes.c_int, vp, vp, ctypes.c_int]
     for name in SYMBOLS:
         if name not in ('cae_abi_version', 'cae_last_error', 'cae_launch_count',
-                        'cae_packed_weight_bytes', 'cae_rans_enc_table_bytes'):
+                        'cae_packed_weight_bytes', 'cae_rans_enc_table_bytes',
+                        'cae_proj_weight_bytes', 'cae_proj_bytes'):
             getattr(L, name).restype = ctypes.c_int
     if L.cae_abi_version() != ABI_VERSION:
         raise CaeError('libcae_b200.so ABI version mismatch')

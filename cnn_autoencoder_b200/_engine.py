@@ -60,6 +60,8 @@ class Step:
             C.PAD_REFLECT if conv.padding_mode == 'reflect' else C.PAD_ZERO)
         self._cache_key = None
         self._cache = None
+        self._proj_key = None
+        self._proj_cache = None
 
     # weights in the form the chosen kernel wants, rebuilt when a parameter changes
     def materialise(self, igemm):
@@ -94,6 +96,36 @@ class Step:
             self._cache = (wdev, b.contiguous() if b is not None else None)
         self._cache_key = key
         return self._cache
+
+
+    def _folded(self):
+        """(weight, bias, per-output-channel scale) with eval-mode BatchNorm folded."""
+        w = self.conv.weight.detach().float()
+        b = self.conv.bias.detach().float() if self.conv.bias is not None else None
+        scale = None
+        if self.bn is not None:
+            inv = torch.rsqrt(self.bn.running_var.float() + self.bn.eps)
+            gamma = self.bn.weight.float() if self.bn.weight is not None else torch.ones_like(inv)
+            beta = self.bn.bias.float() if self.bn.bias is not None else torch.zeros_like(inv)
+            scale = gamma * inv
+            b0 = b if b is not None else torch.zeros_like(inv)
+            b = (b0 - self.bn.running_mean.float()) * scale + beta
+        return w, b, scale
+
+    def materialise_proj(self):
+        """The image layer as the projection operand of the layer before it (cae_conv_desc.proj)."""
+        params = [self.conv.weight, self.conv.bias]
+        if self.bn is not None:
+            params += [self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var]
+        key = ('proj',) + tuple((p.data_ptr(), p._version) if p is not None else None for p in params)
+        if key == self._proj_key:
+            return self._proj_cache
+        with torch.no_grad():
+            w, b, scale = self._folded()
+            self._proj_cache = (O.pack_proj_weights(w, scale=scale),
+                                b.contiguous() if b is not None else None)
+        self._proj_key = key
+        return self._proj_cache
 
 
 def steps_from_units(units):
@@ -167,6 +199,8 @@ class TrackExecutor:
         # the extra launches and the wave quantisation of the smaller grids cost more than the HBM
         # round trip they save, so the whole-batch schedule stays.
         self.tail_l2_bytes = int(os.environ.get('CAE_TAIL_L2_MB', '0')) << 20
+        # projection fusion of the last two synthesis layers (cae_conv_desc.proj)
+        self.fuse_proj = not os.environ.get('CAE_NO_PROJ_FUSION')
 
     @staticmethod
     def _use_igemm(step, x):
@@ -215,6 +249,51 @@ class TrackExecutor:
             if fmt == C.FMT_F16_PLANAR:
                 return span
         return 0
+
+    def _proj_match(self, k, cur, keep, final_fmt):
+        """True when steps k, k + 1 are the last two layers of a synthesis track in the form the
+        projection fusion covers: ConvTranspose2d(c, 128, s2) -> [act], then the <= 3 channel
+        image layer (``cae_conv_desc.proj``: the 128-channel tensor between them never reaches
+        HBM)."""
+        if not self.fuse_proj or k != len(self.steps) - 2 or (k + 1) in keep:
+            return False
+        a, b = self.steps[k], self.steps[k + 1]
+        if not (a.kind == C.CONVT_S2 and b.kind == C.CONVT_S2 and a.c_out == 128 and b.c_in == 128
+                and b.c_out <= 3 and a.c_in % 16 == 0):
+            return False
+        if any(s.gdn is not None or s.skip is not None or s.groups != 1 for s in (a, b)):
+            return False
+        if a.post_act is not None:
+            return False
+        return cur.fmt == C.FMT_F16_PLANAR and final_fmt in (C.FMT_U8_HWC, C.FMT_F32_NCHW)
+
+    def _run_proj(self, k, cur, final_fmt, aux_last):
+        a, b = self.steps[k], self.steps[k + 1]
+        wa, ba = a.materialise(True)
+        vb, bb = b.materialise_proj()
+        hu, wu = O.KIND_OUT[a.kind](cur.h, cur.w)
+        ho, wo = O.KIND_OUT[b.kind](hu, wu)
+        dev = cur.t.device
+        key = ((k, 'proj'), cur.n, hu, wu, str(dev))
+        buf = self._buffers.get((k, 'proj'))
+        if buf is None or buf[0] != key:
+            buf = (key, O.alloc_proj(cur.n, hu, wu, dev))
+            self._buffers[(k, 'proj')] = buf
+        rec = buf[1]
+        out = O.alloc_act(C.FMT_U8_HWC, cur.n, b.c_out, ho, wo, device=dev) if final_fmt == C.FMT_U8_HWC else None
+        aux = torch.empty((cur.n, b.c_out, ho, wo), dtype=torch.float32, device=dev) \
+            if (aux_last or final_fmt != C.FMT_U8_HWC) else None
+        call_a = ((a.kind, cur, wa, a.c_out, None),
+                  dict(igemm=True, bias=ba, skip=None, pre_act=act_code(a.pre_act),
+                       post_act=C.ACT_NONE, pad_mode=a.pad_mode, aux=None, proj=(vb, rec)))
+        O.conv(*call_a[0], **call_a[1])
+        call_b = ('image_from_proj', (rec, cur.n, hu, wu, b.c_out),
+                  dict(bias=bb, pre_act=act_code(b.pre_act), post_act=act_code(b.post_act),
+                       out=out, aux=aux))
+        O.image_from_proj(*call_b[1], **call_b[2])
+        self.last_calls[k], self.last_calls[k + 1] = call_a, call_b
+        last = out if out is not None else O.Act(aux, C.FMT_F32_NCHW, cur.n, b.c_out, ho, wo)
+        return last, aux
 
     def _buffer(self, key, fmt, n, c, h, w, halo, device):
         full = (key, fmt, n, c, h, w, halo, str(device))
@@ -290,6 +369,10 @@ class TrackExecutor:
             if skip_steps:                # consumed by the fused head launched before
                 skip_steps -= 1
                 continue
+            if self._proj_match(k, cur, keep, final_fmt):
+                cur, aux = self._run_proj(k, cur, final_fmt, aux_last)
+                tensors[k + 2] = cur
+                break
             sub_n = self._tail_match(k, cur, keep, final_fmt)
             if sub_n:
                 cur, aux = self._run_tail(k, cur, sub_n, final_fmt, aux_last)

@@ -109,11 +109,43 @@ def pack_weights(kind, weight, scale=None, ck=0):
     return packed
 
 
+def pack_proj_weights(weight, scale=None):
+    """fp32 ConvTranspose2d weight (128, c, 3, 3) of the image layer (device) -> the packed
+    projection operand of ``cae_conv_desc.proj`` (``cae_pack_proj_weights``)."""
+    _require_cuda(weight, 'weight')
+    w = weight.detach().contiguous().float()
+    L = C.lib()
+    packed = torch.empty(L.cae_proj_weight_bytes() // 2, dtype=torch.float16, device=w.device)
+    sc = scale.detach().contiguous().float() if scale is not None else None
+    C.check(L.cae_pack_proj_weights(w.shape[0], w.shape[1], w.data_ptr(),
+                                    sc.data_ptr() if sc is not None else None,
+                                    packed.data_ptr(), _stream_ptr()))
+    return packed
+
+
+def alloc_proj(n, h, w, device):
+    """Record buffer of the projection fusion for an n x h x w intermediate tensor."""
+    return torch.empty(C.lib().cae_proj_bytes(n, h, w) // 2, dtype=torch.float16, device=device)
+
+
+def image_from_proj(proj, n, h, w, c_out, *, bias=None, pre_act=C.ACT_NONE, post_act=C.ACT_NONE,
+                    out=None, aux=None):
+    """Second half of the projection fusion (``cae_image_from_proj``): records of the h x w
+    intermediate tensor -> uint8 HWC ``out`` (an Act) and / or fp32 NCHW ``aux``, both 2h x 2w."""
+    C.check(C.lib().cae_image_from_proj(
+        proj.data_ptr(), n, h, w, c_out, bias.data_ptr() if bias is not None else None,
+        pre_act, post_act, out.t.data_ptr() if out is not None else None,
+        aux.data_ptr() if aux is not None else None, _stream_ptr()))
+    return out
+
+
 def conv(kind, x, weights, c_out, out, *, igemm, bias=None, skip=None, pre_act=C.ACT_NONE,
          post_act=C.ACT_NONE, pad_mode=C.PAD_REFLECT, aux=None, ck=0, mt=0, grid=0, quant=None,
-         groups=1):
+         groups=1, proj=None):
     """out = post_act(pre_act(conv(x) + bias) + skip) through the C ABI.  ``quant``: a
-    ``_cabi.QuantFuse`` for the latent layer (igemm, fp32 NCHW output)."""
+    ``_cabi.QuantFuse`` for the latent layer (igemm, fp32 NCHW output).  ``proj``: (packed
+    projection weights, record buffer) -- the layer writes the records of the projection fusion
+    instead of ``out`` (which is then None)."""
     d = C.ConvDesc()
     d.kind = kind
     d.n, d.h_in, d.w_in, d.c_in, d.c_out = x.n, x.h, x.w, x.c, c_out
@@ -127,6 +159,10 @@ def conv(kind, x, weights, c_out, out, *, igemm, bias=None, skip=None, pre_act=C
     d.aux_out = aux.data_ptr() if aux is not None else None
     d.quant = ctypes.addressof(quant) if quant is not None else None
     d.groups = groups
+    pf = None
+    if proj is not None:
+        pf = C.ProjFuse(proj[0].data_ptr(), proj[1].data_ptr())
+        d.proj = ctypes.addressof(pf)
     L = C.lib()
     fn = L.cae_conv_igemm if igemm else L.cae_conv_direct
     C.check(fn(ctypes.byref(d), _stream_ptr()))
@@ -160,6 +196,8 @@ def replay(call):
     """Re-issue a call recorded by ``TrackExecutor.last_calls`` (benchmarks / profiling)."""
     if call[0] == 'head':
         return conv_head(*call[1], **call[2])
+    if call[0] == 'image_from_proj':
+        return image_from_proj(*call[1], **call[2])
     return conv(*call[0], **call[1])
 
 

@@ -38,7 +38,33 @@ constexpr int kMaxSB = 12;
 constexpr int kMaxEpiWarps = 12;  // 3 per TMEM lane quadrant
 constexpr int kThreads = 128 + 32 * kMaxEpiWarps;
 
-enum { EPI_ACT = 0, EPI_LATENT = 1, EPI_IMAGE = 2 };
+enum { EPI_ACT = 0, EPI_LATENT = 1, EPI_IMAGE = 2, EPI_PROJ = 3 };
+
+// Projection fusion (EPI_PROJ): the last wide transposed layer does not write its 128-channel
+// output U at all.  The image layer that follows it (ConvTranspose 128 -> c, c <= 3) is linear
+// in U: I[2a+qy][2b+qx] = sum over (dy <= qy, dx <= qx) of V[qy+1-2dy][qx+1-2dx]^T U[a+dy][b+dx],
+// so the nine per-pixel products P_t = V_t^T U[a][b] (t = kernel tap; 9 * c <= 27 numbers) are
+// all the image layer ever needs from U.  The epilogue of this kernel stages the activated fp16
+// tile of a pass (256 pixels x 128 channels) in shared memory as a K-major operand, a dedicated
+// warp issues a second GEMM (M = 2 x 128 pixels, N = 32, K = 128) into the columns of the
+// accumulator buffer that has just been drained, and P (64 bytes per pixel of U instead of 256,
+// never read back as a 3x3 neighbourhood of 128 channels) goes to HBM.  image_from_proj_kernel
+// then sums the up to four taps of every output pixel.  No halo, no recomputation: the spatial
+// part of the image layer moved behind its channel reduction.
+//
+// Column order of P (and of the packed projection weights), three slots per tap, chosen so that
+// what a neighbour needs from a record is one 16-byte unit:
+//   unit 0-1: own taps (1,1) (1,2) (2,1) (2,2) at 0, 3, 6, 9; tap (0,0) at 12 (diagonal neighbour)
+//   unit 2:   taps (1,0) (2,0) at 16, 19 (read by the left neighbour)
+//   unit 3:   taps (0,1) (0,2) at 24, 27 (read by the upper neighbour)
+constexpr int kProjN = 32;
+constexpr int kProjK = 128;
+constexpr int kProjStageBytes = (kProjK / 8) * 256 * 16;   // 16 planes x 256 pixels x 8 channels fp16
+constexpr int kProjWBytes = (kProjK / 8) * kProjN * 16;    // [kplane][n][8] fp16
+__host__ __device__ inline int proj_slot(int kh, int kw) {
+  const int slot[3][3] = {{12, 24, 27}, {16, 0, 3}, {19, 6, 9}};
+  return slot[kh][kw];
+}
 
 struct IgTap {
   uint32_t a_off;  // byte offset of the tap's view inside an A stage
@@ -97,6 +123,10 @@ struct IgParams {
   double *q_rate;
   ActView q_pl;
   uint32_t q_pitch, q_ps, q_is;
+  // projection fusion (EPI_PROJ only)
+  const uint8_t *proj_w;   // packed [16][32][8] fp16
+  __half *proj_out;        // [n][out_h][out_w][32] fp16
+  uint32_t idesc2;
 };
 
 struct TapDef {
@@ -638,12 +668,13 @@ __device__ __forceinline__ void epilogue_job(const IgParams &p, uint32_t tmem_la
 
 // ------------------------------------------------------------------ kernel
 template <int EPI, int FAST>
-__global__ void __launch_bounds__(FAST == 1 ? 128 + 32 * 16 : kThreads, 1)
+__global__ void __launch_bounds__(EPI == EPI_PROJ ? 128 + 32 * 17 : (FAST == 1 ? 128 + 32 * 16 : kThreads), 1)
 igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ IgParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[kMaxSA], a_empty[kMaxSA];
   __shared__ __align__(8) uint64_t b_full[kMaxSB], b_empty[kMaxSB];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t u_full, u_free, d2_full;   // EPI_PROJ
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -681,7 +712,21 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&acc_full[i], 2);
       mbar_init(&acc_empty[i], (uint32_t)p.epi_warps);
     }
+    if (EPI == EPI_PROJ) {
+      mbar_init(&u_full, (uint32_t)p.epi_warps);
+      mbar_init(&u_free, 1);
+      mbar_init(&d2_full, 1);
+    }
     fence_barrier_init();
+  }
+  // EPI_PROJ: the staged output tile and the projection weights behind the rings
+  uint8_t *u_stage = smem_b + (size_t)p.sb * p.b_stage_bytes;
+  uint8_t *proj_w_s = u_stage + kProjStageBytes;
+  if (EPI == EPI_PROJ) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(p.proj_w);
+    uint4 *dst = reinterpret_cast<uint4 *>(proj_w_s);
+    for (int i = threadIdx.x; i < kProjWBytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    fence_proxy_async();       // read by the tensor cores (async proxy) below
   }
   if (warp == 3) tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
   if (warp == 0 && lane == 0) prefetch_tensormap(&tmA);
@@ -841,6 +886,66 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       mbar_wait(&acc_full[buf], (j / p.n_buf) & 1);
       tc_fence_after();
+      if (EPI == EPI_PROJ) {
+        // E1: accumulators -> bias / activation -> fp16 -> the staged tile.  Stage row = px * 128
+        // + TMEM lane (the order of the rows of the second GEMM is free), plane stride 4096 bytes:
+        // a warp's 16-byte stores are contiguous, so the staging costs no bank conflicts.
+        mbar_wait(&u_free, (j & 1u) ^ 1u);            // the previous pass's GEMM has read the stage
+        const __half2 pre2 = __float2half2_rn(pre_s), post2 = __float2half2_rn(post_s);
+        for (int job = half; job < (kProjK >> 4); job += n_halves) {
+          const int c_first = job * 16;
+          uint32_t r0[16], r1[16];
+          const uint32_t t = lane_base + (uint32_t)(buf * acc_per_buf * p.N + c_first);
+          __syncwarp();
+          tmem_ld16(t, r0);
+          tmem_ld16(t + (uint32_t)p.N, r1);
+          tmem_ld_wait();
+          __half2 ha[8], hb[8];
+          fast_half16<false>(p, r0, c_first, pre_s, pre2, post2, nullptr, ha);
+          fast_half16<false>(p, r1, c_first, pre_s, pre2, post2, nullptr, hb);
+          uint4 *dst = reinterpret_cast<uint4 *>(u_stage + (size_t)(c_first >> 3) * 4096) + row;
+          dst[0] = make_uint4(h2u(ha[0]), h2u(ha[1]), h2u(ha[2]), h2u(ha[3]));
+          dst[128] = make_uint4(h2u(hb[0]), h2u(hb[1]), h2u(hb[2]), h2u(hb[3]));
+          dst[256] = make_uint4(h2u(ha[4]), h2u(ha[5]), h2u(ha[6]), h2u(ha[7]));
+          dst[384] = make_uint4(h2u(hb[4]), h2u(hb[5]), h2u(hb[6]), h2u(hb[7]));
+        }
+        fence_proxy_async();                           // generic-proxy writes -> UMMA reads
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&u_full);
+        // E2: the projected tile (block = px, TMEM lane = input pixel) from the first 64 columns
+        // of the drained buffer -> HBM, one 32-byte sector per thread and unit
+        mbar_wait(&d2_full, j & 1u);
+        tc_fence_after();
+        const uint32_t d2 = lane_base + (uint32_t)(buf * acc_per_buf * p.N);
+        const int x = txi * 8 + txl;
+        for (int unit = half; unit < 4; unit += n_halves) {
+          const int blk = unit >> 1, hh = unit & 1;
+          uint32_t r[16];
+          __syncwarp();
+          tmem_ld16(d2 + (uint32_t)(blk * kProjN + hh * 16), r);
+          tmem_ld_wait();
+          if (y < p.dom_h && x < p.dom_w && !(p.debug & 8)) {
+            __half *o = p.proj_out +
+                        (((size_t)n * p.out_h + (y * 2 + pass)) * p.out_w + (x * 2 + blk)) * kProjN +
+                        hh * 16;
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o),
+                         "r"(pack2(__uint_as_float(r[0]), __uint_as_float(r[1]))),
+                         "r"(pack2(__uint_as_float(r[2]), __uint_as_float(r[3]))),
+                         "r"(pack2(__uint_as_float(r[4]), __uint_as_float(r[5]))),
+                         "r"(pack2(__uint_as_float(r[6]), __uint_as_float(r[7]))),
+                         "r"(pack2(__uint_as_float(r[8]), __uint_as_float(r[9]))),
+                         "r"(pack2(__uint_as_float(r[10]), __uint_as_float(r[11]))),
+                         "r"(pack2(__uint_as_float(r[12]), __uint_as_float(r[13]))),
+                         "r"(pack2(__uint_as_float(r[14]), __uint_as_float(r[15])))
+                         : "memory");
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        continue;
+      }
       for (int job = half; job < n_jobs; job += n_halves) {
         const int m = job / jobs_per_m, jj = job - m * jobs_per_m;
         const int x = (txi * p.mt + m) * 8 + txl;
@@ -855,6 +960,33 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (EPI == EPI_LATENT && p.quant && p.q_rate) {
       for (int o = 16; o > 0; o >>= 1) q_bits += __shfl_xor_sync(0xffffffffu, q_bits, o);
       if (lane == 0 && q_bits != 0.f) atomicAdd(p.q_rate, (double)q_bits);
+    }
+  } else if (EPI == EPI_PROJ && warp == 4 + p.epi_warps) {
+    // ===== projection GEMM: P[2 x 128 pixels][32] = U_stage[256 x 128] * V[128 x 32] =====
+    // A warp of its own, so the two main issuers never wait for the epilogue; the result goes
+    // into the first 64 columns of the accumulator buffer the epilogue has just drained.
+    const bool leader = elect_one();
+    const uint32_t us = smem_u32(u_stage), ws = smem_u32(proj_w_s);
+    const uint32_t buf_cols = (uint32_t)(p.mt * p.n_acc * p.N);
+    uint32_t j = 0;
+    for (int vt = blockIdx.x; vt < p.n_tiles * p.n_pass; vt += gridDim.x, ++j) {
+      mbar_wait(&u_full, j & 1u);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t d2 = tmem_base + (j % (uint32_t)p.n_buf) * buf_cols;
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+#pragma unroll
+          for (int k = 0; k < kProjK / 16; ++k) {
+            const uint64_t da = make_smem_desc(us + blk * 2048 + k * 8192, 4096, 128);
+            const uint64_t db = make_smem_desc(ws + k * (2 * kProjN * 16), kProjN * 16, 128);
+            umma_f16(d2 + blk * kProjN, da, db, p.idesc2, k > 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&u_free);
+        umma_commit(&d2_full);
+      }
+      __syncwarp();
     }
   }
 
@@ -874,6 +1006,114 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   }
   if (warp == 3) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------- projection fusion: helpers
+// packed[kplane][n][8] fp16 from the image layer's ConvTranspose2d weight (128, c_out, 3, 3)
+__global__ void pack_proj_kernel(const float *__restrict__ w, const float *__restrict__ scale,
+                                 int c_out, __half *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kProjK * kProjN) return;
+  const int k8 = i & 7, n = (i >> 3) % kProjN, kplane = i / (8 * kProjN);
+  const int ci = kplane * 8 + k8;
+  float v = 0.f;
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw) {
+      const int c = n - proj_slot(kh, kw);
+      if (c >= 0 && c < c_out && c < 3)
+        v = w[(((size_t)ci * c_out + c) * 3 + kh) * 3 + kw] * (scale ? scale[c] : 1.f);
+    }
+  out[i] = __float2half_rn(v);
+}
+
+struct ProjGatherParams {
+  const uint4 *proj;     // [n][h][w] records of four 16-byte units
+  int n, h, w, c_out;    // h, w: size of U (the projected layer's output)
+  const float *bias;
+  float pre_s, post_s;
+  uint8_t *out;          // [n][2h][2w][c_out] or nullptr
+  float *aux;            // [n][c_out][2h][2w] or nullptr
+};
+
+__device__ __forceinline__ void unpack8(const uint4 &u, float (&f)[8]) {
+  const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 t = __half22float2(h[k]);
+    f[2 * k] = t.x;
+    f[2 * k + 1] = t.y;
+  }
+}
+
+// One thread per pixel (a, b) of U = the 2x2 output pixels (2a + qy, 2b + qx):
+//   o00 = R(a,b)[0..]   o01 = R(a,b)[3..] + R(a,b+1)[16..]   o10 = R(a,b)[6..] + R(a+1,b)[24..]
+//   o11 = R(a,b)[9..] + R(a,b+1)[19..] + R(a+1,b)[27..] + R(a+1,b+1)[12..]
+// HBM bound: 64 bytes read (neighbour units come from L1 / L2), 4 * c_out bytes written per thread.
+template <int CO>
+__global__ void __launch_bounds__(256) image_from_proj_kernel(const ProjGatherParams q) {
+  const int b = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int a = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int n = blockIdx.z;
+  if (a >= q.h || b >= q.w) return;
+  const uint4 *r = q.proj + (((size_t)n * q.h + a) * q.w + b) * 4;
+  const bool right = b + 1 < q.w, down = a + 1 < q.h;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  const uint4 u0 = __ldg(r), u1 = __ldg(r + 1);
+  const uint4 ur = right ? __ldg(r + 4 + 2) : zero;
+  const uint4 ud = down ? __ldg(r + (size_t)q.w * 4 + 3) : zero;
+  const uint4 ux = (right && down) ? __ldg(r + (size_t)q.w * 4 + 4 + 1) : zero;
+  float f0[8], f1[8], fr[8], fd[8], fx[8];
+  unpack8(u0, f0);
+  unpack8(u1, f1);
+  unpack8(ur, fr);
+  unpack8(ud, fd);
+  unpack8(ux, fx);
+  float own[16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    own[i] = f0[i];
+    own[8 + i] = f1[i];
+  }
+  float t[4][CO];
+#pragma unroll
+  for (int c = 0; c < CO; ++c) {
+    t[0][c] = own[c];
+    t[1][c] = own[3 + c] + fr[c];
+    t[2][c] = own[6 + c] + fd[c];
+    t[3][c] = own[9 + c] + fr[3 + c] + fd[3 + c] + fx[4 + c];
+  }
+#pragma unroll
+  for (int ph = 0; ph < 4; ++ph)
+#pragma unroll
+    for (int c = 0; c < CO; ++c) {
+      float u = t[ph][c] + (q.bias ? __ldg(q.bias + c) : 0.f);
+      u = fmaxf(u, u * q.pre_s);
+      t[ph][c] = fmaxf(u, u * q.post_s);
+    }
+  const int H2 = 2 * q.h, W2 = 2 * q.w;
+  if (q.aux) {
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph)
+#pragma unroll
+      for (int c = 0; c < CO; ++c)
+        q.aux[(((size_t)n * CO + c) * H2 + (2 * a + (ph >> 1))) * W2 + 2 * b + (ph & 1)] = t[ph][c];
+  }
+  if (q.out) {
+#pragma unroll
+    for (int py = 0; py < 2; ++py) {
+      // two adjacent pixels = 2 * CO contiguous bytes, 2-byte aligned (2 b * CO is even)
+      uint16_t *row = reinterpret_cast<uint16_t *>(
+          q.out + (((size_t)n * H2 + (2 * a + py)) * W2 + 2 * b) * CO);
+      uint8_t v[2 * CO];
+#pragma unroll
+      for (int c = 0; c < CO; ++c) {
+        v[c] = to_u8_trunc(t[py * 2][c]);
+        v[CO + c] = to_u8_trunc(t[py * 2 + 1][c]);
+      }
+#pragma unroll
+      for (int k = 0; k < CO; ++k) row[k] = (uint16_t)(v[2 * k] | ((uint16_t)v[2 * k + 1] << 8));
+    }
+  }
 }
 
 // ------------------------------------------------------------ host helpers
@@ -1063,6 +1303,16 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
     }
   }
   budget -= q_bytes;
+  // projection fusion: the staged tile and the projection weights live behind the rings
+  const bool proj = d->proj != nullptr;
+  if (proj) {
+    CAE_CHECK(convt2 && p.n_pass == 2 && p.mt == 1 && p.N == kProjK && d->c_out == kProjK, 2,
+              "cae_conv_igemm(proj): needs ConvTranspose2d stride 2 with %d output channels", kProjK);
+    CAE_CHECK(d->proj->weights && d->proj->proj, 2, "cae_conv_igemm(proj): null pointer");
+    CAE_CHECK(!d->skip.ptr && !d->quant && !d->aux_out, 2,
+              "cae_conv_igemm(proj): no skip / quantizer / aux output on a projected layer");
+    budget -= kProjStageBytes + kProjWBytes;
+  }
   p.b_tap_bytes = p.N * p.ck * 2;
   int pass_ntaps[2] = {p.n_taps, 0};
   p.pass_tap0[0] = p.pass_tap0[1] = 0;
@@ -1131,7 +1381,8 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   }
   p.sa = sa;
   p.sb = sb;
-  const int smem_bytes = sa * p.a_stage_bytes + sb * p.b_stage_bytes + 1024 + q_bytes;
+  const int smem_bytes = sa * p.a_stage_bytes + sb * p.b_stage_bytes + 1024 + q_bytes +
+                         (proj ? kProjStageBytes + kProjWBytes : 0);
   p.q_smem = q_bytes > 0;
   if (cae_knob(CAE_KNOB_IGEMM_VERBOSE))
     fprintf(stderr, "cae_conv_igemm: kind %d %d->%d @%dx%d N=%d ck=%d mt=%d n_pass=%d n_acc=%d n_buf=%d "
@@ -1152,7 +1403,12 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   p.bias = d->bias;
   p.aux = (float *)d->aux_out;
   int epi;
-  if (merged) {
+  if (proj) {
+    epi = EPI_PROJ;
+    p.proj_w = (const uint8_t *)d->proj->weights;
+    p.proj_out = (__half *)d->proj->proj;
+    p.idesc2 = make_idesc_f16(128, kProjN);
+  } else if (merged) {
     epi = EPI_IMAGE;
     CAE_CHECK(d->out.fmt == CAE_FMT_U8_HWC || d->out.fmt == CAE_FMT_NONE, 2,
               "cae_conv_igemm: final layer writes U8_HWC (and/or aux fp32)");
@@ -1195,7 +1451,7 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
       CAE_CHECK(p.out_h % 2 == 0 && p.out_w % 2 == 0, 2, "cae_conv_igemm: split output needs even size");
     p.out.ptr = d->out.ptr;
   }
-  p.out.fmt = d->out.fmt;
+  p.out.fmt = proj ? CAE_FMT_NONE : d->out.fmt;
   p.out.planes = d->out.planes;
   p.out.halo = d->out.halo;
   p.out.H = p.out_h;
@@ -1272,8 +1528,10 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   if (epi == EPI_ACT && !cae_knob(CAE_KNOB_IGEMM_NO_FAST_EPILOGUE)) fast = p.skip.ptr ? 2 : 1;
   if (!cae_knob(CAE_KNOB_IGEMM_EPI_WARPS)) p.epi_warps = fast == 1 ? 16 : ((fast == 2 || p.quant) ? 12 : 8);
   if (fast != 1 && p.epi_warps > kMaxEpiWarps) p.epi_warps = kMaxEpiWarps;
-  const int threads = 128 + 32 * p.epi_warps;
+  if (proj) p.epi_warps = 16;
+  const int threads = 128 + 32 * p.epi_warps + (proj ? 32 : 0);    // + the projection-GEMM warp
   void (*kern)(const CUtensorMap, const IgParams) =
+      epi == EPI_PROJ ? igemm_conv_kernel<EPI_PROJ, 1> :
       epi == EPI_ACT ? (fast == 1 ? igemm_conv_kernel<EPI_ACT, 1>
                                   : (fast == 2 ? igemm_conv_kernel<EPI_ACT, 2>
                                                : igemm_conv_kernel<EPI_ACT, 0>))
@@ -1282,6 +1540,49 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   static_assert(sizeof(IgParams) + sizeof(CUtensorMap) <= 4096, "kernel parameters exceed 4 KB");
   CAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   kern<<<grid, threads, smem_bytes, (cudaStream_t)stream>>>(tm, p);
+  cae_count_launch();
+  CAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------- projection fusion
+extern "C" size_t cae_proj_weight_bytes(void) { return (size_t)kProjWBytes; }
+
+extern "C" size_t cae_proj_bytes(int n, int h, int w) {
+  return (size_t)n * h * w * kProjN * sizeof(__half);
+}
+
+extern "C" int cae_pack_proj_weights(int c_in, int c_out, const float *w, const float *scale,
+                                     void *packed, void *stream) {
+  CAE_CHECK(c_in == kProjK && c_out >= 1 && c_out <= 3, 2,
+            "cae_pack_proj_weights: needs c_in = %d and c_out <= 3 (got %d -> %d)", kProjK, c_in, c_out);
+  CAE_CHECK(w && packed, 2, "cae_pack_proj_weights: null pointer");
+  pack_proj_kernel<<<(kProjK * kProjN + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      w, scale, c_out, (__half *)packed);
+  cae_count_launch();
+  CAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int cae_image_from_proj(const void *proj, int n, int h, int w, int c_out,
+                                   const float *bias, int pre_act, int post_act, void *out_u8,
+                                   float *aux, void *stream) {
+  CAE_CHECK(proj && (out_u8 || aux), 2, "cae_image_from_proj: null pointer");
+  CAE_CHECK(n > 0 && h > 0 && w > 0 && c_out >= 1 && c_out <= 3, 2, "cae_image_from_proj: bad shape");
+  CAE_CHECK(n <= 65535 && (h + 7) / 8 <= 65535, 2, "cae_image_from_proj: batch too large for one grid");
+  ProjGatherParams q;
+  q.proj = (const uint4 *)proj;
+  q.n = n; q.h = h; q.w = w; q.c_out = c_out;
+  q.bias = bias;
+  q.pre_s = pre_act == CAE_ACT_LEAKY_RELU ? 0.01f : (pre_act == CAE_ACT_RELU ? 0.f : 1.f);
+  q.post_s = post_act == CAE_ACT_LEAKY_RELU ? 0.01f : (post_act == CAE_ACT_RELU ? 0.f : 1.f);
+  q.out = (uint8_t *)out_u8;
+  q.aux = aux;
+  const dim3 grid((unsigned)((w + 31) / 32), (unsigned)((h + 7) / 8), (unsigned)n);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c_out == 1) image_from_proj_kernel<1><<<grid, 256, 0, st>>>(q);
+  else if (c_out == 2) image_from_proj_kernel<2><<<grid, 256, 0, st>>>(q);
+  else image_from_proj_kernel<3><<<grid, 256, 0, st>>>(q);
   cae_count_launch();
   CAE_CUDA(cudaGetLastError());
   return 0;

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CAE_ABI_VERSION 3
+#define CAE_ABI_VERSION 4
 
 /* ---- tensor formats ------------------------------------------------------ */
 enum {
@@ -93,6 +93,8 @@ typedef struct {
                               weights stay in torch layout (c_out, c_in/groups, 3, 3) resp.
                               (c_in, c_out/groups, 3, 3)                                 */
   int32_t reserved;
+  const struct cae_proj_fuse *proj;   /* igemm, CAE_CONVT_S2 with 128 output channels only: the
+                                         image layer that follows is folded in (below), or NULL */
 } cae_conv_desc;
 
 /* ---- library ------------------------------------------------------------- */
@@ -151,6 +153,27 @@ typedef struct cae_head_desc {
   int32_t reserved;
 } cae_head_desc;
 int cae_conv_head(const cae_head_desc *d, void *stream);
+
+/* Projection fusion of the last two synthesis layers (Synthesizer.forward R:442-455: the last
+ * UpsamplingUnit's ConvTranspose2d(128, 128, k3 s2) -> act, then the image layer
+ * ConvTranspose2d(128, c, k3 s2), c <= 3).  The image layer is linear in the 128-channel tensor U
+ * between them, so the wide layer's epilogue multiplies each pixel of U with the image layer's
+ * nine 128 x c tap matrices on the tensor cores and writes those 9 * c products (a 32 x fp16
+ * record per pixel of U, `proj`: n x 2h x 2w x 32) instead of U itself (128 x fp16 per pixel);
+ * cae_image_from_proj then adds the up to four records that meet in each output pixel, applies
+ * bias / activations and writes the uint8 HWC image (truncating cast, R:577-578) and / or the
+ * fp32 NCHW tensor.  U never reaches HBM.  h, w of cae_image_from_proj / cae_proj_bytes are the
+ * size of U (twice the wide layer's input).  `scale` as in cae_pack_weights.                  */
+typedef struct cae_proj_fuse {
+  const void *weights;   /* cae_pack_proj_weights: cae_proj_weight_bytes() bytes */
+  void *proj;            /* cae_proj_bytes(n, 2 * h_in, 2 * w_in) bytes          */
+} cae_proj_fuse;
+size_t cae_proj_weight_bytes(void);
+size_t cae_proj_bytes(int n, int h, int w);
+int cae_pack_proj_weights(int c_in, int c_out, const float *w /* (c_in, c_out, 3, 3) */,
+                          const float *scale, void *packed, void *stream);
+int cae_image_from_proj(const void *proj, int n, int h, int w, int c_out, const float *bias,
+                        int pre_act, int post_act, void *out_u8, float *aux_nchw, void *stream);
 
 /* ---- GDN / IGDN ---------------------------------------------------------- */
 /* compressai.layers.GDN forward as used by _define_act_layer (R:29-30):

@@ -23,7 +23,7 @@ def test_library_exports_every_symbol():
     lib = ctypes.CDLL(C.LIB_PATH)
     for name in _declared():
         assert hasattr(lib, name), name
-    assert C.lib().cae_abi_version() == C.ABI_VERSION == 3
+    assert C.lib().cae_abi_version() == C.ABI_VERSION == 4
 
 
 def test_struct_layout_matches_header(tmp_path):

@@ -482,6 +482,39 @@ def test_fused_head_matches_the_two_kernel_path(shape, c_org):
     assert torch.allclose(y_fused, y_plain, atol=1e-2, rtol=1e-2)
 
 
+@pytest.mark.parametrize('shape,c_org', [((2, 8, 8), 3), ((3, 16, 24), 3), ((1, 20, 12), 3),
+                                         ((2, 7, 5), 1), ((2, 32, 32), 2)])
+def test_projection_fusion_matches_the_two_kernel_path(shape, c_org):
+    """cae_conv_desc.proj (the last 128-channel transposed layer projected onto the image
+    layer's taps in its epilogue + cae_image_from_proj) against the two tensor-core layers run
+    one after the other, and against the oracle.  shape = latent n x h x w (image 8x larger)."""
+    from oracle import cae_oracle as O
+    arch = dict(O.NAMED_ARCHS['A'], channels_org=c_org)
+    chk = O.make_checkpoint(arch, seed=31)
+    model = _model(chk)
+    n, h, w = shape
+    g = torch.Generator().manual_seed(3)
+    y_q = torch.round(torch.randn(n, arch['channels_bn'], h, w, generator=g) * 3.0)
+    dec = model['decoder']
+    ex = dec.module._executor()
+    last = len(ex.steps) - 1
+    ex.fuse_proj = True
+    x_f, _, u8_f = dec(y_q.cuda(), as_uint8=True)
+    assert ex.last_calls[last][0] == 'image_from_proj'
+    x_f, u8_f = x_f[0].clone(), u8_f.clone()
+    ex.fuse_proj = False
+    x_p, _, u8_p = dec(y_q.cuda(), as_uint8=True)
+    assert ex.last_calls[last][0] != 'image_from_proj'
+    ex.fuse_proj = True
+    ref = O.OracleModel(chk).decoder(y_q)[0][0]
+    # the records are fp16: one extra rounding of each of the up to four partial sums
+    assert torch.allclose(x_f, x_p[0], atol=2e-3, rtol=2e-3), (x_f - x_p[0]).abs().max()
+    assert torch.allclose(x_f.cpu(), ref, atol=4e-3, rtol=1e-2), (x_f.cpu() - ref).abs().max()
+    assert np.array_equal(u8_f.cpu().numpy(), _to_u8(x_f))
+    d = (u8_f.int() - u8_p.int()).abs()
+    assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 0.05
+
+
 def test_training_mode_bottleneck_kernels_match_autograd():
     """``cae_eb_train_fwd`` / ``cae_eb_train_bwd`` against the same model written with torch
     autograd ops (CompressAI's formulation): outputs, d/dy and the gradient of

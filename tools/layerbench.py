@@ -93,13 +93,18 @@ def main():
                     print(f'  {name[:3]}{k}+{k + 1} fused head {st.c_in}->{st.c_in}->{call[1][5]} '
                           f'@{xin.h}x{xin.w} {ms * 1e3:9.1f} us')
                     continue
+                if call[0] == 'image_from_proj':
+                    print(f'  {name[:3]}{k} image_from_proj {call[1][4]} ch @{call[1][2]}x{call[1][3]} '
+                          f'{ms * 1e3:9.1f} us')
+                    continue
                 xin = call[0][1]
                 flops = 2.0 * 9 * st.c_in * st.c_out * xin.n * xin.h * xin.w
                 if st.kind == C.CONV_S2:
                     flops /= 4
                 print(f'  {name[:3]}{k} {KIND[st.kind]:9s} {st.c_in:4d}->{st.c_out:4d} @{xin.h}x{xin.w} '
                       f'{"igemm" if call[1]["igemm"] else "direct":6s} {ms * 1e3:9.1f} us '
-                      f'{flops / ms / 1e9:8.1f} TFLOP/s{" +skip" if call[1].get("skip") is not None else ""}')
+                      f'{flops / ms / 1e9:8.1f} TFLOP/s{" +skip" if call[1].get("skip") is not None else ""}'
+                      f'{" +proj" if call[1].get("proj") is not None else ""}')
         print(f'  sum of conv layers {total * 1e3:.1f} us')
 
 
