@@ -24,7 +24,7 @@ int cae_sm_count();   // SMs of the current device (cached per device)
   X(IGEMM_ONE_PASS) X(IGEMM_MT) X(IGEMM_SWAP_LBO_SBO) X(QUANT_NO_SMEM) X(IGEMM_TPB)           \
   X(IGEMM_VERBOSE) X(QUANT_NO_HIST) X(QUANT_NO_RATE) X(QUANT_NO_YQ) X(IGEMM_DEBUG)            \
   X(IGEMM_NO_PAIR_STORE) X(IGEMM_EPI_WARPS) X(IGEMM_NO_FAST_EPILOGUE) X(IGEMM_NO_TMA_STORE)   \
-  X(IGEMM_NO_PAIR_MMA) X(RANS_V1) X(RANS_V2)
+  X(IGEMM_PAIR_MMA) X(IGEMM_CK_PAIR) X(IGEMM_NO_RESIDENT) X(RANS_V1) X(RANS_V2)
 enum CaeKnob {
 #define X(n) CAE_KNOB_##n,
   CAE_KNOB_LIST(X)
@@ -183,6 +183,20 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap *map, uint64_t *ba
       : "memory");
 }
 
+// The same load issued by either CTA of a pair, completing on an mbarrier of the LEADER CTA
+// (`bar_cluster` = its shared::cluster address, mapa_u32): the leader waits on one barrier for
+// the patches of both CTAs.
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap *map, uint32_t bar_cluster,
+                                                 void *dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"((uint64_t)map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3)
+      : "memory");
+}
+
 // TMA: 1-D bulk copy global -> shared (bytes multiple of 16, 16-byte aligned).
 __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes,
                                              uint64_t *bar) {
@@ -278,6 +292,132 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- CTA pairs (cta_group::2): one MMA instruction drives the tensor cores of both SMs of a
+// cluster of two; each CTA supplies its own 128 rows of A and HALF of the rows of B, the
+// accumulator rows of a CTA's tile land in its own TMEM.  PAIR is a template parameter because
+// every tcgen05 instruction of a kernel must name the same cta_group.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::
+                   : "memory");
+}
+
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+
+// wait on a local barrier whose arrivals come from the peer CTA (cluster-scope acquire)
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+static __device__ __noinline__ void mbar_wait_cluster_slow(uint64_t *bar, uint32_t parity) {
+  const uint64_t t0 = global_timer_ns();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (global_timer_ns() - t0 > 4000000000ull) {
+      printf("cae_b200: cluster mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
+             (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+  if (!mbar_try_wait_cluster(bar, parity)) mbar_wait_cluster_slow(bar, parity);
+}
+
+template <int PAIR>
+__device__ __forceinline__ void tmem_alloc_g(uint32_t *dst_smem, uint32_t ncols) {
+  if (PAIR) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  } else {
+    tmem_alloc(dst_smem, ncols);
+  }
+}
+
+template <int PAIR>
+__device__ __forceinline__ void tmem_dealloc_g(uint32_t taddr, uint32_t ncols) {
+  if (PAIR)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+                 : "memory");
+  else
+    tmem_dealloc(taddr, ncols);
+}
+
+template <int PAIR>
+__device__ __forceinline__ void umma_f16_lohi_g(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi,
+                                                uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                uint32_t accumulate) {
+  if (PAIR) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+        :
+        : "r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    umma_f16_lohi(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+  }
+}
+
+template <int PAIR>
+__device__ __forceinline__ void umma_f16_g(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                           uint32_t idesc, uint32_t accumulate) {
+  if (PAIR) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    umma_f16(tmem_d, desc_a, desc_b, idesc, accumulate);
+  }
+}
+
+// PAIR: the arrival is multicast to the barrier at this offset in BOTH CTAs of the pair
+template <int PAIR>
+__device__ __forceinline__ void umma_commit_g(uint64_t *bar) {
+  if (PAIR) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+        "[%0], %1;" ::"r"(smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+  } else {
+    umma_commit(bar);
+  }
 }
 
 // Shared-memory matrix descriptor, K-major, no swizzle ("interleave") layout:

@@ -103,6 +103,11 @@ struct IgParams {
   uint32_t lbo_a, sbo_a, lbo_b, sbo_b, idesc;
   IgTap taps[kMaxTaps];
   const uint8_t *wpack;
+  size_t wpack_half_bytes;   // PAIR: bytes of one rank's half of the packed weights
+  // resident: the CTA's whole share of the weights is loaded once and stays in shared memory
+  // (one "stage" of all chunks; b_chunk16 = 16-byte units per channel chunk)
+  int resident;
+  uint32_t b_chunk16;
   // epilogue
   int up;  // 1, or 2 for the pixel-shuffling transposed stride-2 layers
   int c_out, pre_act, post_act;
@@ -174,7 +179,30 @@ inline int mma_n(int kind, int c_out) {
   return is_merged(kind, c_out) ? 16 : round_up(c_out, 16);
 }
 
-inline int auto_ck(int kind, int c_in_p, bool merged = false) {
+// CTA-pair (cta_group::2) form: the 128-output-channel layers, whose weight stream is what
+// bounds the single-CTA kernel.  Decided from the layer alone, so that the packer (which lays
+// the weights out as two halves of output channels) and the launcher agree.
+//
+// Measured on B200 (net A, 128 x 256^2, round 2, gpurun_out/r2_layer_pair*.log): correct, but not
+// faster -- conv s1 128->128 447 us either way (that layer is bound by the 64-cycle N = 128
+// instruction and the power-limited clock, not by L2 or shared-memory bandwidth), the stride-2
+// layers lose 12-40 % (their activation ring next to 144 KB of resident weights is too shallow
+// for the L2 latency, and every accumulator hand-over crosses the cluster).  Hence opt-in:
+// CAE_DEBUG=1 CAE_IGEMM_PAIR_MMA=1.
+inline bool use_pair(int kind, int c_out) {
+  return !is_merged(kind, c_out) && mma_n(kind, c_out) == 128 && cae_knob(CAE_KNOB_IGEMM_PAIR_MMA);
+}
+
+inline int auto_ck(int kind, int c_in_p, bool merged = false, bool pair = false) {
+  if (pair && c_in_p % 32 == 0) {
+    // CTA-pair layers keep their share of the weights resident (up to 144 KB); the chunk size
+    // then only sets the size of an activation stage: three or more must fit beside the weights
+    if (const char *e = cae_knob(CAE_KNOB_IGEMM_CK_PAIR)) {
+      const int v = atoi(e);
+      if ((v == 16 || v == 32 || v == 64) && c_in_p % v == 0) return v;
+    }
+    return kind == CAE_CONV_S2 ? 16 : (kind == CAE_CONVT_S2 ? 64 : 32);
+  }
   // final image layer (N = 16): the MMAs are tiny and the layer is bound by the barrier round
   // trips per stage, so take the whole K = 128 in one stage
   if (merged && c_in_p % 128 == 0 && !cae_knob(CAE_KNOB_IGEMM_MERGED_CK64)) return 128;
@@ -193,11 +221,12 @@ inline int auto_ck(int kind, int c_in_p, bool merged = false) {
 
 // ---------------------------------------------------------------- packing
 struct PackParams {
-  int kind, merged, c_in, c_out, ck, N, n_taps, n_chunks;
+  int kind, merged, c_in, c_out, ck, N, n_taps, n_chunks, pair;
   TapDef taps[kMaxTaps];
 };
 
-// packed[chunk][tap][kplane][n][8]: the shared-memory image of operand B.
+// packed[chunk][tap][kplane][n][8]: the shared-memory image of operand B.  pair: two such
+// images back to back, [rank][chunk][tap][kplane][n - rank * N / 2][8], one per CTA of a pair.
 __global__ void pack_weights_kernel(PackParams q, const float *__restrict__ w,
                                     const float *__restrict__ scale, __half *__restrict__ out,
                                     size_t total) {
@@ -228,7 +257,13 @@ __global__ void pack_weights_kernel(PackParams q, const float *__restrict__ w,
     v = w[idx];
     if (scale) v *= scale[co];
   }
-  out[i] = __float2half_rn(v);
+  size_t o = i;
+  if (q.pair) {
+    const int half = q.N >> 1, r = n / half, nl = n - r * half;
+    o = (size_t)r * (total >> 1) +
+        ((((size_t)chunk * q.n_taps + t) * (q.ck / 8) + kplane) * half + nl) * 8 + k8;
+  }
+  out[o] = __float2half_rn(v);
 }
 
 // --------------------------------------------------------------- epilogues
@@ -667,17 +702,28 @@ __device__ __forceinline__ void epilogue_job(const IgParams &p, uint32_t tmem_la
 }
 
 // ------------------------------------------------------------------ kernel
-template <int EPI, int FAST>
+template <int EPI, int FAST, int PAIR>
 __global__ void __launch_bounds__(EPI == EPI_PROJ ? 128 + 32 * 17 : (FAST == 1 ? 128 + 32 * 16 : kThreads), 1)
 igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ IgParams p) {
+  // PAIR: a cluster of two CTAs works on two tiles at a time with cta_group::2 MMAs (M = 256):
+  // each CTA loads its own activation patch and only HALF of every weight stage (N / 2 rows of
+  // B), which halves the L2 -> SM weight traffic per MMA -- the bound of the single-CTA form
+  // (~2.6 KB per 128x128x16 MMA against ~43 B/clk/SM of L2 bandwidth) -- and the issue count.
+  // The leader (rank 0) issues; the peer's idle issuing warps relay its full barriers.
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[kMaxSA], a_empty[kMaxSA];
   __shared__ __align__(8) uint64_t b_full[kMaxSB], b_empty[kMaxSB];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t b_peer[kMaxSB];   // PAIR: the peer's weight stages landed
   __shared__ __align__(8) uint64_t u_full, u_free, d2_full;   // EPI_PROJ
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  // work units (tile, pass) are walked by clusters; rank r of a pair takes tile 2 * pairtile + r
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_units = (PAIR ? (p.n_tiles + 1) >> 1 : p.n_tiles) * p.n_pass;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
   uint8_t *smem_a = smem;
@@ -710,10 +756,13 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 2);
-      mbar_init(&acc_empty[i], (uint32_t)p.epi_warps);
+      mbar_init(&acc_empty[i], (uint32_t)p.epi_warps * (PAIR ? 2u : 1u));
+    }
+    if (PAIR) {
+      for (int i = 0; i < p.sb; ++i) mbar_init(&b_peer[i], 1);
     }
     if (EPI == EPI_PROJ) {
-      mbar_init(&u_full, (uint32_t)p.epi_warps);
+      mbar_init(&u_full, (uint32_t)p.epi_warps * (PAIR ? 2u : 1u));
       mbar_init(&u_free, 1);
       mbar_init(&d2_full, 1);
     }
@@ -723,15 +772,18 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t *u_stage = smem_b + (size_t)p.sb * p.b_stage_bytes;
   uint8_t *proj_w_s = u_stage + kProjStageBytes;
   if (EPI == EPI_PROJ) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(p.proj_w);
+    // PAIR: rows [16 r, 16 r + 16) of V, from the pair-ordered copy behind the full one
+    const uint4 *src = reinterpret_cast<const uint4 *>(
+        p.proj_w + (PAIR ? kProjWBytes + rank * (kProjWBytes / 2) : 0));
     uint4 *dst = reinterpret_cast<uint4 *>(proj_w_s);
-    for (int i = threadIdx.x; i < kProjWBytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < kProjWBytes / 16 / (PAIR ? 2 : 1); i += blockDim.x)
+      dst[i] = __ldg(src + i);
     fence_proxy_async();       // read by the tensor cores (async proxy) below
   }
-  if (warp == 3) tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
+  if (warp == 3) tmem_alloc_g<PAIR>(&tmem_base_s, (uint32_t)p.tmem_cols);
   if (warp == 0 && lane == 0) prefetch_tensormap(&tmA);
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
@@ -739,14 +791,25 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===== activation patches: TMA box loads =====
     if (lane == 0) {
       uint32_t it = 0;
-      for (int vt = blockIdx.x; vt < p.n_tiles * p.n_pass; vt += gridDim.x) {
-        const int tile = vt / p.n_pass;
+      for (int vt = unit0; vt < n_units; vt += unit_step) {
+        // (a pair's tile beyond the last one reads outside the tensor: zero fill, full byte count)
+        const int tile = PAIR ? (vt / p.n_pass) * 2 + (int)rank : vt / p.n_pass;
         const int n = tile / p.tiles_per_img, rem = tile - n * p.tiles_per_img;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         const int y0 = ty * 16 + p.org_y, x0 = tx * 8 * p.mt + p.org_x;
         for (int ch = 0; ch < p.n_chunks; ++ch, ++it) {
           const int s = it % p.sa;
           mbar_wait(&a_empty[s], ((it / p.sa) & 1) ^ 1);
+          if (PAIR) {
+            // both patches complete on the leader's barrier, which expects the bytes of both
+            if (rank == 0) mbar_expect_tx(&a_full[s], 2u * (uint32_t)(p.n_par * p.a_box_bytes));
+            const uint32_t bar = mapa_u32(smem_u32(&a_full[s]), 0);
+            for (int par = 0; par < p.n_par; ++par)
+              tma_load_4d_pair(&tmA, bar,
+                               smem_a + (size_t)s * p.a_stage_bytes + (size_t)par * p.par_stride,
+                               x0 * 8, y0, ch * (p.ck >> 3), n * p.n_par + par);
+            continue;
+          }
           if (p.debug & 1) { mbar_arrive(&a_full[s]); continue; }
           mbar_expect_tx(&a_full[s], (uint32_t)(p.n_par * p.a_box_bytes));
           for (int par = 0; par < p.n_par; ++par)
@@ -760,7 +823,15 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===== packed weights: 1-D bulk copies =====
     if (lane == 0) {
       uint32_t it = 0;
-      for (int vt = blockIdx.x; vt < p.n_tiles * p.n_pass; vt += gridDim.x) {
+      // PAIR: rank r streams rows [r * N / 2, (r + 1) * N / 2) of B (the second half of wpack)
+      const uint8_t *wsrc = p.wpack + (size_t)rank * p.wpack_half_bytes;
+      if (p.resident) {
+        mbar_expect_tx(&b_full[0], (uint32_t)p.b_stage_bytes);
+        for (int k = 0; k < p.n_chunks * p.n_taps; ++k)
+          bulk_load_1d(smem_b + (size_t)k * p.b_tap_bytes, wsrc + (size_t)k * p.b_tap_bytes,
+                       (uint32_t)p.b_tap_bytes, &b_full[0]);
+      }
+      for (int vt = unit0; vt < n_units && !p.resident; vt += unit_step) {
         const int pass = vt % p.n_pass;
         for (int ch = 0; ch < p.n_chunks; ++ch) {
           for (int st = 0; st < p.n_stages[pass]; ++st, ++it) {
@@ -769,15 +840,33 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (p.debug & 2) { mbar_arrive(&b_full[s]); continue; }
             mbar_expect_tx(&b_full[s], (uint32_t)p.b_stage_bytes);
             bulk_load_1d(smem_b + (size_t)s * p.b_stage_bytes,
-                         p.wpack + (size_t)(ch * p.n_taps + p.pass_tap0[pass] + st * p.tpb) *
-                                       p.b_tap_bytes,
+                         wsrc + (size_t)(ch * p.n_taps + p.pass_tap0[pass] + st * p.tpb) *
+                                    p.b_tap_bytes,
                          (uint32_t)p.b_stage_bytes, &b_full[s]);
           }
         }
       }
     }
   }
-  if (warp == 2 || warp == 3) {
+  if (PAIR && rank != 0 && (warp == 2 || warp == 3)) {
+    // ===== peer CTA: its issuing warps are idle; warp 3 relays "weights landed" to the leader
+    // (the activation patches complete on the leader's barrier by themselves) =====
+    if (warp == 3 && lane == 0) {
+      if (p.resident) {
+        mbar_wait(&b_full[0], 0);
+        mbar_arrive_cluster(mapa_u32(smem_u32(&b_peer[0]), 0));
+      }
+      uint32_t it = 0;
+      for (int vt = unit0; vt < n_units && !p.resident; vt += unit_step) {
+        const int pass = vt % p.n_pass;
+        for (int k = 0; k < p.n_chunks * p.n_stages[pass]; ++k, ++it) {
+          const int s = it % p.sb;
+          mbar_wait(&b_full[s], (it / p.sb) & 1);
+          mbar_arrive_cluster(mapa_u32(smem_u32(&b_peer[s]), 0));
+        }
+      }
+    }
+  } else if (warp == 2 || warp == 3) {
     // ===== MMA issue: two issuing warps =====
     // tcgen05.mma is issued by one thread, and with M=128,N<=128 tiles an instruction only
     // covers 64 tensor-pipe cycles, so issue cost bounds the pipe.  Hence: (1) warps 2 and 3
@@ -806,21 +895,31 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t j = 0;
     int sA = 0, sB = 0;
     uint32_t phA = 0, phB = 0;
-    for (int vt = blockIdx.x; vt < p.n_tiles * p.n_pass; vt += gridDim.x, ++j) {
+    const bool resident = p.resident != 0;
+    if (resident) {
+      mbar_wait(&b_full[0], 0);
+      if (PAIR) mbar_wait_cluster(&b_peer[0], 0);
+    }
+    for (int vt = unit0; vt < n_units; vt += unit_step, ++j) {
       const int pass = vt % p.n_pass;
       const int n_stages = p.n_stages[pass];
       const int buf = j % p.n_buf;
-      mbar_wait(&acc_empty[buf], ((j / p.n_buf) & 1) ^ 1);
+      if (PAIR) mbar_wait_cluster(&acc_empty[buf], ((j / p.n_buf) & 1) ^ 1);
+      else mbar_wait(&acc_empty[buf], ((j / p.n_buf) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_buf = tmem_base + (uint32_t)buf * buf_cols;
       for (int ch = 0; ch < p.n_chunks; ++ch) {
-        mbar_wait(&a_full[sA], phA);
+        if (PAIR) mbar_wait_cluster(&a_full[sA], phA); else mbar_wait(&a_full[sA], phA);
         const uint32_t a_stage = ((sa_base + (uint32_t)sA * a_stage16) & 0x3FFFu) | a_lbo;
         const uint32_t later = ch > 0 ? 1u : 0u;
         for (int st = 0; st < n_stages; ++st) {
-          mbar_wait(&b_full[sB], phB);
+          if (!resident) {
+            mbar_wait(&b_full[sB], phB);
+            if (PAIR) mbar_wait_cluster(&b_peer[sB], phB);
+          }
           tc_fence_after();
-          const uint32_t b_stage = ((sb_base + (uint32_t)sB * b_stage16) & 0x3FFFu) | b_lbo;
+          const uint32_t b_stage =
+              ((sb_base + (resident ? (uint32_t)ch * p.b_chunk16 : (uint32_t)sB * b_stage16)) & 0x3FFFu) | b_lbo;
           const int i1 = p.item_start[pass][issuer][st + 1];
           for (int i = p.item_start[pass][issuer][st]; i < i1; ++i) {
             const IgItem it = p.items[pass][issuer][i];
@@ -830,7 +929,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (leader && !no_mma) {
 #pragma unroll 4
               for (int k = 0; k < ksteps; ++k) {
-                umma_f16_lohi(d, a_lo, a_hi, b_lo, b_hi, idesc, flag);
+                umma_f16_lohi_g<PAIR>(d, a_lo, a_hi, b_lo, b_hi, idesc, flag);
                 a_lo += a_kstep;
                 b_lo += b_kstep;
                 flag = 1u;
@@ -838,11 +937,11 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
           if (leader) {
-            umma_commit(&b_empty[sB]);
-            if (st == n_stages - 1) umma_commit(&a_empty[sA]);
-            if (st == n_stages - 1 && ch == p.n_chunks - 1) umma_commit(&acc_full[buf]);
+            if (!resident) umma_commit_g<PAIR>(&b_empty[sB]);
+            if (st == n_stages - 1) umma_commit_g<PAIR>(&a_empty[sA]);
+            if (st == n_stages - 1 && ch == p.n_chunks - 1) umma_commit_g<PAIR>(&acc_full[buf]);
           }
-          if (++sB == p.sb) { sB = 0; phB ^= 1u; }
+          if (!resident && ++sB == p.sb) { sB = 0; phB ^= 1u; }
         }
         if (++sA == p.sa) { sA = 0; phA ^= 1u; }
       }
@@ -862,12 +961,17 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const float pre_s = act_slope(p.pre_act), post_s = act_slope(p.post_act);
     float q_bits = 0.f;
     uint32_t j = 0;
-    for (int vt = blockIdx.x; vt < p.n_tiles * p.n_pass; vt += gridDim.x, ++j) {
-      const int tile = vt / p.n_pass, pass = vt - tile * p.n_pass;
+    const uint32_t u_full_addr = PAIR ? mapa_u32(smem_u32(&u_full), 0) : smem_u32(&u_full);
+    const uint32_t acc_empty_addr0 = PAIR ? mapa_u32(smem_u32(&acc_empty[0]), 0) : 0u;
+    const uint32_t acc_empty_addr1 = PAIR ? mapa_u32(smem_u32(&acc_empty[1]), 0) : 0u;
+    for (int vt = unit0; vt < n_units; vt += unit_step, ++j) {
+      const int pass = vt % p.n_pass;
+      const int tile = PAIR ? (vt / p.n_pass) * 2 + (int)rank : vt / p.n_pass;
       const int n = tile / p.tiles_per_img, rem = tile - n * p.tiles_per_img;
       const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
       const int buf = j % p.n_buf;
-      const int y = tyi * 16 + ty;
+      // rows past the image (and the whole tile past the last one of an odd count) are not stored
+      const int y = tile < p.n_tiles ? tyi * 16 + ty : p.dom_h;
       if (FAST == 2 && p.up == 1 && (txl == 0 || txl == 7) && y < p.dom_h && !(p.debug & 64)) {
         // pull this warp's share of the residual tile into L2 while the MMAs still run: 8
         // pixels x 16 B per plane row, so the first and last lane of a row cover its lines
@@ -912,7 +1016,9 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         fence_proxy_async();                           // generic-proxy writes -> UMMA reads
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&u_full);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(u_full_addr); else mbar_arrive(&u_full);
+        }
         // E2: the projected tile (block = px, TMEM lane = input pixel) from the first 64 columns
         // of the drained buffer -> HBM, one 32-byte sector per thread and unit
         mbar_wait(&d2_full, j & 1u);
@@ -943,7 +1049,9 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(buf ? acc_empty_addr1 : acc_empty_addr0); else mbar_arrive(&acc_empty[buf]);
+      }
         continue;
       }
       for (int job = half; job < n_jobs; job += n_halves) {
@@ -955,13 +1063,15 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(buf ? acc_empty_addr1 : acc_empty_addr0); else mbar_arrive(&acc_empty[buf]);
+      }
     }
     if (EPI == EPI_LATENT && p.quant && p.q_rate) {
       for (int o = 16; o > 0; o >>= 1) q_bits += __shfl_xor_sync(0xffffffffu, q_bits, o);
       if (lane == 0 && q_bits != 0.f) atomicAdd(p.q_rate, (double)q_bits);
     }
-  } else if (EPI == EPI_PROJ && warp == 4 + p.epi_warps) {
+  } else if (EPI == EPI_PROJ && warp == 4 + p.epi_warps && rank == 0) {
     // ===== projection GEMM: P[2 x 128 pixels][32] = U_stage[256 x 128] * V[128 x 32] =====
     // A warp of its own, so the two main issuers never wait for the epilogue; the result goes
     // into the first 64 columns of the accumulator buffer the epilogue has just drained.
@@ -969,8 +1079,9 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t us = smem_u32(u_stage), ws = smem_u32(proj_w_s);
     const uint32_t buf_cols = (uint32_t)(p.mt * p.n_acc * p.N);
     uint32_t j = 0;
-    for (int vt = blockIdx.x; vt < p.n_tiles * p.n_pass; vt += gridDim.x, ++j) {
-      mbar_wait(&u_full, j & 1u);
+    constexpr uint32_t kRowsB = kProjN / (PAIR ? 2 : 1);     // rows of V held by this CTA
+    for (int vt = unit0; vt < n_units; vt += unit_step, ++j) {
+      if (PAIR) mbar_wait_cluster(&u_full, j & 1u); else mbar_wait(&u_full, j & 1u);
       tc_fence_after();
       if (leader) {
         const uint32_t d2 = tmem_base + (j % (uint32_t)p.n_buf) * buf_cols;
@@ -979,19 +1090,19 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int k = 0; k < kProjK / 16; ++k) {
             const uint64_t da = make_smem_desc(us + blk * 2048 + k * 8192, 4096, 128);
-            const uint64_t db = make_smem_desc(ws + k * (2 * kProjN * 16), kProjN * 16, 128);
-            umma_f16(d2 + blk * kProjN, da, db, p.idesc2, k > 0 ? 1u : 0u);
+            const uint64_t db = make_smem_desc(ws + k * (2 * kRowsB * 16), kRowsB * 16, 128);
+            umma_f16_g<PAIR>(d2 + blk * kProjN, da, db, p.idesc2, k > 0 ? 1u : 0u);
           }
         }
-        umma_commit(&u_free);
-        umma_commit(&d2_full);
+        umma_commit_g<PAIR>(&u_free);
+        umma_commit_g<PAIR>(&d2_full);
       }
       __syncwarp();
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   if (EPI == EPI_LATENT && qs.hist) {
     // core bins of this CTA -> the global histogram (same clamping as the direct path)
     const int nh = p.c_out * p.q_core_len, bins = p.qt.hist_bins;
@@ -1005,13 +1116,14 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   }
-  if (warp == 3) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (warp == 3) tmem_dealloc_g<PAIR>(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 // ------------------------------------------------- projection fusion: helpers
 // packed[kplane][n][8] fp16 from the image layer's ConvTranspose2d weight (128, c_out, 3, 3)
 __global__ void pack_proj_kernel(const float *__restrict__ w, const float *__restrict__ scale,
                                  int c_out, __half *__restrict__ out) {
+  // first kProjWBytes: [kplane][n][8]; then the CTA-pair order [rank][kplane][n - 16 rank][8]
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kProjK * kProjN) return;
   const int k8 = i & 7, n = (i >> 3) % kProjN, kplane = i / (8 * kProjN);
@@ -1024,6 +1136,9 @@ __global__ void pack_proj_kernel(const float *__restrict__ w, const float *__res
         v = w[(((size_t)ci * c_out + c) * 3 + kh) * 3 + kw] * (scale ? scale[c] : 1.f);
     }
   out[i] = __float2half_rn(v);
+  const int half = kProjN / 2, r = n / half;
+  out[kProjK * kProjN + r * (kProjK * half) + (kplane * half + (n - r * half)) * 8 + k8] =
+      __float2half_rn(v);
 }
 
 struct ProjGatherParams {
@@ -1146,7 +1261,7 @@ int pow2_cols(int c) {
 // ------------------------------------------------------------------- C ABI
 extern "C" size_t cae_packed_weight_bytes(int kind, int c_in, int c_out, int ck) {
   const int c_in_p = round_up(c_in, 16);
-  if (ck <= 0) ck = auto_ck(kind, c_in_p, is_merged(kind, c_out));
+  if (ck <= 0) ck = auto_ck(kind, c_in_p, is_merged(kind, c_out), use_pair(kind, c_out));
   TapDef taps[kMaxTaps];
   const int n_taps = build_taps(kind, is_merged(kind, c_out), taps);
   return (size_t)(c_in_p / ck) * n_taps * mma_n(kind, c_out) * ck * sizeof(__half);
@@ -1157,7 +1272,7 @@ extern "C" int cae_pack_weights(int kind, int c_in, int c_out, int ck, const flo
   CAE_CHECK(kind >= CAE_CONV_S1 && kind <= CAE_CONVT_S2, 2, "cae_pack_weights: bad kind %d", kind);
   CAE_CHECK(w && packed, 2, "cae_pack_weights: null pointer");
   const int c_in_p = round_up(c_in, 16);
-  if (ck <= 0) ck = auto_ck(kind, c_in_p, is_merged(kind, c_out));
+  if (ck <= 0) ck = auto_ck(kind, c_in_p, is_merged(kind, c_out), use_pair(kind, c_out));
   CAE_CHECK(ck % 16 == 0 && ck <= 128 && c_in_p % ck == 0, 2,
             "cae_pack_weights: ck=%d does not divide padded c_in=%d", ck, c_in_p);
   PackParams q;
@@ -1170,6 +1285,7 @@ extern "C" int cae_pack_weights(int kind, int c_in, int c_out, int ck, const flo
   q.N = mma_n(kind, c_out);
   q.n_taps = build_taps(kind, q.merged, q.taps);
   q.n_chunks = c_in_p / ck;
+  q.pair = use_pair(kind, c_out) ? 1 : 0;
   const size_t total = (size_t)q.n_chunks * q.n_taps * q.N * ck;
   const int threads = 256;
   pack_weights_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0,
@@ -1203,10 +1319,14 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   p.n_img = d->n;
   p.N = mma_n(kind, d->c_out);
   CAE_CHECK(p.N <= 256, 2, "cae_conv_igemm: c_out=%d too large", d->c_out);
-  p.ck = d->ck > 0 ? d->ck : auto_ck(kind, c_in_p, merged);
+  const bool pair = use_pair(kind, d->c_out);
+  p.ck = d->ck > 0 ? d->ck : auto_ck(kind, c_in_p, merged, pair);
   CAE_CHECK(p.ck % 16 == 0 && p.ck <= 128 && c_in_p % p.ck == 0, 2, "cae_conv_igemm: bad ck=%d",
             p.ck);
   p.n_chunks = c_in_p / p.ck;
+  CAE_CHECK(!(pair && d->out.fmt == CAE_FMT_F32_NCHW), 2,
+            "cae_conv_igemm: a 128-channel fp32 latent layer is not covered by the CTA-pair form "
+            "(unset CAE_IGEMM_PAIR_MMA)");
   TapDef taps[kMaxTaps];
   p.n_taps = build_taps(kind, merged, taps);
   // transposed stride-2 (not merged): four phase accumulators of N columns.  When they do not
@@ -1267,13 +1387,13 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   p.a_stage_bytes = round_up(p.par_stride * p.n_par, 128);
   p.lbo_a = (uint32_t)(p.PH * p.PW * 16);
   p.sbo_a = (uint32_t)(p.PW * 16);
-  p.lbo_b = (uint32_t)(p.N * 16);
+  p.lbo_b = (uint32_t)((pair ? p.N / 2 : p.N) * 16);
   p.sbo_b = 128;
   if (cae_knob(CAE_KNOB_IGEMM_SWAP_LBO_SBO)) {  // bring-up knob, see DESIGN.md
     uint32_t t = p.lbo_a; p.lbo_a = p.sbo_a; p.sbo_a = t;
     t = p.lbo_b; p.lbo_b = p.sbo_b; p.sbo_b = t;
   }
-  p.idesc = make_idesc_f16(128, p.N);
+  p.idesc = make_idesc_f16(pair ? 256 : 128, p.N);
   for (int t = 0; t < p.n_taps; ++t) {
     p.taps[t].a_off = (uint32_t)(taps[t].par * p.par_stride + (taps[t].dy * p.PW + taps[t].dx) * 16);
     p.taps[t].acc = (uint32_t)taps[t].acc;
@@ -1313,7 +1433,8 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
               "cae_conv_igemm(proj): no skip / quantizer / aux output on a projected layer");
     budget -= kProjStageBytes + kProjWBytes;
   }
-  p.b_tap_bytes = p.N * p.ck * 2;
+  p.b_tap_bytes = (pair ? p.N / 2 : p.N) * p.ck * 2;     // what ONE CTA holds of a tap
+  p.wpack_half_bytes = (size_t)p.n_chunks * p.n_taps * p.b_tap_bytes;
   int pass_ntaps[2] = {p.n_taps, 0};
   p.pass_tap0[0] = p.pass_tap0[1] = 0;
   if (p.n_pass == 2) {
@@ -1324,21 +1445,31 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   auto divides = [&](int v) {
     return pass_ntaps[0] % v == 0 && (p.n_pass == 1 || pass_ntaps[1] % v == 0);
   };
+  // CTA-pair layers: this CTA's share of ALL weights stays in shared memory when two activation
+  // stages still fit beside it; then there is no weight ring at all
+  const int resident_bytes = p.n_chunks * p.n_taps * p.b_tap_bytes;
+  const bool resident = pair && !cae_knob(CAE_KNOB_IGEMM_NO_RESIDENT) &&
+                        resident_bytes + 2 * p.a_stage_bytes <= budget;
+  p.resident = resident ? 1 : 0;
+  p.b_chunk16 = (uint32_t)((p.n_taps * p.b_tap_bytes) >> 4);
   int tpb = 1;
-  for (int cand = p.n_taps; cand >= 1; --cand) {
+  for (int cand = p.n_taps; cand >= 1 && !resident; --cand) {
     if (!divides(cand)) continue;
     if (2 * p.a_stage_bytes + 2 * cand * p.b_tap_bytes <= budget && cand * p.b_tap_bytes <= 73728) {
       tpb = cand;
       break;
     }
   }
-  if (const char *e = cae_knob(CAE_KNOB_IGEMM_TPB)) {
+  if (const char *e = resident ? nullptr : cae_knob(CAE_KNOB_IGEMM_TPB)) {
     const int v = atoi(e);
     if (v >= 1 && divides(v) && 2 * p.a_stage_bytes + 2 * v * p.b_tap_bytes <= budget) tpb = v;
   }
   p.tpb = tpb;
-  p.b_stage_bytes = tpb * p.b_tap_bytes;
+  p.b_stage_bytes = resident ? resident_bytes : tpb * p.b_tap_bytes;
   for (int ps = 0; ps < p.n_pass; ++ps) {
+    // resident: one "stage" per chunk holding every tap of the pass, offsets inside the chunk
+    if (resident) tpb = pass_ntaps[ps];
+    const int b_tap0 = resident ? p.pass_tap0[ps] : 0;
     p.n_stages[ps] = pass_ntaps[ps] / tpb;
     CAE_CHECK(p.n_stages[ps] <= kMaxStages, 2, "cae_conv_igemm: too many weight stages");
     int cnt[2] = {0, 0};
@@ -1355,7 +1486,7 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
           IgItem &it = p.items[ps][who][cnt[who]++];
           it.a_off16 = (uint32_t)((taps[t].par * p.par_stride + (taps[t].dy * p.PW + taps[t].dx) * 16 +
                                    m * 128) >> 4);
-          it.b_off16 = (uint32_t)((tt * p.b_tap_bytes) >> 4);
+          it.b_off16 = (uint32_t)(((b_tap0 + tt) * p.b_tap_bytes) >> 4);
           it.d_off = (uint32_t)(acc * p.N);
           it.first = (seen >> acc) & 1u ? 0u : 1u;
           seen |= 1u << acc;
@@ -1365,18 +1496,19 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
     p.item_start[ps][0][p.n_stages[ps]] = cnt[0];
     p.item_start[ps][1][p.n_stages[ps]] = cnt[1];
   }
-  int sa = 2, sb = 2;
+  int sa = 2, sb = resident ? 1 : 2;
   CAE_CHECK(sa * p.a_stage_bytes + sb * p.b_stage_bytes <= budget, 2,
             "cae_conv_igemm: tile does not fit shared memory (A %d B %d)", p.a_stage_bytes,
             p.b_stage_bytes);
   for (;;) {
     bool grew = false;
-    if (sb < 3 && sa * p.a_stage_bytes + (sb + 1) * p.b_stage_bytes <= budget) { ++sb; grew = true; }
+    const int sb_max = resident ? 1 : kMaxSB;
+    if (sb < 3 && sb < sb_max && sa * p.a_stage_bytes + (sb + 1) * p.b_stage_bytes <= budget) { ++sb; grew = true; }
     else if (sa < 3 && (sa + 1) * p.a_stage_bytes + sb * p.b_stage_bytes <= budget) { ++sa; grew = true; }
-    else if (sb < 4 && sa * p.a_stage_bytes + (sb + 1) * p.b_stage_bytes <= budget) { ++sb; grew = true; }
+    else if (sb < 4 && sb < sb_max && sa * p.a_stage_bytes + (sb + 1) * p.b_stage_bytes <= budget) { ++sb; grew = true; }
     else if (sa < 4 && (sa + 1) * p.a_stage_bytes + sb * p.b_stage_bytes <= budget) { ++sa; grew = true; }
     else if (sa < kMaxSA && (sa + 1) * p.a_stage_bytes + sb * p.b_stage_bytes <= budget) { ++sa; grew = true; }
-    else if (sb < kMaxSB && sa * p.a_stage_bytes + (sb + 1) * p.b_stage_bytes <= budget) { ++sb; grew = true; }
+    else if (sb < sb_max && sa * p.a_stage_bytes + (sb + 1) * p.b_stage_bytes <= budget) { ++sb; grew = true; }
     if (!grew) break;
   }
   p.sa = sa;
@@ -1384,16 +1516,16 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   const int smem_bytes = sa * p.a_stage_bytes + sb * p.b_stage_bytes + 1024 + q_bytes +
                          (proj ? kProjStageBytes + kProjWBytes : 0);
   p.q_smem = q_bytes > 0;
-  if (cae_knob(CAE_KNOB_IGEMM_VERBOSE))
-    fprintf(stderr, "cae_conv_igemm: kind %d %d->%d @%dx%d N=%d ck=%d mt=%d n_pass=%d n_acc=%d n_buf=%d "
-            "tpb=%d a_stage=%d x%d b_stage=%d x%d smem=%d tiles=%d\n", kind, d->c_in, d->c_out, d->h_in,
-            d->w_in, p.N, p.ck, p.mt, p.n_pass, p.n_acc, p.n_buf, p.tpb, p.a_stage_bytes, sa,
-            p.b_stage_bytes, sb, smem_bytes, p.n_tiles);
-
   p.tiles_x = (p.dom_w + 8 * mt - 1) / (8 * mt);
   const int tiles_y = (p.dom_h + 15) / 16;
   p.tiles_per_img = p.tiles_x * tiles_y;
   p.n_tiles = p.tiles_per_img * d->n;
+  if (cae_knob(CAE_KNOB_IGEMM_VERBOSE))
+    fprintf(stderr, "cae_conv_igemm: kind %d %d->%d @%dx%d N=%d ck=%d mt=%d n_pass=%d n_acc=%d n_buf=%d "
+            "tpb=%d a_stage=%d x%d b_stage=%d x%d smem=%d tiles=%d pair=%d resident=%d\n", kind, d->c_in, d->c_out, d->h_in,
+            d->w_in, p.N, p.ck, p.mt, p.n_pass, p.n_acc, p.n_buf, p.tpb, p.a_stage_bytes, sa,
+            p.b_stage_bytes, sb, smem_bytes, p.n_tiles, (int)pair, p.resident);
+
   p.wpack = (const uint8_t *)d->weights;
 
   // epilogue
@@ -1407,7 +1539,7 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
     epi = EPI_PROJ;
     p.proj_w = (const uint8_t *)d->proj->weights;
     p.proj_out = (__half *)d->proj->proj;
-    p.idesc2 = make_idesc_f16(128, kProjN);
+    p.idesc2 = make_idesc_f16(pair ? 256 : 128, kProjN);
   } else if (merged) {
     epi = EPI_IMAGE;
     CAE_CHECK(d->out.fmt == CAE_FMT_U8_HWC || d->out.fmt == CAE_FMT_NONE, 2,
@@ -1511,7 +1643,12 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
 
   const int sm_count = cae_sm_count();
   int grid = d->grid > 0 ? d->grid : sm_count;
-  if (grid > p.n_tiles * p.n_pass) grid = p.n_tiles * p.n_pass;
+  if (pair) {
+    const int units = ((p.n_tiles + 1) / 2) * p.n_pass;
+    grid &= ~1;
+    if (grid > 2 * units) grid = 2 * units;
+    CAE_CHECK(grid >= 2, 2, "cae_conv_igemm: the CTA-pair form needs at least two CTAs");
+  } else if (grid > p.n_tiles * p.n_pass) grid = p.n_tiles * p.n_pass;
 
   p.debug = 0;
   if (const char *e = cae_knob(CAE_KNOB_IGEMM_DEBUG)) p.debug = atoi(e);
@@ -1530,23 +1667,44 @@ extern "C" int cae_conv_igemm(const cae_conv_desc *d, void *stream) {
   if (fast != 1 && p.epi_warps > kMaxEpiWarps) p.epi_warps = kMaxEpiWarps;
   if (proj) p.epi_warps = 16;
   const int threads = 128 + 32 * p.epi_warps + (proj ? 32 : 0);    // + the projection-GEMM warp
-  void (*kern)(const CUtensorMap, const IgParams) =
-      epi == EPI_PROJ ? igemm_conv_kernel<EPI_PROJ, 1> :
-      epi == EPI_ACT ? (fast == 1 ? igemm_conv_kernel<EPI_ACT, 1>
-                                  : (fast == 2 ? igemm_conv_kernel<EPI_ACT, 2>
-                                               : igemm_conv_kernel<EPI_ACT, 0>))
-                     : (epi == EPI_LATENT ? igemm_conv_kernel<EPI_LATENT, 0>
-                                          : igemm_conv_kernel<EPI_IMAGE, 0>);
+  typedef void (*KernFn)(const CUtensorMap, const IgParams);
+  KernFn kern;
+  if (pair) {
+    kern = epi == EPI_PROJ ? (KernFn)igemm_conv_kernel<EPI_PROJ, 1, 1>
+           : (fast == 1 ? (KernFn)igemm_conv_kernel<EPI_ACT, 1, 1>
+                        : (fast == 2 ? (KernFn)igemm_conv_kernel<EPI_ACT, 2, 1>
+                                     : (KernFn)igemm_conv_kernel<EPI_ACT, 0, 1>));
+    CAE_CHECK(epi == EPI_PROJ || epi == EPI_ACT, 2, "cae_conv_igemm: internal (pair form of epilogue %d)", epi);
+  } else {
+    kern = epi == EPI_PROJ ? (KernFn)igemm_conv_kernel<EPI_PROJ, 1, 0>
+           : epi == EPI_ACT ? (fast == 1 ? (KernFn)igemm_conv_kernel<EPI_ACT, 1, 0>
+                                         : (fast == 2 ? (KernFn)igemm_conv_kernel<EPI_ACT, 2, 0>
+                                                      : (KernFn)igemm_conv_kernel<EPI_ACT, 0, 0>))
+                            : (epi == EPI_LATENT ? (KernFn)igemm_conv_kernel<EPI_LATENT, 0, 0>
+                                                 : (KernFn)igemm_conv_kernel<EPI_IMAGE, 0, 0>);
+  }
   static_assert(sizeof(IgParams) + sizeof(CUtensorMap) <= 4096, "kernel parameters exceed 4 KB");
   CAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  kern<<<grid, threads, smem_bytes, (cudaStream_t)stream>>>(tm, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CAE_CUDA(cudaLaunchKernelEx(&cfg, kern, tm, p));
   cae_count_launch();
   CAE_CUDA(cudaGetLastError());
   return 0;
 }
 
 // ---------------------------------------------------------- projection fusion
-extern "C" size_t cae_proj_weight_bytes(void) { return (size_t)kProjWBytes; }
+extern "C" size_t cae_proj_weight_bytes(void) { return (size_t)2 * kProjWBytes; }
 
 extern "C" size_t cae_proj_bytes(int n, int h, int w) {
   return (size_t)n * h * w * kProjN * sizeof(__half);

@@ -515,6 +515,43 @@ def test_projection_fusion_matches_the_two_kernel_path(shape, c_org):
     assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 0.05
 
 
+def test_cta_pair_form_matches_the_single_cta_kernels(tmp_path):
+    """The opt-in cta_group::2 form of the 128-channel layers (CAE_IGEMM_PAIR_MMA: M = 256 across
+    a CTA pair, each CTA holding half of the weights, resident when they fit) against the default
+    single-CTA kernels: same operands and accumulation order, so latent and image agree to fp16
+    noise.  Knobs are read once per process, hence the child process."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from oracle import cae_oracle as O
+import cnn_autoencoder_b200 as M
+chk = O.make_checkpoint(O.NAMED_ARCHS['A'], seed=5)
+model = M.autoencoder_from_state_dict(chk, gpu=True, train=False)
+x = O.synth_natural(3, 3, 96, 160, seed=2).permute(0, 2, 3, 1).contiguous().cuda()
+y = model['encoder'](x)
+y_q = torch.round(y)
+x_r, _, u8 = model['decoder'](y_q, as_uint8=True)
+torch.cuda.synchronize()
+torch.save(dict(y=y.cpu(), x_r=x_r[0].cpu(), u8=u8.cpu()), sys.argv[1])
+''' % root
+    outs = {}
+    for name, env in (('single', {}), ('pair', {'CAE_DEBUG': '1', 'CAE_IGEMM_PAIR_MMA': '1'})):
+        path = str(tmp_path / (name + '.pt'))
+        e = dict(os.environ)
+        e.pop('CAE_IGEMM_PAIR_MMA', None)
+        e.update(env)
+        subprocess.run([sys.executable, '-c', script, path], check=True, env=e, timeout=300)
+        outs[name] = torch.load(path)
+    a, b = outs['single'], outs['pair']
+    assert torch.allclose(a['y'], b['y'], atol=2e-3, rtol=2e-3), (a['y'] - b['y']).abs().max()
+    # y_q = round(y) may differ in a symbol sitting on a rounding boundary; compare the image loosely
+    d = (a['u8'].int() - b['u8'].int()).abs()
+    assert float((d > 1).float().mean()) < 1e-3
+
+
 def test_training_mode_bottleneck_kernels_match_autograd():
     """``cae_eb_train_fwd`` / ``cae_eb_train_bwd`` against the same model written with torch
     autograd ops (CompressAI's formulation, SURVEY.md A.1): outputs, d/dy and the gradient of
