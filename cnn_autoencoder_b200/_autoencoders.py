@@ -21,6 +21,7 @@ ops on the device (interim: the backward kernels are scheduled).
 import base64
 import io
 import math
+import os
 import struct
 import threading
 
@@ -32,6 +33,7 @@ import torch.nn.functional as F
 from . import _cabi as C
 from . import _engine as E
 from . import _ops as O
+from . import _train_conv as T
 from ._entropy import EntropyBottleneck
 
 try:                                    # zarr / numcodecs are optional at import time
@@ -240,6 +242,8 @@ class _Track(nn.Module):
         super().__init__()
         self._exec = None
         self._lock = threading.Lock()
+        # train() mode: run the wide layers on the CUDA kernels (CAE_TRAIN_TORCH=1: torch ops)
+        self.train_kernels = not os.environ.get('CAE_TRAIN_TORCH')
 
     def _units(self):
         raise NotImplementedError
@@ -288,6 +292,12 @@ class Analyzer(_Track):
         if self.training:
             if x.dtype == torch.uint8:
                 x = x.permute(0, 3, 1, 2).float() / 255.0
+            if self.train_kernels and x.is_cuda:
+                # wide layers forward / backward on this repo's kernels (_train_conv.py); tracks
+                # they do not cover run the torch formulation below
+                r = T.run_track(self, x)
+                if r is not None:
+                    return r[0]
             return self.analysis_track(x)
         self._check_input(x)
         if not self._units():
@@ -359,6 +369,16 @@ class Synthesizer(_Track):
         by the last kernel's epilogue: ``(x_r, fx_brg, u8)``; ``as_uint8='only'`` skips the
         fp32 copy (``x_r`` / ``fx_brg`` entries are then None)."""
         if self.training:
+            if self.train_kernels and x.is_cuda and not self.multiscale and not self.bridges:
+                r = T.run_track(self, x)
+                if r is not None:
+                    final, tensors = r
+                    idx = self._unit_output_indices()
+                    # bridges inside the fused run are not materialised (as in eval mode)
+                    fx_brg = [tensors.get(i) for i in idx]
+                    x_r = [None] * len(idx)
+                    x_r[0] = final
+                    return x_r, fx_brg
             fx, fx_brg, x_r = x, [], []
             for up, col in zip(self.synthesis_track, self.color_layers):
                 fx = up(fx)

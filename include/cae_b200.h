@@ -248,6 +248,34 @@ int cae_eb_train_bwd(const float *y_hat, const float *blob, int n, int c, int hw
                      const float *g_yhat, const float *g_lik, float *g_y, float *g_blob,
                      void *stream);
 
+/* ---- training: backward of the 3x3 (transposed) convolutions ---------------------------------
+ * `loss.backward()` through nn.Conv2d / nn.ConvTranspose2d + activation of the units
+ * (src/train_cae_ms.py:209-219 -> R:53-304).  Per layer, with z = conv(x) + b, out = act(z):
+ *
+ *  cae_act_grad   dz = fold(g) * act'(out) * scale, db += sum over pixels (unscaled).  g is the
+ *                 gradient w.r.t. `out` as the next layer's data-gradient kernel left it; `fold`
+ *                 adds the mirrored ring of a reflect-padded Conv2d consumer (g then covers the
+ *                 PADDED input of that consumer: logical size g_h x g_w, pixel (0,0) of this
+ *                 layer at (fold_shift + 1, fold_shift + 1)).  g / out / dz may each be fp32
+ *                 NCHW, planar or split fp16; (oy, ox) place this layer's pixel (0,0) inside a
+ *                 larger zero-ringed buffer (dz embedded for the data gradient of a reflect-padded
+ *                 Conv2d: cae_conv_igemm of the TRANSPOSED kind on the embedded dz yields the
+ *                 gradient of the padded input).  `scale` is a device scalar (loss scaling into
+ *                 fp16 range) or NULL.
+ *  data gradient  = cae_conv_igemm with the transposed kind on dz and the SAME weight tensor
+ *                 (torch stores Conv2d weights as (out, in, 3, 3) and ConvTranspose2d weights
+ *                 as (in, out, 3, 3), so cae_pack_weights(transposed kind, W) is the adjoint).
+ *  cae_conv_wgrad dW += scale * sum_pixels dz (x) window(x) on the tensor cores (fp32, torch
+ *                 layout, accumulated).  x: the layer's forward input in the layout the forward
+ *                 kernel read (planar; split for CAE_CONV_S2); dz: planar (split for
+ *                 CAE_CONVT_S2), zero halo; dz_embed = 1 when dz is embedded as above.          */
+int cae_act_grad(cae_tensor g, int g_h, int g_w, int g_oy, int g_ox, int fold, int fold_shift,
+                 cae_tensor out, int out_h, int out_w, int act, cae_tensor dz, int dz_h, int dz_w,
+                 int dz_oy, int dz_ox, int n, int h, int w, int c, const float *scale, float *db,
+                 void *stream);
+int cae_conv_wgrad(int kind, int n, int h_in, int w_in, int c_in, int c_out, cae_tensor x,
+                   cae_tensor dz, int dz_embed, float *dw, const float *scale, void *stream);
+
 /* The same quantizer fused into the epilogue of the last analysis convolution
  * (cae_conv_desc.quant; the layer whose output is the fp32 NCHW latent y, Analyzer.forward
  * R:359-361 followed by fact_ent R:549 / _taskutils.py:97): while y is still in registers the
