@@ -25,7 +25,7 @@ SYMBOLS = ['cae_abi_version', 'cae_last_error', 'cae_device_info', 'cae_launch_c
            'cae_image_from_proj',
            'cae_nchw_to_planar', 'cae_planar_to_nchw', 'cae_eb_quantize', 'cae_eb_dequantize_planar',
            'cae_eb_train_blob_size', 'cae_eb_train_fwd', 'cae_eb_train_bwd', 'cae_gdn',
-           'cae_act_grad', 'cae_conv_wgrad',
+           'cae_act_grad', 'cae_conv_wgrad', 'cae_conv_wgrad_workspace_bytes',
            'cae_pmf_to_quantized_cdf', 'cae_rans_encode', 'cae_rans_decode',
            'cae_rans_enc_table_bytes', 'cae_rans_build_enc_table',
            'cae_rans_encode_batch', 'cae_rans_scan', 'cae_rans_compact', 'cae_rans_decode_batch',
@@ -156,7 +156,9 @@ def lib():
     ci = ctypes.c_int
     L.cae_act_grad.argtypes = [Tensor, ci, ci, ci, ci, ci, ci, Tensor, ci, ci, ci, Tensor, ci, ci,
                                ci, ci, ci, ci, ci, ci, vp, vp, vp]
-    L.cae_conv_wgrad.argtypes = [ci, ci, ci, ci, ci, ci, Tensor, Tensor, ci, vp, vp, vp]
+    L.cae_conv_wgrad.argtypes = [ci, ci, ci, ci, ci, ci, Tensor, Tensor, ci, vp, vp, vp, sz, vp]
+    L.cae_conv_wgrad_workspace_bytes.restype = sz
+    L.cae_conv_wgrad_workspace_bytes.argtypes = []
     L.cae_tiles_upload_u8.argtypes = [vp, i64, i64, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int,
                                       vp, vp]
     L.cae_tiles_download_u8.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, i64,
@@ -170,7 +172,8 @@ def lib():
     for name in SYMBOLS:
         if name not in ('cae_abi_version', 'cae_last_error', 'cae_launch_count',
                         'cae_packed_weight_bytes', 'cae_rans_enc_table_bytes',
-                        'cae_proj_weight_bytes', 'cae_proj_bytes'):
+                        'cae_proj_weight_bytes', 'cae_proj_bytes',
+                        'cae_conv_wgrad_workspace_bytes'):
             getattr(L, name).restype = ctypes.c_int
     if L.cae_abi_version() != ABI_VERSION:
         raise CaeError('libcae_b200.so ABI version mismatch')

@@ -40,8 +40,17 @@ _NONE = C.Tensor(None, C.FMT_NONE, 0, 0, 0)
 
 
 def _wide(st):
-    return (16 <= st.c_in <= 128 and 16 <= st.c_out <= 128 and st.groups == 1 and st.bn is None
+    """Layers the kernels cover: up to 128 channels on either side.  Thin sides (the 3-channel
+    image) ride the same tensor-core kernels with their channels padded to 16 -- those layers
+    are bound by the wide tensor's HBM traffic either way."""
+    return (1 <= st.c_in <= 128 and 1 <= st.c_out <= 128 and st.groups == 1 and st.bn is None
             and st.gdn is None and st.skip is None and st.post_act is None)
+
+
+def _merged(kind, c_out):
+    """cae_conv_igemm runs a transposed stride-2 layer with <= 4 output channels as the merged
+    image-layer kernel, which writes fp32 NCHW (aux) instead of the planar layout."""
+    return kind == C.CONVT_S2 and 4 * c_out <= 16
 
 
 def _plain(st):
@@ -68,6 +77,8 @@ def eligible_chain(track):
     for k in range(wide[0], wide[-1] + 1):
         if steps[k].pad_mode != (C.PAD_ZERO if steps[k].transposed else C.PAD_REFLECT):
             return None
+        if _merged(steps[k].kind, steps[k].c_out) and k != wide[-1]:
+            return None                       # an image-type layer in the middle of the run
     return steps, wide[0], wide[-1] + 1
 
 
@@ -112,6 +123,13 @@ class WideChain:
             self._bufs[key] = b
         return b[1]
 
+    def _workspace(self, device):
+        ws = self._bufs.get('ws')
+        if ws is None or ws.device != device:
+            ws = torch.empty(C.lib().cae_conv_wgrad_workspace_bytes(), dtype=torch.uint8, device=device)
+            self._bufs['ws'] = ws
+        return ws
+
     # ------------------------------------------------------------------ forward
     def forward(self, x, weights, biases):
         """x: fp32 NCHW (device).  Returns (y fp32 NCHW, saved)."""
@@ -126,14 +144,20 @@ class WideChain:
             last = k == len(steps) - 1
             wp = O.pack_weights(st.kind, weights[k].detach())
             b = biases[k].detach().float().contiguous() if biases[k] is not None else None
-            if last and st.kind != C.CONVT_S2:
+            aux = None
+            if last and _merged(st.kind, st.c_out):
+                aux = torch.empty((n, st.c_out, ho, wo), dtype=torch.float32, device=x.device)
+                out = None
+            elif last and st.kind != C.CONVT_S2:
                 out = O.alloc_act(C.FMT_F32_NCHW, n, st.c_out, ho, wo, device=x.device)
             else:
                 f2, h2 = _consumer_layout(steps[k + 1]) if not last else (C.FMT_F16_PLANAR, C.HALO_KEEP)
                 # fresh buffers: they are saved for the backward pass of THIS call
                 out = O.alloc_act(f2, n, st.c_out, ho, wo, h2, device=x.device)
             O.conv(st.kind, cur, wp, st.c_out, out, igemm=True, bias=b, skip=None,
-                   pre_act=E.act_code(st.pre_act), post_act=C.ACT_NONE, pad_mode=st.pad_mode)
+                   pre_act=E.act_code(st.pre_act), post_act=C.ACT_NONE, pad_mode=st.pad_mode, aux=aux)
+            if aux is not None:
+                out = O.Act(aux, C.FMT_F32_NCHW, n, st.c_out, ho, wo)
             xin.append(cur)
             outs.append(out)
             cur = out
@@ -194,9 +218,10 @@ class WideChain:
                 db.mul_(inv_scale)            # below the top layer g already carries the scale
             dbs[k] = db
             dW = torch.zeros_like(weights[k], dtype=torch.float32)
+            ws = self._workspace(dev)
             C.check(C.lib().cae_conv_wgrad(st.kind, n, x.h, x.w, st.c_in, st.c_out, x.desc(),
                                            dz.desc(), embed, dW.data_ptr(), inv_scale.data_ptr(),
-                                           _sptr()))
+                                           ws.data_ptr(), ws.numel(), _sptr()))
             dWs[k] = dW
             if k == 0 and not need_dx:
                 g_desc = None
@@ -204,10 +229,19 @@ class WideChain:
             kt = _ADJOINT[st.kind]
             wt = O.pack_weights(kt, weights[k].detach())
             gh, gw = O.KIND_OUT[kt](dz.h, dz.w)
-            gbuf = self._buf(('g', k), C.FMT_F16_PLANAR, n, st.c_in, gh, gw, C.HALO_KEEP, dev)
-            O.conv(kt, dz, wt, st.c_in, gbuf, igemm=True, bias=None, skip=None, pre_act=C.ACT_NONE,
-                   post_act=C.ACT_NONE, pad_mode=C.PAD_ZERO)
-            g_desc, g_dims, g_off = gbuf.desc(), (gh, gw), (0, 0)
+            if _merged(kt, st.c_in):
+                # adjoint of a stride-2 Conv2d with a thin input: the merged kernel, fp32 NCHW out
+                gt = torch.empty((n, st.c_in, gh, gw), dtype=torch.float32, device=dev)
+                O.conv(kt, dz, wt, st.c_in, None, igemm=True, bias=None, skip=None,
+                       pre_act=C.ACT_NONE, post_act=C.ACT_NONE, pad_mode=C.PAD_ZERO, aux=gt)
+                g_desc = C.Tensor(gt.data_ptr(), C.FMT_F32_NCHW, 0, 0, 0)
+                keep.append(gt)
+            else:
+                gbuf = self._buf(('g', k), C.FMT_F16_PLANAR, n, st.c_in, gh, gw, C.HALO_KEEP, dev)
+                O.conv(kt, dz, wt, st.c_in, gbuf, igemm=True, bias=None, skip=None,
+                       pre_act=C.ACT_NONE, post_act=C.ACT_NONE, pad_mode=C.PAD_ZERO)
+                g_desc = gbuf.desc()
+            g_dims, g_off = (gh, gw), (0, 0)
             fold, fold_shift = (1, 0 if st.kind == C.CONV_S1 else 1) if conv_like else (0, 0)
             keep.append(wt)
         dx = None

@@ -18,9 +18,11 @@
 // UMMA operand, so both operands are read in place (instruction descriptor a_major = b_major =
 // MN, LBO = pitch between rows of eight pixels, SBO = plane stride).  A CTA owns one channel
 // chunk of Q and a strided share of the 16x8-pixel tiles, accumulates all nine taps (9 x 48
-// TMEM columns) over its whole share without ever draining, and adds its partial result to dW
-// (fp32, torch layout) with atomics at the end.  Persistent, one CTA per SM; warp 0 = TMA,
-// warp 1 = MMA issue, warps 2-5 = the final drain.
+// TMEM columns) over its whole share without ever draining, and stores its partial result
+// ([slot][chunk][tap][m][48] fp32, coalesced) at the end; wgrad_reduce_kernel sums the slots,
+// applies the loss scale and accumulates into dW in torch layout (one writer per element: 8 M
+// contended atomics per layer were 2-3 ms, the partials are ~30 MB of streaming traffic).
+// Persistent, one CTA per SM; warp 0 = TMA, warp 1 = MMA issue, warps 2-5 = the final drain.
 #include <string.h>
 
 #include "cae_common.cuh"
@@ -45,6 +47,8 @@ struct WgParams {
   int kind, c_in, c_out, c_m, c_n; // c_m / c_n: real channels of P / Q
   float *dw;
   const float *scale;              // device scalar multiplied into the result, or nullptr
+  float *partial;                  // [n_slots][n_chunks][9][128][kWgNc]
+  int n_slots;
 };
 
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -130,42 +134,59 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CU
       }
       __syncwarp();
     }
-  } else if (my_tiles > 0) {
+  } else if (active) {
     // ===== drain: lane = channel m of P, columns = (tap, channel of Q) =====
     const int quad = warp & 3;
     const int m = quad * 32 + lane;
-    mbar_wait(&done, 0);
-    tc_fence_after();
-    const float sc = p.scale ? __ldg(p.scale) : 1.f;
+    if (my_tiles > 0) {
+      mbar_wait(&done, 0);
+      tc_fence_after();
+    }
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    float *dst = p.partial + ((size_t)(slot * p.n_chunks + chunk) * 9 * 128 + m) * kWgNc;
     for (int t = 0; t < 9; ++t) {
-      // torch index of (m, n, tap) for this kind
-      const int dy = t / 3, dx = t - dy * 3;
       for (int c0 = 0; c0 < kWgNc; c0 += 16) {
         uint32_t r[16];
         __syncwarp();
         tmem_ld16(lane_base + (uint32_t)(t * kWgNc + c0), r);
         tmem_ld_wait();
-        if (m >= p.c_m) continue;
+        float4 *o = reinterpret_cast<float4 *>(dst + (size_t)t * 128 * kWgNc + c0);
+        if (my_tiles == 0) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = chunk * kWgNc + c0 + j;
-          if (n >= p.c_n) continue;
-          size_t idx;
-          if (p.kind == CAE_CONV_S1 || p.kind == CAE_CONV_S2)
-            idx = ((size_t)m * p.c_in + n) * 9 + t;                       // P = dz (c_out), Q = x (c_in)
-          else if (p.kind == CAE_CONVT_S1)
-            idx = ((size_t)n * p.c_out + m) * 9 + (2 - dy) * 3 + (2 - dx); // flipped correlation
-          else
-            idx = ((size_t)m * p.c_out + n) * 9 + t;                       // P = x (c_in), Q = dz (c_out)
-          atomicAdd(p.dw + idx, __uint_as_float(r[j]) * sc);
+          for (int q4 = 0; q4 < 16; ++q4) r[q4] = 0u;
         }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          o[q4] = make_float4(__uint_as_float(r[4 * q4]), __uint_as_float(r[4 * q4 + 1]),
+                              __uint_as_float(r[4 * q4 + 2]), __uint_as_float(r[4 * q4 + 3]));
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// dW[torch index of (m, n, tap)] += scale * sum over slots of partial[slot][chunk][tap][m][n']
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // over (tap, m, n), n fastest
+  const int total = 9 * p.c_m * p.c_n;
+  if (i >= total) return;
+  const int n = i % p.c_n, m = (i / p.c_n) % p.c_m, t = i / (p.c_n * p.c_m);
+  const int chunk = n / kWgNc, nl = n - chunk * kWgNc;
+  const float *src = p.partial + ((size_t)chunk * 9 * 128 + (size_t)t * 128 + m) * kWgNc + nl;
+  const size_t slot_stride = (size_t)p.n_chunks * 9 * 128 * kWgNc;
+  float acc = 0.f;
+  for (int s = 0; s < p.n_slots; ++s) acc += __ldg(src + (size_t)s * slot_stride);
+  const int dy = t / 3, dx = t - dy * 3;
+  size_t idx;
+  if (p.kind == CAE_CONV_S1 || p.kind == CAE_CONV_S2)
+    idx = ((size_t)m * p.c_in + n) * 9 + t;                        // P = dz (c_out), Q = x (c_in)
+  else if (p.kind == CAE_CONVT_S1)
+    idx = ((size_t)n * p.c_out + m) * 9 + (2 - dy) * 3 + (2 - dx);  // flipped correlation
+  else
+    idx = ((size_t)m * p.c_out + n) * 9 + t;                        // P = x (c_in), Q = dz (c_out)
+  p.dw[idx] += acc * (p.scale ? __ldg(p.scale) : 1.f);
 }
 
 // ---------------------------------------------------------------- cae_act_grad
@@ -220,38 +241,49 @@ __device__ __forceinline__ void ag_load8(const AgView &v, int n, int plane, int 
 }
 
 __global__ void __launch_bounds__(256) act_grad_kernel(const AgParams q) {
-  const int planes = (q.c + 7) >> 3;
-  const size_t total = (size_t)q.n * planes * q.h * q.w;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  // block-level bias sums: threads of a block that share a plane reduce through shared memory
+  const uint32_t planes = (uint32_t)(q.c + 7) >> 3;
+  const uint32_t total = (uint32_t)q.n * planes * (uint32_t)q.h * (uint32_t)q.w;   // < 2^31 (host check)
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   __shared__ float s_db[128];
   if (q.db) {
-    for (int k = threadIdx.x; k < 128; k += blockDim.x) s_db[k] = 0.f;
+    if (threadIdx.x < 128) s_db[threadIdx.x] = 0.f;
     __syncthreads();
   }
   if (i < total) {
-    const int x = (int)(i % q.w);
-    size_t r = i / q.w;
-    const int y = (int)(r % q.h);
-    r /= q.h;
+    const int x = (int)(i % (uint32_t)q.w);
+    uint32_t r = i / (uint32_t)q.w;
+    const int y = (int)(r % (uint32_t)q.h);
+    r /= (uint32_t)q.h;
     const int plane = (int)(r % planes), n = (int)(r / planes);
-    float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float g[8];
     if (!q.fold) {
       ag_load8(q.g, n, plane, y + q.g.oy, x + q.g.ox, q.c, g);
     } else {
-      // padded index P of the reflect-padded input: P = y + 1, plus the mirrored ring rows
-      // (P = 0 mirrors pixel 1, P = h + 1 mirrors pixel h - 2); buffer index = P + fold_shift
-      const int ys[3] = {y + 1, y == 1 ? 0 : -1, y == q.h - 2 ? q.h + 1 : -1};
-      const int xs[3] = {x + 1, x == 1 ? 0 : -1, x == q.w - 2 ? q.w + 1 : -1};
-      for (int a = 0; a < 3; ++a)
-        for (int b = 0; b < 3; ++b) {
-          const int Y = ys[a] + q.fold_shift, X = xs[b] + q.fold_shift;
-          if (ys[a] < 0 || xs[b] < 0 || Y >= q.g.H || X >= q.g.W) continue;
-          float t[8];
-          ag_load8(q.g, n, plane, Y, X, q.c, t);
+      // padded index P of the reflect-padded input: P = y + 1, plus the mirrored ring (P = 0
+      // mirrors pixel 1, P = h + 1 mirrors pixel h - 2); buffer index = P + fold_shift
+      const int fs = q.fold_shift;
+      const int y2 = y == 1 ? fs : (y == q.h - 2 ? q.h + 1 + fs : -1);
+      const int x2 = x == 1 ? fs : (x == q.w - 2 ? q.w + 1 + fs : -1);
+      const bool ry = y2 >= 0 && y2 < q.g.H, rx = x2 >= 0 && x2 < q.g.W;
+      ag_load8(q.g, n, plane, y + 1 + fs, x + 1 + fs, q.c, g);
+      if (ry | rx) {               // border pixels only
+        float t[8];
+        if (ry) {
+          ag_load8(q.g, n, plane, y2, x + 1 + fs, q.c, t);
 #pragma unroll
           for (int k = 0; k < 8; ++k) g[k] += t[k];
         }
+        if (rx) {
+          ag_load8(q.g, n, plane, y + 1 + fs, x2, q.c, t);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) g[k] += t[k];
+        }
+        if (ry & rx) {
+          ag_load8(q.g, n, plane, y2, x2, q.c, t);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) g[k] += t[k];
+        }
+      }
     }
     if (q.out.ptr && q.slope != 1.f) {
       float o[8];
@@ -260,9 +292,20 @@ __global__ void __launch_bounds__(256) act_grad_kernel(const AgParams q) {
       for (int k = 0; k < 8; ++k) g[k] = o[k] > 0.f ? g[k] : g[k] * q.slope;
     }
     if (q.db) {
+      // a warp's 32 consecutive units almost always share their plane: shuffle-reduce, one
+      // shared-memory atomic per warp and channel
+      const unsigned peers = __match_any_sync(__activemask(), plane);
+      const bool whole = peers == 0xffffffffu;
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (plane * 8 + k < q.c && g[k] != 0.f) atomicAdd(&s_db[(plane * 8 + k) & 127], g[k]);
+      for (int k = 0; k < 8; ++k) {
+        float v = g[k];
+        if (whole) {
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if ((threadIdx.x & 31) == 0 && plane * 8 + k < q.c) atomicAdd(&s_db[(plane * 8 + k) & 127], v);
+        } else if (plane * 8 + k < q.c && v != 0.f) {
+          atomicAdd(&s_db[(plane * 8 + k) & 127], v);
+        }
+      }
     }
     const float sc = q.scale ? __ldg(q.scale) : 1.f;
     if (q.dz.fmt == CAE_FMT_F32_NCHW) {
@@ -286,9 +329,9 @@ __global__ void __launch_bounds__(256) act_grad_kernel(const AgParams q) {
   }
   if (q.db) {
     __syncthreads();
-    // (the sums of the scaled gradient are taken before scaling: db is in loss units)
-    for (int k = threadIdx.x; k < 128 && k < q.c; k += blockDim.x)
-      if (s_db[k] != 0.f) atomicAdd(q.db + k, s_db[k]);
+    // (the sums are taken before scaling)
+    if (threadIdx.x < 128 && (int)threadIdx.x < q.c && s_db[threadIdx.x] != 0.f)
+      atomicAdd(q.db + threadIdx.x, s_db[threadIdx.x]);
   }
 }
 
@@ -338,11 +381,18 @@ int wg_tensor_map(CUtensorMap *tm, const cae_tensor &t, int n, int H, int W, boo
 
 }  // namespace
 
+extern "C" size_t cae_conv_wgrad_workspace_bytes(void) {
+  return (size_t)cae_sm_count() * 9 * 128 * kWgNc * sizeof(float);
+}
+
 extern "C" int cae_conv_wgrad(int kind, int n, int h_in, int w_in, int c_in, int c_out,
                               cae_tensor x, cae_tensor dz, int dz_embed, float *dw,
-                              const float *scale, void *stream) {
+                              const float *scale, void *workspace, size_t workspace_bytes,
+                              void *stream) {
   CAE_CHECK(kind >= CAE_CONV_S1 && kind <= CAE_CONVT_S2, 2, "cae_conv_wgrad: bad kind %d", kind);
-  CAE_CHECK(x.ptr && dz.ptr && dw, 2, "cae_conv_wgrad: null pointer");
+  CAE_CHECK(x.ptr && dz.ptr && dw && workspace, 2, "cae_conv_wgrad: null pointer");
+  CAE_CHECK(workspace_bytes >= cae_conv_wgrad_workspace_bytes(), 2,
+            "cae_conv_wgrad: workspace smaller than cae_conv_wgrad_workspace_bytes()");
   CAE_CHECK(n > 0 && h_in > 0 && w_in > 0 && c_in > 0 && c_out > 0, 2, "cae_conv_wgrad: bad shape");
   CAE_CHECK(c_in <= 128 && c_out <= 128, 2, "cae_conv_wgrad: at most 128 channels per side");
   const bool down = kind == CAE_CONV_S2, up = kind == CAE_CONVT_S2;
@@ -382,7 +432,10 @@ extern "C" int cae_conv_wgrad(int kind, int n, int h_in, int w_in, int c_in, int
   p.par_stride = wg_round_up(p.q_box_bytes, 128);
   p.p_bytes = p.planes_p * 16 * 8 * 16;
   p.stage_bytes = wg_round_up(p.p_bytes + p.par_stride * p.n_par, 1024);
-  p.stages = (227 * 1024 - 2048) / p.stage_bytes;
+  // the M = 128 instruction always reads 16 planes of P: with fewer real planes the rest are
+  // rows nobody drains, but the reads must stay inside the allocation (slack behind the ring)
+  const int slack = 16 * 2048 - p.p_bytes;
+  p.stages = (227 * 1024 - 2048 - slack) / p.stage_bytes;
   if (p.stages > kWgMaxStages) p.stages = kWgMaxStages;
   CAE_CHECK(p.stages >= 1, 2, "cae_conv_wgrad: a stage does not fit shared memory");
   for (int t = 0; t < 9; ++t) {
@@ -416,10 +469,14 @@ extern "C" int cae_conv_wgrad(int kind, int n, int h_in, int w_in, int c_in, int
   int grid = cae_sm_count();
   grid -= grid % p.n_chunks;
   if (grid > p.n_tiles * p.n_chunks) grid = p.n_tiles * p.n_chunks;
-  const int smem_bytes = p.stages * p.stage_bytes + 1024;
+  const int smem_bytes = p.stages * p.stage_bytes + 1024 + slack;
   CAE_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  p.partial = (float *)workspace;
+  p.n_slots = grid / p.n_chunks;
   wgrad_kernel<<<grid, kWgThreads, smem_bytes, (cudaStream_t)stream>>>(tmP, tmQ, p);
-  cae_count_launch();
+  const int total = 9 * c_m * c_n;
+  wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+  cae_count_launch(2);
   CAE_CUDA(cudaGetLastError());
   return 0;
 }
@@ -447,6 +504,7 @@ extern "C" int cae_act_grad(cae_tensor g, int g_h, int g_w, int g_oy, int g_ox, 
   q.scale = scale;
   q.db = db;
   const size_t total = (size_t)n * ((c + 7) / 8) * h * w;
+  CAE_CHECK(total < 2147483648ull, 2, "cae_act_grad: tensor too large for one launch; split the batch");
   act_grad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(q);
   cae_count_launch();
   CAE_CUDA(cudaGetLastError());

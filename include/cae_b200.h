@@ -273,8 +273,10 @@ int cae_act_grad(cae_tensor g, int g_h, int g_w, int g_oy, int g_ox, int fold, i
                  cae_tensor out, int out_h, int out_w, int act, cae_tensor dz, int dz_h, int dz_w,
                  int dz_oy, int dz_ox, int n, int h, int w, int c, const float *scale, float *db,
                  void *stream);
+size_t cae_conv_wgrad_workspace_bytes(void);   /* scratch for the per-CTA partial sums */
 int cae_conv_wgrad(int kind, int n, int h_in, int w_in, int c_in, int c_out, cae_tensor x,
-                   cae_tensor dz, int dz_embed, float *dw, const float *scale, void *stream);
+                   cae_tensor dz, int dz_embed, float *dw, const float *scale, void *workspace,
+                   size_t workspace_bytes, void *stream);
 
 /* The same quantizer fused into the epilogue of the last analysis convolution
  * (cae_conv_desc.quant; the layer whose output is the fp32 NCHW latent y, Analyzer.forward

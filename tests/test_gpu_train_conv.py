@@ -21,7 +21,8 @@ def _rel(a, b):
 
 @pytest.mark.parametrize('kind,c_in,c_out,h,w', [
     ('conv_s1', 128, 128, 32, 48), ('conv_s2', 128, 48, 32, 32), ('convt_s1', 48, 48, 20, 24),
-    ('convt_s2', 48, 128, 16, 24), ('conv_s1', 32, 64, 16, 8), ('convt_s2', 128, 128, 24, 16)])
+    ('convt_s2', 48, 128, 16, 24), ('conv_s1', 32, 64, 16, 8), ('convt_s2', 128, 128, 24, 16),
+    ('conv_s1', 3, 3, 32, 40), ('conv_s2', 3, 128, 32, 48), ('convt_s2', 128, 3, 16, 24)])
 def test_single_layer_gradients_match_autograd(kind, c_in, c_out, h, w):
     from cnn_autoencoder_b200 import _engine as E, _train_conv as T
     import torch.nn as nn

@@ -11,8 +11,9 @@ Prints the bench.py JSON line: ``value`` = samples/s of the whole job with the b
 HBM (CUDA events, max over ranks), ``e2e`` = the same with each step's batch copied from pinned
 host memory and the loss read back, plus the gradient-bucket size, the all-reduce's share, the
 loss trajectory and whether every rank holds bit-identical parameters after the last step.
-Kernels: the training-mode bottleneck runs on this repo's fused kernels; the transforms'
-train()-mode forward / backward are torch autograd (cuDNN) -- see DESIGN.md."""
+Kernels: the training-mode bottleneck (cae_eb_train_fwd / bwd) and the transforms' forward /
+backward (cae_conv_igemm, cae_act_grad, cae_conv_wgrad) run on this repo's kernels; CAE_TRAIN_TORCH=1
+switches the transforms back to torch autograd (cuDNN) for comparison."""
 import json
 import os
 import sys
@@ -112,6 +113,14 @@ def run(args):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    def on_kernels(key):
+        t = model[key].module
+        return bool(getattr(t, 'train_kernels', False) and getattr(t, '_train_chain', None))
+    if on_kernels('encoder') and on_kernels('decoder'):
+        transforms = ('this repo: cae_conv_igemm forward and data gradient, cae_act_grad, cae_conv_wgrad '
+                      '(tcgen05), fp16 operands / fp32 accumulate and master weights')
+    else:
+        transforms = 'torch autograd (cuDNN)'
     if rank == 0:
         step_ms = ms.item() / args.steps
         lv = [float(torch.mean(v).item()) for v in losses]
@@ -123,7 +132,7 @@ def run(args):
             'config': {'workload': 'train_cae_ms rate-distortion step, net %s, batch %d x 3 x 256 x 256 per GPU, '
                                    'RateMSE lambda 0.01, Adam 1e-4 / aux 1e-3, clip 1.0' % (args.arch, batch),
                        'kernels': 'bottleneck fwd/bwd: cae_eb_train_fwd / cae_eb_train_bwd (this repo); '
-                                  'transforms fwd/bwd: torch autograd (cuDNN)',
+                                  'transforms fwd/bwd: ' + transforms,
                        'parallelism': 'dp%d, one persistent flat fp32 gradient bucket, NCCL all-reduce, '
                                       'synthesis half launched under the analysis backward' % world},
             'e2e': {'value': round(world * batch * args.steps / (e2e_ms.item() / 1e3), 1), 'unit': 'samples/s',
