@@ -186,5 +186,15 @@ def check(rc):
         raise CaeError(f'[{rc}] ' + lib().cae_last_error().decode())
 
 
+_replayed = 0
+
+
+def note_graph_replay(kernels):
+    """Kernels of this library launched by replaying a CUDA graph (the library's own counter
+    only sees them once, when the graph is captured)."""
+    global _replayed
+    _replayed += int(kernels)
+
+
 def launch_count():
-    return int(lib().cae_launch_count())
+    return int(lib().cae_launch_count()) + _replayed

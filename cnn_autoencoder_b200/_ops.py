@@ -91,15 +91,20 @@ KIND_OUT = {C.CONV_S1: lambda h, w: (h, w), C.CONV_S2: lambda h, w: ((h - 1) // 
             C.CONVT_S1: lambda h, w: (h, w), C.CONVT_S2: lambda h, w: (2 * h, 2 * w)}
 
 
-def pack_weights(kind, weight, scale=None, ck=0):
-    """fp32 torch-layout weight (device) -> packed fp16 image for the igemm kernel."""
+def pack_weights(kind, weight, scale=None, ck=0, out=None):
+    """fp32 torch-layout weight (device) -> packed fp16 image for the igemm kernel (``out``: a
+    buffer from an earlier call with the same shape, refilled in place)."""
     _require_cuda(weight, 'weight')
-    w = weight.detach().contiguous().float()
+    w = weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.contiguous().float()
     transposed = kind in (C.CONVT_S1, C.CONVT_S2)
     c_in, c_out = (w.shape[0], w.shape[1]) if transposed else (w.shape[1], w.shape[0])
     L = C.lib()
     nbytes = L.cae_packed_weight_bytes(kind, c_in, c_out, ck)
-    packed = torch.empty(nbytes // 2, dtype=torch.float16, device=w.device)
+    packed = out if out is not None else torch.empty(nbytes // 2, dtype=torch.float16, device=w.device)
+    if packed.numel() * 2 != nbytes:
+        raise C.CaeError('pack_weights: the buffer given does not match this layer')
     sc = None
     if scale is not None:
         sc = scale.detach().contiguous().float()

@@ -25,6 +25,7 @@ autograd stitches the pieces together; tracks with features the kernels do not c
 the torch formulation entirely (``eligible_chain``).
 """
 import ctypes
+import os
 
 import torch
 import torch.nn as nn
@@ -108,61 +109,140 @@ def _sptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-class WideChain:
-    """Forward / backward of steps[k0:k1] of a track on the kernels."""
+class _Plan:
+    """Everything one input shape needs, allocated once: the activations of the forward pass
+    (kept for the backward pass), packed weights (refilled every step), gradient buffers, and
+    the two CUDA graphs that replay the launches."""
 
-    def __init__(self, steps):
-        self.steps = steps
-        self._bufs = {}
-
-    def _buf(self, key, fmt, n, c, h, w, halo, device):
-        full = (fmt, n, c, h, w, halo, str(device))
-        b = self._bufs.get(key)
-        if b is None or b[0] != full:
-            b = (full, O.alloc_act(fmt, n, c, h, w, halo, device=device))
-            self._bufs[key] = b
-        return b[1]
-
-    def _workspace(self, device):
-        ws = self._bufs.get('ws')
-        if ws is None or ws.device != device:
-            ws = torch.empty(C.lib().cae_conv_wgrad_workspace_bytes(), dtype=torch.uint8, device=device)
-            self._bufs['ws'] = ws
-        return ws
-
-    # ------------------------------------------------------------------ forward
-    def forward(self, x, weights, biases):
-        """x: fp32 NCHW (device).  Returns (y fp32 NCHW, saved)."""
-        steps = self.steps
-        n = x.shape[0]
+    def __init__(self, chain, shape, device, weights, biases):
+        steps = chain.steps
+        n, c, h, w = shape
+        self.shape, self.device = tuple(shape), device
+        self.busy = False
         fmt, halo = _consumer_layout(steps[0])
-        cur = O.nchw_to_planar(x.detach(), fmt, halo)      # (fresh: saved for the backward pass)
-        xin, outs = [], []
-        y = None
+        self.x0 = O.alloc_act(fmt, n, c, h, w, halo, device=device)
+        self.xin, self.outs, self.wp, self.wt = [], [], [], []
+        self.dz, self.embed, self.dz_off, self.gbuf = [], [], [], []
+        cur = self.x0
         for k, st in enumerate(steps):
             ho, wo = O.KIND_OUT[st.kind](cur.h, cur.w)
             last = k == len(steps) - 1
-            wp = O.pack_weights(st.kind, weights[k].detach())
-            b = biases[k].detach().float().contiguous() if biases[k] is not None else None
-            aux = None
             if last and _merged(st.kind, st.c_out):
-                aux = torch.empty((n, st.c_out, ho, wo), dtype=torch.float32, device=x.device)
-                out = None
+                out = O.Act(torch.empty((n, st.c_out, ho, wo), dtype=torch.float32, device=device),
+                            C.FMT_F32_NCHW, n, st.c_out, ho, wo)
             elif last and st.kind != C.CONVT_S2:
-                out = O.alloc_act(C.FMT_F32_NCHW, n, st.c_out, ho, wo, device=x.device)
+                out = O.alloc_act(C.FMT_F32_NCHW, n, st.c_out, ho, wo, device=device)
             else:
                 f2, h2 = _consumer_layout(steps[k + 1]) if not last else (C.FMT_F16_PLANAR, C.HALO_KEEP)
-                # fresh buffers: they are saved for the backward pass of THIS call
-                out = O.alloc_act(f2, n, st.c_out, ho, wo, h2, device=x.device)
-            O.conv(st.kind, cur, wp, st.c_out, out, igemm=True, bias=b, skip=None,
-                   pre_act=E.act_code(st.pre_act), post_act=C.ACT_NONE, pad_mode=st.pad_mode, aux=aux)
-            if aux is not None:
-                out = O.Act(aux, C.FMT_F32_NCHW, n, st.c_out, ho, wo)
-            xin.append(cur)
-            outs.append(out)
+                out = O.alloc_act(f2, n, st.c_out, ho, wo, h2, device=device)
+            self.xin.append(cur)
+            self.outs.append(out)
+            self.wp.append(O.pack_weights(st.kind, weights[k]))
+            self.wt.append(O.pack_weights(_ADJOINT[st.kind], weights[k]))
+            # gradient of the pre-activation output, in the layout its two consumers want
+            if st.kind == C.CONV_S1:
+                dz, off, emb = O.alloc_act(C.FMT_F16_PLANAR, n, st.c_out, ho + 2, wo + 2, device=device), (1, 1), 1
+            elif st.kind == C.CONV_S2:
+                dz, off, emb = O.alloc_act(C.FMT_F16_PLANAR, n, st.c_out, ho + 1, wo + 1, device=device), (1, 1), 1
+            elif st.kind == C.CONVT_S1:
+                dz, off, emb = O.alloc_act(C.FMT_F16_PLANAR, n, st.c_out, ho, wo, device=device), (0, 0), 0
+            else:
+                dz, off, emb = O.alloc_act(C.FMT_F16_SPLIT, n, st.c_out, ho, wo, device=device), (0, 0), 0
+            self.dz.append(dz)
+            self.dz_off.append(off)
+            self.embed.append(emb)
+            kt = _ADJOINT[st.kind]
+            gh, gw = O.KIND_OUT[kt](dz.h, dz.w)
+            if _merged(kt, st.c_in):      # adjoint of a thin stride-2 Conv2d: fp32 NCHW from the merged kernel
+                g = O.Act(torch.empty((n, st.c_in, gh, gw), dtype=torch.float32, device=device),
+                          C.FMT_F32_NCHW, n, st.c_in, gh, gw)
+            else:
+                g = O.alloc_act(C.FMT_F16_PLANAR, n, st.c_in, gh, gw, device=device)
+            self.gbuf.append(g)
             cur = out
-        y = cur.t if cur.fmt == C.FMT_F32_NCHW else O.planar_to_nchw(cur)
-        return y, (xin, outs)
+        last_out = self.outs[-1]
+        self.y = last_out.t if last_out.fmt == C.FMT_F32_NCHW else \
+            torch.empty((n, last_out.c, last_out.h, last_out.w), dtype=torch.float32, device=device)
+        # gradients: one flat fp32 buffer, [dW_0 .. dW_L-1 | db_0 ..]
+        sizes = [wt.numel() for wt in weights] + [b.numel() if b is not None else 0 for b in biases]
+        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
+        offs = [0]
+        for sz in sizes:
+            offs.append(offs[-1] + sz)
+        L = len(steps)
+        self.dW = [self.flat[offs[k]:offs[k + 1]].view_as(weights[k]) for k in range(L)]
+        self.db = [self.flat[offs[L + k]:offs[L + k + 1]] if biases[k] is not None else None for k in range(L)]
+        self.offs = offs
+        self.g_in = torch.empty_like(self.y)
+        self.dx = torch.empty((n, c, h, w), dtype=torch.float32, device=device)
+        self.scale = torch.ones(1, dtype=torch.float32, device=device)
+        self.inv_scale = torch.ones(1, dtype=torch.float32, device=device)
+        self.ws = torch.empty(C.lib().cae_conv_wgrad_workspace_bytes(), dtype=torch.uint8, device=device)
+        self.graph_fwd = self.graph_bwd = None
+        self.fwd_ptrs = self.bwd_key = None
+
+
+class WideChain:
+    """Forward / backward of a run of steps of a track on the kernels."""
+
+    def __init__(self, steps):
+        self.steps = steps
+        self._plans = {}
+        self.use_graphs = not os.environ.get('CAE_TRAIN_NO_GRAPH')
+
+    def _plan(self, x, weights, biases):
+        key = (tuple(x.shape), str(x.device))
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) > 4:
+                self._plans.clear()
+            plan = self._plans[key] = _Plan(self, x.shape, x.device, weights, biases)
+        elif plan.busy:
+            # a second forward pass before the first one's backward: its own set of buffers
+            plan = _Plan(self, x.shape, x.device, weights, biases)
+        return plan
+
+    # ------------------------------------------------------------------ forward
+    def _launch_forward(self, plan, weights, biases):
+        for k, st in enumerate(self.steps):
+            O.pack_weights(st.kind, weights[k], out=plan.wp[k])
+            out = plan.outs[k]
+            aux = out.t if _merged(st.kind, st.c_out) else None
+            O.conv(st.kind, plan.xin[k], plan.wp[k], st.c_out, None if aux is not None else out,
+                   igemm=True, bias=biases[k], skip=None, pre_act=E.act_code(st.pre_act),
+                   post_act=C.ACT_NONE, pad_mode=st.pad_mode, aux=aux)
+        last = plan.outs[-1]
+        if last.fmt != C.FMT_F32_NCHW:
+            C.check(C.lib().cae_planar_to_nchw(last.desc(), last.n, last.c, last.h, last.w,
+                                               plan.y.data_ptr(), _sptr()))
+
+    def forward(self, x, weights, biases):
+        """x: fp32 NCHW (device).  Returns (y fp32 NCHW, plan)."""
+        weights = [w.detach() for w in weights]
+        biases = [b.detach() if b is not None else None for b in biases]
+        for t in weights + [b for b in biases if b is not None]:
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise C.CaeError('the training kernels expect contiguous fp32 parameters')
+        plan = self._plan(x, weights, biases)
+        plan.busy = True
+        O.nchw_to_planar(x.detach(), plan.x0.fmt, plan.x0.halo, out=plan.x0)
+        if not self.use_graphs:
+            self._launch_forward(plan, weights, biases)
+        else:
+            ptrs = tuple(t.data_ptr() for t in weights) + tuple(b.data_ptr() if b is not None else 0 for b in biases)
+            if plan.graph_fwd is None or plan.fwd_ptrs != ptrs:
+                # warm-up launch outside the capture (kernel attributes, lazy module loading)
+                self._launch_forward(plan, weights, biases)
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                n0 = C.lib().cae_launch_count()
+                with torch.cuda.graph(g):
+                    self._launch_forward(plan, weights, biases)
+                plan.fwd_kernels = int(C.lib().cae_launch_count() - n0)
+                plan.graph_fwd, plan.fwd_ptrs = g, ptrs
+            plan.graph_fwd.replay()
+            C.note_graph_replay(plan.fwd_kernels)
+        return plan.y.clone(), plan
 
     # ----------------------------------------------------------------- backward
     def _act_grad(self, g, g_dims, g_off, fold, fold_shift, out, act, dz, dz_dims, dz_off, n, h, w,
@@ -175,82 +255,83 @@ class WideChain:
             scale.data_ptr() if scale is not None else None,
             db.data_ptr() if db is not None else None, _sptr()))
 
-    def backward(self, saved, g, weights, biases, need_dx=True):
-        """g: fp32 NCHW gradient of the chain's output.  Returns (dx fp32 NCHW or None,
-        [dW...], [db...]) with dW / db in torch layout, fp32."""
+    def _launch_backward(self, plan, weights, need_dx):
         steps = self.steps
-        xin, outs = saved
-        dev = g.device
-        n = g.shape[0]
-        g = g.contiguous().float()
-        # power-of-two loss scale: max |g| * s ~ 64 (fp16 head-room for the growth through the
-        # layers, sub-normals 9 decades below)
-        amax = g.abs().amax().clamp_min(1e-30)
-        scale = torch.exp2(torch.floor(torch.log2(64.0 / amax))).reshape(1).float()
-        inv_scale = (1.0 / scale).float()
-        dWs, dbs = [None] * len(steps), [None] * len(steps)
-        g_desc = C.Tensor(g.data_ptr(), C.FMT_F32_NCHW, 0, 0, 0)
-        g_dims, g_off, fold, fold_shift = (g.shape[2], g.shape[3]), (0, 0), 0, 0
-        keep = [g]
-        for k in range(len(steps) - 1, -1, -1):
+        n = plan.shape[0]
+        L = len(steps)
+        plan.flat.zero_()
+        g_desc = C.Tensor(plan.g_in.data_ptr(), C.FMT_F32_NCHW, 0, 0, 0)
+        g_dims, g_off, fold, fold_shift = (plan.g_in.shape[2], plan.g_in.shape[3]), (0, 0), 0, 0
+        for k in range(L - 1, -1, -1):
             st = steps[k]
-            x, o = xin[k], outs[k]
-            ho, wo = o.h, o.w
-            conv_like = not st.transposed
-            if st.kind == C.CONV_S1:
-                dz = self._buf(('dz', k), C.FMT_F16_PLANAR, n, st.c_out, ho + 2, wo + 2, C.HALO_KEEP, dev)
-                dz_off, embed = (1, 1), 1
-            elif st.kind == C.CONV_S2:
-                dz = self._buf(('dz', k), C.FMT_F16_PLANAR, n, st.c_out, ho + 1, wo + 1, C.HALO_KEEP, dev)
-                dz_off, embed = (1, 1), 1
-            elif st.kind == C.CONVT_S1:
-                dz = self._buf(('dz', k), C.FMT_F16_PLANAR, n, st.c_out, ho, wo, C.HALO_KEEP, dev)
-                dz_off, embed = (0, 0), 0
-            else:
-                dz = self._buf(('dz', k), C.FMT_F16_SPLIT, n, st.c_out, ho, wo, C.HALO_KEEP, dev)
-                dz_off, embed = (0, 0), 0
-            last = k == len(steps) - 1
-            db = torch.zeros(st.c_out, dtype=torch.float32, device=dev) if biases[k] is not None else None
+            x, o, dz = plan.xin[k], plan.outs[k], plan.dz[k]
+            last = k == L - 1
             self._act_grad(g_desc, g_dims, g_off, fold, fold_shift, o, E.act_code(st.pre_act),
-                           dz.desc(), (dz.h, dz.w), dz_off, n, ho, wo, st.c_out,
-                           scale if last else None, db)
-            if db is not None and not last:
-                db.mul_(inv_scale)            # below the top layer g already carries the scale
-            dbs[k] = db
-            dW = torch.zeros_like(weights[k], dtype=torch.float32)
-            ws = self._workspace(dev)
+                           dz.desc(), (dz.h, dz.w), plan.dz_off[k], n, o.h, o.w, st.c_out,
+                           plan.scale if last else None, plan.db[k])
             C.check(C.lib().cae_conv_wgrad(st.kind, n, x.h, x.w, st.c_in, st.c_out, x.desc(),
-                                           dz.desc(), embed, dW.data_ptr(), inv_scale.data_ptr(),
-                                           ws.data_ptr(), ws.numel(), _sptr()))
-            dWs[k] = dW
+                                           dz.desc(), plan.embed[k], plan.dW[k].data_ptr(),
+                                           plan.inv_scale.data_ptr(), plan.ws.data_ptr(),
+                                           plan.ws.numel(), _sptr()))
             if k == 0 and not need_dx:
                 g_desc = None
                 break
             kt = _ADJOINT[st.kind]
-            wt = O.pack_weights(kt, weights[k].detach())
-            gh, gw = O.KIND_OUT[kt](dz.h, dz.w)
-            if _merged(kt, st.c_in):
-                # adjoint of a stride-2 Conv2d with a thin input: the merged kernel, fp32 NCHW out
-                gt = torch.empty((n, st.c_in, gh, gw), dtype=torch.float32, device=dev)
-                O.conv(kt, dz, wt, st.c_in, None, igemm=True, bias=None, skip=None,
-                       pre_act=C.ACT_NONE, post_act=C.ACT_NONE, pad_mode=C.PAD_ZERO, aux=gt)
-                g_desc = C.Tensor(gt.data_ptr(), C.FMT_F32_NCHW, 0, 0, 0)
-                keep.append(gt)
+            O.pack_weights(kt, weights[k], out=plan.wt[k])
+            gb = plan.gbuf[k]
+            if gb.fmt == C.FMT_F32_NCHW:
+                O.conv(kt, dz, plan.wt[k], st.c_in, None, igemm=True, bias=None, skip=None,
+                       pre_act=C.ACT_NONE, post_act=C.ACT_NONE, pad_mode=C.PAD_ZERO, aux=gb.t)
             else:
-                gbuf = self._buf(('g', k), C.FMT_F16_PLANAR, n, st.c_in, gh, gw, C.HALO_KEEP, dev)
-                O.conv(kt, dz, wt, st.c_in, gbuf, igemm=True, bias=None, skip=None,
+                O.conv(kt, dz, plan.wt[k], st.c_in, gb, igemm=True, bias=None, skip=None,
                        pre_act=C.ACT_NONE, post_act=C.ACT_NONE, pad_mode=C.PAD_ZERO)
-                g_desc = gbuf.desc()
-            g_dims, g_off = (gh, gw), (0, 0)
-            fold, fold_shift = (1, 0 if st.kind == C.CONV_S1 else 1) if conv_like else (0, 0)
-            keep.append(wt)
-        dx = None
+            g_desc = C.Tensor(gb.t.data_ptr(), gb.fmt, gb.planes, 0, 0)
+            g_dims, g_off = (gb.h, gb.w), (0, 0)
+            fold, fold_shift = (1, 0 if st.kind == C.CONV_S1 else 1) if not st.transposed else (0, 0)
         if g_desc is not None:
-            x0 = xin[0]
-            dx = torch.empty((n, x0.c, x0.h, x0.w), dtype=torch.float32, device=dev)
+            x0 = plan.x0
             self._act_grad(g_desc, g_dims, g_off, fold, fold_shift, None, C.ACT_NONE,
-                           C.Tensor(dx.data_ptr(), C.FMT_F32_NCHW, 0, 0, 0), (x0.h, x0.w), (0, 0),
-                           n, x0.h, x0.w, x0.c, inv_scale, None)
+                           C.Tensor(plan.dx.data_ptr(), C.FMT_F32_NCHW, 0, 0, 0), (x0.h, x0.w), (0, 0),
+                           n, x0.h, x0.w, x0.c, plan.inv_scale, None)
+        # below the top layer the incoming gradient already carries the loss scale
+        if L > 1 and plan.offs[2 * L] > plan.offs[L]:
+            lo = plan.offs[L]
+            hi = plan.offs[2 * L - 1]        # the biases of layers 0 .. L-2
+            if hi > lo:
+                plan.flat[lo:hi].mul_(plan.inv_scale)
+
+    def backward(self, plan, g, weights, biases, need_dx=True):
+        """g: fp32 NCHW gradient of the chain's output.  Returns (dx fp32 NCHW or None,
+        [dW...], [db...]) with dW / db in torch layout, fp32."""
+        weights = [w.detach() for w in weights]
+        plan.g_in.copy_(g)
+        # power-of-two loss scale: max |g| * s ~ 64 (fp16 head-room for the growth through the
+        # layers, sub-normals 9 decades below); computed on the device, no host round trip
+        amax = plan.g_in.abs().amax().clamp_min(1e-30)
+        plan.scale.copy_(torch.exp2(torch.floor(torch.log2(64.0 / amax))).reshape(1))
+        plan.inv_scale.copy_(1.0 / plan.scale)
+        if not self.use_graphs:
+            self._launch_backward(plan, weights, need_dx)
+        else:
+            ptrs = tuple(t.data_ptr() for t in weights)
+            if plan.graph_bwd is None or plan.bwd_key != (need_dx, ptrs):
+                self._launch_backward(plan, weights, need_dx)
+                torch.cuda.current_stream().synchronize()
+                gr = torch.cuda.CUDAGraph()
+                n0 = C.lib().cae_launch_count()
+                with torch.cuda.graph(gr):
+                    self._launch_backward(plan, weights, need_dx)
+                plan.bwd_kernels = int(C.lib().cae_launch_count() - n0)
+                plan.graph_bwd, plan.bwd_key = gr, (need_dx, ptrs)
+            plan.graph_bwd.replay()
+            C.note_graph_replay(plan.bwd_kernels)
+        grads = plan.flat.clone()              # (autograd may keep what it is handed)
+        L = len(self.steps)
+        offs = plan.offs
+        dWs = [grads[offs[k]:offs[k + 1]].view_as(weights[k]) for k in range(L)]
+        dbs = [grads[offs[L + k]:offs[L + k + 1]] if biases[k] is not None else None for k in range(L)]
+        dx = plan.dx.clone() if need_dx else None
+        plan.busy = False
         return dx, dWs, dbs
 
 
@@ -258,21 +339,21 @@ class _ChainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, chain, n_layers, *params):
         weights, biases = params[:n_layers], params[n_layers:]
-        y, saved = chain.forward(x, weights, biases)
-        ctx.chain, ctx.saved = chain, saved
+        y, plan = chain.forward(x, weights, biases)
+        ctx.chain, ctx.plan = chain, plan
         ctx.n_layers = n_layers
         ctx.params = params
         ctx.need_dx = x.requires_grad
+        if not any(ctx.needs_input_grad):
+            plan.busy = False             # nobody will come back for the saved activations
         return y
 
     @staticmethod
     def backward(ctx, g):
         n = ctx.n_layers
         weights, biases = ctx.params[:n], ctx.params[n:]
-        dx, dWs, dbs = ctx.chain.backward(ctx.saved, g, weights, biases, need_dx=ctx.need_dx)
-        grads = [dw.to(w.dtype) for dw, w in zip(dWs, weights)]
-        grads += [db.to(b.dtype) if b is not None else None for db, b in zip(dbs, biases)]
-        return (dx, None, None, *grads)
+        dx, dWs, dbs = ctx.chain.backward(ctx.plan, g, weights, biases, need_dx=ctx.need_dx)
+        return (dx, None, None, *dWs, *dbs)
 
 
 def run_track(track, x):

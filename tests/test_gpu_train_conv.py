@@ -86,3 +86,47 @@ def test_whole_model_gradients_match_autograd(arch):
     assert abs(losses['kernels'] - losses['torch']) <= 2e-3 * abs(losses['torch'])
     for n, gt in grads['torch'].items():
         assert _rel(grads['kernels'][n], gt) < 2e-2, (n, _rel(grads['kernels'][n], gt))
+
+
+def test_train_step_matches_the_torch_formulation():
+    """One whole rate-distortion step (train_cae_ms.py:209-230: forward closure, criterion, two
+    backward passes, clip, Adam) with the transforms on the kernels against the same step with
+    the transforms as torch autograd ops (the reference's formulation) from identical parameters,
+    batch and noise: loss terms, the clipped gradients Adam saw (exp_avg after the first step =
+    0.1 x gradient) and the post-step weights."""
+    from oracle import cae_oracle as O
+    import cnn_autoencoder_b200 as M
+    chk = O.make_checkpoint(O.NAMED_ARCHS['A'], seed=7)
+    x = (O.synth_natural(4, 3, 128, 128, seed=5).float() / 255.0).cuda()
+    res = {}
+    for mode in ('kernels', 'torch'):
+        model = M.autoencoder_from_state_dict(chk, gpu=True, train=True)
+        for k in ('encoder', 'decoder'):
+            model[k].module.train_kernels = mode == 'kernels'
+        fwd = M.decorate_trainable_modules(trainable_modules=['encoder', 'decoder', 'fact_ent'],
+                                           enabled_modules=['encoder', 'decoder', 'fact_ent'])
+        crit = M.setup_loss('RateMSE', distortion_lambda=0.01)
+        opts = M.setup_optimizers(model, lr=1e-4, aux_lr=1e-3)
+        bucket = M.GradBucket(model)
+        torch.manual_seed(11)                    # the bottleneck's additive noise
+        out = M.train_step(x, model, crit, opts, fwd, bucket=bucket, step=0)
+        torch.cuda.synchronize()
+        res[mode] = dict(
+            loss=float(torch.mean(out['loss'])), dist=float(torch.mean(out['dist_loss'])),
+            rate=float(torch.mean(out['rate_loss'])),
+            m={k: torch.cat([opts[k].state[p]['exp_avg'].reshape(-1) for p in opts[k].param_groups[0]['params']])
+               for k in ('encoder', 'decoder')},
+            w={k: torch.cat([p.detach().reshape(-1) for p in model[k].parameters()]).clone()
+               for k in ('encoder', 'decoder')})
+        if mode == 'kernels':
+            assert model['encoder'].module._train_chain and model['decoder'].module._train_chain
+    a, b = res['kernels'], res['torch']
+    for key in ('loss', 'dist', 'rate'):
+        assert abs(a[key] - b[key]) <= 2e-3 * abs(b[key]), (key, a[key], b[key])
+    for k in ('encoder', 'decoder'):
+        assert _rel(a['m'][k], b['m'][k]) < 3e-2, (k, _rel(a['m'][k], b['m'][k]))
+        # Adam's first step moves every weight by +-lr: a gradient entry near zero may take the
+        # other sign, never more than 2 lr away, and only a few of them
+        d = (a['w'][k] - b['w'][k]).abs()
+        assert float(d.max()) <= 2.05e-4, (k, float(d.max()))
+        assert float((d > 2e-5).float().mean()) < 0.03, (k, float((d > 2e-5).float().mean()))
