@@ -241,21 +241,20 @@ __device__ __forceinline__ void ag_load8(const AgView &v, int n, int plane, int 
 }
 
 __global__ void __launch_bounds__(256) act_grad_kernel(const AgParams q) {
-  const uint32_t planes = (uint32_t)(q.c + 7) >> 3;
-  const uint32_t total = (uint32_t)q.n * planes * (uint32_t)q.h * (uint32_t)q.w;   // < 2^31 (host check)
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  __shared__ float s_db[128];
+  // grid (w / 32, h / 8, n * planes), block 32 x 8: a warp = 32 consecutive pixels of one row
+  // and plane (coalesced 16-byte units, no index divisions, one shuffle reduction per channel)
+  const int planes = (q.c + 7) >> 3;
+  const int x = (int)(blockIdx.x * 32 + (threadIdx.x & 31));
+  const int y = (int)(blockIdx.y * 8 + (threadIdx.x >> 5));
+  const int plane = (int)(blockIdx.z % (unsigned)planes), n = (int)(blockIdx.z / (unsigned)planes);
+  const bool inside = x < q.w && y < q.h;
+  __shared__ float s_db[8];
   if (q.db) {
-    if (threadIdx.x < 128) s_db[threadIdx.x] = 0.f;
+    if (threadIdx.x < 8) s_db[threadIdx.x] = 0.f;
     __syncthreads();
   }
-  if (i < total) {
-    const int x = (int)(i % (uint32_t)q.w);
-    uint32_t r = i / (uint32_t)q.w;
-    const int y = (int)(r % (uint32_t)q.h);
-    r /= (uint32_t)q.h;
-    const int plane = (int)(r % planes), n = (int)(r / planes);
-    float g[8];
+  float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (inside) {
     if (!q.fold) {
       ag_load8(q.g, n, plane, y + q.g.oy, x + q.g.ox, q.c, g);
     } else {
@@ -291,22 +290,16 @@ __global__ void __launch_bounds__(256) act_grad_kernel(const AgParams q) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) g[k] = o[k] > 0.f ? g[k] : g[k] * q.slope;
     }
-    if (q.db) {
-      // a warp's 32 consecutive units almost always share their plane: shuffle-reduce, one
-      // shared-memory atomic per warp and channel
-      const unsigned peers = __match_any_sync(__activemask(), plane);
-      const bool whole = peers == 0xffffffffu;
+  }
+  if (q.db) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float v = g[k];
-        if (whole) {
-          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if ((threadIdx.x & 31) == 0 && plane * 8 + k < q.c) atomicAdd(&s_db[(plane * 8 + k) & 127], v);
-        } else if (plane * 8 + k < q.c && v != 0.f) {
-          atomicAdd(&s_db[(plane * 8 + k) & 127], v);
-        }
-      }
+    for (int k = 0; k < 8; ++k) {
+      float v = g[k];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0 && v != 0.f) atomicAdd(&s_db[k], v);
     }
+  }
+  if (inside) {
     const float sc = q.scale ? __ldg(q.scale) : 1.f;
     if (q.dz.fmt == CAE_FMT_F32_NCHW) {
       float *dst = reinterpret_cast<float *>(q.dz.ptr);
@@ -330,8 +323,8 @@ __global__ void __launch_bounds__(256) act_grad_kernel(const AgParams q) {
   if (q.db) {
     __syncthreads();
     // (the sums are taken before scaling)
-    if (threadIdx.x < 128 && (int)threadIdx.x < q.c && s_db[threadIdx.x] != 0.f)
-      atomicAdd(q.db + threadIdx.x, s_db[threadIdx.x]);
+    if (threadIdx.x < 8 && plane * 8 + (int)threadIdx.x < q.c && s_db[threadIdx.x] != 0.f)
+      atomicAdd(q.db + plane * 8 + threadIdx.x, s_db[threadIdx.x]);
   }
 }
 
@@ -503,9 +496,11 @@ extern "C" int cae_act_grad(cae_tensor g, int g_h, int g_w, int g_oy, int g_ox, 
   q.slope = act == CAE_ACT_LEAKY_RELU ? 0.01f : (act == CAE_ACT_RELU ? 0.f : 1.f);
   q.scale = scale;
   q.db = db;
-  const size_t total = (size_t)n * ((c + 7) / 8) * h * w;
-  CAE_CHECK(total < 2147483648ull, 2, "cae_act_grad: tensor too large for one launch; split the batch");
-  act_grad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(q);
+  const int planes = (c + 7) / 8;
+  CAE_CHECK((long long)n * planes <= 65535 && (h + 7) / 8 <= 65535, 2,
+            "cae_act_grad: tensor too large for one launch; split the batch");
+  const dim3 grid((unsigned)((w + 31) / 32), (unsigned)((h + 7) / 8), (unsigned)(n * planes));
+  act_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(q);
   cae_count_launch();
   CAE_CUDA(cudaGetLastError());
   return 0;
