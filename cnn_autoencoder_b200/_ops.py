@@ -11,7 +11,12 @@ import torch
 from . import _cabi as C
 
 
-def _stream_ptr():
+def _stream_ptr(t=None):
+    """Current stream of the current device.  The library launches on the CURRENT device, so a
+    tensor living on another one is refused here instead of faulting inside a kernel."""
+    if t is not None and t.is_cuda and t.device.index != torch.cuda.current_device():
+        raise C.CaeError(f'tensor on {t.device} but the current CUDA device is '
+                         f'cuda:{torch.cuda.current_device()}: wrap the call in torch.cuda.device(...)')
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -110,7 +115,7 @@ def pack_weights(kind, weight, scale=None, ck=0, out=None):
         sc = scale.detach().contiguous().float()
     C.check(L.cae_pack_weights(kind, c_in, c_out, ck, w.data_ptr(),
                                sc.data_ptr() if sc is not None else None,
-                               packed.data_ptr(), _stream_ptr()))
+                               packed.data_ptr(), _stream_ptr(w)))
     return packed
 
 
@@ -124,7 +129,7 @@ def pack_proj_weights(weight, scale=None):
     sc = scale.detach().contiguous().float() if scale is not None else None
     C.check(L.cae_pack_proj_weights(w.shape[0], w.shape[1], w.data_ptr(),
                                     sc.data_ptr() if sc is not None else None,
-                                    packed.data_ptr(), _stream_ptr()))
+                                    packed.data_ptr(), _stream_ptr(w)))
     return packed
 
 
@@ -140,7 +145,7 @@ def image_from_proj(proj, n, h, w, c_out, *, bias=None, pre_act=C.ACT_NONE, post
     C.check(C.lib().cae_image_from_proj(
         proj.data_ptr(), n, h, w, c_out, bias.data_ptr() if bias is not None else None,
         pre_act, post_act, out.t.data_ptr() if out is not None else None,
-        aux.data_ptr() if aux is not None else None, _stream_ptr()))
+        aux.data_ptr() if aux is not None else None, _stream_ptr(proj)))
     return out
 
 
@@ -170,7 +175,7 @@ def conv(kind, x, weights, c_out, out, *, igemm, bias=None, skip=None, pre_act=C
         d.proj = ctypes.addressof(pf)
     L = C.lib()
     fn = L.cae_conv_igemm if igemm else L.cae_conv_direct
-    C.check(fn(ctypes.byref(d), _stream_ptr()))
+    C.check(fn(ctypes.byref(d), _stream_ptr(x.t)))
     return out
 
 
@@ -193,7 +198,7 @@ def conv_head(x, w_stem, b_stem, w_down, b_down, c_out, out, *, act_stem=C.ACT_N
         d.w_stem2 = w_stem2.data_ptr()
         d.b_stem2 = b_stem2.data_ptr() if b_stem2 is not None else None
         d.act_mid = act_mid
-    C.check(C.lib().cae_conv_head(ctypes.byref(d), _stream_ptr()))
+    C.check(C.lib().cae_conv_head(ctypes.byref(d), _stream_ptr(x.t)))
     return out
 
 
@@ -213,14 +218,14 @@ def nchw_to_planar(x, fmt=C.FMT_F16_PLANAR, halo=C.HALO_KEEP, out=None):
     if out is None:
         out = alloc_act(fmt, a.n, a.c, a.h, a.w, halo, device=x.device)
     C.check(C.lib().cae_nchw_to_planar(a.t.data_ptr(), a.n, a.c, a.h, a.w, out.desc(),
-                                       _stream_ptr()))
+                                       _stream_ptr(a.t)))
     return out
 
 
 def planar_to_nchw(a):
     out = torch.empty((a.n, a.c, a.h, a.w), dtype=torch.float32, device=a.t.device)
     C.check(C.lib().cae_planar_to_nchw(a.desc(), a.n, a.c, a.h, a.w, out.data_ptr(),
-                                       _stream_ptr()))
+                                       _stream_ptr(a.t)))
     return out
 
 
@@ -229,5 +234,5 @@ def gdn(x, out, beta, gamma, inverse, skip=None):
     none = C.Tensor(None, C.FMT_NONE, 0, 0, 0)
     C.check(C.lib().cae_gdn(x.desc(), out.desc(), skip.desc() if skip is not None else none,
                             x.n, x.h, x.w, x.c, beta.data_ptr(), gamma.data_ptr(),
-                            1 if inverse else 0, _stream_ptr()))
+                            1 if inverse else 0, _stream_ptr(x.t)))
     return out

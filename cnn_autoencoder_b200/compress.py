@@ -114,6 +114,42 @@ def open_source(input_filename, data_group='0/0'):
     return _View()
 
 
+class _AxesView:
+    """Y x X x C view of an array stored with other axes (``compress.py:89-101`` of the
+    reference: transpose to <other axes> + YXC and take index 0 of every other axis)."""
+
+    def __init__(self, arr, axes):
+        self.arr, self.axes = arr, axes
+        pos = {a: i for i, a in enumerate(axes)}
+        self.shape = (arr.shape[pos['Y']], arr.shape[pos['X']], arr.shape[pos['C']])
+        self.dtype = arr.dtype
+        self.pos = pos
+
+    def __getitem__(self, key):
+        key = key if isinstance(key, tuple) else (key,)
+        key = tuple(key) + (slice(None),) * (3 - len(key))
+        index = [0] * len(self.axes)
+        for a, k in zip('YXC', key):
+            index[self.pos[a]] = k
+        block = np.asarray(self.arr[tuple(index)])
+        kept = [a for a in self.axes if a in 'YXC' and not isinstance(index[self.pos[a]], int)]
+        return np.ascontiguousarray(block.transpose([kept.index(a) for a in 'YXC' if a in kept]))
+
+
+def as_yxc(src, data_axes):
+    """The source as an H x W x C array-like.  Arrays that already are three-dimensional are
+    taken as YXC whatever ``data_axes`` says (the ndarray / ``.npy`` / directory-array sources of
+    this package); anything else is mapped like the reference does."""
+    shape = tuple(src.shape)
+    if len(shape) == 3:
+        return src
+    axes = str(data_axes).upper()
+    if len(axes) != len(shape) or not set('YXC') <= set(axes) or len(set(axes)) != len(axes):
+        raise ValueError('source has shape %r, which data_axes=%r does not describe (need one '
+                         'letter per axis including Y, X and C)' % (shape, data_axes))
+    return _AxesView(src, axes)
+
+
 def compress_image(codec, checkpoint, input_filename, output_filename, patch_size=512,
                    source_format='zarr', data_group='0/0', data_axes='TCZYX',
                    progress_bar=False, save_as_bottleneck=False, gpu=False, *,
@@ -128,7 +164,7 @@ def compress_image(codec, checkpoint, input_filename, output_filename, patch_siz
         raise RuntimeError('compress_image needs a CUDA device (no CPU fallback)')
     rank, world_size = _dist_info(rank, world_size)
     workers = workers or default_workers()
-    src = open_source(input_filename, data_group)
+    src = as_yxc(open_source(input_filename, data_group), data_axes)
     H, W, C = src.shape
     ps = patch_size
 

@@ -206,3 +206,24 @@ def test_engine_plans_the_fused_head_where_it_applies():
     assert span(dict(compression_level=3, act_layer_type='LeakyReLU'), fmt=C.FMT_F16_PLANAR)[0] == 0
     # a caller that wants the stem's output kept gets the separate kernels
     assert span(dict(compression_level=3, act_layer_type='LeakyReLU'), keep=(1,))[0] == 0
+
+
+def test_source_axes_are_mapped_like_the_reference():
+    """data_axes (compress.py:89-101 of the reference): a TCZYX source is read as Y x X x C with
+    index 0 of the other axes; three-dimensional sources are YXC already."""
+    import numpy as np
+    from cnn_autoencoder_b200.compress import as_yxc
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 255, size=(2, 3, 2, 20, 30), dtype=np.uint8)       # T C Z Y X
+    v = as_yxc(a, 'TCZYX')
+    assert v.shape == (20, 30, 3)
+    want = a[0, :, 0].transpose(1, 2, 0)
+    assert np.array_equal(v[3:11, 5:30], want[3:11, 5:30])
+    assert np.array_equal(v[0:20, 0:30, :], want)
+    b = rng.integers(0, 255, size=(4, 5, 3, 1), dtype=np.uint8)            # Y X C Z
+    assert np.array_equal(as_yxc(b, 'YXCZ')[1:3, 0:5], b[1:3, 0:5, :, 0])
+    c = rng.integers(0, 255, size=(6, 7, 3), dtype=np.uint8)
+    assert as_yxc(c, 'TCZYX') is c
+    import pytest
+    with pytest.raises(ValueError):
+        as_yxc(a, 'YXC')
