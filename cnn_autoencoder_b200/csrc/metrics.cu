@@ -1,0 +1,183 @@
+// Evaluation sums of the reference's src/test_cae.py on the device, for uint8
+// H x W x C images that are already in HBM (the reconstruction as the synthesis transform left it):
+//
+//  cae_ssim_u8     skimage.metrics.structural_similarity(x, x_r, channel_axis=2) as test_cae.py:52-54
+//                  calls it (defaults: 7x7 uniform window, K1 = 0.01, K2 = 0.03, sample covariance,
+//                  data_range 255, mean over the map cropped by 3 pixels, mean over channels):
+//                  per image the SUM of the SSIM map over the cropped region and the channels, in
+//                  double; the caller divides by (H - 6)(W - 6)C.
+//  cae_delta_e_u8  mean CIE76 colour difference as compute_deltaCIELAB (test_cae.py:21-44):
+//                  skimage.color.rgb2lab (sRGB -> linear -> XYZ, D65 / 2 degree observer -> L*a*b*)
+//                  of both images and deltaE_cie76: per image the SUM of the per-pixel distances.
+//
+// Both are HBM bound (two uint8 images in, a handful of doubles out): 16-byte-free scalar loads
+// through shared-memory tiles for SSIM (each input byte is read once per 32 x 32 output tile plus
+// its 6-pixel apron), one pixel per thread for the colour difference; warp-shuffle + one double
+// atomic per block.
+#include "cae_common.cuh"
+
+namespace {
+
+constexpr int kSsimWin = 7, kSsimPad = 3;
+constexpr int kSsimTile = 32;                       // outputs per block side
+constexpr int kSsimIn = kSsimTile + kSsimWin - 1;   // 38
+
+struct SsimParams {
+  const uint8_t *a, *b;
+  int n, H, W, C;
+  double *sum;    // [n]
+};
+
+// Block = one 32 x 32 tile of window positions (top-left corners) of one image; the window sums of
+// every channel are built separably: horizontal 7-sums of the five moment images into shared
+// memory, then vertical 7-sums per output.
+__global__ void __launch_bounds__(256) ssim_u8_kernel(const SsimParams p) {
+  __shared__ float tile_a[kSsimIn][kSsimIn + 1], tile_b[kSsimIn][kSsimIn + 1];
+  __shared__ float h[5][kSsimIn][kSsimTile + 1];     // horizontal sums: a, b, aa, bb, ab
+  __shared__ double s_part[8];
+  const int n = blockIdx.z;
+  const int oy0 = blockIdx.y * kSsimTile, ox0 = blockIdx.x * kSsimTile;
+  const int OH = p.H - kSsimWin + 1, OW = p.W - kSsimWin + 1;     // number of window positions
+  const uint8_t *A = p.a + (size_t)n * p.H * p.W * p.C, *B = p.b + (size_t)n * p.H * p.W * p.C;
+  const double C1 = (0.01 * 255.0) * (0.01 * 255.0), C2 = (0.03 * 255.0) * (0.03 * 255.0);
+  const double inv_np = 1.0 / 49.0, cov_norm = 49.0 / 48.0;
+  double acc = 0.0;
+  for (int c = 0; c < p.C; ++c) {
+    for (int i = threadIdx.x; i < kSsimIn * kSsimIn; i += blockDim.x) {
+      const int r = i / kSsimIn, q = i - r * kSsimIn;
+      const int y = oy0 + r, x = ox0 + q;
+      float va = 0.f, vb = 0.f;
+      if (y < p.H && x < p.W) {
+        const size_t o = ((size_t)y * p.W + x) * p.C + c;
+        va = (float)A[o];
+        vb = (float)B[o];
+      }
+      tile_a[r][q] = va;
+      tile_b[r][q] = vb;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSsimIn * kSsimTile; i += blockDim.x) {
+      const int r = i / kSsimTile, q = i - r * kSsimTile;
+      float sa = 0.f, sb = 0.f, saa = 0.f, sbb = 0.f, sab = 0.f;
+#pragma unroll
+      for (int k = 0; k < kSsimWin; ++k) {
+        const float va = tile_a[r][q + k], vb = tile_b[r][q + k];
+        sa += va;
+        sb += vb;
+        saa += va * va;
+        sbb += vb * vb;
+        sab += va * vb;
+      }
+      h[0][r][q] = sa;
+      h[1][r][q] = sb;
+      h[2][r][q] = saa;
+      h[3][r][q] = sbb;
+      h[4][r][q] = sab;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSsimTile * kSsimTile; i += blockDim.x) {
+      const int r = i / kSsimTile, q = i - r * kSsimTile;
+      if (oy0 + r >= OH || ox0 + q >= OW) continue;
+      float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < kSsimWin; ++k)
+#pragma unroll
+        for (int m = 0; m < 5; ++m) s[m] += h[m][r + k][q];
+      // the sums are integers < 49 * 255^2 < 2^24, exact in fp32; the moments cancel, so the
+      // rest is done in double like skimage does
+      const double ux = (double)s[0] * inv_np, uy = (double)s[1] * inv_np;
+      const double vx = cov_norm * ((double)s[2] * inv_np - ux * ux);
+      const double vy = cov_norm * ((double)s[3] * inv_np - uy * uy);
+      const double vxy = cov_norm * ((double)s[4] * inv_np - ux * uy);
+      const double a1 = 2.0 * ux * uy + C1, a2 = 2.0 * vxy + C2;
+      const double b1 = ux * ux + uy * uy + C1, b2 = vx + vy + C2;
+      acc += (a1 * a2) / (b1 * b2);
+    }
+    __syncthreads();
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_part[w];
+    atomicAdd(p.sum + n, t);
+  }
+}
+
+// skimage.color.rgb2lab for one 8-bit sRGB pixel (D65, 2 degree observer)
+__device__ __forceinline__ void rgb_to_lab(float r, float g, float b, float &L, float &A, float &Bv) {
+  auto lin = [](float v) {
+    v *= (1.f / 255.f);
+    return v > 0.04045f ? powf((v + 0.055f) / 1.055f, 2.4f) : v / 12.92f;
+  };
+  const float R = lin(r), G = lin(g), Bl = lin(b);
+  float X = 0.412453f * R + 0.357580f * G + 0.180423f * Bl;
+  float Y = 0.212671f * R + 0.715160f * G + 0.072169f * Bl;
+  float Z = 0.019334f * R + 0.119193f * G + 0.950227f * Bl;
+  X /= 0.95047f;
+  Z /= 1.08883f;
+  auto f = [](float t) { return t > 0.008856f ? cbrtf(t) : 7.787f * t + 16.f / 116.f; };
+  const float fx = f(X), fy = f(Y), fz = f(Z);
+  L = 116.f * fy - 16.f;
+  A = 500.f * (fx - fy);
+  Bv = 200.f * (fy - fz);
+}
+
+__global__ void __launch_bounds__(256) delta_e_u8_kernel(const uint8_t *__restrict__ a,
+                                                         const uint8_t *__restrict__ b,
+                                                         size_t pixels, double *__restrict__ sum) {
+  __shared__ double s_part[8];
+  const int n = blockIdx.y;
+  const uint8_t *A = a + (size_t)n * pixels * 3, *B = b + (size_t)n * pixels * 3;
+  double acc = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pixels;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float L1, a1, b1, L2, a2, b2;
+    rgb_to_lab((float)A[3 * i], (float)A[3 * i + 1], (float)A[3 * i + 2], L1, a1, b1);
+    rgb_to_lab((float)B[3 * i], (float)B[3 * i + 1], (float)B[3 * i + 2], L2, a2, b2);
+    const float dL = L1 - L2, da = a1 - a2, db = b1 - b2;
+    acc += (double)sqrtf(dL * dL + da * da + db * db);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_part[w];
+    atomicAdd(sum + n, t);
+  }
+}
+
+}  // namespace
+
+extern "C" int cae_ssim_u8(const uint8_t *a, const uint8_t *b, int n_images, int h, int w, int c,
+                           double *sum, void *stream) {
+  CAE_CHECK(a && b && sum && n_images > 0 && c > 0, 2, "cae_ssim_u8: bad argument");
+  CAE_CHECK(h >= kSsimWin && w >= kSsimWin, 2, "cae_ssim_u8: images smaller than the 7x7 window");
+  CAE_CHECK(n_images <= 65535, 2, "cae_ssim_u8: more than 65535 images per call");
+  SsimParams p{a, b, n_images, h, w, c, sum};
+  const int OH = h - kSsimWin + 1, OW = w - kSsimWin + 1;
+  const dim3 grid((unsigned)((OW + kSsimTile - 1) / kSsimTile), (unsigned)((OH + kSsimTile - 1) / kSsimTile),
+                  (unsigned)n_images);
+  CAE_CHECK(grid.y <= 65535, 2, "cae_ssim_u8: image too tall for one launch");
+  ssim_u8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  cae_count_launch();
+  CAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int cae_delta_e_u8(const uint8_t *a, const uint8_t *b, int n_images, int64_t pixels,
+                              double *sum, void *stream) {
+  CAE_CHECK(a && b && sum && n_images > 0 && pixels > 0, 2, "cae_delta_e_u8: bad argument");
+  CAE_CHECK(n_images <= 65535, 2, "cae_delta_e_u8: more than 65535 images per call");
+  int bx = (int)((pixels + 255) / 256);
+  const int want = (8 * cae_sm_count() + n_images - 1) / n_images;
+  if (bx > want) bx = want;
+  if (bx < 1) bx = 1;
+  delta_e_u8_kernel<<<dim3((unsigned)bx, (unsigned)n_images), 256, 0, (cudaStream_t)stream>>>(
+      a, b, (size_t)pixels, sum);
+  cae_count_launch();
+  CAE_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -6,6 +6,12 @@ computed on the device:
   without widening (the differences wrap); here the squared differences are
   summed exactly in 64-bit integers by ``cae_sse_u8``.
 * ``bpp``: ``compute_rate`` :71-73 — ``8 * bytes_stored / (H * W)``.
+* ``ssim``: ``compute_ssim`` :52-54 — ``skimage.metrics.structural_similarity(x, x_r,
+  channel_axis=2)`` with its defaults (7x7 uniform window, sample covariance, data range 255, map
+  cropped by 3 pixels), window sums on the device (``cae_ssim_u8``).
+* ``delta_cielab``: ``compute_deltaCIELAB`` :21-44 — mean CIE76 distance after
+  ``skimage.color.rgb2lab`` of both images (``cae_delta_e_u8``).
+(``ms-ssim`` :46-50 uses the ``pytorch_msssim`` package and is not part of this module.)
 
 The reference computes these on the host after downloading the whole reconstruction; here the
 reconstruction can stay where the synthesis transform left it.  Inputs are uint8 CUDA tensors
@@ -73,3 +79,43 @@ def psnr(x, x_r, max_val=255.0):
 def bpp(nbytes_stored, height, width):
     """``compute_rate`` (test_cae.py:71-73)."""
     return 8.0 * float(nbytes_stored) / (height * width)
+
+
+def _pair(x, x_r):
+    dev = x.device if isinstance(x, torch.Tensor) and x.is_cuda else (
+        x_r.device if isinstance(x_r, torch.Tensor) and x_r.is_cuda else None)
+    a, b = _as_cuda_u8(x, dev), _as_cuda_u8(x_r, dev)
+    if a.shape != b.shape:
+        raise ValueError('shape mismatch %r vs %r' % (tuple(a.shape), tuple(b.shape)))
+    if a.dim() == 3:
+        a, b = a[None], b[None]
+    if a.dim() != 4:
+        raise ValueError('expected H x W x C or N x H x W x C uint8 images')
+    return a, b
+
+
+def ssim(x, x_r, per_image=False):
+    """``compute_ssim`` (test_cae.py:52-54) of uint8 H x W x C images (or a batch N x H x W x C:
+    the mean over the batch unless ``per_image``)."""
+    a, b = _pair(x, x_r)
+    n, h, w, c = a.shape
+    out = torch.zeros(n, dtype=torch.float64, device=a.device)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
+    with torch.cuda.device(a.device):
+        C.check(C.lib().cae_ssim_u8(a.data_ptr(), b.data_ptr(), n, h, w, c, out.data_ptr(), stream))
+    out = out / float((h - 6) * (w - 6) * c)
+    return out if per_image else float(out.mean().item())
+
+
+def delta_cielab(x, x_r, per_image=False):
+    """``compute_deltaCIELAB`` (test_cae.py:21-44): mean CIE76 distance of 8-bit sRGB images."""
+    a, b = _pair(x, x_r)
+    n, h, w, c = a.shape
+    if c != 3:
+        raise ValueError('delta_cielab needs RGB images')
+    out = torch.zeros(n, dtype=torch.float64, device=a.device)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
+    with torch.cuda.device(a.device):
+        C.check(C.lib().cae_delta_e_u8(a.data_ptr(), b.data_ptr(), n, h * w, out.data_ptr(), stream))
+    out = out / float(h * w)
+    return out if per_image else float(out.mean().item())

@@ -376,6 +376,19 @@ int cae_tiles_download_u8(const uint8_t *src, int n, int ps, int c, const int32_
 int cae_sse_u8(const uint8_t *a, const uint8_t *b, int n_images, int64_t per_image,
                uint64_t *sse, void *stream);
 
+/* skimage.metrics.structural_similarity(x, x_r, channel_axis=2) with its defaults, as
+ * compute_ssim calls it (src/test_cae.py:52-54): 7x7 uniform window, K1 0.01, K2 0.03, sample
+ * covariance, data range 255.  a, b: n_images x h x w x c uint8 on the device; sum[i] += the SSIM
+ * map of image i summed over the (h - 6) x (w - 6) window positions skimage keeps (its crop by 3)
+ * and over the channels; SSIM = sum / ((h - 6)(w - 6) c).                                       */
+int cae_ssim_u8(const uint8_t *a, const uint8_t *b, int n_images, int h, int w, int c, double *sum,
+                void *stream);
+/* compute_deltaCIELAB (src/test_cae.py:21-44): skimage.color.rgb2lab of both 8-bit sRGB images
+ * (D65, 2 degree observer) and deltaE_cie76; sum[i] += the per-pixel colour distances of image i
+ * (n_images x pixels x 3 uint8); mean = sum / pixels.                                           */
+int cae_delta_e_u8(const uint8_t *a, const uint8_t *b, int n_images, int64_t pixels, double *sum,
+                   void *stream);
+
 #ifdef __cplusplus
 }
 #endif

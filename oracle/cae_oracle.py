@@ -689,3 +689,49 @@ def synth_tissue_tile(ty, tx, ps=512, seed=2):
     img = base * (0.6 + 0.4 * lo) + 0.25 * (mid - 0.5) + 0.15 * (noise - 0.5)
     img = (img.clamp(0, 1) * 255).round().to(torch.uint8)
     return np.ascontiguousarray(img[0].permute(1, 2, 0).numpy())
+
+
+def ssim_u8(x, x_r):
+    """compute_ssim, ``test_cae.py:52-54``: ``skimage.metrics.structural_similarity(x, x_r,
+    channel_axis=2)`` with its defaults, restated from the published algorithm (scikit-image is
+    not installed here -- parity unpinned by the real package): per channel, float64, 7x7
+    ``scipy.ndimage.uniform_filter`` moments, sample covariance (NP / (NP - 1)), K1 = 0.01,
+    K2 = 0.03, data range 255 for uint8, the map cropped by (win - 1) // 2 = 3 pixels, mean; then
+    the mean over the channels."""
+    from scipy.ndimage import uniform_filter
+    win, K1, K2, R = 7, 0.01, 0.03, 255.0
+    NP = win * win
+    cov_norm = NP / (NP - 1.0)
+    C1, C2 = (K1 * R) ** 2, (K2 * R) ** 2
+    pad = (win - 1) // 2
+    vals = []
+    for c in range(x.shape[2]):
+        a, b = x[..., c].astype(np.float64), x_r[..., c].astype(np.float64)
+        ux, uy = uniform_filter(a, size=win), uniform_filter(b, size=win)
+        uxx, uyy, uxy = uniform_filter(a * a, size=win), uniform_filter(b * b, size=win), uniform_filter(a * b, size=win)
+        vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
+        S = ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux ** 2 + uy ** 2 + C1) * (vx + vy + C2))
+        vals.append(S[pad:-pad, pad:-pad].mean(dtype=np.float64))
+    return float(np.mean(vals))
+
+
+def rgb2lab_u8(x):
+    """``skimage.color.rgb2lab`` of an 8-bit sRGB image (D65, 2 degree observer), restated from the
+    published algorithm (parity unpinned by the real package)."""
+    v = x.astype(np.float64) / 255.0
+    lin = np.where(v > 0.04045, ((v + 0.055) / 1.055) ** 2.4, v / 12.92)
+    M = np.array([[0.412453, 0.357580, 0.180423], [0.212671, 0.715160, 0.072169],
+                  [0.019334, 0.119193, 0.950227]])
+    xyz = lin @ M.T
+    xyz = xyz / np.array([0.95047, 1.0, 1.08883])
+    f = np.where(xyz > 0.008856, np.cbrt(xyz), 7.787 * xyz + 16.0 / 116.0)
+    L = 116.0 * f[..., 1] - 16.0
+    a = 500.0 * (f[..., 0] - f[..., 1])
+    b = 200.0 * (f[..., 1] - f[..., 2])
+    return np.stack([L, a, b], axis=-1)
+
+
+def delta_cielab_u8(x, x_r):
+    """compute_deltaCIELAB, ``test_cae.py:21-44``: mean ``deltaE_cie76`` of the two images."""
+    d = rgb2lab_u8(x) - rgb2lab_u8(x_r)
+    return float(np.sqrt((d ** 2).sum(axis=-1)).mean())

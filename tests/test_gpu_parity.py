@@ -590,3 +590,28 @@ def test_training_mode_bottleneck_kernels_match_autograd():
     for k in a[3]:
         scale = b[3][k].abs().max().item() + 1e-12
         assert (a[3][k] - b[3][k]).abs().max().item() <= 2e-4 * scale + 1e-7, k
+
+
+def test_ssim_and_delta_e_kernels_match_the_oracle():
+    """cae_ssim_u8 / cae_delta_e_u8 (metrics.ssim, metrics.delta_cielab: compute_ssim and
+    compute_deltaCIELAB of src/test_cae.py on the device) against the float64 restatement of the
+    scikit-image algorithms, on a tissue-like image and its noisy / shifted versions, ragged
+    sizes included."""
+    from oracle import cae_oracle as O
+    from cnn_autoencoder_b200 import metrics
+    rng = np.random.default_rng(1)
+    for h, w in ((64, 64), (71, 45), (200, 333)):
+        x = O.synth_natural(1, 3, h, w, seed=h)[0].permute(1, 2, 0).contiguous().numpy()
+        noisy = np.clip(x.astype(np.int32) + rng.integers(-20, 21, size=x.shape), 0, 255).astype(np.uint8)
+        dark = (x * 0.8).astype(np.uint8)
+        for y in (x, noisy, dark):
+            got, want = metrics.ssim(x, y), O.ssim_u8(x, y)
+            assert abs(got - want) < 1e-9, (h, w, got, want)
+            got, want = metrics.delta_cielab(x, y), O.delta_cielab_u8(x, y)
+            assert abs(got - want) <= 2e-4 * max(1.0, want), (h, w, got, want)
+    # batch form
+    xb = O.synth_natural(3, 3, 48, 40, seed=9).permute(0, 2, 3, 1).contiguous()
+    yb = (xb.float() * 0.9).to(torch.uint8)
+    per = metrics.ssim(xb.cuda(), yb.cuda(), per_image=True).cpu().numpy()
+    for i in range(3):
+        assert abs(per[i] - O.ssim_u8(xb[i].numpy(), yb[i].numpy())) < 1e-9

@@ -62,3 +62,22 @@ def test_image_io_casts():
     buf = np.arange(12, dtype=np.uint8).reshape(2, 2, 3)
     f = O.to_float_chw(buf)
     assert f.shape == (1, 3, 2, 2) and f[0, 1, 0, 1].item() == np.float32(4) / np.float32(255)
+
+
+def test_oracle_ssim_and_delta_e_known_answers():
+    """Hand-checkable corners of the restated evaluation metrics (test_cae.py:21-54): identical
+    images, a constant offset (closed form), the Lab values of black / white / the sRGB primaries
+    (published values)."""
+    import numpy as np
+    from oracle import cae_oracle as O
+    rng = np.random.default_rng(0)
+    x = rng.integers(0, 256, size=(40, 50, 3), dtype=np.uint8)
+    assert abs(O.ssim_u8(x, x) - 1.0) < 1e-12
+    assert O.delta_cielab_u8(x, x) == 0.0
+    # constant images a, b: variances vanish, SSIM = (2ab + C1) / (a^2 + b^2 + C1)
+    a, b = np.full((20, 20, 1), 100, np.uint8), np.full((20, 20, 1), 120, np.uint8)
+    C1 = (0.01 * 255) ** 2
+    assert abs(O.ssim_u8(a, b) - (2 * 100 * 120 + C1) / (100 ** 2 + 120 ** 2 + C1)) < 1e-12
+    lab = O.rgb2lab_u8(np.array([[[0, 0, 0], [255, 255, 255], [255, 0, 0], [0, 255, 0], [0, 0, 255]]], np.uint8))[0]
+    want = np.array([[0, 0, 0], [100, 0, 0], [53.24, 80.09, 67.20], [87.73, -86.18, 83.18], [32.30, 79.19, -107.86]])
+    assert np.abs(lab - want).max() < 0.05, lab
