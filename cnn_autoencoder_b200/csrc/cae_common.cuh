@@ -321,6 +321,15 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
                : "memory");
 }
 
+// The same without release semantics, for arrivals that only hand TMEM / shared-memory stages
+// back (ordered by tcgen05.fence / the async proxy): a cluster-scope release is MEMBAR + ERRBAR
+// and waits for the warp's outstanding GLOBAL stores -- on the accumulator hand-over that put the
+// HBM write latency of the epilogue on the tensor pipe's critical path (ncu source page).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+
 // wait on a local barrier whose arrivals come from the peer CTA (cluster-scope acquire)
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t *bar, uint32_t parity) {
   uint32_t ok;

@@ -1050,7 +1050,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-        if (PAIR) mbar_arrive_cluster(buf ? acc_empty_addr1 : acc_empty_addr0); else mbar_arrive(&acc_empty[buf]);
+        if (PAIR) mbar_arrive_cluster_relaxed(buf ? acc_empty_addr1 : acc_empty_addr0); else mbar_arrive(&acc_empty[buf]);
       }
         continue;
       }
@@ -1064,7 +1064,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (PAIR) mbar_arrive_cluster(buf ? acc_empty_addr1 : acc_empty_addr0); else mbar_arrive(&acc_empty[buf]);
+        if (PAIR) mbar_arrive_cluster_relaxed(buf ? acc_empty_addr1 : acc_empty_addr0); else mbar_arrive(&acc_empty[buf]);
       }
     }
     if (EPI == EPI_LATENT && p.quant && p.q_rate) {
