@@ -400,7 +400,11 @@ def run_wsi(args):
         os.makedirs(work, exist_ok=True)
     c.barrier()
 
-    kw = dict(rank=rank, world_size=world, batch_tiles=args.batch_tiles, coder_tiles=args.coder_tiles)
+    if args.coder_tiles <= 0:
+        args.coder_tiles = T
+    if args.e2e_coder_tiles <= 0:
+        args.e2e_coder_tiles = max(args.batch_tiles, T // 2)
+    kw = dict(rank=rank, world_size=world, batch_tiles=args.batch_tiles, coder_tiles=args.e2e_coder_tiles)
 
     def step(to_files=False):
         cs = CMP.compress_image('CAE', chk, slide, comp_dir, patch_size=PS, gpu=True, **kw)
@@ -566,6 +570,7 @@ def run_wsi(args):
         'config': {'workload': wsi_workload_text(args, world),
                    'l2': f'inputs larger than L2 ({px_step * 3 / 1e9:.2f} GB of tiles per step per GPU)',
                    'accumulate': 'f32', 'batch_tiles': args.batch_tiles, 'coder_tiles': args.coder_tiles,
+                   'e2e_coder_tiles': args.e2e_coder_tiles,
                    'value_is': 'tiles resident in HBM -> transforms + quantizer + device rANS encode + '
                                'decode + transforms -> tiles in HBM (no host transfer)',
                    'e2e_is': 'compress_image -> decompress_image: slide in page-locked host memory -> chunk '
@@ -712,7 +717,11 @@ def main():
     ap.add_argument('--batch', type=int, default=BATCH, help='patches per step (workload patches)')
     ap.add_argument('--tiles', type=int, default=TILES, help='512x512 chunks per GPU per step (workload wsi)')
     ap.add_argument('--batch-tiles', type=int, default=32, help='chunks per CUDA-graph replay')
-    ap.add_argument('--coder-tiles', type=int, default=TILES, help='chunk streams entropy-coded per device call')
+    ap.add_argument('--coder-tiles', type=int, default=0,
+                    help='chunk streams entropy-coded per device call of the device-resident run (0 = the shard)')
+    ap.add_argument('--e2e-coder-tiles', type=int, default=0,
+                    help='the same for compress_image / decompress_image (0 = half the shard: the chunk files '
+                         'of one group are written / read while the next group is on the GPU)')
     ap.add_argument('--parity-tiles', type=int, default=8)
     ap.add_argument('--no-parity', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')

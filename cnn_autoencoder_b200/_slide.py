@@ -311,9 +311,11 @@ def compress_tiles(tc, src, tiles, chunk_path, header_hw, workers, coder_tiles, 
                 if ev_free[slot] is not None:
                     s_in.wait_event(ev_free[slot])
                 if pinned_src:
-                    C.check(L.cae_tiles_upload_u8(src.ctypes.data, H, W, c, ps,
-                                                  tile_yx[k0:k0 + n].ctypes.data, n,
-                                                  tc.x[slot].data_ptr(), _stream_ptr(s_in)))
+                    band = tc.buffer('band_in%d' % slot, (B * ps * ps * c,), torch.uint8)
+                    C.check(L.cae_tiles_upload_u8_banded(src.ctypes.data, H, W, c, ps,
+                                                         tile_yx[k0:k0 + n].ctypes.data, n,
+                                                         tc.x[slot].data_ptr(), band.data_ptr(),
+                                                         _stream_ptr(s_in)))
                 else:
                     sb = b & 1
                     if stage_ev[sb] is not None:
@@ -454,9 +456,11 @@ def decompress_tiles(tc, tiles, chunk_path, workers, coder_tiles, stats, H, W, o
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev)
                 if out_image is not None:
-                    C.check(L.cae_tiles_download_u8(u8.data_ptr(), n, ps, c,
-                                                    tile_yx[k0:k0 + n].ctypes.data,
-                                                    out_image.ctypes.data, H, W, _stream_ptr(s_out)))
+                    band = tc.buffer('band_out%d' % slot, (B * ps * ps * c,), torch.uint8)
+                    C.check(L.cae_tiles_download_u8_banded(u8.data_ptr(), n, ps, c,
+                                                           tile_yx[k0:k0 + n].ctypes.data,
+                                                           out_image.ctypes.data, H, W,
+                                                           band.data_ptr(), _stream_ptr(s_out)))
                     d = torch.cuda.Event()
                     d.record(s_out)
                     slot_busy[slot] = d

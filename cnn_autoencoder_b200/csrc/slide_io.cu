@@ -47,6 +47,105 @@ extern "C" int cae_tiles_download_u8(const uint8_t *src, int n, int ps, int c,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Banded variants.  The per-tile copies above move rows of ps * c bytes (1.5 KB for 512^2 RGB
+// tiles): 38-42 GB/s on a link that does 56 GB/s with long rows (tools/micro/iobench.py).  Tiles
+// that sit side by side in one tile row of the slide (the order the tile loops walk them) are
+// therefore exchanged as ONE two-dimensional copy of the whole band segment -- rows of r * ps * c
+// bytes -- with a device kernel re-tiling between the tile-major buffer and a band-major scratch
+// buffer of the same size (16-byte units, HBM bound, ~1 % of the copy's time).
+namespace {
+// tiles [r][ps][row16] <-> band [ps][r][row16], 16-byte units
+__global__ void __launch_bounds__(256) retile_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst,
+                                                     int r, int ps, int row16, int to_band) {
+  const size_t total = (size_t)r * ps * row16;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int u = (int)(i % row16);
+    const size_t q = i / row16;
+    // i indexes the band: (y, k, u)
+    const int k = (int)(q % r), y = (int)(q / r);
+    const size_t t = ((size_t)k * ps + y) * row16 + u;
+    if (to_band) dst[i] = src[t]; else dst[t] = src[i];
+  }
+}
+
+// length of the run of full-size tiles starting at k that continue tile k's row to the right
+inline int band_run(const int32_t *tile_yx, int k, int n, int ps, int64_t H, int64_t W) {
+  const int64_t y0 = (int64_t)tile_yx[2 * k] * ps;
+  if (y0 + ps > H) return 0;
+  int r = 0;
+  while (k + r < n && tile_yx[2 * (k + r)] == tile_yx[2 * k] &&
+         tile_yx[2 * (k + r) + 1] == tile_yx[2 * k + 1] + r &&
+         ((int64_t)tile_yx[2 * (k + r) + 1] + 1) * ps <= W)
+    ++r;
+  return r;
+}
+}  // namespace
+
+extern "C" int cae_tiles_download_u8_banded(const uint8_t *src, int n, int ps, int c,
+                                            const int32_t *tile_yx, uint8_t *dst, int64_t H,
+                                            int64_t W, uint8_t *scratch, void *stream) {
+  CAE_CHECK(src && dst && tile_yx && scratch && H > 0 && W > 0 && c > 0 && ps > 0 && n >= 0, 2,
+            "cae_tiles_download_u8_banded: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t row = (size_t)ps * c, tile = row * ps;
+  const bool units = row % 16 == 0 && ((uintptr_t)src % 16 == 0) && ((uintptr_t)scratch % 16 == 0);
+  for (int k = 0; k < n;) {
+    const int r = units ? band_run(tile_yx, k, n, ps, H, W) : 0;
+    if (r < 2) {
+      if (int rc = cae_tiles_download_u8(src + (size_t)k * tile, 1, ps, c, tile_yx + 2 * k, dst, H, W, stream))
+        return rc;
+      ++k;
+      continue;
+    }
+    const int64_t y0 = (int64_t)tile_yx[2 * k] * ps, x0 = (int64_t)tile_yx[2 * k + 1] * ps;
+    uint8_t *band = scratch + (size_t)k * tile;
+    const size_t total = (size_t)r * ps * (row / 16);
+    const int blocks = (int)((total + 255) / 256 < (size_t)(8 * cae_sm_count()) ? (total + 255) / 256 : 8 * cae_sm_count());
+    retile_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4 *>(src + (size_t)k * tile),
+                                          reinterpret_cast<uint4 *>(band), r, ps, (int)(row / 16), 1);
+    cae_count_launch();
+    CAE_CUDA(cudaGetLastError());
+    CAE_CUDA(cudaMemcpy2DAsync(dst + ((size_t)y0 * W + x0) * c, (size_t)W * c, band, (size_t)r * row,
+                               (size_t)r * row, (size_t)ps, cudaMemcpyDeviceToHost, st));
+    k += r;
+  }
+  return 0;
+}
+
+extern "C" int cae_tiles_upload_u8_banded(const uint8_t *src, int64_t H, int64_t W, int c, int ps,
+                                          const int32_t *tile_yx, int n, uint8_t *dst,
+                                          uint8_t *scratch, void *stream) {
+  CAE_CHECK(src && dst && tile_yx && scratch && H > 0 && W > 0 && c > 0 && ps > 0 && n >= 0, 2,
+            "cae_tiles_upload_u8_banded: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t row = (size_t)ps * c, tile = row * ps;
+  const bool units = row % 16 == 0 && ((uintptr_t)dst % 16 == 0) && ((uintptr_t)scratch % 16 == 0);
+  for (int k = 0; k < n;) {
+    const int r = units ? band_run(tile_yx, k, n, ps, H, W) : 0;
+    if (r < 2) {
+      if (int rc = cae_tiles_upload_u8(src, H, W, c, ps, tile_yx + 2 * k, 1, dst + (size_t)k * tile, stream))
+        return rc;
+      ++k;
+      continue;
+    }
+    const int64_t y0 = (int64_t)tile_yx[2 * k] * ps, x0 = (int64_t)tile_yx[2 * k + 1] * ps;
+    uint8_t *band = scratch + (size_t)k * tile;
+    CAE_CUDA(cudaMemcpy2DAsync(band, (size_t)r * row, src + ((size_t)y0 * W + x0) * c, (size_t)W * c,
+                               (size_t)r * row, (size_t)ps, cudaMemcpyHostToDevice, st));
+    const size_t total = (size_t)r * ps * (row / 16);
+    const int blocks = (int)((total + 255) / 256 < (size_t)(8 * cae_sm_count()) ? (total + 255) / 256 : 8 * cae_sm_count());
+    retile_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4 *>(band),
+                                          reinterpret_cast<uint4 *>(dst + (size_t)k * tile), r, ps,
+                                          (int)(row / 16), 0);
+    cae_count_launch();
+    CAE_CUDA(cudaGetLastError());
+    k += r;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Evaluation sums on the device (src/test_cae.py:60-63 PSNR, :57-58 RMSE and the
 // distortion term of src/models/criteria/_ratedist.py:57-63 in uint8 units): per image
 //   sse[i] += sum (a - b)^2   over the `per_image` uint8 values of image i.

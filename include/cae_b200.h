@@ -368,6 +368,17 @@ int cae_tiles_upload_u8(const uint8_t *src /*HOST*/, int64_t H, int64_t W, int c
 int cae_tiles_download_u8(const uint8_t *src, int n, int ps, int c, const int32_t *tile_yx /*HOST*/,
                           uint8_t *dst /*HOST*/, int64_t H, int64_t W, void *stream);
 
+/* The same with tiles that sit side by side in one tile row of the slide moved as ONE copy of the
+ * band segment (rows of r * ps * c bytes instead of ps * c: the DMA engines reach the link's
+ * contiguous rate) and re-tiled on the device; `scratch`: device buffer of n * ps * ps * c bytes.
+ * Isolated and edge tiles take the per-tile copies above.                                      */
+int cae_tiles_upload_u8_banded(const uint8_t *src /*HOST*/, int64_t H, int64_t W, int c, int ps,
+                               const int32_t *tile_yx /*HOST*/, int n, uint8_t *dst,
+                               uint8_t *scratch, void *stream);
+int cae_tiles_download_u8_banded(const uint8_t *src, int n, int ps, int c,
+                                 const int32_t *tile_yx /*HOST*/, uint8_t *dst /*HOST*/, int64_t H,
+                                 int64_t W, uint8_t *scratch, void *stream);
+
 /* ---- evaluation sums on the device ------------------------------------------ */
 /* sse[i] += sum over the per_image uint8 values of image i of (a - b)^2: the numerator of
  * compute_rmse / compute_psnr (src/test_cae.py:57-63, computed there on the host after a full

@@ -1,0 +1,49 @@
+"""Host-side phase trace of one compress_image -> decompress_image step (CAE_SLIDE_TRACE=1):
+when the symbols are ready, coded, on the host, written; when the files are read, decoded, the
+last batch issued, the GPU done.
+
+    python tools/micro/trace_slide.py [chunks=4096] [coder_tiles=chunks]
+"""
+import os
+import shutil
+import sys
+import time
+
+os.environ['CAE_SLIDE_TRACE'] = '1'
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import bench  # noqa: E402
+from oracle import cae_oracle as O  # noqa: E402
+from cnn_autoencoder_b200 import compress as CMP, decompress as DEC, _slide  # noqa: E402
+
+T = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+G = int(sys.argv[2]) if len(sys.argv) > 2 else T
+chk = O.make_checkpoint(O.NAMED_ARCHS['A'], seed=1234)
+rows = T // bench.GX
+H, W = rows * bench.PS, bench.GX * bench.PS
+slide = bench.aligned_empty(H * W * 3).reshape(H, W, 3)
+tile = bench.slide_tile(O, 0, 0)
+for i in range(rows):
+    for j in range(bench.GX):
+        slide[i * 512:(i + 1) * 512, j * 512:(j + 1) * 512] = tile if (i + j) % 7 else bench.slide_tile(O, i % 3, j % 5)
+pin = _slide.pin_array(slide)
+recon = bench.aligned_empty(H * W * 3).reshape(H, W, 3)
+recon[:] = 0
+pin_r = _slide.pin_array(recon)
+work = '/dev/shm/cae_trace'
+shutil.rmtree(work, ignore_errors=True)
+os.makedirs(work)
+kw = dict(batch_tiles=32, coder_tiles=G)
+for it in range(4):
+    t0 = time.perf_counter()
+    cs = CMP.compress_image('CAE', chk, slide, work + '/s.zarr', patch_size=512, gpu=True, **kw)
+    t1 = time.perf_counter()
+    ds = DEC.decompress_image(work + '/s.zarr', recon, checkpoint=chk, gpu=True, **kw)
+    t2 = time.perf_counter()
+print('compress %.4f s  decompress %.4f s' % (t1 - t0, t2 - t1))
+print('compress trace', cs.get('trace'))
+print('decompress trace', ds.get('trace'))
+print({k: v for k, v in cs.items() if k != 'trace'})
+print({k: v for k, v in ds.items() if k != 'trace'})
+shutil.rmtree(work, ignore_errors=True)
