@@ -207,3 +207,41 @@ def test_save_as_bottleneck_refuses_unsupported_edges_up_front(tmp_path):
         compress.compress_image('CAE', chk, slide, str(tmp_path / 'x.zarr'), patch_size=128,
                                 save_as_bottleneck=True)
     assert not os.path.exists(str(tmp_path / 'x.zarr' / '0' / '0' / '0.0.0'))
+
+
+@pytest.mark.gpu
+def test_banded_tile_copies_equal_the_per_tile_copies():
+    """cae_tiles_upload_u8_banded / cae_tiles_download_u8_banded (one 2-D copy per run of tiles in
+    a tile row + device re-tiling) against the per-tile strided copies, on a ragged slide with
+    runs of different lengths, an isolated tile and edge tiles."""
+    import ctypes
+    import numpy as np
+    import torch
+    from cnn_autoencoder_b200 import _cabi as C
+    rng = np.random.default_rng(3)
+    H, W, c, ps = 5 * 64 + 20, 7 * 64 + 33, 3, 64
+    img = torch.from_numpy(rng.integers(0, 256, size=(H, W, c), dtype=np.uint8)).pin_memory()
+    tiles = [(0, 0), (0, 1), (0, 2), (1, 4), (2, 1), (2, 2), (2, 3), (2, 4), (2, 5), (2, 6), (2, 7),
+             (5, 0), (5, 1), (3, 7), (4, 2), (4, 3)]
+    yx = np.ascontiguousarray(np.array(tiles, dtype=np.int32))
+    n = len(tiles)
+    L = C.lib()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    a = torch.full((n, ps, ps, c), 7, dtype=torch.uint8, device='cuda')
+    b = torch.full((n, ps, ps, c), 9, dtype=torch.uint8, device='cuda')
+    scratch = torch.empty(n * ps * ps * c, dtype=torch.uint8, device='cuda')
+    C.check(L.cae_tiles_upload_u8(img.data_ptr(), H, W, c, ps, yx.ctypes.data, n, a.data_ptr(), st))
+    C.check(L.cae_tiles_upload_u8_banded(img.data_ptr(), H, W, c, ps, yx.ctypes.data, n, b.data_ptr(),
+                                         scratch.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    out1 = torch.zeros((H, W, c), dtype=torch.uint8).pin_memory()
+    out2 = torch.zeros((H, W, c), dtype=torch.uint8).pin_memory()
+    C.check(L.cae_tiles_download_u8(a.data_ptr(), n, ps, c, yx.ctypes.data, out1.data_ptr(), H, W, st))
+    C.check(L.cae_tiles_download_u8_banded(a.data_ptr(), n, ps, c, yx.ctypes.data, out2.data_ptr(), H, W,
+                                           scratch.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert torch.equal(out1, out2)
+    for i, j in tiles:
+        y0, x0 = i * ps, j * ps
+        assert torch.equal(out2[y0:y0 + ps, x0:x0 + ps], img[y0:y0 + ps, x0:x0 + ps])
