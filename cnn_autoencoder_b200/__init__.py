@@ -9,10 +9,11 @@ from ._autoencoders import (Analyzer, Synthesizer, ConvolutionalAutoencoder,
 from ._entropy import EntropyBottleneck
 from ._taskutils import decorate_trainable_modules
 from ._lossutils import GeneralLoss, RateLoss, DistMSELoss, setup_loss
-from .train_step import train_step, setup_optimizers, allreduce_gradients, GradBucket
+from .train_step import (train_step, setup_optimizers, allreduce_gradients, GradBucket,
+                         GraphedTrainStep)
 
 __all__ = ['Analyzer', 'Synthesizer', 'ConvolutionalAutoencoder',
            'ConvolutionalAutoencoderBottleneck', 'autoencoder_from_state_dict', 'setup_modules',
            'load_state_dict', 'ModuleHandle', 'EntropyBottleneck', 'decorate_trainable_modules',
            'GeneralLoss', 'RateLoss', 'DistMSELoss', 'setup_loss', 'train_step',
-           'setup_optimizers', 'allreduce_gradients', 'GradBucket']
+           'setup_optimizers', 'allreduce_gradients', 'GradBucket', 'GraphedTrainStep']

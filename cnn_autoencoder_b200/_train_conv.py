@@ -226,7 +226,9 @@ class WideChain:
         plan = self._plan(x, weights, biases)
         plan.busy = True
         O.nchw_to_planar(x.detach(), plan.x0.fmt, plan.x0.halo, out=plan.x0)
-        if not self.use_graphs:
+        # (under an outer capture -- train_step.GraphedTrainStep -- the launches go straight into
+        # that graph)
+        if not self.use_graphs or torch.cuda.is_current_stream_capturing():
             self._launch_forward(plan, weights, biases)
         else:
             ptrs = tuple(t.data_ptr() for t in weights) + tuple(b.data_ptr() if b is not None else 0 for b in biases)
@@ -310,7 +312,7 @@ class WideChain:
         amax = plan.g_in.abs().amax().clamp_min(1e-30)
         plan.scale.copy_(torch.exp2(torch.floor(torch.log2(64.0 / amax))).reshape(1))
         plan.inv_scale.copy_(1.0 / plan.scale)
-        if not self.use_graphs:
+        if not self.use_graphs or torch.cuda.is_current_stream_capturing():
             self._launch_backward(plan, weights, need_dx)
         else:
             ptrs = tuple(t.data_ptr() for t in weights)

@@ -40,10 +40,12 @@ def _split_params(model):
     return groups
 
 
-def setup_optimizers(model, lr=1e-4, aux_lr=1e-3):
-    """Per-module Adam optimizers split like ``train_cae_ms.py:592-596``."""
+def setup_optimizers(model, lr=1e-4, aux_lr=1e-3, capturable=False):
+    """Per-module Adam optimizers split like ``train_cae_ms.py:592-596``.  ``capturable``: keep
+    Adam's step counters on the device so that the step can be part of a CUDA graph
+    (``GraphedTrainStep``)."""
     groups = _split_params(model)
-    return {k: torch.optim.Adam(v, lr=aux_lr if k == 'fact_ent_aux' else lr)
+    return {k: torch.optim.Adam(v, lr=aux_lr if k == 'fact_ent_aux' else lr, capturable=capturable)
             for k, v in groups.items() if v}
 
 
@@ -182,3 +184,47 @@ def train_step(x, model, criterion, optimizers, forward_func, targets=None, max_
         else:
             opt.zero_grad()
     return loss_dict
+
+
+class GraphedTrainStep:
+    """``train_step`` captured once as ONE CUDA graph and replayed: forward closure, criterion,
+    both backward passes, the gradient all-reduce (NCCL kernels are graph nodes like any other),
+    clipping and the Adam updates.  The eager step spends more host time on launching its ~500
+    small kernels than the GPU spends running them; replayed, a step costs one launch.
+
+    Restrictions of a static graph: fixed batch shape (``x`` is copied into a static buffer),
+    every optimizer steps on every call (``mod_grad_accumulate`` periods of 1), optimizers built
+    with ``capturable=True``.  The warm-up iterations before the capture ARE training steps (the
+    capture itself records a step without running it).
+    Returns the loss dict of the step as static tensors (overwritten by the next call)."""
+
+    def __init__(self, x_example, model, criterion, optimizers, forward_func, bucket,
+                 max_norm=1.0, group=None, warmup=3):
+        for k, opt in optimizers.items():
+            if not all(g.get('capturable', False) for g in opt.param_groups):
+                raise ValueError(f'optimizer {k!r} must be built with capturable=True')
+        self.x = x_example.detach().clone()
+        args = (model, criterion, optimizers, forward_func)
+        kw = dict(max_norm=max_norm, group=group, bucket=bucket, step=0)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                train_step(self.x, *args, **kw)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        from . import _cabi
+        n0 = _cabi.lib().cae_launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            out = train_step(self.x, *args, **kw)
+            self.out = {k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
+        self.kernels = int(_cabi.lib().cae_launch_count() - n0)
+        self._note = _cabi.note_graph_replay
+
+    def __call__(self, x):
+        self.x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        self._note(self.kernels)
+        return self.out

@@ -130,3 +130,48 @@ def test_train_step_matches_the_torch_formulation():
         d = (a['w'][k] - b['w'][k]).abs()
         assert float(d.max()) <= 2.05e-4, (k, float(d.max()))
         assert float((d > 2e-5).float().mean()) < 0.03, (k, float((d > 2e-5).float().mean()))
+
+
+def test_graphed_train_step_tracks_the_eager_step():
+    """GraphedTrainStep (the whole rate-distortion step replayed as one CUDA graph) against the
+    eager train_step from the same start: the additive noise of the bottleneck comes from
+    different generator offsets, so the two runs agree statistically, not bit for bit -- after
+    the same number of Adam steps every weight sits within (steps x lr) of the eager run, the
+    losses are finite and close, and a replay really advances the model."""
+    from oracle import cae_oracle as O
+    import cnn_autoencoder_b200 as M
+    chk = O.make_checkpoint(O.NAMED_ARCHS['A'], seed=9)
+    x = (O.synth_natural(4, 3, 128, 128, seed=6).float() / 255.0).cuda()
+    steps, warm = 3, 2
+
+    def build():
+        model = M.autoencoder_from_state_dict(chk, gpu=True, train=True)
+        fwd = M.decorate_trainable_modules(trainable_modules=['encoder', 'decoder', 'fact_ent'],
+                                           enabled_modules=['encoder', 'decoder', 'fact_ent'])
+        crit = M.setup_loss('RateMSE', distortion_lambda=0.01)
+        opts = M.setup_optimizers(model, lr=1e-4, aux_lr=1e-3, capturable=True)
+        return model, fwd, crit, opts, M.GradBucket(model)
+
+    torch.manual_seed(0)
+    model, fwd, crit, opts, bucket = build()
+    for k in range(warm + steps):            # (capturing records a step, it does not run one)
+        out = M.train_step(x, model, crit, opts, fwd, bucket=bucket, step=0)
+    loss_e = float(torch.mean(out['loss']).detach())
+    w_e = torch.cat([p.detach().reshape(-1) for k in ('encoder', 'decoder') for p in model[k].parameters()])
+
+    torch.manual_seed(0)
+    model, fwd, crit, opts, bucket = build()
+    w0 = torch.cat([p.detach().reshape(-1) for k in ('encoder', 'decoder') for p in model[k].parameters()]).clone()
+    g = M.GraphedTrainStep(x, model, crit, opts, fwd, bucket, warmup=warm)     # warm steps so far
+    before = torch.cat([p.detach().reshape(-1) for k in ('encoder', 'decoder') for p in model[k].parameters()]).clone()
+    for k in range(steps):
+        out = g(x)
+    torch.cuda.synchronize()
+    loss_g = float(torch.mean(out['loss']))
+    w_g = torch.cat([p.detach().reshape(-1) for k in ('encoder', 'decoder') for p in model[k].parameters()])
+    n_steps = warm + steps
+    assert loss_g == loss_g and abs(loss_g - loss_e) <= 0.05 * abs(loss_e), (loss_g, loss_e)
+    assert float((w_g - before).abs().max()) > 1e-5, 'a replay must move the weights'
+    assert float((w_g - w0).abs().max()) <= 1.05e-4 * n_steps
+    assert float((w_g - w_e).abs().max()) <= 2.1e-4 * n_steps
+    assert float((w_g - w_e).abs().mean()) <= 0.5e-4 * n_steps

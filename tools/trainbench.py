@@ -44,7 +44,8 @@ def run(args):
     fwd = M.decorate_trainable_modules(trainable_modules=['encoder', 'decoder', 'fact_ent'],
                                        enabled_modules=['encoder', 'decoder', 'fact_ent'])
     crit = M.setup_loss('RateMSE', distortion_lambda=0.01)
-    opts = M.setup_optimizers(model, lr=1e-4, aux_lr=1e-3)
+    use_graph = not os.environ.get('CAE_TRAIN_EAGER_STEP')
+    opts = M.setup_optimizers(model, lr=1e-4, aux_lr=1e-3, capturable=use_graph)
     bucket = M.GradBucket(model)
     x_pin = (O.synth_natural(batch, 3, 256, 256, seed=100 + rank).float() / 255.0).pin_memory()
     x = x_pin.cuda(non_blocking=True)
@@ -56,9 +57,24 @@ def run(args):
         torch.cuda.synchronize()
 
     step = [0]
+    graphed = None
+    step_form = 'eager launches'
+    if use_graph:
+        # the whole step as one CUDA graph (train_step.GraphedTrainStep); eager if capture fails
+        try:
+            graphed = M.GraphedTrainStep(x, model, crit, opts, fwd, bucket, warmup=3)
+            step_form = 'one CUDA graph per step (%d kernels of this library inside)' % graphed.kernels
+        except Exception as exc:        # noqa: BLE001 -- report and fall back
+            print('trainbench: graph capture failed (%s: %s), eager step' % (type(exc).__name__, exc),
+                  file=sys.stderr)
+            graphed = None
+            torch.cuda.synchronize()
 
     def one(xb):
-        out = M.train_step(xb, model, crit, opts, fwd, bucket=bucket, step=step[0])
+        if graphed is not None:
+            out = graphed(xb)
+        else:
+            out = M.train_step(xb, model, crit, opts, fwd, bucket=bucket, step=step[0])
         step[0] += 1
         return out
 
@@ -73,7 +89,7 @@ def run(args):
         s.record()
         out = one(x)
         e.record()
-        losses.append(out['loss'].detach())
+        losses.append(out['loss'].detach().clone())
     barrier()
     launches = _cabi.launch_count() - launches0
     ms = torch.tensor([sum(s.elapsed_time(e) for s, e in ev)], dtype=torch.float64, device='cuda')
@@ -133,6 +149,7 @@ def run(args):
                                    'RateMSE lambda 0.01, Adam 1e-4 / aux 1e-3, clip 1.0' % (args.arch, batch),
                        'kernels': 'bottleneck fwd/bwd: cae_eb_train_fwd / cae_eb_train_bwd (this repo); '
                                   'transforms fwd/bwd: ' + transforms,
+                       'step': step_form,
                        'parallelism': 'dp%d, one persistent flat fp32 gradient bucket, NCCL all-reduce, '
                                       'synthesis half launched under the analysis backward' % world},
             'e2e': {'value': round(world * batch * args.steps / (e2e_ms.item() / 1e3), 1), 'unit': 'samples/s',
@@ -142,7 +159,20 @@ def run(args):
             'replicas_identical': bool(torch.equal(lo, hi)),
             'loss_first': lv[0], 'loss_last': lv[-1], 'finite': all(v == v for v in lv)}))
     if world > 1:
+        # a captured graph holds NCCL kernels: release it before the communicator goes away, and do
+        # not let a stuck teardown keep the GPUs (observed: destroy_process_group hanging with the
+        # graph alive)
+        import gc
+        import threading
+        graphed = None
+        gc.collect()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 if __name__ == '__main__':
