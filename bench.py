@@ -298,7 +298,8 @@ def dominant_kernel_roofline(c, model, x_u8_dev, peaks, traffic=None):
             'peak_sustained': peaks['bf16_sustained'],
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this shape, a constant
             # copied from the committed ncu --set full capture (profiles/), not measured per run
-            'traffic': traffic, 'traffic_source': 'profiles/r01_ncu_full_enc2_128to128_s1_batch128.json',
+            'traffic': traffic, 'traffic_source': 'profiles/r02_ncu_step.csv row 2: dram__bytes_read.sum + dram__bytes_write.sum of one '
+                              'ncu --set full capture of this kernel at this shape (a constant, not re-measured per run)',
             'kernel': 'igemm_conv_kernel<EPI_ACT> conv3x3 s1 %d->%d @%dx%d x%d' % (
                 st.c_in, st.c_out, x_in.h, x_in.w, x_in.n),
             'algorithmic_flops_per_launch': flops,
@@ -539,7 +540,7 @@ def run_wsi(args):
             dist.destroy_process_group()
         return
     roof = dominant_kernel_roofline(c, model, tc.x[0], peaks,
-                                    traffic=1113868800 if args.batch_tiles * 4 == BATCH else None)
+                                    traffic=1119336448 if args.batch_tiles * 4 == BATCH else None)
 
     # ---- CPU baseline (bounded sample, rank 0, N = 1 only) ----
     cpu = None
@@ -684,7 +685,7 @@ def run_patches(args):
             dist.destroy_process_group()
         return
     roof = dominant_kernel_roofline(c, model, x_dev, peaks,
-                                    traffic=1113868800 if (B == BATCH and args.arch == ARCH_NAME) else None)
+                                    traffic=1119336448 if (B == BATCH and args.arch == ARCH_NAME) else None)
     line = {
         'metric': 'patch_encode_decode_megapixels_per_sec', 'value': sub['value'], 'unit': 'MP/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': warmup, 'ms_per_step': sub['ms_per_step'],
