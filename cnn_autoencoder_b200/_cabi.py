@@ -30,7 +30,8 @@ SYMBOLS = ['cae_abi_version', 'cae_last_error', 'cae_device_info', 'cae_launch_c
            'cae_rans_enc_table_bytes', 'cae_rans_build_enc_table',
            'cae_rans_encode_batch', 'cae_rans_scan', 'cae_rans_compact', 'cae_rans_decode_batch',
            'cae_tiles_upload_u8', 'cae_tiles_download_u8', 'cae_tiles_upload_u8_banded',
-           'cae_tiles_download_u8_banded', 'cae_sse_u8', 'cae_ssim_u8', 'cae_delta_e_u8', 'cae_tiles_gather_u8', 'cae_files_write', 'cae_files_stat', 'cae_files_read']
+           'cae_tiles_download_u8_banded', 'cae_sse_u8', 'cae_ssim_u8', 'cae_delta_e_u8', 'cae_u8_to_planes_f32',
+           'cae_avgpool2_planes_f32', 'cae_ssim_gauss_planes_f32', 'cae_tiles_gather_u8', 'cae_files_write', 'cae_files_stat', 'cae_files_read']
 
 
 class Tensor(ctypes.Structure):
@@ -171,6 +172,10 @@ def lib():
     L.cae_sse_u8.argtypes = [vp, vp, ctypes.c_int, i64, vp, vp]
     L.cae_ssim_u8.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
     L.cae_delta_e_u8.argtypes = [vp, vp, ctypes.c_int, i64, vp, vp]
+    L.cae_u8_to_planes_f32.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
+    L.cae_avgpool2_planes_f32.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
+    L.cae_ssim_gauss_planes_f32.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                            vp, vp, vp]
     L.cae_tiles_gather_u8.argtypes = [vp, i64, i64, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp,
                                       ctypes.c_int]
     L.cae_files_write.argtypes = [ctypes.c_char_p, ctypes.c_int, vp, ctypes.c_int, vp, vp, ctypes.c_int]

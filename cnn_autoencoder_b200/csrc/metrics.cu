@@ -149,7 +149,183 @@ __global__ void __launch_bounds__(256) delta_e_u8_kernel(const uint8_t *__restri
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// MS-SSIM (pytorch_msssim.ms_ssim as compute_ms_ssim calls it, src/test_cae.py:46-50): five
+// scales of Gaussian-window (11 taps, sigma 1.5, valid convolution) SSIM / contrast-structure
+// means on fp32 planes, 2x2 average pooling (zero padding on odd sizes, pad counted) in between.
+constexpr int kMsWin = 11;
+constexpr int kMsIn = kSsimTile + kMsWin - 1;    // 42
+
+struct MsParams {
+  const float *a, *b;   // [planes][H][W]
+  int planes, H, W;
+  float win[kMsWin];
+  float c1, c2;
+  double *sum_ssim, *sum_cs;   // [planes]
+};
+
+__global__ void __launch_bounds__(256) msssim_level_kernel(const MsParams p) {
+  __shared__ float tile_a[kMsIn][kMsIn + 1], tile_b[kMsIn][kMsIn + 1];
+  __shared__ float h[5][kMsIn][kSsimTile + 1];
+  __shared__ double s_part[2][8];
+  const int pl = blockIdx.z;
+  const int oy0 = blockIdx.y * kSsimTile, ox0 = blockIdx.x * kSsimTile;
+  const int OH = p.H - kMsWin + 1, OW = p.W - kMsWin + 1;
+  const float *A = p.a + (size_t)pl * p.H * p.W, *B = p.b + (size_t)pl * p.H * p.W;
+  for (int i = threadIdx.x; i < kMsIn * kMsIn; i += blockDim.x) {
+    const int r = i / kMsIn, q = i - r * kMsIn;
+    const int y = oy0 + r, x = ox0 + q;
+    const bool in = y < p.H && x < p.W;
+    tile_a[r][q] = in ? __ldg(A + (size_t)y * p.W + x) : 0.f;
+    tile_b[r][q] = in ? __ldg(B + (size_t)y * p.W + x) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kMsIn * kSsimTile; i += blockDim.x) {
+    const int r = i / kSsimTile, q = i - r * kSsimTile;
+    float sa = 0.f, sb = 0.f, saa = 0.f, sbb = 0.f, sab = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMsWin; ++k) {
+      const float w = p.win[k], va = tile_a[r][q + k], vb = tile_b[r][q + k];
+      sa += w * va;
+      sb += w * vb;
+      saa += w * va * va;
+      sbb += w * vb * vb;
+      sab += w * va * vb;
+    }
+    h[0][r][q] = sa;
+    h[1][r][q] = sb;
+    h[2][r][q] = saa;
+    h[3][r][q] = sbb;
+    h[4][r][q] = sab;
+  }
+  __syncthreads();
+  double acc_s = 0.0, acc_c = 0.0;
+  for (int i = threadIdx.x; i < kSsimTile * kSsimTile; i += blockDim.x) {
+    const int r = i / kSsimTile, q = i - r * kSsimTile;
+    if (oy0 + r >= OH || ox0 + q >= OW) continue;
+    float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < kMsWin; ++k)
+#pragma unroll
+      for (int m = 0; m < 5; ++m) s[m] += p.win[k] * h[m][r + k][q];
+    const float mu1 = s[0], mu2 = s[1];
+    const float s1 = s[2] - mu1 * mu1, s2 = s[3] - mu2 * mu2, s12 = s[4] - mu1 * mu2;
+    const float cs = (2.f * s12 + p.c2) / (s1 + s2 + p.c2);
+    const float ss = ((2.f * mu1 * mu2 + p.c1) / (mu1 * mu1 + mu2 * mu2 + p.c1)) * cs;
+    acc_s += (double)ss;
+    acc_c += (double)cs;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    acc_s += __shfl_xor_sync(0xffffffffu, acc_s, o);
+    acc_c += __shfl_xor_sync(0xffffffffu, acc_c, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_part[0][threadIdx.x >> 5] = acc_s;
+    s_part[1][threadIdx.x >> 5] = acc_c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      t0 += s_part[0][w];
+      t1 += s_part[1][w];
+    }
+    atomicAdd(p.sum_ssim + pl, t0);
+    atomicAdd(p.sum_cs + pl, t1);
+  }
+}
+
+// N x H x W x C uint8 -> [N * C][H][W] fp32
+__global__ void __launch_bounds__(256) u8_to_planes_kernel(const uint8_t *__restrict__ src, int n,
+                                                           int h, int w, int c, float *__restrict__ dst) {
+  const size_t total = (size_t)n * h * w * c;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c);
+    const size_t px = i / c;
+    const size_t img = px / ((size_t)h * w), rem = px - img * (size_t)h * w;
+    dst[(img * c + ch) * (size_t)h * w + rem] = (float)src[i];
+  }
+}
+
+// F.avg_pool2d(x, 2, padding=(H % 2, W % 2)) with the padding counted: out[i][j] = mean over the
+// 2 x 2 window of the zero-padded plane
+__global__ void __launch_bounds__(256) avgpool2_kernel(const float *__restrict__ src, int planes,
+                                                       int H, int W, float *__restrict__ dst, int OH, int OW) {
+  const int py = H & 1, px = W & 1;
+  const size_t total = (size_t)planes * OH * OW;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % OW);
+    const size_t r = i / OW;
+    const int y = (int)(r % OH);
+    const size_t pl = r / OH;
+    const float *s = src + pl * (size_t)H * W;
+    float acc = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int yy = 2 * y + dy - py, xx = 2 * x + dx - px;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) acc += __ldg(s + (size_t)yy * W + xx);
+      }
+    dst[i] = acc * 0.25f;
+  }
+}
+
 }  // namespace
+
+extern "C" int cae_u8_to_planes_f32(const uint8_t *src, int n, int h, int w, int c, float *dst,
+                                    void *stream) {
+  CAE_CHECK(src && dst && n > 0 && h > 0 && w > 0 && c > 0, 2, "cae_u8_to_planes_f32: bad argument");
+  const size_t total = (size_t)n * h * w * c;
+  const int blocks = (int)((total + 255) / 256 < (size_t)(16 * cae_sm_count()) ? (total + 255) / 256 : 16 * cae_sm_count());
+  u8_to_planes_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, n, h, w, c, dst);
+  cae_count_launch();
+  CAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int cae_avgpool2_planes_f32(const float *src, int planes, int h, int w, float *dst,
+                                       void *stream) {
+  CAE_CHECK(src && dst && planes > 0 && h > 0 && w > 0, 2, "cae_avgpool2_planes_f32: bad argument");
+  const int OH = (h + 2 * (h & 1) - 2) / 2 + 1, OW = (w + 2 * (w & 1) - 2) / 2 + 1;
+  const size_t total = (size_t)planes * OH * OW;
+  const int blocks = (int)((total + 255) / 256 < (size_t)(16 * cae_sm_count()) ? (total + 255) / 256 : 16 * cae_sm_count());
+  avgpool2_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, planes, h, w, dst, OH, OW);
+  cae_count_launch();
+  CAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int cae_ssim_gauss_planes_f32(const float *a, const float *b, int planes, int h, int w,
+                                         float data_range, double *sum_ssim, double *sum_cs,
+                                         void *stream) {
+  CAE_CHECK(a && b && sum_ssim && sum_cs && planes > 0, 2, "cae_ssim_gauss_planes_f32: bad argument");
+  CAE_CHECK(h >= kMsWin && w >= kMsWin, 2, "cae_ssim_gauss_planes_f32: planes smaller than the 11-tap window");
+  CAE_CHECK(planes <= 65535, 2, "cae_ssim_gauss_planes_f32: more than 65535 planes per call");
+  MsParams p;
+  p.a = a; p.b = b; p.planes = planes; p.H = h; p.W = w;
+  float sum = 0.f;
+  for (int k = 0; k < kMsWin; ++k) {
+    const float x = (float)(k - kMsWin / 2);
+    p.win[k] = expf(-(x * x) / (2.f * 1.5f * 1.5f));
+    sum += p.win[k];
+  }
+  for (int k = 0; k < kMsWin; ++k) p.win[k] /= sum;
+  p.c1 = (0.01f * data_range) * (0.01f * data_range);
+  p.c2 = (0.03f * data_range) * (0.03f * data_range);
+  p.sum_ssim = sum_ssim;
+  p.sum_cs = sum_cs;
+  const int OH = h - kMsWin + 1, OW = w - kMsWin + 1;
+  const dim3 grid((unsigned)((OW + kSsimTile - 1) / kSsimTile), (unsigned)((OH + kSsimTile - 1) / kSsimTile),
+                  (unsigned)planes);
+  CAE_CHECK(grid.y <= 65535, 2, "cae_ssim_gauss_planes_f32: plane too tall for one launch");
+  msssim_level_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  cae_count_launch();
+  CAE_CUDA(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int cae_ssim_u8(const uint8_t *a, const uint8_t *b, int n_images, int h, int w, int c,
                            double *sum, void *stream) {

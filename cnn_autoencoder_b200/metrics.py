@@ -11,7 +11,11 @@ computed on the device:
   cropped by 3 pixels), window sums on the device (``cae_ssim_u8``).
 * ``delta_cielab``: ``compute_deltaCIELAB`` :21-44 — mean CIE76 distance after
   ``skimage.color.rgb2lab`` of both images (``cae_delta_e_u8``).
-(``ms-ssim`` :46-50 uses the ``pytorch_msssim`` package and is not part of this module.)
+* ``ms_ssim``: ``compute_ms_ssim`` :46-50 — ``pytorch_msssim.ms_ssim(x_r, x, data_range=255)``
+  with its defaults (11-tap Gaussian window, sigma 1.5, five scales): window moments, average
+  pooling and the u8 -> plane conversion are kernels (``cae_ssim_gauss_planes_f32``,
+  ``cae_avgpool2_planes_f32``, ``cae_u8_to_planes_f32``); the weighted product of the five scale
+  means is a handful of scalar torch ops.
 
 The reference computes these on the host after downloading the whole reconstruction; here the
 reconstruction can stay where the synthesis transform left it.  Inputs are uint8 CUDA tensors
@@ -119,3 +123,45 @@ def delta_cielab(x, x_r, per_image=False):
         C.check(C.lib().cae_delta_e_u8(a.data_ptr(), b.data_ptr(), n, h * w, out.data_ptr(), stream))
     out = out / float(h * w)
     return out if per_image else float(out.mean().item())
+
+
+MS_SSIM_WEIGHTS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)
+
+
+def ms_ssim(x, x_r, per_image=False):
+    """``compute_ms_ssim`` (test_cae.py:46-50) of uint8 H x W x C images (or a batch)."""
+    a, b = _pair(x, x_r)
+    n, h, w, c = a.shape
+    levels = len(MS_SSIM_WEIGHTS)
+    if min(h, w) <= (11 - 1) * 2 ** (levels - 1):
+        raise ValueError('ms_ssim needs images larger than %d pixels on the short side' % ((11 - 1) * 2 ** (levels - 1)))
+    L = C.lib()
+    dev = a.device
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    planes = n * c
+    with torch.cuda.device(dev):
+        pa = torch.empty((planes, h, w), dtype=torch.float32, device=dev)
+        pb = torch.empty_like(pa)
+        C.check(L.cae_u8_to_planes_f32(a.data_ptr(), n, h, w, c, pa.data_ptr(), stream))
+        C.check(L.cae_u8_to_planes_f32(b.data_ptr(), n, h, w, c, pb.data_ptr(), stream))
+        vals = []
+        for lvl in range(levels):
+            hh, ww = pa.shape[1], pa.shape[2]
+            s_ssim = torch.zeros(planes, dtype=torch.float64, device=dev)
+            s_cs = torch.zeros(planes, dtype=torch.float64, device=dev)
+            C.check(L.cae_ssim_gauss_planes_f32(pa.data_ptr(), pb.data_ptr(), planes, hh, ww, 255.0,
+                                                s_ssim.data_ptr(), s_cs.data_ptr(), stream))
+            count = float((hh - 10) * (ww - 10))
+            if lvl < levels - 1:
+                vals.append(torch.relu(s_cs / count))
+                oh, ow = (hh + 2 * (hh & 1) - 2) // 2 + 1, (ww + 2 * (ww & 1) - 2) // 2 + 1
+                na = torch.empty((planes, oh, ow), dtype=torch.float32, device=dev)
+                nb = torch.empty_like(na)
+                C.check(L.cae_avgpool2_planes_f32(pa.data_ptr(), planes, hh, ww, na.data_ptr(), stream))
+                C.check(L.cae_avgpool2_planes_f32(pb.data_ptr(), planes, hh, ww, nb.data_ptr(), stream))
+                pa, pb = na, nb
+            else:
+                vals.append(torch.relu(s_ssim / count))
+        wts = torch.tensor(MS_SSIM_WEIGHTS, dtype=torch.float64, device=dev).view(-1, 1)
+        ms = torch.prod(torch.stack(vals) ** wts, dim=0).view(n, c).mean(dim=1)
+    return ms if per_image else float(ms.mean().item())

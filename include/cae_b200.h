@@ -400,6 +400,20 @@ int cae_ssim_u8(const uint8_t *a, const uint8_t *b, int n_images, int h, int w, 
 int cae_delta_e_u8(const uint8_t *a, const uint8_t *b, int n_images, int64_t pixels, double *sum,
                    void *stream);
 
+/* Building blocks of compute_ms_ssim (src/test_cae.py:46-50: pytorch_msssim.ms_ssim(x_r, x,
+ * data_range=255) with its defaults -- 11-tap Gaussian window, sigma 1.5, five scales, weights
+ * 0.0448 0.2856 0.3001 0.2363 0.1333), all on fp32 planes [planes][h][w] on the device:
+ *  cae_u8_to_planes_f32        N x H x W x C uint8 -> N * C planes
+ *  cae_ssim_gauss_planes_f32   per plane, sum over the (h - 10) x (w - 10) valid window positions
+ *                              of the SSIM map and of the contrast-structure map (accumulated)
+ *  cae_avgpool2_planes_f32     F.avg_pool2d(x, 2, padding = size % 2): the next scale,
+ *                              ((h + 2 (h % 2) - 2) / 2 + 1) x (same for w)
+ * metrics.ms_ssim combines the five scales (relu, weighted product, mean over planes).          */
+int cae_u8_to_planes_f32(const uint8_t *src, int n, int h, int w, int c, float *dst, void *stream);
+int cae_avgpool2_planes_f32(const float *src, int planes, int h, int w, float *dst, void *stream);
+int cae_ssim_gauss_planes_f32(const float *a, const float *b, int planes, int h, int w,
+                              float data_range, double *sum_ssim, double *sum_cs, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

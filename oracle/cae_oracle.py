@@ -735,3 +735,39 @@ def delta_cielab_u8(x, x_r):
     """compute_deltaCIELAB, ``test_cae.py:21-44``: mean ``deltaE_cie76`` of the two images."""
     d = rgb2lab_u8(x) - rgb2lab_u8(x_r)
     return float(np.sqrt((d ** 2).sum(axis=-1)).mean())
+
+
+def ms_ssim_u8(x, x_r):
+    """compute_ms_ssim, ``test_cae.py:46-50``: ``pytorch_msssim.ms_ssim(x_r, x, data_range=255)``
+    with its defaults, restated from the published algorithm (the package is not installed here
+    -- parity unpinned by it): 11-tap Gaussian window (sigma 1.5, normalised), valid separable
+    filtering of X, Y, X^2, Y^2, XY, per-channel means of the contrast-structure map on the first
+    four scales and of the SSIM map on the fifth (all through relu), ``avg_pool2d(2, padding =
+    size % 2)`` between scales, weighted product with (0.0448, 0.2856, 0.3001, 0.2363, 0.1333),
+    mean over channels.  float64 throughout."""
+    X = torch.from_numpy(np.moveaxis(x_r, -1, 0)[None].copy()).double()
+    Y = torch.from_numpy(np.moveaxis(x, -1, 0)[None].copy()).double()
+    coords = torch.arange(11, dtype=torch.float64) - 11 // 2
+    g = torch.exp(-(coords ** 2) / (2 * 1.5 ** 2))
+    g = g / g.sum()
+    C = X.shape[1]
+
+    def gauss(t):
+        t = F.conv2d(t, g.view(1, 1, -1, 1).repeat(C, 1, 1, 1), groups=C)
+        return F.conv2d(t, g.view(1, 1, 1, -1).repeat(C, 1, 1, 1), groups=C)
+
+    C1, C2 = (0.01 * 255) ** 2, (0.03 * 255) ** 2
+    weights = torch.tensor([0.0448, 0.2856, 0.3001, 0.2363, 0.1333], dtype=torch.float64)
+    mcs = []
+    for i in range(5):
+        mu1, mu2 = gauss(X), gauss(Y)
+        s1, s2, s12 = gauss(X * X) - mu1 * mu1, gauss(Y * Y) - mu2 * mu2, gauss(X * Y) - mu1 * mu2
+        cs_map = (2 * s12 + C2) / (s1 + s2 + C2)
+        ssim_map = ((2 * mu1 * mu2 + C1) / (mu1 ** 2 + mu2 ** 2 + C1)) * cs_map
+        ssim_c, cs_c = ssim_map.flatten(2).mean(-1), cs_map.flatten(2).mean(-1)
+        if i < 4:
+            mcs.append(torch.relu(cs_c))
+            pad = [s % 2 for s in X.shape[2:]]
+            X, Y = F.avg_pool2d(X, 2, padding=pad), F.avg_pool2d(Y, 2, padding=pad)
+    vals = torch.stack(mcs + [torch.relu(ssim_c)], dim=0)
+    return float(torch.prod(vals ** weights.view(-1, 1, 1), dim=0).mean())

@@ -615,3 +615,21 @@ def test_ssim_and_delta_e_kernels_match_the_oracle():
     per = metrics.ssim(xb.cuda(), yb.cuda(), per_image=True).cpu().numpy()
     for i in range(3):
         assert abs(per[i] - O.ssim_u8(xb[i].numpy(), yb[i].numpy())) < 1e-9
+
+
+def test_ms_ssim_kernels_match_the_oracle():
+    """metrics.ms_ssim (compute_ms_ssim of src/test_cae.py:46-50 on the device: Gaussian-window
+    moments, average pooling with the odd-size padding, five scales) against the float64
+    restatement of pytorch_msssim's algorithm; even and odd sizes."""
+    from oracle import cae_oracle as O
+    from cnn_autoencoder_b200 import metrics
+    rng = np.random.default_rng(2)
+    for h, w in ((176, 192), (201, 187), (320, 163)):
+        x = O.synth_natural(1, 3, h, w, seed=w)[0].permute(1, 2, 0).contiguous().numpy()
+        noisy = np.clip(x.astype(np.int32) + rng.integers(-25, 26, size=x.shape), 0, 255).astype(np.uint8)
+        dark = (x * 0.7).astype(np.uint8)
+        for y in (x, noisy, dark):
+            got, want = metrics.ms_ssim(x, y), O.ms_ssim_u8(x, y)
+            assert abs(got - want) < 2e-5, (h, w, got, want)
+    with pytest.raises(ValueError):
+        metrics.ms_ssim(np.zeros((100, 200, 3), np.uint8), np.zeros((100, 200, 3), np.uint8))

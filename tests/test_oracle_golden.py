@@ -81,3 +81,19 @@ def test_oracle_ssim_and_delta_e_known_answers():
     lab = O.rgb2lab_u8(np.array([[[0, 0, 0], [255, 255, 255], [255, 0, 0], [0, 255, 0], [0, 0, 255]]], np.uint8))[0]
     want = np.array([[0, 0, 0], [100, 0, 0], [53.24, 80.09, 67.20], [87.73, -86.18, 83.18], [32.30, 79.19, -107.86]])
     assert np.abs(lab - want).max() < 0.05, lab
+
+
+def test_oracle_ms_ssim_known_answers():
+    """Identical images give 1; constant images a, b give the closed form: every contrast term is
+    1 (the variances vanish) and the last scale contributes ((2ab + C1) / (a^2 + b^2 + C1))^0.1333
+    (the 2x2 pooling keeps a constant image constant only away from the zero padding, so sizes
+    that stay even through four halvings are used)."""
+    import numpy as np
+    from oracle import cae_oracle as O
+    rng = np.random.default_rng(1)
+    x = rng.integers(0, 256, size=(192, 208, 3), dtype=np.uint8)
+    assert abs(O.ms_ssim_u8(x, x) - 1.0) < 1e-12
+    a, b = np.full((192, 208, 1), 90, np.uint8), np.full((192, 208, 1), 140, np.uint8)
+    C1 = (0.01 * 255) ** 2
+    want = ((2 * 90 * 140 + C1) / (90 ** 2 + 140 ** 2 + C1)) ** 0.1333
+    assert abs(O.ms_ssim_u8(a, b) - want) < 1e-9
