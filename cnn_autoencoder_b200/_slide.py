@@ -257,7 +257,10 @@ def compress_tiles(tc, src, tiles, chunk_path, header_hw, workers, coder_tiles, 
     sym_all = [tc.buffer('sym_group%d' % k, (G, tc.cb, tc.lh * tc.lw), torch.int32)
                for k in range(2 if n_tiles > G else 1)]
     coded = [None] * len(sym_all)       # per group buffer: (threading.Event, [cuda event]) of its job
-    coder = ThreadPoolExecutor(max_workers=1)
+    # two workers: the device coder calls are serialised by `code_lock` (they share scratch
+    # buffers), but one group's chunk files are written while the next group is being coded
+    coder = ThreadPoolExecutor(max_workers=2)
+    code_lock = threading.Lock()
     jobs = []
     hdr1 = np.frombuffer(struct.pack('>QQ', *header_hw), dtype=np.uint8)
 
@@ -269,9 +272,11 @@ def compress_tiles(tc, src, tiles, chunk_path, header_hw, workers, coder_tiles, 
         if trace is not None:
             trace[name] = round(_t.perf_counter() - t00, 4)
 
-    def code_group(gi, lo, n, ready, launched, holder):
+    def code_group(gi, lo, n, ready, launched, holder, before):
         torch.cuda.set_device(dev)
-        with torch.cuda.stream(s_code):
+        if before is not None:
+            before.result()              # the job that used this group's buffers last is done
+        with code_lock, torch.cuda.stream(s_code):
             s_code.wait_event(ready)
             if trace is not None:
                 ready.synchronize()
@@ -284,7 +289,7 @@ def compress_tiles(tc, src, tiles, chunk_path, header_hw, workers, coder_tiles, 
             finally:
                 launched.set()
             mark('c_coded')
-            host = tc.pinned('streams_out', packed.numel())
+            host = tc.pinned('streams_out%d' % gi, packed.numel())
             host.copy_(packed, non_blocking=True)
             s_code.synchronize()
             mark('c_streams_on_host')
@@ -342,7 +347,8 @@ def compress_tiles(tc, src, tiles, chunk_path, header_hw, workers, coder_tiles, 
             ready = torch.cuda.Event()
             ready.record(main)
             coded[gi] = (threading.Event(), [])
-            jobs.append(coder.submit(code_group, gi, glo, gpos, ready, *coded[gi]))
+            jobs.append(coder.submit(code_group, gi, glo, gpos, ready, *coded[gi],
+                                     jobs[-2] if len(jobs) >= 2 and len(sym_all) == 2 else None))
             glo += gpos
             gpos = 0
             gi = (gi + 1) % len(sym_all)
