@@ -51,6 +51,19 @@ class ConvDesc(ctypes.Structure):
                 ('reserved', ctypes.c_int32), ('proj', ctypes.c_void_p)]
 
 
+class ActGradDesc(ctypes.Structure):
+    _fields_ = [('n', ctypes.c_int32), ('h', ctypes.c_int32), ('w', ctypes.c_int32), ('c', ctypes.c_int32),
+                ('g', Tensor), ('g_h', ctypes.c_int32), ('g_w', ctypes.c_int32),
+                ('g_oy', ctypes.c_int32), ('g_ox', ctypes.c_int32),
+                ('fold', ctypes.c_int32), ('fold_shift', ctypes.c_int32),
+                ('out', Tensor), ('out_h', ctypes.c_int32), ('out_w', ctypes.c_int32),
+                ('act', ctypes.c_int32), ('post_act', ctypes.c_int32),
+                ('dz', Tensor), ('dz_h', ctypes.c_int32), ('dz_w', ctypes.c_int32),
+                ('dz_oy', ctypes.c_int32), ('dz_ox', ctypes.c_int32),
+                ('skip', Tensor), ('gsum', Tensor), ('g2', Tensor),
+                ('scale', ctypes.c_void_p), ('db', ctypes.c_void_p)]
+
+
 class ProjFuse(ctypes.Structure):
     _fields_ = [('weights', ctypes.c_void_p), ('proj', ctypes.c_void_p)]
 
@@ -156,8 +169,7 @@ def lib():
     L.cae_eb_train_bwd.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                    vp, vp, vp, vp, vp]
     ci = ctypes.c_int
-    L.cae_act_grad.argtypes = [Tensor, ci, ci, ci, ci, ci, ci, Tensor, ci, ci, ci, Tensor, ci, ci,
-                               ci, ci, ci, ci, ci, ci, vp, vp, vp]
+    L.cae_act_grad.argtypes = [ctypes.POINTER(ActGradDesc), vp]
     L.cae_conv_wgrad.argtypes = [ci, ci, ci, ci, ci, ci, Tensor, Tensor, ci, vp, vp, vp, sz, vp]
     L.cae_conv_wgrad_workspace_bytes.restype = sz
     L.cae_conv_wgrad_workspace_bytes.argtypes = []

@@ -41,11 +41,17 @@ _NONE = C.Tensor(None, C.FMT_NONE, 0, 0, 0)
 
 
 def _wide(st):
-    """Layers the kernels cover: up to 128 channels on either side.  Thin sides (the 3-channel
-    image) ride the same tensor-core kernels with their channels padded to 16 -- those layers
-    are bound by the wide tensor's HBM traffic either way."""
-    return (1 <= st.c_in <= 128 and 1 <= st.c_out <= 128 and st.groups == 1 and st.bn is None
-            and st.gdn is None and st.skip is None and st.post_act is None)
+    """Layers the kernels cover: up to 256 channels on either side, plain or with the residual
+    add of the residual units (LeakyReLU or nothing after the add: ReLU there is not invertible,
+    and the branch's sign is recovered from the saved sum).  Thin sides (the 3-channel image) ride
+    the same tensor-core kernels with their channels padded to 16 -- those layers are bound by
+    the wide tensor's HBM traffic either way."""
+    if not (1 <= st.c_in <= 256 and 1 <= st.c_out <= 256 and st.groups == 1 and st.bn is None
+            and st.gdn is None):
+        return False
+    if st.skip is None:
+        return st.post_act is None
+    return st.post_act in (None, 'LeakyReLU') and st.kind in (C.CONV_S1, C.CONVT_S1) and st.c_in == st.c_out
 
 
 def _merged(kind, c_out):
@@ -55,8 +61,7 @@ def _merged(kind, c_out):
 
 
 def _plain(st):
-    return (st.groups == 1 and st.bn is None and st.gdn is None and st.skip is None
-            and st.post_act is None)
+    return st.groups == 1 and st.bn is None and st.gdn is None and (st.skip is not None or st.post_act is None)
 
 
 def eligible_chain(track):
@@ -75,11 +80,15 @@ def eligible_chain(track):
     wide = [k for k, s in enumerate(steps) if _wide(s)]
     if not wide or wide != list(range(wide[0], wide[-1] + 1)):
         return None
+    if any(s.skip is not None for k, s in enumerate(steps) if k < wide[0] or k > wide[-1]):
+        return None
     for k in range(wide[0], wide[-1] + 1):
         if steps[k].pad_mode != (C.PAD_ZERO if steps[k].transposed else C.PAD_REFLECT):
             return None
         if _merged(steps[k].kind, steps[k].c_out) and k != wide[-1]:
             return None                       # an image-type layer in the middle of the run
+        if steps[k].skip is not None and steps[k].skip < wide[0]:
+            return None                       # residual source outside the run
     return steps, wide[0], wide[-1] + 1
 
 
@@ -123,6 +132,7 @@ class _Plan:
         self.x0 = O.alloc_act(fmt, n, c, h, w, halo, device=device)
         self.xin, self.outs, self.wp, self.wt = [], [], [], []
         self.dz, self.embed, self.dz_off, self.gbuf = [], [], [], []
+        self.gsum = []                 # residual layers: the gradient handed on to the skip source
         cur = self.x0
         for k, st in enumerate(steps):
             ho, wo = O.KIND_OUT[st.kind](cur.h, cur.w)
@@ -159,6 +169,8 @@ class _Plan:
             else:
                 g = O.alloc_act(C.FMT_F16_PLANAR, n, st.c_in, gh, gw, device=device)
             self.gbuf.append(g)
+            self.gsum.append(O.alloc_act(C.FMT_F16_PLANAR, n, st.c_out, ho, wo, device=device)
+                             if st.skip is not None else None)
             cur = out
         last_out = self.outs[-1]
         self.y = last_out.t if last_out.fmt == C.FMT_F32_NCHW else \
@@ -185,8 +197,9 @@ class _Plan:
 class WideChain:
     """Forward / backward of a run of steps of a track on the kernels."""
 
-    def __init__(self, steps):
+    def __init__(self, steps, first=0):
         self.steps = steps
+        self.first = first             # track index of steps[0] (Step.skip counts track tensors)
         self._plans = {}
         self.use_graphs = not os.environ.get('CAE_TRAIN_NO_GRAPH')
 
@@ -202,15 +215,21 @@ class WideChain:
             plan = _Plan(self, x.shape, x.device, weights, biases)
         return plan
 
+    @staticmethod
+    def _tensor(plan, i):
+        """Tensor i of the chain: 0 = its input, i = the output of step i - 1."""
+        return plan.x0 if i == 0 else plan.outs[i - 1]
+
     # ------------------------------------------------------------------ forward
     def _launch_forward(self, plan, weights, biases):
         for k, st in enumerate(self.steps):
             O.pack_weights(st.kind, weights[k], out=plan.wp[k])
             out = plan.outs[k]
             aux = out.t if _merged(st.kind, st.c_out) else None
+            skip = self._tensor(plan, st.skip - self.first) if st.skip is not None else None
             O.conv(st.kind, plan.xin[k], plan.wp[k], st.c_out, None if aux is not None else out,
-                   igemm=True, bias=biases[k], skip=None, pre_act=E.act_code(st.pre_act),
-                   post_act=C.ACT_NONE, pad_mode=st.pad_mode, aux=aux)
+                   igemm=True, bias=biases[k], skip=skip, pre_act=E.act_code(st.pre_act),
+                   post_act=E.act_code(st.post_act), pad_mode=st.pad_mode, aux=aux)
         last = plan.outs[-1]
         if last.fmt != C.FMT_F32_NCHW:
             C.check(C.lib().cae_planar_to_nchw(last.desc(), last.n, last.c, last.h, last.w,
@@ -248,14 +267,23 @@ class WideChain:
 
     # ----------------------------------------------------------------- backward
     def _act_grad(self, g, g_dims, g_off, fold, fold_shift, out, act, dz, dz_dims, dz_off, n, h, w,
-                  c, scale, db):
-        C.check(C.lib().cae_act_grad(
-            g, g_dims[0], g_dims[1], g_off[0], g_off[1], fold, fold_shift,
-            out.desc() if out is not None else _NONE,
-            out.h if out is not None else 0, out.w if out is not None else 0, act,
-            dz, dz_dims[0], dz_dims[1], dz_off[0], dz_off[1], n, h, w, c,
-            scale.data_ptr() if scale is not None else None,
-            db.data_ptr() if db is not None else None, _sptr()))
+                  c, scale, db, post_act=C.ACT_NONE, skip=None, gsum=None, g2=None):
+        d = C.ActGradDesc()
+        d.n, d.h, d.w, d.c = n, h, w, c
+        d.g = g
+        d.g_h, d.g_w, d.g_oy, d.g_ox = g_dims[0], g_dims[1], g_off[0], g_off[1]
+        d.fold, d.fold_shift = fold, fold_shift
+        d.out = out.desc() if out is not None else _NONE
+        d.out_h, d.out_w = (out.h, out.w) if out is not None else (0, 0)
+        d.act, d.post_act = act, post_act
+        d.dz = dz
+        d.dz_h, d.dz_w, d.dz_oy, d.dz_ox = dz_dims[0], dz_dims[1], dz_off[0], dz_off[1]
+        d.skip = skip.desc() if skip is not None else _NONE
+        d.gsum = gsum.desc() if gsum is not None else _NONE
+        d.g2 = g2.desc() if g2 is not None else _NONE
+        d.scale = scale.data_ptr() if scale is not None else None
+        d.db = db.data_ptr() if db is not None else None
+        C.check(C.lib().cae_act_grad(ctypes.byref(d), _sptr()))
 
     def _launch_backward(self, plan, weights, need_dx):
         steps = self.steps
@@ -264,13 +292,23 @@ class WideChain:
         plan.flat.zero_()
         g_desc = C.Tensor(plan.g_in.data_ptr(), C.FMT_F32_NCHW, 0, 0, 0)
         g_dims, g_off, fold, fold_shift = (plan.g_in.shape[2], plan.g_in.shape[3]), (0, 0), 0, 0
+        pending = {}           # chain tensor index -> gradient arriving through a residual add
         for k in range(L - 1, -1, -1):
             st = steps[k]
             x, o, dz = plan.xin[k], plan.outs[k], plan.dz[k]
             last = k == L - 1
+            skip = gsum = None
+            if st.skip is not None:
+                src = st.skip - self.first
+                if src in pending:
+                    raise C.CaeError('two residual connections from one tensor are not supported')
+                skip, gsum = self._tensor(plan, src), plan.gsum[k]
+                pending[src] = gsum
             self._act_grad(g_desc, g_dims, g_off, fold, fold_shift, o, E.act_code(st.pre_act),
                            dz.desc(), (dz.h, dz.w), plan.dz_off[k], n, o.h, o.w, st.c_out,
-                           plan.scale if last else None, plan.db[k])
+                           plan.scale if last else None, plan.db[k],
+                           post_act=E.act_code(st.post_act), skip=skip, gsum=gsum,
+                           g2=pending.pop(k + 1, None))
             C.check(C.lib().cae_conv_wgrad(st.kind, n, x.h, x.w, st.c_in, st.c_out, x.desc(),
                                            dz.desc(), plan.embed[k], plan.dW[k].data_ptr(),
                                            plan.inv_scale.data_ptr(), plan.ws.data_ptr(),
@@ -294,7 +332,7 @@ class WideChain:
             x0 = plan.x0
             self._act_grad(g_desc, g_dims, g_off, fold, fold_shift, None, C.ACT_NONE,
                            C.Tensor(plan.dx.data_ptr(), C.FMT_F32_NCHW, 0, 0, 0), (x0.h, x0.w), (0, 0),
-                           n, x0.h, x0.w, x0.c, plan.inv_scale, None)
+                           n, x0.h, x0.w, x0.c, plan.inv_scale, None, g2=pending.pop(0, None))
         # below the top layer the incoming gradient already carries the loss scale
         if L > 1 and plan.offs[2 * L] > plan.offs[L]:
             lo = plan.offs[L]
@@ -369,7 +407,7 @@ def run_track(track, x):
             track._train_chain = info = False
         else:
             steps, k0, k1 = found
-            track._train_chain = info = (steps, k0, k1, WideChain(steps[k0:k1]))
+            track._train_chain = info = (steps, k0, k1, WideChain(steps[k0:k1], k0))
     if info is False:
         return None
     steps, k0, k1, chain = info

@@ -40,6 +40,7 @@ struct WgParams {
   int PH, PW, n_par, par_stride;   // Q patch geometry (as the forward kernel's A stage)
   int q_org_y, q_org_x;
   int p_off;                       // P is embedded at (p_off, p_off) of a larger zero-ringed buffer
+  int p_plane0, m0;                // first plane / channel of P handled by this launch (M chunks of 128)
   int p_bytes, q_box_bytes, stage_bytes, stages;
   uint32_t tap_off[9];             // byte offset of a tap's view inside the Q part of a stage
   uint32_t idesc;
@@ -102,7 +103,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CU
         mbar_expect_tx(&full[s], (uint32_t)(p.p_bytes + p.n_par * p.q_box_bytes));
         // P: the 16 x 8 pixel tile itself (interior pixel (y, x) = row y + 1, column x + 4)
         tma_load_4d(&tmP, &full[s], st, (tx * 8 + 1 + CAE_COL_PAD + p.p_off) * 8,
-                    ty * 16 + 1 + p.p_off, 0, n);
+                    ty * 16 + 1 + p.p_off, p.p_plane0, n);
         // Q: the patch the forward kernel reads for this tile, channels of this CTA's chunk
         for (int par = 0; par < p.n_par; ++par)
           tma_load_4d(&tmQ, &full[s], st + p.p_bytes + (size_t)par * p.par_stride,
@@ -179,13 +180,14 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgParams p) {
   float acc = 0.f;
   for (int s = 0; s < p.n_slots; ++s) acc += __ldg(src + (size_t)s * slot_stride);
   const int dy = t / 3, dx = t - dy * 3;
+  const int mg = m + p.m0;                                          // channel of P in the whole layer
   size_t idx;
   if (p.kind == CAE_CONV_S1 || p.kind == CAE_CONV_S2)
-    idx = ((size_t)m * p.c_in + n) * 9 + t;                        // P = dz (c_out), Q = x (c_in)
+    idx = ((size_t)mg * p.c_in + n) * 9 + t;                        // P = dz (c_out), Q = x (c_in)
   else if (p.kind == CAE_CONVT_S1)
-    idx = ((size_t)n * p.c_out + m) * 9 + (2 - dy) * 3 + (2 - dx);  // flipped correlation
+    idx = ((size_t)n * p.c_out + mg) * 9 + (2 - dy) * 3 + (2 - dx); // flipped correlation
   else
-    idx = ((size_t)m * p.c_out + n) * 9 + t;                        // P = x (c_in), Q = dz (c_out)
+    idx = ((size_t)mg * p.c_out + n) * 9 + t;                       // P = x (c_in), Q = dz (c_out)
   p.dw[idx] += acc * (p.scale ? __ldg(p.scale) : 1.f);
 }
 
@@ -202,9 +204,11 @@ struct AgView {
 
 struct AgParams {
   AgView g, out, dz;
+  AgView g2, skip, gsum;   // residual add: extra incoming gradient, the tensor added, where g_sum goes
   int n, h, w, c;
   int fold, fold_shift;
   float slope;       // activation: d/dv max(v, v * slope); 1 = none
+  float post_slope;  // activation after the residual add; 1 = none
   const float *scale;
   float *db;
 };
@@ -237,6 +241,28 @@ __device__ __forceinline__ void ag_load8(const AgView &v, int n, int plane, int 
     const float2 t = __half22float2(h[k]);
     f[2 * k] = t.x;
     f[2 * k + 1] = t.y;
+  }
+}
+
+__device__ __forceinline__ void ag_store8(const AgView &v, int n, int plane, int y, int x, int c,
+                                          const float (&g)[8], float sc) {
+  if (v.fmt == CAE_FMT_F32_NCHW) {
+    float *dst = reinterpret_cast<float *>(v.ptr);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = plane * 8 + k;
+      if (ch < c) dst[(((size_t)n * c + ch) * v.H + y + v.oy) * v.W + x + v.ox] = g[k] * sc;
+    }
+  } else if (plane < v.planes) {
+    uint4 u;
+    __half2 *h = reinterpret_cast<__half2 *>(&u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a = plane * 8 + 2 * k < c ? g[2 * k] * sc : 0.f;
+      const float b = plane * 8 + 2 * k + 1 < c ? g[2 * k + 1] * sc : 0.f;
+      h[k] = __floats2half2_rn(a, b);
+    }
+    reinterpret_cast<uint4 *>(v.ptr)[ag_unit(v, n, plane, y + v.oy, x + v.ox)] = u;
   }
 }
 
@@ -284,11 +310,38 @@ __global__ void __launch_bounds__(256) act_grad_kernel(const AgParams q) {
         }
       }
     }
-    if (q.out.ptr && q.slope != 1.f) {
-      float o[8];
-      ag_load8(q.out, n, plane, y + q.out.oy, x + q.out.ox, q.c, o);
+    if (q.g2.ptr) {             // gradient arriving through a residual connection further up
+      float t[8];
+      ag_load8(q.g2, n, plane, y + q.g2.oy, x + q.g2.ox, q.c, t);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) g[k] = o[k] > 0.f ? g[k] : g[k] * q.slope;
+      for (int k = 0; k < 8; ++k) g[k] += t[k];
+    }
+    if (!q.skip.ptr) {
+      if (q.out.ptr && q.slope != 1.f) {
+        float o[8];
+        ag_load8(q.out, n, plane, y + q.out.oy, x + q.out.ox, q.c, o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = o[k] > 0.f ? g[k] : g[k] * q.slope;
+      }
+    } else {
+      // out = post(pre(z) + skip): g_sum = g * post'(out) goes on to the skip source as it is;
+      // pre'(z) needs the sign of the branch = post^-1(out) - skip
+      float o[8], sk[8];
+      ag_load8(q.out, n, plane, y + q.out.oy, x + q.out.ox, q.c, o);
+      ag_load8(q.skip, n, plane, y + q.skip.oy, x + q.skip.ox, q.c, sk);
+      const float inv_post = q.post_slope != 0.f ? 1.f / q.post_slope : 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (q.post_slope != 1.f && !(o[k] > 0.f)) g[k] *= q.post_slope;
+      }
+      if (q.gsum.ptr) ag_store8(q.gsum, n, plane, y, x, q.c, g, q.scale ? __ldg(q.scale) : 1.f);
+      if (q.slope != 1.f) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float sum = o[k] > 0.f ? o[k] : o[k] * inv_post;
+          if (!(sum - sk[k] > 0.f)) g[k] *= q.slope;
+        }
+      }
     }
   }
   if (q.db) {
@@ -299,27 +352,7 @@ __global__ void __launch_bounds__(256) act_grad_kernel(const AgParams q) {
       if ((threadIdx.x & 31) == 0 && v != 0.f) atomicAdd(&s_db[k], v);
     }
   }
-  if (inside) {
-    const float sc = q.scale ? __ldg(q.scale) : 1.f;
-    if (q.dz.fmt == CAE_FMT_F32_NCHW) {
-      float *dst = reinterpret_cast<float *>(q.dz.ptr);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int ch = plane * 8 + k;
-        if (ch < q.c) dst[(((size_t)n * q.c + ch) * q.dz.H + y + q.dz.oy) * q.dz.W + x + q.dz.ox] = g[k] * sc;
-      }
-    } else if (plane < q.dz.planes) {
-      uint4 u;
-      __half2 *h = reinterpret_cast<__half2 *>(&u);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float a = plane * 8 + 2 * k < q.c ? g[2 * k] * sc : 0.f;
-        const float b = plane * 8 + 2 * k + 1 < q.c ? g[2 * k + 1] * sc : 0.f;
-        h[k] = __floats2half2_rn(a, b);
-      }
-      reinterpret_cast<uint4 *>(q.dz.ptr)[ag_unit(q.dz, n, plane, y + q.dz.oy, x + q.dz.ox)] = u;
-    }
-  }
+  if (inside) ag_store8(q.dz, n, plane, y, x, q.c, g, q.scale ? __ldg(q.scale) : 1.f);
   if (q.db) {
     __syncthreads();
     // (the sums are taken before scaling)
@@ -387,7 +420,7 @@ extern "C" int cae_conv_wgrad(int kind, int n, int h_in, int w_in, int c_in, int
   CAE_CHECK(workspace_bytes >= cae_conv_wgrad_workspace_bytes(), 2,
             "cae_conv_wgrad: workspace smaller than cae_conv_wgrad_workspace_bytes()");
   CAE_CHECK(n > 0 && h_in > 0 && w_in > 0 && c_in > 0 && c_out > 0, 2, "cae_conv_wgrad: bad shape");
-  CAE_CHECK(c_in <= 128 && c_out <= 128, 2, "cae_conv_wgrad: at most 128 channels per side");
+  CAE_CHECK(c_in <= 256 && c_out <= 256, 2, "cae_conv_wgrad: at most 256 channels per side");
   const bool down = kind == CAE_CONV_S2, up = kind == CAE_CONVT_S2;
   if (down)
     CAE_CHECK(h_in % 2 == 0 && w_in % 2 == 0, 2, "cae_conv_wgrad: stride-2 convolution needs an even input size");
@@ -414,7 +447,7 @@ extern "C" int cae_conv_wgrad(int kind, int n, int h_in, int w_in, int c_in, int
   p.tiles_x = (wP + 7) / 8;
   p.tiles_per_img = p.tiles_x * ((hP + 15) / 16);
   p.n_tiles = p.tiles_per_img * n;
-  p.planes_p = P.planes;
+  p.planes_p = P.planes > 16 ? 16 : P.planes;     // one 128-channel slice of P per launch
   p.n_chunks = (Q.planes * 8 + kWgNc - 1) / kWgNc;
   if (q_split) {                 // the stride-2 pattern of igemm_conv.cu (CAE_CONV_S2)
     p.PH = 17; p.PW = 9; p.n_par = 4; p.q_org_y = 0; p.q_org_x = 1;
@@ -456,7 +489,7 @@ extern "C" int cae_conv_wgrad(int kind, int n, int h_in, int w_in, int c_in, int
   // gradient of a reflect-padded Conv2d wants (cae_act_grad)
   const int grow = dz_embed ? (down ? 1 : 2) : 0;
   p.p_off = dz_embed ? 1 : 0;
-  if (int rc = wg_tensor_map(&tmP, P, n, hP + grow, wP + grow, false, 8, 16, P.planes)) return rc;
+  if (int rc = wg_tensor_map(&tmP, P, n, hP + grow, wP + grow, false, 8, 16, p.planes_p)) return rc;
   if (int rc = wg_tensor_map(&tmQ, Q, n, hQ, wQ, q_split, p.PW, p.PH, kWgNc / 8)) return rc;
 
   int grid = cae_sm_count();
@@ -466,40 +499,56 @@ extern "C" int cae_conv_wgrad(int kind, int n, int h_in, int w_in, int c_in, int
   CAE_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   p.partial = (float *)workspace;
   p.n_slots = grid / p.n_chunks;
-  wgrad_kernel<<<grid, kWgThreads, smem_bytes, (cudaStream_t)stream>>>(tmP, tmQ, p);
-  const int total = 9 * c_m * c_n;
-  wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
-  cae_count_launch(2);
+  // P has up to 256 channels, the accumulators 128 lanes: one launch per 128-channel slice of P
+  // (its planes are a coordinate of the same tensor map)
+  const int c_m_total = c_m;
+  for (int m0 = 0; m0 < c_m_total; m0 += 128) {
+    p.m0 = m0;
+    p.p_plane0 = m0 / 8;
+    p.c_m = c_m_total - m0 < 128 ? c_m_total - m0 : 128;
+    wgrad_kernel<<<grid, kWgThreads, smem_bytes, (cudaStream_t)stream>>>(tmP, tmQ, p);
+    const int total = 9 * p.c_m * c_n;
+    wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+    cae_count_launch(2);
+  }
   CAE_CUDA(cudaGetLastError());
   return 0;
 }
 
-// dz = fold(g) * act'(out) * scale in the layout of `dz`, db += per-channel sums (before scaling)
-extern "C" int cae_act_grad(cae_tensor g, int g_h, int g_w, int g_oy, int g_ox, int fold,
-                            int fold_shift, cae_tensor out, int out_h, int out_w, int act,
-                            cae_tensor dz, int dz_h, int dz_w, int dz_oy, int dz_ox, int n, int h,
-                            int w, int c, const float *scale, float *db, void *stream) {
-  CAE_CHECK(g.ptr && dz.ptr, 2, "cae_act_grad: null pointer");
-  CAE_CHECK(n > 0 && h > 0 && w > 0 && c > 0 && c <= 128, 2, "cae_act_grad: bad shape");
+extern "C" int cae_act_grad(const cae_act_grad_desc *d, void *stream) {
+  CAE_CHECK(d && d->g.ptr && d->dz.ptr, 2, "cae_act_grad: null pointer");
+  CAE_CHECK(d->n > 0 && d->h > 0 && d->w > 0 && d->c > 0, 2, "cae_act_grad: bad shape");
   auto ok = [](int fmt) {
     return fmt == CAE_FMT_F32_NCHW || fmt == CAE_FMT_F16_PLANAR || fmt == CAE_FMT_F16_SPLIT;
   };
-  CAE_CHECK(ok(g.fmt) && ok(dz.fmt) && (!out.ptr || ok(out.fmt)), 2, "cae_act_grad: bad format");
+  CAE_CHECK(ok(d->g.fmt) && ok(d->dz.fmt) && (!d->out.ptr || ok(d->out.fmt)), 2, "cae_act_grad: bad format");
+  CAE_CHECK(!d->g2.ptr || ok(d->g2.fmt), 2, "cae_act_grad: bad format of g2");
+  if (d->skip.ptr) {
+    CAE_CHECK(d->out.ptr && ok(d->skip.fmt) && (!d->gsum.ptr || ok(d->gsum.fmt)), 2,
+              "cae_act_grad: a residual layer needs its saved output and the tensor that was added");
+    CAE_CHECK(d->post_act != CAE_ACT_RELU, 2,
+              "cae_act_grad: ReLU after a residual add is not invertible (LeakyReLU or none)");
+  }
+  auto slope = [](int act) { return act == CAE_ACT_LEAKY_RELU ? 0.01f : (act == CAE_ACT_RELU ? 0.f : 1.f); };
   AgParams q;
   memset(&q, 0, sizeof(q));
-  q.g = AgView{g.ptr, g.fmt, g.planes, g_h, g_w, g_oy, g_ox};
-  q.out = AgView{out.ptr, out.fmt, out.planes, out_h, out_w, 0, 0};
-  q.dz = AgView{dz.ptr, dz.fmt, dz.planes, dz_h, dz_w, dz_oy, dz_ox};
-  q.n = n; q.h = h; q.w = w; q.c = c;
-  q.fold = fold;
-  q.fold_shift = fold_shift;
-  q.slope = act == CAE_ACT_LEAKY_RELU ? 0.01f : (act == CAE_ACT_RELU ? 0.f : 1.f);
-  q.scale = scale;
-  q.db = db;
-  const int planes = (c + 7) / 8;
-  CAE_CHECK((long long)n * planes <= 65535 && (h + 7) / 8 <= 65535, 2,
+  q.g = AgView{d->g.ptr, d->g.fmt, d->g.planes, d->g_h, d->g_w, d->g_oy, d->g_ox};
+  q.out = AgView{d->out.ptr, d->out.fmt, d->out.planes, d->out_h, d->out_w, 0, 0};
+  q.dz = AgView{d->dz.ptr, d->dz.fmt, d->dz.planes, d->dz_h, d->dz_w, d->dz_oy, d->dz_ox};
+  q.g2 = AgView{d->g2.ptr, d->g2.fmt, d->g2.planes, d->h, d->w, 0, 0};
+  q.skip = AgView{d->skip.ptr, d->skip.fmt, d->skip.planes, d->h, d->w, 0, 0};
+  q.gsum = AgView{d->gsum.ptr, d->gsum.fmt, d->gsum.planes, d->h, d->w, 0, 0};
+  q.n = d->n; q.h = d->h; q.w = d->w; q.c = d->c;
+  q.fold = d->fold;
+  q.fold_shift = d->fold_shift;
+  q.slope = slope(d->act);
+  q.post_slope = slope(d->post_act);
+  q.scale = d->scale;
+  q.db = d->db;
+  const int planes = (d->c + 7) / 8;
+  CAE_CHECK((long long)d->n * planes <= 65535 && (d->h + 7) / 8 <= 65535, 2,
             "cae_act_grad: tensor too large for one launch; split the batch");
-  const dim3 grid((unsigned)((w + 31) / 32), (unsigned)((h + 7) / 8), (unsigned)(n * planes));
+  const dim3 grid((unsigned)((d->w + 31) / 32), (unsigned)((d->h + 7) / 8), (unsigned)(d->n * planes));
   act_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(q);
   cae_count_launch();
   CAE_CUDA(cudaGetLastError());

@@ -266,13 +266,29 @@ int cae_eb_train_bwd(const float *y_hat, const float *blob, int n, int c, int hw
  *                 (torch stores Conv2d weights as (out, in, 3, 3) and ConvTranspose2d weights
  *                 as (in, out, 3, 3), so cae_pack_weights(transposed kind, W) is the adjoint).
  *  cae_conv_wgrad dW += scale * sum_pixels dz (x) window(x) on the tensor cores (fp32, torch
- *                 layout, accumulated).  x: the layer's forward input in the layout the forward
+ *                 layout, accumulated; up to 256 channels per side).  x: the layer's forward input in the layout the forward
  *                 kernel read (planar; split for CAE_CONV_S2); dz: planar (split for
  *                 CAE_CONVT_S2), zero halo; dz_embed = 1 when dz is embedded as above.          */
-int cae_act_grad(cae_tensor g, int g_h, int g_w, int g_oy, int g_ox, int fold, int fold_shift,
-                 cae_tensor out, int out_h, int out_w, int act, cae_tensor dz, int dz_h, int dz_w,
-                 int dz_oy, int dz_ox, int n, int h, int w, int c, const float *scale, float *db,
-                 void *stream);
+typedef struct cae_act_grad_desc {
+  int32_t n, h, w, c;            /* the layer's OUTPUT: batch, size, channels                        */
+  cae_tensor g;                  /* incoming gradient (fp32 NCHW, planar or split fp16)              */
+  int32_t g_h, g_w, g_oy, g_ox;  /* logical size of g's buffer, position of pixel (0,0) in it        */
+  int32_t fold, fold_shift;      /* fold = 1: g covers the reflect-padded input of the consumer      */
+  cae_tensor out;                /* the layer's saved output (for the activation derivative), or none */
+  int32_t out_h, out_w;
+  int32_t act;                   /* activation between convolution and (optional) residual add       */
+  int32_t post_act;              /* activation after the residual add (CAE_ACT_NONE / LEAKY_RELU)    */
+  cae_tensor dz;                 /* result: gradient of the convolution's output                     */
+  int32_t dz_h, dz_w, dz_oy, dz_ox;
+  /* residual add (R:172, R:302: out = post_act(act(z) + skip)): `skip` = the tensor that was
+   * added (h x w, the layout it was saved in); `gsum` (optional) receives g * post_act'(out), the
+   * gradient that continues to the source of the skip; `g2` (optional, any layer) = such a
+   * gradient arriving at THIS layer's output from a residual connection further up.            */
+  cae_tensor skip, gsum, g2;
+  const float *scale;            /* device scalar multiplied into dz / gsum, or NULL                 */
+  float *db;                     /* c floats, accumulated (sums taken before `scale`), or NULL       */
+} cae_act_grad_desc;
+int cae_act_grad(const cae_act_grad_desc *d, void *stream);
 size_t cae_conv_wgrad_workspace_bytes(void);   /* scratch for the per-CTA partial sums */
 int cae_conv_wgrad(int kind, int n, int h_in, int w_in, int c_in, int c_out, cae_tensor x,
                    cae_tensor dz, int dz_embed, float *dw, const float *scale, void *workspace,

@@ -36,10 +36,11 @@ def test_struct_layout_matches_header(tmp_path):
 #include <stddef.h>
 #include "cae_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(cae_tensor), sizeof(cae_conv_desc),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(cae_tensor), sizeof(cae_conv_desc),
          sizeof(cae_eb_tables), sizeof(cae_head_desc), sizeof(cae_quant_fuse),
          offsetof(cae_conv_desc, quant), offsetof(cae_head_desc, w_stem),
-         offsetof(cae_quant_fuse, y_q_planar));
+         offsetof(cae_quant_fuse, y_q_planar), sizeof(cae_act_grad_desc),
+         offsetof(cae_act_grad_desc, skip), offsetof(cae_act_grad_desc, db));
   return 0;
 }
 ''')
@@ -50,7 +51,8 @@ int main(void) {
                                           check=True).stdout.split()]
     want = [ctypes.sizeof(C.Tensor), ctypes.sizeof(C.ConvDesc), ctypes.sizeof(C.EbTables),
             ctypes.sizeof(C.HeadDesc), ctypes.sizeof(C.QuantFuse), C.ConvDesc.quant.offset,
-            C.HeadDesc.w_stem.offset, C.QuantFuse.y_q_planar.offset]
+            C.HeadDesc.w_stem.offset, C.QuantFuse.y_q_planar.offset, ctypes.sizeof(C.ActGradDesc),
+            C.ActGradDesc.skip.offset, C.ActGradDesc.db.offset]
     assert got == want
     assert ctypes.sizeof(C.Tensor) == 24
 

@@ -62,7 +62,7 @@ def test_single_layer_gradients_match_autograd(kind, c_in, c_out, h, w):
     assert _rel(gx, rx) < 3e-3, ('dx', _rel(gx, rx))
 
 
-@pytest.mark.parametrize('arch', ['A'])
+@pytest.mark.parametrize('arch', ['A', 'A_res', 'B'])
 def test_whole_model_gradients_match_autograd(arch):
     """Encoder and decoder of a named net in train() mode: loss and every parameter gradient,
     kernels against the torch formulation on identical parameters and inputs."""
@@ -82,7 +82,7 @@ def test_whole_model_gradients_match_autograd(arch):
         losses[mode] = loss.item()
         grads[mode] = {n: p.grad.clone() for m in (enc, dec) for n, p in m.named_parameters()}
         if mode == 'kernels':
-            assert enc.module._train_chain and dec.module._train_chain, 'net A is covered by the kernels'
+            assert enc.module._train_chain and dec.module._train_chain, 'the named nets are covered by the kernels'
     assert abs(losses['kernels'] - losses['torch']) <= 2e-3 * abs(losses['torch'])
     for n, gt in grads['torch'].items():
         assert _rel(grads['kernels'][n], gt) < 2e-2, (n, _rel(grads['kernels'][n], gt))
