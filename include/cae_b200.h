@@ -266,9 +266,10 @@ int cae_eb_train_bwd(const float *y_hat, const float *blob, int n, int c, int hw
  *                 (torch stores Conv2d weights as (out, in, 3, 3) and ConvTranspose2d weights
  *                 as (in, out, 3, 3), so cae_pack_weights(transposed kind, W) is the adjoint).
  *  cae_conv_wgrad dW += scale * sum_pixels dz (x) window(x) on the tensor cores (fp32, torch
- *                 layout, accumulated; up to 256 channels per side).  x: the layer's forward input in the layout the forward
- *                 kernel read (planar; split for CAE_CONV_S2); dz: planar (split for
- *                 CAE_CONVT_S2), zero halo; dz_embed = 1 when dz is embedded as above.          */
+ *                 layout, accumulated; up to 256 channels per side).  x: the layer's forward
+ *                 input in the layout the forward kernel read (planar; split for CAE_CONV_S2);
+ *                 dz: planar (split for CAE_CONVT_S2), zero halo; dz_embed = 1 when dz is
+ *                 embedded as above.                                                          */
 typedef struct cae_act_grad_desc {
   int32_t n, h, w, c;            /* the layer's OUTPUT: batch, size, channels                        */
   cae_tensor g;                  /* incoming gradient (fp32 NCHW, planar or split fp16)              */
