@@ -7,7 +7,7 @@ megapixels per second at 1/2/4/8 B200, fraction of the tensor roofline, PSNR / b
 
 Default workload ``wsi`` (BASELINE.json configs 3/4): a synthetic tissue-like whole-slide image
 of 512 x 512 chunks, net A (3->128->128->48, level 3, LeakyReLU, random-init weights), sharded
-over the N ranks by contiguous chunk range (``compress.shard_range``: 4096 chunks = 1.07
+over the N ranks by contiguous chunk range (``compress.shard_range``: 8192 chunks = 2.15
 gigapixel per GPU -- a 50k x 50k slide is 9604 chunks -- no collective; the entropy coder's time
 per call does not depend on the number of chunk streams, so it is handed the whole shard).  One *step* = the rank's shard through the public
 ``compress_image`` -> ``decompress_image`` (the reference's ``src/compress.py:29-128`` /
@@ -41,7 +41,7 @@ sys.path.insert(0, ROOT)
 
 ARCH_NAME = 'A'
 BATCH, SIZE = 128, 256                  # config 2
-PS, TILES, GX = 512, 4096, 64           # configs 3/4: chunk size, chunks per GPU, chunks per row
+PS, TILES, GX = 512, 8192, 64           # configs 3/4: chunk size, chunks per GPU, chunks per row
 FLOPS_PER_PX = {'A': 136746, 'A_res': 321876, 'B': 367236, 'M': 738}
 METRIC = 'wsi_encode_decode_megapixels_per_sec'
 ARCH_TEXT = {'A': 'net A (3->128->128->48 L3 LeakyReLU)', 'A_res': 'net A+res',

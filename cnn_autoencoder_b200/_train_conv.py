@@ -411,6 +411,8 @@ def run_track(track, x):
     if info is False:
         return None
     steps, k0, k1, chain = info
+    if any(st.conv.weight.dtype != torch.float32 or not st.conv.weight.is_cuda for st in steps[k0:k1]):
+        return None                    # (half / CPU parameters: the torch formulation)
     tensors = {0: x}
     cur = x
     for k in range(k0):
