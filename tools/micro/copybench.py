@@ -15,8 +15,30 @@ if world > 1:
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 T, PS, GX = 2048, 512, 64
 H, W = T // GX * PS, GX * PS
-src = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory(); src.fill_(3)
-dst = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+HUGE = '--hugepages' in sys.argv
+if HUGE:
+    # transparent huge pages under the page-locked slide (fewer IOMMU / DMA mappings): 2 MB aligned
+    # anonymous memory, madvise(MADV_HUGEPAGE) before the first touch, then cudaHostRegister
+    from cnn_autoencoder_b200 import _slide
+    libc = ctypes.CDLL(None, use_errno=True)
+    def huge(nbytes):
+        raw = np.empty(nbytes + (2 << 20), dtype=np.uint8)
+        off = (-raw.ctypes.data) % (2 << 20)
+        a = raw[off:off + nbytes]
+        rc = libc.madvise(ctypes.c_void_p(a.ctypes.data), ctypes.c_size_t(nbytes), 14)   # MADV_HUGEPAGE
+        a[:] = 3
+        return a, rc
+    src_np, rc1 = huge(H * W * 3)
+    dst_np, rc2 = huge(H * W * 3)
+    pins = [_slide.pin_array(src_np), _slide.pin_array(dst_np)]
+    src, dst = torch.from_numpy(src_np).view(H, W, 3), torch.from_numpy(dst_np).view(H, W, 3)
+    if rank == 0:
+        thp = open('/sys/kernel/mm/transparent_hugepage/enabled').read().strip()
+        anon = [l for l in open('/proc/self/smaps_rollup') if 'AnonHuge' in l]
+        print('madvise rc', rc1, rc2, 'THP', thp, anon, file=sys.stderr)
+else:
+    src = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory(); src.fill_(3)
+    dst = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
 streams_h = torch.empty(272_000_000, dtype=torch.uint8).pin_memory()
 streams_d = torch.empty(272_000_000, dtype=torch.uint8, device='cuda')
 dev_in = torch.empty((T, PS, PS, 3), dtype=torch.uint8, device='cuda')
