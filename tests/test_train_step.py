@@ -143,3 +143,32 @@ def test_mod_grad_accumulate_gates_the_optimizers():
     M.train_step(x, m, crit, opts, fwd, bucket=bucket, step=2, mod_grad_accumulate=acc)
     assert any(not torch.equal(p, q) for p, q in zip(m['encoder'].parameters(), before['encoder']))
     assert bucket.flat[a:b].abs().sum() == 0
+
+
+def test_training_chain_eligibility_is_decided_from_the_track():
+    """Which tracks train on the kernels (``_train_conv.eligible_chain``, host logic only): the
+    named nets A, A+residual and B in full; BatchNorm, GDN and groups=True fall back to the torch
+    formulation; a ReLU directly after a residual add does too (not invertible)."""
+    from cnn_autoencoder_b200 import _train_conv as T
+    import cnn_autoencoder_b200 as M
+
+    def tracks(**arch):
+        chk = O.make_checkpoint(dict(O.NAMED_ARCHS['A'], **arch), seed=1)
+        model = M.autoencoder_from_state_dict(chk, gpu=False, train=True)
+        return model['encoder'].module, model['decoder'].module
+
+    for arch in (dict(), dict(use_residual=True),
+                 dict(use_residual=True, channels_bn=192, compression_level=4)):
+        for tr in tracks(**arch):
+            found = T.eligible_chain(tr)
+            assert found is not None, arch
+            steps, k0, k1 = found
+            assert (k0, k1) == (0, len(steps)), (arch, k0, k1)      # the whole track, thin layers included
+    for arch in (dict(batch_norm=True), dict(act_layer_type='GDN'), dict(groups=True, channels_net=126, channels_bn=48),
+                 dict(use_residual=True, act_layer_type='ReLU')):
+        try:
+            trs = tracks(**arch)
+        except Exception:          # an architecture the constructors refuse is not a chain either
+            continue
+        enc, dec = trs
+        assert T.eligible_chain(enc) is None or T.eligible_chain(dec) is None, arch
