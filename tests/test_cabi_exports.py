@@ -73,3 +73,31 @@ def test_graft_entry_build_runs():
         sys.path.insert(0, root)
     g = importlib.import_module('__graft_entry__')
     g.build()
+
+
+def test_new_entry_points_refuse_bad_arguments_without_touching_the_device():
+    """Argument checks of the round-2 entries run before any CUDA call: null pointers, channel
+    counts the kernels do not cover and a short workspace come back as error codes with a
+    message (no GPU needed)."""
+    L = C.lib()
+    none = C.Tensor(None, C.FMT_NONE, 0, 0, 0)
+    planar = C.Tensor(1 << 20, C.FMT_F16_PLANAR, 16, 0, 0)
+    assert L.cae_act_grad(None, None) != 0 and b'cae_act_grad' in L.cae_last_error()
+    d = C.ActGradDesc()
+    d.n, d.h, d.w, d.c = 1, 8, 8, 128
+    assert L.cae_act_grad(ctypes.byref(d), None) != 0 and b'null pointer' in L.cae_last_error()
+    d.g, d.dz, d.out, d.skip = planar, planar, none, planar
+    assert L.cae_act_grad(ctypes.byref(d), None) != 0 and b'residual' in L.cae_last_error()
+    assert L.cae_conv_wgrad_workspace_bytes() > 0
+    rc = L.cae_conv_wgrad(C.CONV_S1, 1, 16, 16, 128, 128, planar, planar, 0, None, None, None, 0, None)
+    assert rc != 0 and b'null pointer' in L.cae_last_error()
+    rc = L.cae_conv_wgrad(C.CONV_S1, 1, 16, 16, 300, 128, planar, planar, 0, 1 << 20, None, 1 << 20,
+                          L.cae_conv_wgrad_workspace_bytes(), None)
+    assert rc != 0 and b'256 channels' in L.cae_last_error()
+    rc = L.cae_conv_wgrad(C.CONV_S1, 1, 16, 16, 128, 128, planar, planar, 0, 1 << 20, None, 1 << 20, 16, None)
+    assert rc != 0 and b'workspace' in L.cae_last_error()
+    assert L.cae_pack_proj_weights(64, 3, 1 << 20, None, 1 << 20, None) != 0 and b'c_in = 128' in L.cae_last_error()
+    assert L.cae_image_from_proj(None, 1, 8, 8, 3, None, 0, 0, None, None, None) != 0
+    assert L.cae_ssim_u8(1 << 20, 1 << 20, 1, 4, 4, 3, 1 << 20, None) != 0 and b'7x7' in L.cae_last_error()
+    assert L.cae_ssim_gauss_planes_f32(1 << 20, 1 << 20, 1, 8, 8, 255.0, 1 << 20, 1 << 20, None) != 0
+    assert L.cae_tiles_download_u8_banded(None, 1, 64, 3, None, None, 64, 64, None, None) != 0
