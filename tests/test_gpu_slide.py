@@ -245,3 +245,25 @@ def test_banded_tile_copies_equal_the_per_tile_copies():
     for i, j in tiles:
         y0, x0 = i * ps, j * ps
         assert torch.equal(out2[y0:y0 + ps, x0:x0 + ps], img[y0:y0 + ps, x0:x0 + ps])
+
+
+@pytest.mark.gpu
+def test_test_image_scores_like_the_oracle_metrics(tmp_path):
+    """cnn_autoencoder_b200.test_cae.test_image (src/test_cae.py:91-163): compress -> decompress ->
+    the six metrics on the device, against the float64 restatements on the host arrays."""
+    import numpy as np
+    from oracle import cae_oracle as O
+    from cnn_autoencoder_b200 import test_cae as T
+    from cnn_autoencoder_b200.decompress import decompress_image
+    chk = O.make_checkpoint(O.NAMED_ARCHS['A'], seed=12)
+    img = O.synth_natural(1, 3, 330, 420, seed=4)[0].permute(1, 2, 0).contiguous().numpy()
+    out = T.test_image(chk, img, patch_size=128, temp_output_filename=str(tmp_path / 'temp.zarr'))
+    rec = np.zeros_like(img)
+    decompress_image(str(tmp_path / 'temp.zarr'), rec, checkpoint=chk, gpu=True)
+    assert set(T.metric_fun) <= set(out) and 'execution_time' in out and 'evaluation_time' in out
+    assert abs(out['psnr'] - O.psnr_u8(img, rec)) < 1e-6
+    assert abs(out['dist'] - float(np.sqrt(((img.astype(np.float64) - rec) ** 2).mean()))) < 1e-6
+    assert abs(out['ssim'] - O.ssim_u8(img, rec)) < 1e-9
+    assert abs(out['ms-ssim'] - O.ms_ssim_u8(img, rec)) < 2e-5
+    assert abs(out['delta_cielab'] - O.delta_cielab_u8(img, rec)) <= 2e-4 * max(1.0, out['delta_cielab'])
+    assert out['rate'] > 0
