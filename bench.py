@@ -355,7 +355,8 @@ def run_wsi(args):
     import torch.distributed as dist
     from oracle import cae_oracle as O       # weights / tiles generator + parity + cpu_baseline only
     import cnn_autoencoder_b200 as M
-    from cnn_autoencoder_b200 import _cabi, _slide
+    from concurrent.futures import ThreadPoolExecutor
+    from cnn_autoencoder_b200 import _cabi, _slide, _store
     from cnn_autoencoder_b200 import compress as CMP
     from cnn_autoencoder_b200 import decompress as DEC
     from cnn_autoencoder_b200._entropy import decode_symbols
@@ -395,7 +396,6 @@ def run_wsi(args):
     base = '/dev/shm' if os.path.isdir('/dev/shm') and shutil.disk_usage('/dev/shm').free > 8 * H * W else '/tmp'
     tag = os.environ.get('MASTER_PORT', str(os.getpid()))
     work = os.path.join(base, f'cae_bench_{tag}')
-    comp_dir, recon_dir = os.path.join(work, 'slide.zarr'), os.path.join(work, 'recon.zarr')
     if rank == 0:
         shutil.rmtree(work, ignore_errors=True)
         os.makedirs(work, exist_ok=True)
@@ -403,14 +403,43 @@ def run_wsi(args):
 
     if args.coder_tiles <= 0:
         args.coder_tiles = T
-    if args.e2e_coder_tiles <= 0:
-        args.e2e_coder_tiles = max(args.batch_tiles, T // 2)
-    kw = dict(rank=rank, world_size=world, batch_tiles=args.batch_tiles, coder_tiles=args.e2e_coder_tiles)
+    def schedule(text):
+        v = [int(x) for x in str(text).split(',') if x.strip()]
+        return v[0] if len(v) == 1 else v
+
+    # coder groups of the e2e step: the tile loops' own default (`_slide.default_schedule`) unless named
+    args.e2e_coder_tiles = schedule(args.e2e_coder_tiles) or _slide.default_schedule(T, args.batch_tiles)
+    args.e2e_decoder_tiles = (schedule(args.e2e_decoder_tiles) or
+                              _slide.default_schedule(T, args.batch_tiles, decode=True))
+    kw = dict(rank=rank, world_size=world, batch_tiles=args.batch_tiles)
+
+    # Every step compresses into a store of its own, as a job that works through a list of slides
+    # does (a chunk file renamed over last step's file frees that file's pages inside the rename:
+    # 57 ms instead of 21 ms per 4096 chunk files on this tmpfs, tools/micro/filebench.cpp).  Two
+    # stores alternate; a rank unlinks its own chunk files of step k - 1 on a background thread
+    # while step k runs (inside the timed region); rank 0 removes what is left at the end.
+    my_chunks = [(i, j, 0) for i in range(rank * rows_per_rank, (rank + 1) * rows_per_rank) for j in range(GX)]
+    cleaner = ThreadPoolExecutor(max_workers=1)
+    state = dict(step=0, pending=None, last=None)
+
+    def remove_chunks(root, group):
+        d = os.path.join(root, group)
+        _store.native_remove([os.path.join(d, '.'.join(map(str, idx))) for idx in my_chunks], 4)
 
     def step(to_files=False):
-        cs = CMP.compress_image('CAE', chk, slide, comp_dir, patch_size=PS, gpu=True, **kw)
+        k = state['step']
+        state['step'] += 1
+        comp_dir, recon_dir = (os.path.join(work, f'{name}_{k % 2}.zarr') for name in ('slide', 'recon'))
+        if state['pending'] is not None:
+            state['pending'].result()            # the stores this step writes into are empty again
+        if state['last'] is not None:
+            state['pending'] = cleaner.submit(lambda last=state['last']: [remove_chunks(*a) for a in last])
+        cs = CMP.compress_image('CAE', chk, slide, comp_dir, patch_size=PS, gpu=True,
+                                coder_tiles=args.e2e_coder_tiles, **kw)
         ds = DEC.decompress_image(comp_dir, recon_dir if to_files else recon, checkpoint=chk,
-                                  gpu=True, **kw)
+                                  gpu=True, coder_tiles=args.e2e_decoder_tiles, **kw)
+        state['last'] = [(comp_dir, '0/0')] + ([(recon_dir, 'decompressed/0/0')] if to_files else [])
+        cs['store'] = comp_dir
         return cs, ds
 
     # ---- e2e: host buffers, files on tmpfs, copies inside ----
@@ -442,17 +471,17 @@ def run_wsi(args):
                         (tc.replays_dec - replays0[1]) * tc.launches_dec)
         px_step = T * PS * PS
         e2e_value = world * px_step * args.steps / (e2e_ms / 1e3) / 1e6
-        stored = DirArray(os.path.join(comp_dir, '0/0'), mode='r')
         comp_bytes_rank = cs['bytes']
         # variant: the reconstruction written as raw chunk files on tmpfs (2 steps, reported aside)
         step(to_files=True)
         c.barrier()
         w1 = time.perf_counter()
         for _ in range(2):
-            step(to_files=True)
+            cs, ds = step(to_files=True)
         c.barrier()
         files_ms = c.max_over_ranks((time.perf_counter() - w1) * 1e3)
         e2e_files_value = world * px_step * 2 / (files_ms / 1e3) / 1e6
+        stored = DirArray(os.path.join(cs['store'], '0/0'), mode='r')       # the last step's store is kept
 
         # ---- value: the same codec, everything resident in HBM ----
         x_dev = torch.empty((T, PS, PS, 3), dtype=torch.uint8, device='cuda')
@@ -571,12 +600,14 @@ def run_wsi(args):
         'config': {'workload': wsi_workload_text(args, world),
                    'l2': f'inputs larger than L2 ({px_step * 3 / 1e9:.2f} GB of tiles per step per GPU)',
                    'accumulate': 'f32', 'batch_tiles': args.batch_tiles, 'coder_tiles': args.coder_tiles,
-                   'e2e_coder_tiles': args.e2e_coder_tiles,
+                   'e2e_coder_tiles': args.e2e_coder_tiles, 'e2e_decoder_tiles': args.e2e_decoder_tiles,
                    'value_is': 'tiles resident in HBM -> transforms + quantizer + device rANS encode + '
                                'decode + transforms -> tiles in HBM (no host transfer)',
                    'e2e_is': 'compress_image -> decompress_image: slide in page-locked host memory -> chunk '
                              f'files (header + rANS stream) on {base} -> reconstruction in page-locked host '
-                             'memory; every H2D / D2H copy and file write / read inside the timed region',
+                             'memory; every H2D / D2H copy and file write / read inside the timed region; '
+                             'each step writes a store of its own (two alternate; the previous step\'s chunk '
+                             'files are unlinked by a background thread inside the timed region)',
                    'timed_region_s': {'value': round(total_ms / 1e3, 3), 'e2e': round(e2e_ms / 1e3, 3)},
                    'stored_bpp': round(stored_bpp, 4), 'slide_generation_s': round(t_gen, 1)},
         'clocks': clocks, 'clocks_e2e': clocks_e2e,
@@ -720,9 +751,13 @@ def main():
     ap.add_argument('--batch-tiles', type=int, default=32, help='chunks per CUDA-graph replay')
     ap.add_argument('--coder-tiles', type=int, default=0,
                     help='chunk streams entropy-coded per device call of the device-resident run (0 = the shard)')
-    ap.add_argument('--e2e-coder-tiles', type=int, default=0,
-                    help='the same for compress_image / decompress_image (0 = half the shard: the chunk files '
-                         'of one group are written / read while the next group is on the GPU)')
+    ap.add_argument('--e2e-coder-tiles', default='0',
+                    help='the same for compress_image (0 = the default schedule; one size, or a comma-separated '
+                         'schedule of group sizes: the chunk files of one group are written while the next '
+                         'group is on the GPU, so the last group is the exposed one)')
+    ap.add_argument('--e2e-decoder-tiles', default='0',
+                    help='the same for decompress_image (0 = the coder schedule reversed: the first group is '
+                         'the exposed one)')
     ap.add_argument('--parity-tiles', type=int, default=8)
     ap.add_argument('--no-parity', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -31,7 +31,8 @@ SYMBOLS = ['cae_abi_version', 'cae_last_error', 'cae_device_info', 'cae_launch_c
            'cae_rans_encode_batch', 'cae_rans_scan', 'cae_rans_compact', 'cae_rans_decode_batch',
            'cae_tiles_upload_u8', 'cae_tiles_download_u8', 'cae_tiles_upload_u8_banded',
            'cae_tiles_download_u8_banded', 'cae_sse_u8', 'cae_ssim_u8', 'cae_delta_e_u8', 'cae_u8_to_planes_f32',
-           'cae_avgpool2_planes_f32', 'cae_ssim_gauss_planes_f32', 'cae_tiles_gather_u8', 'cae_files_write', 'cae_files_stat', 'cae_files_read']
+           'cae_avgpool2_planes_f32', 'cae_ssim_gauss_planes_f32', 'cae_tiles_gather_u8', 'cae_files_write', 'cae_files_stat', 'cae_files_read',
+           'cae_files_remove']
 
 
 class Tensor(ctypes.Structure):
@@ -192,6 +193,7 @@ def lib():
                                       ctypes.c_int]
     L.cae_files_write.argtypes = [ctypes.c_char_p, ctypes.c_int, vp, ctypes.c_int, vp, vp, ctypes.c_int]
     L.cae_files_stat.argtypes = [ctypes.c_char_p, ctypes.c_int, vp, ctypes.c_int]
+    L.cae_files_remove.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
     L.cae_files_read.argtypes = [ctypes.c_char_p, ctypes.c_int, vp, ctypes.c_int, vp, vp, ctypes.c_int]
     for name in SYMBOLS:
         if name not in ('cae_abi_version', 'cae_last_error', 'cae_launch_count',

@@ -229,6 +229,48 @@ class _Stats(dict):
         self[k] = self.get(k, 0) + v
 
 
+def group_sizes(n_tiles, coder_tiles, batch):
+    """How the tiles of a shard are split into entropy-coder groups.  ``coder_tiles`` is either
+    one size (equal groups) or a sequence of sizes, the last of which repeats: a coder call
+    costs the same whatever its stream count, so few groups are best for the device, but what
+    follows the LAST group of ``compress_tiles`` (its coder call, the stream download and its
+    chunk-file writes) and what precedes the FIRST group of ``decompress_tiles`` (file reads,
+    upload, decode) has nothing to hide under -- a tapered schedule such as (4096, 3072, 1024)
+    keeps those two exposed groups small.  Every size is rounded up to whole batches."""
+    seq = [coder_tiles] if isinstance(coder_tiles, (int, np.integer)) else list(coder_tiles)
+    if not seq or any(int(g) <= 0 for g in seq):
+        raise ValueError('coder_tiles must be a positive size or a non-empty sequence of them')
+    sizes, left, k = [], n_tiles, 0
+    while left > 0:
+        g = int(seq[min(k, len(seq) - 1)])
+        g = -(-max(batch, g) // batch) * batch
+        g = min(g, left)
+        sizes.append(g)
+        left -= g
+        k += 1
+    return sizes
+
+
+def default_schedule(n_tiles, batch, decode=False, cap=8192):
+    """The group schedule the tile loops use when the caller names none (``coder_tiles=None``).
+    Measured on a B200 at 8192 chunks of 512^2 (``tools/micro/trace_slide.py``): a
+    coder call costs 19 ms (encode) / 33 ms (decode) whatever its size and slows the transforms
+    it runs beside, so a shard is two equal groups (more only beyond 2 x ``cap`` tiles: a group
+    of ``cap`` is 6.4 GB of symbols); from 6144 tiles on ``compress_tiles`` splits the last group
+    3 : 1 so that the exposed tail (coder call, stream download, chunk-file writes of the last
+    group) is short -- (4096, 3072, 1024): 368 -> 338 ms; for ``decompress_tiles`` equal groups
+    measured best.  Shards under 2048 tiles are one group."""
+    if n_tiles < 2048:
+        return [max(batch, n_tiles)]
+    n_groups = max(2, -(-n_tiles // cap))
+    sizes = group_sizes(n_tiles, -(-n_tiles // n_groups), batch)
+    if decode or n_tiles < 6144:
+        return sizes
+    last = sizes.pop()
+    tail = max(batch, last // 4 // batch * batch)
+    return group_sizes(n_tiles, sizes + [last - tail, tail], batch)
+
+
 def compress_tiles(tc, src, tiles, chunk_path, header_hw, workers, coder_tiles, stats,
                    device_source=None):
     """The 'cae' codec over ``tiles`` (list of (i, j) chunk indices) of the H x W x c uint8 slide
@@ -252,10 +294,10 @@ def compress_tiles(tc, src, tiles, chunk_path, header_hw, workers, coder_tiles, 
     if device_source is None and not pinned_src:
         stage = [tc.pinned('stage_in%d' % k, B * ps * ps * c).view(B, ps, ps, c) for k in range(2)]
         stage_ev = [None, None]
-    G = max(B, min(coder_tiles, n_tiles))
-    G = -(-G // B) * B
+    sizes = group_sizes(n_tiles, coder_tiles, B)
+    G = max(sizes)
     sym_all = [tc.buffer('sym_group%d' % k, (G, tc.cb, tc.lh * tc.lw), torch.int32)
-               for k in range(2 if n_tiles > G else 1)]
+               for k in range(2 if len(sizes) > 1 else 1)]
     coded = [None] * len(sym_all)       # per group buffer: (threading.Event, [cuda event]) of its job
     # two workers: the device coder calls are serialised by `code_lock` (they share scratch
     # buffers), but one group's chunk files are written while the next group is being coded
@@ -280,7 +322,7 @@ def compress_tiles(tc, src, tiles, chunk_path, header_hw, workers, coder_tiles, 
             s_code.wait_event(ready)
             if trace is not None:
                 ready.synchronize()
-                mark('c_symbols_ready_g%d' % gi)
+                mark('c_symbols_ready@%d' % lo)
             try:
                 packed, off = fe.encode_symbols_device(sym_all[gi][:n])
                 done = torch.cuda.Event()
@@ -288,15 +330,15 @@ def compress_tiles(tc, src, tiles, chunk_path, header_hw, workers, coder_tiles, 
                 holder.append(done)          # the coder kernels have read the group buffer
             finally:
                 launched.set()
-            mark('c_coded')
+            mark('c_coded@%d' % lo)
             host = tc.pinned('streams_out%d' % gi, packed.numel())
             host.copy_(packed, non_blocking=True)
             s_code.synchronize()
-            mark('c_streams_on_host')
+            mark('c_streams_on_host@%d' % lo)
         hdr = np.broadcast_to(hdr1, (n, 16))
         native_write([chunk_path((int(i), int(j), 0)) for i, j in tile_yx[lo:lo + n]], hdr,
                      host.numpy(), off, workers)
-        mark('c_files_written')
+        mark('c_files_written@%d' % lo)
         stats.add('bytes', int(off[-1]) + 16 * n)
         stats.add('device_coded', n)
 
@@ -343,7 +385,7 @@ def compress_tiles(tc, src, tiles, chunk_path, header_hw, workers, coder_tiles, 
         sym_all[gi][gpos:gpos + n].copy_(sym.reshape(n, tc.cb, -1), non_blocking=True)
         gpos += n
         stats.add('pixels', n * ps * ps)
-        if gpos >= G or k0 + n >= n_tiles:
+        if gpos >= sizes[len(jobs)] or k0 + n >= n_tiles:
             ready = torch.cuda.Event()
             ready.record(main)
             coded[gi] = (threading.Event(), [])
@@ -373,9 +415,8 @@ def decompress_tiles(tc, tiles, chunk_path, workers, coder_tiles, stats, H, W, o
     L = C.lib()
     main = torch.cuda.current_stream(dev)
     s_out, s_code = tc.s_out, tc.s_code
-    G = max(B, min(coder_tiles, n_tiles))
-    G = -(-G // B) * B
-    groups = [(lo, min(G, n_tiles - lo)) for lo in range(0, n_tiles, G)]
+    sizes = group_sizes(n_tiles, coder_tiles, B)
+    groups = [(int(sum(sizes[:k])), g) for k, g in enumerate(sizes)]
     reader = ThreadPoolExecutor(max_workers=1)
     tile_bytes = ps * ps * c
     out_pins = [tc.pinned('tiles_out%d' % k, B * tile_bytes).view(B, ps, ps, c)

@@ -79,6 +79,13 @@ class DirArray:
         sl = self.chunk_slices(idx)
         return full[tuple(slice(0, s.stop - s.start) for s in sl)]
 
+    def remove_chunks(self, threads=1):
+        """Delete every chunk file of the array (what ``overwrite=True`` of the reference's
+        ``to_zarr`` calls does before writing, compress.py:123-128); metadata stays."""
+        names = [os.path.join(self.path, f) for f in os.listdir(self.path) if not f.startswith('.')]
+        native_remove([n for n in names if os.path.isfile(n)], threads)
+        return len(names)
+
     def nbytes_stored(self):
         return sum(os.path.getsize(os.path.join(self.path, f)) for f in os.listdir(self.path)
                    if not f.startswith('.'))
@@ -130,6 +137,13 @@ def native_write(paths, headers, payload, payload_off, threads):
     C.check(C.lib().cae_files_write(_paths_blob(paths), len(paths),
                                     headers.ctypes.data if headers is not None else None, hdr_len,
                                     payload.ctypes.data, off.ctypes.data, threads))
+
+
+def native_remove(paths, threads):
+    """Unlink ``paths`` (missing files are skipped) by native threads (``cae_files_remove``)."""
+    from . import _cabi as C
+    if len(paths):
+        C.check(C.lib().cae_files_remove(_paths_blob(paths), len(paths), threads))
 
 
 def native_read(paths, hdr_len, threads, alloc=None):

@@ -153,10 +153,10 @@ def as_yxc(src, data_axes):
 def compress_image(codec, checkpoint, input_filename, output_filename, patch_size=512,
                    source_format='zarr', data_group='0/0', data_axes='TCZYX',
                    progress_bar=False, save_as_bottleneck=False, gpu=False, *,
-                   rank=None, world_size=None, batch_tiles=16, workers=None, coder_tiles=1024):
+                   rank=None, world_size=None, batch_tiles=16, workers=None, coder_tiles=None):
     """Same positional signature as the reference (``compress.py:29-36``); the keyword-only
     arguments select this process's shard, the GPU batch size and how many tiles are entropy
-    coded per device call.  Returns a dict of counters (tiles, pixels, bytes, seconds,
+    coded per device call (one size, or a schedule of group sizes: ``_slide.group_sizes``).  Returns a dict of counters (tiles, pixels, bytes, seconds,
     device_coded) for the caller's throughput report."""
     if 'CAE' not in codec:
         raise ValueError('Codec %s not supported' % codec)
@@ -198,6 +198,11 @@ def compress_image(codec, checkpoint, input_filename, output_filename, patch_siz
         meta = dict(shape=(H, W, C), chunks=(ps, ps, C), dtype=np.uint8)
     if rank == 0:
         dst = DirArray(out_path, compressor=comp, mode='w', **meta)
+        if world_size == 1:
+            # overwrite=True of the reference's to_zarr (compress.py:123-128): the chunks of an
+            # array that was there before are gone.  The ranks of a sharded job have no barrier
+            # between this and the first chunk another rank writes, so there stale chunks stay.
+            dst.remove_chunks(workers)
     else:
         while not os.path.exists(os.path.join(out_path, '.zarray')):
             time.sleep(0.05)
@@ -205,6 +210,8 @@ def compress_image(codec, checkpoint, input_filename, output_filename, patch_siz
 
     tiles = [(i, j) for i in range(gy) for j in range(gx)]
     mine = [tiles[k] for k in shard_range(len(tiles), rank, world_size)]
+    if coder_tiles is None:
+        coder_tiles = _slide.default_schedule(len(mine), batch_tiles, decode=False)
     stats = dict(tiles=len(mine), pixels=0, bytes=0, seconds=0.0, device_coded=0,
                  t_read=0.0, t_stage=0.0, t_gpu=0.0, t_code=0.0, t_write_wait=0.0)
     t_start = time.perf_counter()
@@ -222,6 +229,8 @@ def compress_image(codec, checkpoint, input_filename, output_filename, patch_siz
         stats['engine'] = 'slide'
         stats['seconds'] = time.perf_counter() - t_start
         return stats
+    if not isinstance(coder_tiles, int):
+        coder_tiles = max(int(g) for g in coder_tiles)     # a group schedule (_slide.group_sizes)
     pool = ThreadPoolExecutor(max_workers=workers)
     writes = []                     # futures of chunk-file writes
     acc = {}                        # latent shape -> dict(sym=[device tensors], meta=[(idx, h, w)])

@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <sys/stat.h>
+#include <sys/uio.h>
 #include <unistd.h>
 
 #include <atomic>
@@ -47,6 +48,20 @@ bool write_all(int fd, const uint8_t *p, size_t n) {
     n -= (size_t)w;
   }
   return true;
+}
+
+// header + payload of one chunk file as one system call (short writes finished by write_all)
+bool write_two(int fd, const uint8_t *a, size_t na, const uint8_t *b, size_t nb) {
+  if (na == 0) return write_all(fd, b, nb);
+  iovec v[2] = {{const_cast<uint8_t *>(a), na}, {const_cast<uint8_t *>(b), nb}};
+  const ssize_t w = ::writev(fd, v, 2);
+  if (w < 0) return false;
+  size_t done = (size_t)w;
+  if (done < na) {
+    if (!write_all(fd, a + done, na - done)) return false;
+    done = na;
+  }
+  return write_all(fd, b + (done - na), nb - (done - na));
 }
 
 }  // namespace
@@ -101,8 +116,9 @@ extern "C" int cae_files_write(const char *paths, int n, const uint8_t *headers,
     const std::string tmp = std::string(name[k]) + ".partial";
     const int fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
     bool ok = fd >= 0;
-    if (ok && hdr_len > 0) ok = write_all(fd, headers + (size_t)k * hdr_len, (size_t)hdr_len);
-    if (ok) ok = write_all(fd, payload + payload_off[k], (size_t)(payload_off[k + 1] - payload_off[k]));
+    if (ok)
+      ok = write_two(fd, hdr_len > 0 ? headers + (size_t)k * hdr_len : nullptr, (size_t)hdr_len,
+                     payload + payload_off[k], (size_t)(payload_off[k + 1] - payload_off[k]));
     if (fd >= 0) ::close(fd);
     if (ok) ok = ::rename(tmp.c_str(), name[k]) == 0;
     if (!ok) failed.store(k);
@@ -111,6 +127,23 @@ extern "C" int cae_files_write(const char *paths, int n, const uint8_t *headers,
     cae_set_error("cae_files_write: could not write %s", name[failed.load()]);
     return 4;
   }
+  return 0;
+}
+
+// Remove n files (missing ones are not an error): what zarr's `overwrite=True` does to the chunks
+// of an existing array (compress.py:123-128 of the reference), by native threads.
+extern "C" int cae_files_remove(const char *paths, int n, int threads) {
+  if (!paths || n < 0) {
+    cae_set_error("cae_files_remove: bad argument");
+    return 2;
+  }
+  std::vector<const char *> name(n);
+  const char *p = paths;
+  for (int k = 0; k < n; ++k) {
+    name[k] = p;
+    p += strlen(p) + 1;
+  }
+  parallel_for(n, threads, [&](int k) { ::unlink(name[k]); });
   return 0;
 }
 

@@ -31,7 +31,7 @@ from .compress import _dist_info, default_workers, load_model, shard_range
 def decompress_image(input_filename, output_filename, destination_format='zarr',
                      data_group='0/0', decomp_group='decompressed', checkpoint=None,
                      progress_bar=False, gpu=False, *, rank=None, world_size=None,
-                     batch_tiles=16, workers=None, coder_tiles=1024):
+                     batch_tiles=16, workers=None, coder_tiles=None):
     """Same positional signature as the reference (``decompress.py:40-47``).  Returns a
     dict of counters (tiles, pixels, seconds, device_decoded)."""
     if not torch.cuda.is_available():
@@ -81,6 +81,8 @@ def decompress_image(input_filename, output_filename, destination_format='zarr',
     elif rank == 0:
         dst = DirArray(out_path, shape=(H, W, c_img), chunks=(ps, ps, c_img), dtype=np.uint8,
                        compressor=None, mode='w')
+        if world_size == 1:
+            dst.remove_chunks(workers)       # overwrite=True (decompress.py:92-96), see compress_image
     else:
         while not os.path.exists(os.path.join(out_path, '.zarray')):
             time.sleep(0.05)
@@ -88,6 +90,8 @@ def decompress_image(input_filename, output_filename, destination_format='zarr',
 
     tiles = [(i, j) for i in range(gy) for j in range(gx)]
     mine = [tiles[k] for k in shard_range(len(tiles), rank, world_size)]
+    if coder_tiles is None:
+        coder_tiles = _slide.default_schedule(len(mine), batch_tiles, decode=True)
     stats = dict(tiles=len(mine), pixels=0, seconds=0.0, device_decoded=0,
                  t_read=0.0, t_decode=0.0, t_gpu=0.0, t_write_wait=0.0)
     t_start = time.perf_counter()
@@ -107,6 +111,8 @@ def decompress_image(input_filename, output_filename, destination_format='zarr',
         stats['engine'] = 'slide'
         stats['seconds'] = time.perf_counter() - t_start
         return stats
+    if not isinstance(coder_tiles, int):
+        coder_tiles = max(int(g) for g in coder_tiles)     # a group schedule (_slide.group_sizes)
     pool = ThreadPoolExecutor(max_workers=workers)
 
     def read_tile(idx):

@@ -365,12 +365,15 @@ int cae_rans_decode_batch(const uint32_t *words, const int64_t *word_offsets, in
  *  cae_files_write: file k = headers[k*hdr_len ..][hdr_len] + payload[payload_off[k] ..
  *    payload_off[k+1]); paths = n NUL-terminated strings back to back; written as
  *    <path>.partial then renamed.
- *  cae_files_stat / cae_files_read: sizes, then header / payload split back the same way.   */
+ *  cae_files_stat / cae_files_read: sizes, then header / payload split back the same way.
+ *  cae_files_remove: unlink n files (missing ones are skipped) -- the chunks of an array that
+ *    is created again with overwrite=True (compress.py:123-128, decompress.py:92-96).       */
 int cae_tiles_gather_u8(const uint8_t *src, int64_t H, int64_t W, int c, int ps,
                         const int32_t *tile_yx, int n, uint8_t *dst, int threads);
 int cae_files_write(const char *paths, int n, const uint8_t *headers, int hdr_len,
                     const uint8_t *payload, const int64_t *payload_off, int threads);
 int cae_files_stat(const char *paths, int n, int64_t *sizes, int threads);
+int cae_files_remove(const char *paths, int n, int threads);
 int cae_files_read(const char *paths, int n, uint8_t *headers, int hdr_len, uint8_t *payload,
                    const int64_t *payload_off, int threads);
 

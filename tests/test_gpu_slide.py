@@ -95,6 +95,30 @@ def test_slide_engine_matches_the_general_tile_loop(tmp_path, monkeypatch):
             assert A.read_encoded((i, j, 0)) == B.read_encoded((i, j, 0))
 
 
+def test_coder_group_schedule_writes_the_same_files(tmp_path):
+    """A tapered group schedule (small last group in compress, small first group in decompress:
+    ``_slide.group_sizes``) only moves the coder calls: same chunk files, same reconstruction."""
+    from oracle import cae_oracle as O
+    from cnn_autoencoder_b200 import compress, decompress, _store
+    chk = O.make_checkpoint(ARCH, seed=5)
+    slide = _slide(12, 13, (24, 40))
+    a, b = str(tmp_path / 'a.zarr'), str(tmp_path / 'b.zarr')
+    sa = compress.compress_image('CAE', chk, slide, a, patch_size=PS, batch_tiles=16, coder_tiles=156)
+    sb = compress.compress_image('CAE', chk, slide, b, patch_size=PS, batch_tiles=16,
+                                 coder_tiles=(64, 48, 16))
+    assert sa['engine'] == 'slide' and sb['engine'] == 'slide' and sb['device_coded'] == 156
+    A, B = (_store.DirArray(os.path.join(p, '0/0'), mode='r') for p in (a, b))
+    for i in range(12):
+        for j in range(13):
+            assert A.read_encoded((i, j, 0)) == B.read_encoded((i, j, 0))
+    ca = torch.zeros(slide.shape, dtype=torch.uint8).pin_memory().numpy()
+    cb = torch.zeros(slide.shape, dtype=torch.uint8).pin_memory().numpy()
+    decompress.decompress_image(a, ca, checkpoint=chk, batch_tiles=16, coder_tiles=156)
+    ds = decompress.decompress_image(b, cb, checkpoint=chk, batch_tiles=16, coder_tiles=(16, 48, 64))
+    assert ds['engine'] == 'slide' and ds['device_decoded'] == 156
+    assert np.array_equal(ca, cb)
+
+
 def test_device_roundtrip_and_phase_record():
     from oracle import cae_oracle as O
     import cnn_autoencoder_b200 as M

@@ -227,3 +227,38 @@ def test_source_axes_are_mapped_like_the_reference():
     import pytest
     with pytest.raises(ValueError):
         as_yxc(a, 'YXC')
+
+
+def test_coder_group_schedules():
+    """``_slide.group_sizes``: one size = equal groups; a sequence = a schedule whose last entry
+    repeats; sizes are whole batches; every tile is in exactly one group."""
+    from cnn_autoencoder_b200._slide import group_sizes
+    assert group_sizes(8192, 4096, 32) == [4096, 4096]
+    assert group_sizes(8192, 8192, 32) == [8192]
+    assert group_sizes(8192, 100000, 32) == [8192]
+    assert group_sizes(8192, (4096, 3072, 1024), 32) == [4096, 3072, 1024]
+    assert group_sizes(8192, [1024, 3072], 32) == [1024, 3072, 3072, 1024]
+    assert group_sizes(156, 96, 16) == [96, 60]
+    assert group_sizes(156, (64, 48, 16), 16) == [64, 48, 16, 16, 12]
+    assert group_sizes(100, 10, 32) == [32, 32, 32, 4]        # never below one batch
+    assert group_sizes(5, 1024, 16) == [5]
+    for bad in (0, (), (16, 0), -3):
+        with pytest.raises(ValueError):
+            group_sizes(64, bad, 16)
+
+
+def test_chunk_files_are_removed_like_overwrite_true(tmp_path):
+    """``cae_files_remove`` / ``DirArray.remove_chunks``: what ``to_zarr(overwrite=True)`` of the
+    reference (compress.py:123-128) does to the chunks of an array that exists already."""
+    arr = _store.DirArray(str(tmp_path / 'a'), shape=(8, 8, 3), chunks=(4, 4, 3), dtype=np.uint8, mode='w')
+    for i in range(2):
+        for j in range(2):
+            arr.write_chunk((i, j, 0), np.full((4, 4, 3), i + j, dtype=np.uint8))
+    paths = [arr.chunk_file((i, j, 0)) for i in range(2) for j in range(2)]
+    assert all(os.path.exists(p) for p in paths)
+    _store.native_remove(paths[:2] + [str(tmp_path / 'a' / 'missing.0.0')], 3)     # missing: skipped
+    assert [os.path.exists(p) for p in paths] == [False, False, True, True]
+    assert arr.remove_chunks(2) == 2
+    assert not any(os.path.exists(p) for p in paths)
+    assert os.path.exists(os.path.join(arr.path, '.zarray'))                        # metadata stays
+    _store.native_remove([], 2)
