@@ -194,12 +194,18 @@ class TileCodec:
 
     def warm(self, encode=True, decode=True):
         """Build the graphs of every slot up front (outside any timed region)."""
+        if not self.graphs:
+            return
+        built = False
         for s in range(self.slots):
-            if encode:
+            if encode and self._enc_g[s] is None:
                 self.encode(s, self.batch)
-            if decode:
+                built = True
+            if decode and self._dec_g[s] is None:
                 self.decode(s, self.batch)
-        torch.cuda.synchronize(self.dev)
+                built = True
+        if built:
+            torch.cuda.synchronize(self.dev)
 
 
 _codecs = {}
