@@ -551,10 +551,12 @@ class EntropyBottleneck(nn.Module):
         host = packed.cpu().numpy()
         return [host[int(off[i]):int(off[i + 1])].tobytes() for i in range(len(off) - 1)]
 
-    def decode_streams_device(self, words, word_off, hw):
+    def decode_streams_device(self, words, word_off, hw, defer_status=False):
         """``words``: int32 device tensor holding N streams back to back, ``word_off``: N + 1
         word offsets (host array) -> int32 symbols N x C x hw on the device, all streams decoded
-        concurrently (``cae_rans_decode_batch``)."""
+        concurrently (``cae_rans_decode_batch``).  ``defer_status``: do not wait for the kernel;
+        returns (symbols, status tensor) and the caller hands the tensor to
+        ``check_decode_status`` once it has synchronised anyway."""
         if self._offset.numel() == 0:
             raise C.CaeError('EntropyBottleneck.update() must be called before compress/decompress')
         dev = words.device
@@ -567,9 +569,15 @@ class EntropyBottleneck(nn.Module):
         C.check(C.lib().cae_rans_decode_batch(words.data_ptr(), off_d.data_ptr(), n, c, hw,
                                               cdf.data_ptr(), cdf.shape[1], sizes.data_ptr(),
                                               offs.data_ptr(), sym.data_ptr(), status.data_ptr(), stream))
+        if defer_status:
+            return sym, status
+        self.check_decode_status(status)
+        return sym
+
+    @staticmethod
+    def check_decode_status(status):
         if int(status.item()) & 2:
             raise C.CaeError('device entropy decoder: a stream is truncated')
-        return sym
 
     def decode_streams_gpu(self, strings, hw):
         """list of N byte strings -> int32 symbols N x C x hw on the device."""

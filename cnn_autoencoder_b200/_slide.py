@@ -241,8 +241,8 @@ def group_sizes(n_tiles, coder_tiles, batch):
     costs the same whatever its stream count, so few groups are best for the device, but what
     follows the LAST group of ``compress_tiles`` (its coder call, the stream download and its
     chunk-file writes) and what precedes the FIRST group of ``decompress_tiles`` (file reads,
-    upload, decode) has nothing to hide under -- a tapered schedule such as (4096, 3072, 1024)
-    keeps those two exposed groups small.  Every size is rounded up to whole batches."""
+    upload, decode) has nothing to hide under -- an uneven schedule such as (6144, 2048) keeps
+    the exposed group of ``compress_tiles`` small.  Every size is rounded up to whole batches."""
     seq = [coder_tiles] if isinstance(coder_tiles, (int, np.integer)) else list(coder_tiles)
     if not seq or any(int(g) <= 0 for g in seq):
         raise ValueError('coder_tiles must be a positive size or a non-empty sequence of them')
@@ -259,22 +259,25 @@ def group_sizes(n_tiles, coder_tiles, batch):
 
 def default_schedule(n_tiles, batch, decode=False, cap=8192):
     """The group schedule the tile loops use when the caller names none (``coder_tiles=None``).
-    Measured on a B200 at 8192 chunks of 512^2 (``tools/micro/trace_slide.py``, DESIGN 6.8): a
-    coder call costs 19 ms (encode) / 33 ms (decode) whatever its size and slows the transforms
-    it runs beside, so a shard is two equal groups (more only beyond 2 x ``cap`` tiles: a group
-    of ``cap`` is 6.4 GB of symbols); from 6144 tiles on ``compress_tiles`` splits the last group
-    3 : 1 so that the exposed tail (coder call, stream download, chunk-file writes of the last
-    group) is short -- (4096, 3072, 1024): 368 -> 338 ms; for ``decompress_tiles`` equal groups
-    measured best.  Shards under 2048 tiles are one group."""
+    Measured on a B200 at 8192 chunks of 512^2 (``tools/micro/trace_slide.py``, DESIGN 6.9): a
+    coder call costs 19 ms (encode) / 33 ms (decode) whatever its size and its blocks keep the
+    transforms' persistent kernels off their SMs meanwhile, so groups are few and large (at most
+    ``cap`` tiles: 6.4 GB of symbols).  What follows the last group of ``compress_tiles`` (coder
+    call, stream download, chunk-file writes) has nothing to hide under, so from 6144 tiles on the
+    shard is split 3 : 1 -- (6144, 2048): 318 ms, (4096, 4096): 350 ms, one group: 351 ms, (4096,
+    3072, 1024): 324-336 ms; for ``decompress_tiles`` two equal groups measured best (200-211 ms
+    against 220-239 ms for five tapered alternatives).  Shards under 2048 tiles are one group."""
     if n_tiles < 2048:
         return [max(batch, n_tiles)]
-    n_groups = max(2, -(-n_tiles // cap))
-    sizes = group_sizes(n_tiles, -(-n_tiles // n_groups), batch)
     if decode or n_tiles < 6144:
-        return sizes
-    last = sizes.pop()
-    tail = max(batch, last // 4 // batch * batch)
-    return group_sizes(n_tiles, sizes + [last - tail, tail], batch)
+        n_groups = max(2, -(-n_tiles // cap))
+        return group_sizes(n_tiles, -(-n_tiles // n_groups), batch)
+    sizes, left = [], n_tiles
+    while left > cap * 4 // 3:
+        sizes.append(cap)
+        left -= cap
+    tail = max(batch, left // 4 // batch * batch)
+    return group_sizes(n_tiles, sizes + [left - tail, tail], batch)
 
 
 def compress_tiles(tc, src, tiles, chunk_path, header_hw, workers, coder_tiles, stats,
@@ -445,15 +448,29 @@ def decompress_tiles(tc, tiles, chunk_path, workers, coder_tiles, stats, H, W, o
         torch.cuda.set_device(dev)
         paths = [chunk_path((int(i), int(j), 0)) for i, j in tile_yx[lo:lo + n]]
 
+        words = [None]
+
         def alloc(nbytes):
+            words[0] = torch.empty(nbytes // 4, dtype=torch.int32, device=dev)
+            if uploaded[gk & 1] is not None:
+                uploaded[gk & 1].synchronize()       # the staging buffer's last upload has left it
             return tc.pinned('streams_in%d' % (gk & 1), nbytes).numpy()
-        hdr, payload, off = native_read(paths, 16, workers, alloc=alloc)
+
+        def upload(buf, lo, hi):
+            # the streams of one run of files go up while the next run is read
+            with torch.cuda.stream(s_code):
+                words[0].view(torch.uint8)[lo:hi].copy_(torch.from_numpy(buf[lo:hi]), non_blocking=True)
+                uploaded[gk & 1] = torch.cuda.Event()
+                uploaded[gk & 1].record(s_code)
+        with torch.cuda.stream(s_code):              # (the allocation belongs to the coder stream)
+            hdr, payload, off = native_read(paths, 16, workers, alloc=alloc, slices=4, on_slice=upload)
         mark('d_files_read_g%d' % gk)
         if (off % 4).any() or bytes(hdr[0]) != expect_hdr or (hdr != hdr[0]).any():
             raise C.CaeError('chunk headers differ from the (patch, patch) the codec wrote')
         with torch.cuda.stream(s_code):
-            words = torch.from_numpy(payload).view(torch.int32).to(dev, non_blocking=True)
-            sym = fe.decode_streams_device(words, off // 4, tc.lh * tc.lw)
+            # (no wait for the decoder here: this thread goes on to read the next group's files)
+            sym, status = fe.decode_streams_device(words[0], off // 4, tc.lh * tc.lw, defer_status=True)
+            statuses.append(status)
             done = torch.cuda.Event()
             done.record(s_code)
             if trace is not None:
@@ -475,6 +492,8 @@ def decompress_tiles(tc, tiles, chunk_path, workers, coder_tiles, stats, H, W, o
         native_write([out_chunk_path((int(i), int(j), 0)) for i, j in tile_yx[k0:k0 + n]], None,
                      img.reshape(-1), np.arange(n + 1, dtype=np.int64) * tile_bytes, workers)
 
+    statuses = []
+    uploaded = [None, None]
     nxt = reader.submit(load_group, 0)
     b = 0
     for gk, (lo, gn) in enumerate(groups):
@@ -482,6 +501,9 @@ def decompress_tiles(tc, tiles, chunk_path, workers, coder_tiles, stats, H, W, o
         if gk + 1 < len(groups):
             nxt = reader.submit(load_group, gk + 1)
         main.wait_event(done)
+        # allocated on the coder stream, read by this group's batches on the main stream: the
+        # allocator must not hand the block to a later group's decoder before those have run
+        sym.record_stream(main)
         for p0 in range(0, gn, B):
             n = min(B, gn - p0)
             slot = b % tc.slots
@@ -537,6 +559,8 @@ def decompress_tiles(tc, tiles, chunk_path, workers, coder_tiles, stats, H, W, o
     if writer is not None:
         writer.shutdown()
     torch.cuda.synchronize(dev)
+    for status in statuses:
+        fe.check_decode_status(status)
 
 
 def device_roundtrip(tc, x_dev, out_dev, coder_tiles):

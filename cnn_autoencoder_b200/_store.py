@@ -146,12 +146,16 @@ def native_remove(paths, threads):
         C.check(C.lib().cae_files_remove(_paths_blob(paths), len(paths), threads))
 
 
-def native_read(paths, hdr_len, threads, alloc=None):
+def native_read(paths, hdr_len, threads, alloc=None, slices=1, on_slice=None):
     """Read files whole: returns (headers uint8 n x hdr_len, payload uint8 1-D, int64 offsets
-    n + 1).  ``alloc(nbytes)`` provides the payload buffer (a pinned one for uploads)."""
+    n + 1).  ``alloc(nbytes)`` provides the payload buffer (a pinned one for uploads).  With
+    ``slices`` > 1 the files are read in that many runs and ``on_slice(payload, lo, hi)`` is
+    called after each with the byte range that has just arrived (the caller starts its upload
+    while the next run is read)."""
     from . import _cabi as C
     n = len(paths)
-    blob = _paths_blob(paths)
+    enc = [os.fsencode(p) for p in paths]
+    blob = b'\0'.join(enc) + b'\0' if n else b''
     sizes = np.empty(n, dtype=np.int64)
     C.check(C.lib().cae_files_stat(blob, n, sizes.ctypes.data, threads))
     if (sizes < hdr_len).any():
@@ -161,6 +165,21 @@ def native_read(paths, hdr_len, threads, alloc=None):
     np.cumsum(sizes - hdr_len, out=off[1:])
     headers = np.empty((n, max(hdr_len, 1)), dtype=np.uint8)
     payload = alloc(int(off[-1])) if alloc is not None else np.empty(int(off[-1]), dtype=np.uint8)
-    C.check(C.lib().cae_files_read(blob, n, headers.ctypes.data, hdr_len, payload.ctypes.data,
-                                   off.ctypes.data, threads))
+    slices = max(1, min(int(slices), n))
+    if slices == 1 or on_slice is None:
+        C.check(C.lib().cae_files_read(blob, n, headers.ctypes.data, hdr_len, payload.ctypes.data,
+                                       off.ctypes.data, threads))
+        if on_slice is not None:
+            on_slice(payload, 0, int(off[-1]))
+        return headers[:, :hdr_len], payload, off
+    ends = np.cumsum([len(e) + 1 for e in enc])                      # byte offsets into the blob
+    for k in range(slices):
+        a, b = k * n // slices, (k + 1) * n // slices
+        if a == b:
+            continue
+        sub = blob[int(ends[a - 1]) if a else 0:int(ends[b - 1])]
+        # payload_off is read relative to the payload base: pass the slice of the offset table
+        C.check(C.lib().cae_files_read(sub, b - a, headers[a:].ctypes.data, hdr_len,
+                                       payload.ctypes.data, off[a:].ctypes.data, threads))
+        on_slice(payload, int(off[a]), int(off[b]))
     return headers[:, :hdr_len], payload, off

@@ -262,3 +262,46 @@ def test_chunk_files_are_removed_like_overwrite_true(tmp_path):
     assert not any(os.path.exists(p) for p in paths)
     assert os.path.exists(os.path.join(arr.path, '.zarray'))                        # metadata stays
     _store.native_remove([], 2)
+
+
+def test_native_read_in_slices_reports_byte_ranges(tmp_path):
+    """``native_read(slices=k, on_slice=...)``: same result as one run; the callback sees
+    consecutive byte ranges that cover the payload (the upload of a range starts while the next
+    run of files is read)."""
+    g = np.random.default_rng(3)
+    n = 37
+    sizes = g.integers(0, 900, size=n)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    payload = g.integers(0, 256, size=int(off[-1]), dtype=np.uint8)
+    hdr = g.integers(0, 256, size=(n, 16), dtype=np.uint8)
+    paths = [str(tmp_path / ('%d.%d.0' % (k // 6, k % 6))) for k in range(n)]
+    _store.native_write(paths, hdr, payload, off, 4)
+    h1, p1, o1 = _store.native_read(paths, 16, 3)
+    seen = []
+    h2, p2, o2 = _store.native_read(paths, 16, 3, slices=4,
+                                    on_slice=lambda buf, lo, hi: seen.append((lo, hi, bytes(buf[lo:hi]))))
+    assert np.array_equal(h1, hdr) and np.array_equal(p1, payload) and np.array_equal(o1, off)
+    assert np.array_equal(h2, hdr) and np.array_equal(p2, payload) and np.array_equal(o2, off)
+    assert len(seen) == 4 and seen[0][0] == 0 and seen[-1][1] == off[-1]
+    assert all(a[1] == b[0] for a, b in zip(seen, seen[1:]))
+    assert b''.join(s[2] for s in seen) == payload.tobytes()           # each range had arrived
+    seen.clear()
+    _store.native_read(paths[:2], 16, 3, slices=8, on_slice=lambda buf, lo, hi: seen.append((lo, hi)))
+    assert seen[0][0] == 0 and seen[-1][1] == off[2]
+
+
+def test_default_coder_schedule():
+    """``_slide.default_schedule`` (what ``coder_tiles=None`` means): one group for small shards,
+    two for a shard, the last group of compress_image a quarter (the measured optimum at 8192
+    chunks), groups capped at 8192 tiles; every tile in exactly one group."""
+    from cnn_autoencoder_b200._slide import default_schedule, group_sizes
+    assert default_schedule(156, 16) == [156] and default_schedule(156, 16, decode=True) == [156]
+    assert default_schedule(4096, 32) == [2048, 2048]
+    assert default_schedule(8192, 32) == [6144, 2048]
+    assert default_schedule(8192, 32, decode=True) == [4096, 4096]
+    assert default_schedule(16384, 32) == [8192, 6144, 2048]
+    for n in (1, 31, 2047, 2048, 6143, 6144, 9604, 11000, 40000, 100001):
+        for dec in (False, True):
+            sizes = group_sizes(n, default_schedule(n, 32, decode=dec), 32)
+            assert sum(sizes) == n and max(sizes) <= 8192 + 32 and min(sizes) > 0
+            assert all(g % 32 == 0 for g in sizes[:-1])
