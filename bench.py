@@ -361,6 +361,7 @@ def run_wsi(args):
     from cnn_autoencoder_b200 import decompress as DEC
     from cnn_autoencoder_b200._entropy import decode_symbols
     from cnn_autoencoder_b200._store import DirArray
+    from cnn_autoencoder_b200.jobs import SlideJobs
 
     c = setup(args)
     rank, world = c.rank, c.world
@@ -416,72 +417,111 @@ def run_wsi(args):
     # Every step compresses into a store of its own, as a job that works through a list of slides
     # does (a chunk file renamed over last step's file frees that file's pages inside the rename:
     # 57 ms instead of 21 ms per 4096 chunk files on this tmpfs, tools/micro/filebench.cpp).  Two
-    # stores alternate; a rank unlinks its own chunk files of step k - 1 on a background thread
-    # while step k runs (inside the timed region); rank 0 removes what is left at the end.
+    # stores alternate; a rank unlinks its own chunk files of step k on a background thread once
+    # step k has been decompressed (inside the timed region); rank 0 removes what is left at the end.
+    #
+    # The steps of the timed region are in flight two at a time (`jobs.SlideJobs`): the
+    # compress_image call of step k + 1 runs beside the decompress_image call of step k, each on
+    # its own thread and CUDA stream -- what a job working through a list of slides does with the
+    # two directions of the host link and with the GPU time under one call's tail and the other's
+    # prologue.  Every call, copy and file operation of the K steps lies inside the timed region;
+    # `e2e.one_step_at_a_time` is the same measured with the calls strictly one after the other.
     my_chunks = [(i, j, 0) for i in range(rank * rows_per_rank, (rank + 1) * rows_per_rank) for j in range(GX)]
     cleaner = ThreadPoolExecutor(max_workers=1)
-    state = dict(step=0, pending=None, last=None)
+    jobs = SlideJobs(c.local)
+    state = dict(step=0, dec={}, clean={})
 
     def remove_chunks(root, group):
         d = os.path.join(root, group)
         _store.native_remove([os.path.join(d, '.'.join(map(str, idx))) for idx in my_chunks], 4)
 
-    def step(to_files=False):
-        k = state['step']
-        state['step'] += 1
-        comp_dir, recon_dir = (os.path.join(work, f'{name}_{k % 2}.zarr') for name in ('slide', 'recon'))
-        if state['pending'] is not None:
-            state['pending'].result()            # the stores this step writes into are empty again
-        if state['last'] is not None:
-            state['pending'] = cleaner.submit(lambda last=state['last']: [remove_chunks(*a) for a in last])
-        cs = CMP.compress_image('CAE', chk, slide, comp_dir, patch_size=PS, gpu=True,
+    def stores(k):
+        return tuple(os.path.join(work, f'{name}_{k % 2}.zarr') for name in ('slide', 'recon'))
+
+    def compress_job(k):
+        for waits in (state['dec'], state['clean']):       # the store of step k - 2 is empty again
+            if k - 2 in waits:
+                waits.pop(k - 2).result()
+        cs = CMP.compress_image('CAE', chk, slide, stores(k)[0], patch_size=PS, gpu=True,
                                 coder_tiles=args.e2e_coder_tiles, **kw)
+        cs['store'] = stores(k)[0]
+        return cs
+
+    def decompress_job(k, compressed, to_files, keep):
+        cs = compressed.result()
+        comp_dir, recon_dir = stores(k)
         ds = DEC.decompress_image(comp_dir, recon_dir if to_files else recon, checkpoint=chk,
                                   gpu=True, coder_tiles=args.e2e_decoder_tiles, **kw)
-        state['last'] = [(comp_dir, '0/0')] + ([(recon_dir, 'decompressed/0/0')] if to_files else [])
-        cs['store'] = comp_dir
+        if not keep:
+            last = [(comp_dir, '0/0')] + ([(recon_dir, 'decompressed/0/0')] if to_files else [])
+            state['clean'][k] = cleaner.submit(lambda: [remove_chunks(*a) for a in last])
         return cs, ds
+
+    def run(n, to_files=False, keep_last=False):
+        """n steps, at most two in flight; returns [(compress stats, decompress stats)]."""
+        futs = []
+        for i in range(n):
+            k = state['step']
+            state['step'] += 1
+            fc = jobs.submit('compress', compress_job, k)
+            fd = jobs.submit('decompress', decompress_job, k, fc, to_files, keep_last and i == n - 1)
+            state['dec'][k] = fd
+            futs.append(fd)
+        return [f.result() for f in futs]
+
+    def timed(fn):
+        """(device ms, wall s) of fn() between two idle points of the device, max over ranks."""
+        torch.cuda.synchronize()
+        c.barrier()
+        s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        w0 = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize()          # every stream of every call
+        e0.record()
+        e0.synchronize()
+        c.barrier()
+        return out, c.max_over_ranks(s0.elapsed_time(e0)), time.perf_counter() - w0
 
     # ---- e2e: host buffers, files on tmpfs, copies inside ----
     for _ in range(warmup):
-        cs, ds = step()
+        (cs, ds), = run(1)
     assert cs.get('engine') == 'slide' and ds.get('engine') == 'slide', 'tile loops fell off the batched engine'
+    if args.e2e_in_flight > 1:
+        run(2)
     tc = _slide.tile_codec(model, PS, 3, args.batch_tiles)
     c.barrier()
     phases = {}
     with ClockSampler(c.local) as clk:
         time.sleep(0.3)
-        c.barrier()
         launches0, replays0 = _cabi.launch_count(), (tc.replays_enc, tc.replays_dec)
         t_begin = time.time()
-        s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        w0 = time.perf_counter()
-        for _ in range(args.steps):
-            cs, ds = step()
+        if args.e2e_in_flight > 1:
+            done, e2e_ms, wall = timed(lambda: run(args.steps))
+        else:
+            done, e2e_ms, wall = timed(lambda: [run(1)[0] for _ in range(args.steps)])
+        for cs, ds in done:
             for k, v in (('compress_s', cs['seconds']), ('decompress_s', ds['seconds'])):
                 phases[k] = phases.get(k, 0.0) + v
-        e0.record()
-        c.barrier()
-        wall = time.perf_counter() - w0
         clk_e2e_window = (t_begin, time.time())
-        e2e_ms = c.max_over_ranks(s0.elapsed_time(e0))
         launches_e2e = (_cabi.launch_count() - launches0 +
                         (tc.replays_enc - replays0[0]) * tc.launches_enc +
                         (tc.replays_dec - replays0[1]) * tc.launches_dec)
         px_step = T * PS * PS
         e2e_value = world * px_step * args.steps / (e2e_ms / 1e3) / 1e6
-        comp_bytes_rank = cs['bytes']
+        # the same with one call after the other (2 steps)
+        seq, seq_ms, _ = timed(lambda: [run(1)[0] for _ in range(2)])
+        e2e_seq = {'value': round(world * px_step * 2 / (seq_ms / 1e3) / 1e6, 2), 'unit': 'MP/s', 'steps': 2,
+                   'ms_per_step': round(seq_ms / 2, 3),
+                   'compress_s': round(sum(a['seconds'] for a, _ in seq) / 2, 4),
+                   'decompress_s': round(sum(b['seconds'] for _, b in seq) / 2, 4)}
         # variant: the reconstruction written as raw chunk files on tmpfs (2 steps, reported aside)
-        step(to_files=True)
-        c.barrier()
-        w1 = time.perf_counter()
-        for _ in range(2):
-            cs, ds = step(to_files=True)
-        c.barrier()
-        files_ms = c.max_over_ranks((time.perf_counter() - w1) * 1e3)
+        run(1, to_files=True)
+        files, files_ms, _ = timed(lambda: [run(1, to_files=True, keep_last=(i == 1))[0] for i in range(2)])
+        cs, ds = files[-1]
         e2e_files_value = world * px_step * 2 / (files_ms / 1e3) / 1e6
         stored = DirArray(os.path.join(cs['store'], '0/0'), mode='r')       # the last step's store is kept
+        comp_bytes_rank = cs['bytes']
 
         # ---- value: the same codec, everything resident in HBM ----
         x_dev = torch.empty((T, PS, PS, 3), dtype=torch.uint8, device='cuda')
@@ -513,6 +553,20 @@ def run_wsi(args):
     clocks = clk.summary()
     clk.window(*clk_e2e_window)
     clocks_e2e = clk.summary()
+
+    # ---- the reconstruction the e2e calls left in host memory against the device-resident run's
+    # (same kernels, and the coder is lossless: identical bytes expected), 64 sampled chunks ----
+    torch.cuda.synchronize()
+    same_tiles = 0
+    sample = [tiles_mine[(k * 131) % T] for k in range(64)]
+    for (i, j) in sample:
+        got = recon[i * PS:(i + 1) * PS, j * PS:(j + 1) * PS]
+        ref = out_dev[(i - rank * rows_per_rank) * GX + j].cpu().numpy()
+        same_tiles += int(np.array_equal(got, ref))
+    e2e_matches_device = {'chunks': len(sample), 'identical': same_tiles}
+    if same_tiles != len(sample):
+        print(f'WARNING: e2e reconstruction differs from the device-resident run: {e2e_matches_device}',
+              file=sys.stderr)
 
     # ---- per-phase device times of one step (events around each phase, rank 0) ----
     per_phase = _slide.phase_times(tc, x_dev[:min(T, args.coder_tiles)], args.coder_tiles)
@@ -606,8 +660,14 @@ def run_wsi(args):
                    'e2e_is': 'compress_image -> decompress_image: slide in page-locked host memory -> chunk '
                              f'files (header + rANS stream) on {base} -> reconstruction in page-locked host '
                              'memory; every H2D / D2H copy and file write / read inside the timed region; '
-                             'each step writes a store of its own (two alternate; the previous step\'s chunk '
-                             'files are unlinked by a background thread inside the timed region)',
+                             'each step writes a store of its own (two alternate; a step\'s chunk files are '
+                             'unlinked by a background thread inside the timed region once it has been '
+                             'decompressed)' + ('; two steps in flight: the compress_image call of step k + 1 '
+                             'runs beside the decompress_image call of step k, each on its own thread and CUDA '
+                             'stream (jobs.SlideJobs) -- all calls of the K steps start and end inside the timed '
+                             'region; e2e.one_step_at_a_time is the same with the calls one after the other'
+                             if args.e2e_in_flight > 1 else ''),
+                   'e2e_steps_in_flight': args.e2e_in_flight,
                    'timed_region_s': {'value': round(total_ms / 1e3, 3), 'e2e': round(e2e_ms / 1e3, 3)},
                    'stored_bpp': round(stored_bpp, 4), 'slide_generation_s': round(t_gen, 1)},
         'clocks': clocks, 'clocks_e2e': clocks_e2e,
@@ -617,8 +677,11 @@ def run_wsi(args):
                 'ms_per_step': round(e2e_ms / args.steps, 3), 'wall_s': round(wall, 3),
                 'phase_s_per_step': {k: round(v / args.steps, 4) for k, v in phases.items()},
                 'gpu_launches': int(launches_e2e),
+                'one_step_at_a_time': e2e_seq,
+                'reconstruction_vs_device_resident_run': e2e_matches_device,
                 'with_reconstruction_written_as_raw_chunk_files': {
-                    'value': round(e2e_files_value, 2), 'unit': 'MP/s', 'steps': 2}},
+                    'value': round(e2e_files_value, 2), 'unit': 'MP/s', 'steps': 2,
+                    'one_step_at_a_time': True}},
         'gpu_launches': int(launches),
         'device_phase_ms': per_phase,
         'pipeline_tflops': round(tf, 2),
@@ -758,6 +821,9 @@ def main():
     ap.add_argument('--e2e-decoder-tiles', default='0',
                     help='the same for decompress_image (0 = the coder schedule reversed: the first group is '
                          'the exposed one)')
+    ap.add_argument('--e2e-in-flight', type=int, default=2, choices=[1, 2],
+                    help='steps in flight in the e2e region: 2 = the compress_image call of step k + 1 runs '
+                         'beside the decompress_image call of step k (jobs.SlideJobs); 1 = one call after the other')
     ap.add_argument('--parity-tiles', type=int, default=8)
     ap.add_argument('--no-parity', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -106,6 +106,9 @@ class TileCodec:
         # streams live as long as the codec: the caching allocator pools memory per stream, so a
         # fresh stream per call would cudaMalloc its gigabyte-sized scratch again every time
         self.s_in, self.s_out, self.s_code = (torch.cuda.Stream(self.dev) for _ in range(3))
+        # the decoder's own coder stream: a decompress_image call may run beside a compress_image
+        # call on the same model (two slides in flight, each call on its own thread and stream)
+        self.s_dec = torch.cuda.Stream(self.dev)
         self._bufs = {}
 
     # ---- the per-batch work, eager form (also what the graphs capture) ----
@@ -407,7 +410,8 @@ def compress_tiles(tc, src, tiles, chunk_path, header_hw, workers, coder_tiles, 
     for j in jobs:
         j.result()
     coder.shutdown()
-    torch.cuda.synchronize(dev)
+    for st in (main, s_in, s_code):        # this call's streams only: another call may be in flight
+        st.synchronize()
     mark('c_done')
 
 
@@ -423,7 +427,7 @@ def decompress_tiles(tc, tiles, chunk_path, workers, coder_tiles, stats, H, W, o
     tile_yx = np.ascontiguousarray(np.array(tiles, dtype=np.int32).reshape(-1, 2))
     L = C.lib()
     main = torch.cuda.current_stream(dev)
-    s_out, s_code = tc.s_out, tc.s_code
+    s_out, s_code = tc.s_out, tc.s_dec
     sizes = group_sizes(n_tiles, coder_tiles, B)
     groups = [(int(sum(sizes[:k])), g) for k, g in enumerate(sizes)]
     reader = ThreadPoolExecutor(max_workers=1)
@@ -558,7 +562,8 @@ def decompress_tiles(tc, tiles, chunk_path, workers, coder_tiles, stats, H, W, o
     reader.shutdown()
     if writer is not None:
         writer.shutdown()
-    torch.cuda.synchronize(dev)
+    for st in (main, s_out, s_code):
+        st.synchronize()
     for status in statuses:
         fe.check_decode_status(status)
 

@@ -119,6 +119,53 @@ def test_coder_group_schedule_writes_the_same_files(tmp_path):
     assert np.array_equal(ca, cb)
 
 
+def test_two_slides_in_flight_give_the_same_files_and_pixels(tmp_path):
+    """``jobs.SlideJobs``: a compress_image call of one slide beside the decompress_image call of
+    another (two threads, two main streams, one model) -- same chunk files and the same
+    reconstruction as the calls one after the other."""
+    from oracle import cae_oracle as O
+    from cnn_autoencoder_b200 import compress, decompress, _store
+    from cnn_autoencoder_b200.jobs import SlideJobs
+    chk = O.make_checkpoint(ARCH, seed=5)
+    slides = [_slide(12, 13, (24, 40)), _slide(12, 13, (24, 40))[::-1].copy()]
+    kw = dict(patch_size=PS, batch_tiles=16)
+
+    def pinned_zeros(shape):
+        return torch.zeros(shape, dtype=torch.uint8).pin_memory().numpy()
+    # one after the other
+    ref_dirs = [str(tmp_path / ('ref%d.zarr' % k)) for k in range(2)]
+    ref_rec = [pinned_zeros(s.shape) for s in slides]
+    for k in range(2):
+        compress.compress_image('CAE', chk, slides[k], ref_dirs[k], coder_tiles=(96, 60), **kw)
+        decompress.decompress_image(ref_dirs[k], ref_rec[k], checkpoint=chk, batch_tiles=16, coder_tiles=96)
+    # six steps, two in flight
+    dirs = [str(tmp_path / ('s%d.zarr' % k)) for k in range(2)]
+    rec = [pinned_zeros(s.shape) for s in slides]
+    with SlideJobs() as jobs:
+        def comp(k, prev):
+            if prev is not None:
+                prev.result()
+            return compress.compress_image('CAE', chk, slides[k % 2], dirs[k % 2], coder_tiles=(96, 60), **kw)
+
+        def dec(k, fc):
+            fc.result()
+            return decompress.decompress_image(dirs[k % 2], rec[k % 2], checkpoint=chk, batch_tiles=16,
+                                               coder_tiles=96)
+        fds = []
+        for k in range(6):
+            fc = jobs.submit('compress', comp, k, fds[k - 2] if k >= 2 else None)
+            fds.append(jobs.submit('decompress', dec, k, fc))
+        stats = [f.result() for f in fds]
+    torch.cuda.synchronize()
+    assert all(st['engine'] == 'slide' and st['device_decoded'] == 156 for st in stats)
+    for k in range(2):
+        assert np.array_equal(rec[k], ref_rec[k])
+        A, B = (_store.DirArray(os.path.join(p, '0/0'), mode='r') for p in (ref_dirs[k], dirs[k]))
+        for i in range(12):
+            for j in range(13):
+                assert A.read_encoded((i, j, 0)) == B.read_encoded((i, j, 0))
+
+
 def test_device_roundtrip_and_phase_record():
     from oracle import cae_oracle as O
     import cnn_autoencoder_b200 as M

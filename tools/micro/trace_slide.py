@@ -13,6 +13,11 @@ import shutil
 import sys
 import time
 
+IN_FLIGHT = 1
+if '--in-flight' in sys.argv:         # two steps in flight (jobs.SlideJobs), plain timings
+    sys.argv.remove('--in-flight')
+    IN_FLIGHT = 2
+    sys.argv.append('--no-trace') if '--no-trace' not in sys.argv else None
 if '--no-trace' in sys.argv:          # plain timings: the trace marks synchronise the helper threads
     sys.argv.remove('--no-trace')
 else:
@@ -51,7 +56,41 @@ pin_r = _slide.pin_array(recon)
 work = '/dev/shm/cae_trace'
 shutil.rmtree(work, ignore_errors=True)
 os.makedirs(work)
+def pipelined(G, GD, steps=6):
+    """`steps` steps with the compress call of step k + 1 beside the decompress call of step k."""
+    from cnn_autoencoder_b200.jobs import SlideJobs
+    stores = [work + '/p%d.zarr' % k for k in range(2)]
+    with SlideJobs() as jobs:
+        def comp(k, prev):
+            if prev is not None:
+                prev.result()          # (compress_image empties the store it overwrites by itself)
+            return CMP.compress_image('CAE', chk, slide, stores[k % 2], patch_size=512, gpu=True,
+                                      batch_tiles=32, coder_tiles=G)
+
+        def dec(k, fc):
+            fc.result()
+            return DEC.decompress_image(stores[k % 2], recon, checkpoint=chk, gpu=True, batch_tiles=32,
+                                        coder_tiles=GD)
+        for rep in range(2):
+            for st in stores:
+                shutil.rmtree(st, ignore_errors=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fds = []
+            for k in range(steps):
+                fc = jobs.submit('compress', comp, k, fds[k - 2] if k >= 2 else None)
+                fds.append(jobs.submit('decompress', dec, k, fc))
+            out = [f.result() for f in fds]
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / steps
+    print('chunks %d  coder groups %s  decoder groups %s  TWO STEPS IN FLIGHT: %.4f s per step '
+          '(%.0f MP/s; store removal inside)' % (T, G, GD, dt, T * 512 * 512 / dt / 1e6), flush=True)
+
+
 for G, GD in schedules:
+    if IN_FLIGHT == 2:
+        pipelined(G, GD)
+        continue
     best = None
     for it in range(4):
         shutil.rmtree(work + '/s.zarr', ignore_errors=True)      # a fresh store per step (untimed)
