@@ -10,7 +10,9 @@ prologue of a decompress call (file reads, upload, first decode).  ``SlideJobs``
 of call on two worker threads, each with a CUDA stream of its own as the call's main stream, so
 that a compress call of one slide overlaps the decompress call of another.  The calls themselves
 are the public tile loops, unchanged; the batched engine keeps separate buffers, graphs and coder
-streams for the two directions (``_slide.TileCodec``).
+streams for the two directions (``_slide.TileCodec``).  CUDA graphs are captured on a model's first
+call of each kind, and a capture does not tolerate launches from another thread: run one compress
+and one decompress call alone before putting two in flight.
 """
 import threading
 from concurrent.futures import ThreadPoolExecutor

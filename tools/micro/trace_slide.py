@@ -60,6 +60,10 @@ def pipelined(G, GD, steps=6):
     """`steps` steps with the compress call of step k + 1 beside the decompress call of step k."""
     from cnn_autoencoder_b200.jobs import SlideJobs
     stores = [work + '/p%d.zarr' % k for k in range(2)]
+    # (CUDA graphs are captured on first use, and a capture does not tolerate another thread's
+    # launches: one step alone first)
+    CMP.compress_image('CAE', chk, slide, stores[0], patch_size=512, gpu=True, batch_tiles=32, coder_tiles=G)
+    DEC.decompress_image(stores[0], recon, checkpoint=chk, gpu=True, batch_tiles=32, coder_tiles=GD)
     with SlideJobs() as jobs:
         def comp(k, prev):
             if prev is not None:
