@@ -305,3 +305,12 @@ def test_default_coder_schedule():
             sizes = group_sizes(n, default_schedule(n, 32, decode=dec), 32)
             assert sum(sizes) == n and max(sizes) <= 8192 + 32 and min(sizes) > 0
             assert all(g % 32 == 0 for g in sizes[:-1])
+
+
+def test_slide_jobs_need_a_gpu():
+    """No CPU fallback: the two-slides-in-flight runner refuses to start without a CUDA device."""
+    from cnn_autoencoder_b200.jobs import SlideJobs
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present: covered by tests/test_gpu_slide.py')
+    with pytest.raises(RuntimeError):
+        SlideJobs()
