@@ -467,7 +467,7 @@ def run_wsi(args):
             fd = jobs.submit('decompress', decompress_job, k, fc, to_files, keep_last and i == n - 1)
             state['dec'][k] = fd
             futs.append(fd)
-        return [f.result() for f in futs]
+        return [f.result(timeout=300) for f in futs]       # (a hang becomes an error, not a dead box)
 
     def timed(fn):
         """(device ms, wall s) of fn() between two idle points of the device, max over ranks."""
@@ -497,8 +497,16 @@ def run_wsi(args):
         launches0, replays0 = _cabi.launch_count(), (tc.replays_enc, tc.replays_dec)
         t_begin = time.time()
         if args.e2e_in_flight > 1:
-            done, e2e_ms, wall = timed(lambda: run(args.steps))
-        else:
+            try:
+                done, e2e_ms, wall = timed(lambda: run(args.steps))
+            except Exception as exc:       # report the one-at-a-time figure rather than nothing
+                print(f'WARNING: two steps in flight failed ({exc!r}); measuring one step at a time',
+                      file=sys.stderr)
+                args.e2e_in_flight = 1
+                jobs.close(wait=False)
+                jobs = SlideJobs(c.local)
+                state.update(step=state['step'] + 2, dec={}, clean={})
+        if args.e2e_in_flight == 1:
             done, e2e_ms, wall = timed(lambda: [run(1)[0] for _ in range(args.steps)])
         for cs, ds in done:
             for k, v in (('compress_s', cs['seconds']), ('decompress_s', ds['seconds'])):

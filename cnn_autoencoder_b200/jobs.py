@@ -46,9 +46,9 @@ class SlideJobs:
         calls of one stage run in submission order.  Returns a ``concurrent.futures.Future``."""
         return self._pools[stage].submit(self._run, fn, args, kwargs)
 
-    def close(self):
+    def close(self, wait=True):
         for p in self._pools.values():
-            p.shutdown(wait=True)
+            p.shutdown(wait=wait)
 
     def __enter__(self):
         return self
