@@ -126,6 +126,16 @@ int main(int argc, char **argv) {
     missing.push_back('\0');
     int64_t s1 = 0;
     (void)cae_files_stat(missing.c_str(), 1, &s1, 1);
+    REQUIRE(s1 == -1);
+    // header-less files (raw chunks), then the removal of everything incl. a name that is not there
+    REQUIRE(cae_files_write(paths.c_str(), n, nullptr, 0, payload.data(), off.data(), 3) == 0);
+    REQUIRE(cae_files_stat(paths.c_str(), n, sz.data(), 2) == 0);
+    for (int k = 0; k < n; ++k) REQUIRE(sz[k] == off[k + 1] - off[k]);
+    std::string all = paths + missing;
+    REQUIRE(cae_files_remove(all.c_str(), n + 1, 4) == 0);
+    REQUIRE(cae_files_stat(paths.c_str(), n, sz.data(), 4) == 0);
+    for (int k = 0; k < n; ++k) REQUIRE(sz[k] == -1);
+    REQUIRE(cae_files_remove(nullptr, 1, 1) != 0);
   }
   printf("sanitize_host: ok\n");
   return 0;
