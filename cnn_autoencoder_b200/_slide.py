@@ -455,7 +455,7 @@ def decompress_tiles(tc, tiles, chunk_path, workers, coder_tiles, stats, H, W, o
         words = [None]
 
         def alloc(nbytes):
-            words[0] = torch.empty(nbytes // 4, dtype=torch.int32, device=dev)
+            words[0] = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=dev)
             if uploaded[gk & 1] is not None:
                 uploaded[gk & 1].synchronize()       # the staging buffer's last upload has left it
             return tc.pinned('streams_in%d' % (gk & 1), nbytes).numpy()
