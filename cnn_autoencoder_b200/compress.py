@@ -229,7 +229,7 @@ def compress_image(codec, checkpoint, input_filename, output_filename, patch_siz
         stats['engine'] = 'slide'
         stats['seconds'] = time.perf_counter() - t_start
         return stats
-    if not isinstance(coder_tiles, int):
+    if not isinstance(coder_tiles, (int, np.integer)):
         coder_tiles = max(int(g) for g in coder_tiles)     # a group schedule (_slide.group_sizes)
     pool = ThreadPoolExecutor(max_workers=workers)
     writes = []                     # futures of chunk-file writes

@@ -111,7 +111,7 @@ def decompress_image(input_filename, output_filename, destination_format='zarr',
         stats['engine'] = 'slide'
         stats['seconds'] = time.perf_counter() - t_start
         return stats
-    if not isinstance(coder_tiles, int):
+    if not isinstance(coder_tiles, (int, np.integer)):
         coder_tiles = max(int(g) for g in coder_tiles)     # a group schedule (_slide.group_sizes)
     pool = ThreadPoolExecutor(max_workers=workers)
 
